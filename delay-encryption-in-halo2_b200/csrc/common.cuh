@@ -1,0 +1,145 @@
+// common.cuh — host-side plumbing shared by the translation units of libde_b200.so: the context object, grow-only
+// device workspaces, error capture.  No arithmetic lives here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/de_b200.h"
+#include "field.cuh"
+
+namespace de {
+
+struct NttPlan;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    // returns nullptr on allocation failure
+    void* ensure(size_t bytes) {
+        if (bytes <= cap && p) return p;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes < 256 ? 256 : bytes;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            return nullptr;
+        }
+        cap = want;
+        return p;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* ensure(size_t bytes) {
+        if (bytes <= cap && p) return p;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes < 256 ? 256 : bytes;
+        if (cudaMallocHost(&p, want) != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            return nullptr;
+        }
+        cap = want;
+        return p;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum { WS_IO_A = 0, WS_IO_B, WS_NTT_SCRATCH, WS_MSM_KEYS, WS_MSM_VALS, WS_MSM_SORTED, WS_MSM_COUNTS, WS_MSM_BUCKETS,
+       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_COUNT };
+
+}  // namespace de
+
+struct de_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int sm_count = 148;
+    std::string err;
+    uint64_t launches = 0;
+    de::DevBuf ws[de::WS_COUNT];
+    de::PinnedBuf pinned;
+    std::vector<de::NttPlan*> plans;
+};
+
+namespace de {
+
+extern thread_local std::string g_create_error;
+
+inline int fail(de_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define DE_CUDA(ctx, expr)                                                                                  \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess) {                                                                           \
+            cudaGetLastError();                                                                             \
+            return de::fail((ctx), e__ == cudaErrorMemoryAllocation ? DE_ERR_OOM : DE_ERR_CUDA,             \
+                            std::string(#expr) + ": " + cudaGetErrorString(e__));                           \
+        }                                                                                                   \
+    } while (0)
+
+#define DE_CHECK_LAUNCH(ctx)                                                                                \
+    do {                                                                                                    \
+        (ctx)->launches++;                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                                               \
+        if (e__ != cudaSuccess)                                                                             \
+            return de::fail((ctx), DE_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__) +  \
+                                                    " at " + __FILE__ + ":" + std::to_string(__LINE__));    \
+    } while (0)
+
+#define DE_TRY(expr)                 \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != DE_OK) return rc__; \
+    } while (0)
+
+#define DE_WS(ctx, var, type, slot, bytes)                                                      \
+    type* var = (type*)(ctx)->ws[slot].ensure(bytes);                                           \
+    if (!var) return de::fail((ctx), DE_ERR_OOM, std::string("device workspace allocation of ") + \
+                                                     std::to_string((size_t)(bytes)) + " bytes failed")
+
+inline Fr fr_from_host(const de_fr& v) {
+    Fr r;
+    for (int i = 0; i < 4; i++) {
+        r.l[2 * i] = (uint32_t)v.l[i];
+        r.l[2 * i + 1] = (uint32_t)(v.l[i] >> 32);
+    }
+    return r;
+}
+inline de_fr fr_to_host(const Fr& v) {
+    de_fr r;
+    for (int i = 0; i < 4; i++) r.l[i] = (uint64_t)v.l[2 * i] | ((uint64_t)v.l[2 * i + 1] << 32);
+    return r;
+}
+
+// ntt.cu
+int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, size_t src_stride, Fr* d_dst, size_t dst_stride,
+            size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3);
+void ntt_free_plans(de_ctx* ctx);
+// device-side Fr helpers running single-thread kernels, used for domain constants (ntt.cu)
+int fr_host_pow(de_ctx* ctx, const de_fr& base, uint64_t e, de_fr* out);
+
+}  // namespace de

@@ -1,0 +1,304 @@
+// msm.cu — host side of the MSM entry points: window-shape selection, workspace layout, the launch sequence of
+// msm.cuh, and the C ABI functions de_msm*, de_params_*, de_commit*, de_g1_sum.
+// Reference semantics: halo2_proofs::arithmetic::best_multiexp and ParamsKZG::{commit, commit_lagrange}
+// (SURVEY.md Appendix B.1 / B.4).
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "msm.cuh"
+
+namespace de {
+
+struct MsmCfg {
+    unsigned int c, W, nsets, ntables;
+};
+
+static unsigned int windows_for(unsigned int c) { return (255 + c - 1) / c; }
+
+// cost model in field multiplications: 10 per mixed add in the bucket fill, ~40 per bucket in the reduction
+static MsmCfg choose_cfg(unsigned long long n, bool precomputed, unsigned long long max_tables) {
+    MsmCfg best = {0, 0, 0, 0};
+    double best_cost = 1e300;
+    const char* env = getenv("DE_MSM_C");
+    unsigned int forced = env ? (unsigned int)atoi(env) : 0;
+    for (unsigned int c = 8; c <= 20; c++) {
+        if (forced && c != forced) continue;
+        unsigned int W = windows_for(c);
+        unsigned int ntables = 1, nsets = W;
+        if (precomputed) {
+            ntables = W;
+            if (ntables > max_tables) ntables = (unsigned int)max_tables;
+            if (ntables < 1) ntables = 1;
+            nsets = (W + ntables - 1) / ntables;
+            ntables = (W + nsets - 1) / nsets;
+        }
+        double cost = 10.0 * (double)n * W + 40.0 * (double)nsets * (double)(1u << (c - 1));
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = {c, W, nsets, ntables};
+        }
+    }
+    return best;
+}
+
+static int scan_u32(de_ctx* ctx, const unsigned int* in, unsigned long long n, unsigned int* out, unsigned int* block_sums,
+                    unsigned int* grand_total) {
+    const unsigned long long per_block = DE_SCAN_THREADS * DE_SCAN_ITEMS;
+    unsigned long long nblocks = (n + per_block - 1) / per_block;
+    if (nblocks > per_block) return fail(ctx, DE_ERR_UNSUPPORTED, "msm: too many buckets for the scan");
+    k_scan_blocks<<<(unsigned int)nblocks, DE_SCAN_THREADS, 0, ctx->stream>>>(in, n, out, block_sums);
+    DE_CHECK_LAUNCH(ctx);
+    k_scan_tops<<<1, DE_SCAN_THREADS, 0, ctx->stream>>>(block_sums, (unsigned int)nblocks, grand_total);
+    DE_CHECK_LAUNCH(ctx);
+    k_scan_add<<<(unsigned int)((n + 255) / 256), 256, 0, ctx->stream>>>(out, n, block_sums);
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// d_scalars: `count` polynomials of n Montgomery scalars, `stride` elements apart.  d_tables: cfg.ntables base tables,
+// table_stride elements apart.  Writes `count` Jacobian points to host_out.
+static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, size_t count, const Affine* d_tables,
+                    size_t table_stride, size_t base_offset, const MsmCfg& cfg, de_g1* host_out) {
+    if (count == 0) return DE_OK;
+    if (n == 0) {
+        memset(host_out, 0, sizeof(de_g1) * count);
+        return DE_OK;
+    }
+    if ((unsigned long long)cfg.ntables * table_stride >= (1ull << 31)) return fail(ctx, DE_ERR_UNSUPPORTED, "msm: base table exceeds 2^31 points");
+    MsmShape sh;
+    sh.c = cfg.c; sh.W = cfg.W; sh.nsets = cfg.nsets; sh.NB = 1u << (cfg.c - 1);
+    sh.count = (unsigned int)count; sh.n = n; sh.table_stride = table_stride; sh.base_offset = base_offset;
+    const unsigned long long E = (unsigned long long)count * sh.W * n;
+    const unsigned long long nbuckets = (unsigned long long)count * sh.nsets * sh.NB;
+    if (E >= (1ull << 32) || nbuckets >= (1ull << 31)) return fail(ctx, DE_ERR_UNSUPPORTED, "msm: batch too large for 32-bit entry indices");
+    unsigned int CH = (unsigned int)(4 * ((E + nbuckets - 1) / nbuckets));
+    if (CH < 32) CH = 32;
+    const unsigned long long max_tasks = E / CH + nbuckets + 1;
+    const unsigned int CK = sh.NB >= 4096 ? 32 : (sh.NB >= 256 ? 8 : 1);
+    const unsigned int chunks_per_set = sh.NB / CK;
+    const unsigned int nsets_total = (unsigned int)(count * sh.nsets);
+
+    DE_WS(ctx, keys, unsigned int, WS_MSM_KEYS, sizeof(unsigned int) * E);
+    DE_WS(ctx, vals, unsigned int, WS_MSM_VALS, sizeof(unsigned int) * E);
+    DE_WS(ctx, sorted, unsigned int, WS_MSM_SORTED, sizeof(unsigned int) * E);
+    // u32 arrays of nbuckets + 1 entries each: counts, offsets, cursor, ntasks, task_off, multi_list; then block sums + scalars
+    const size_t nb1 = align_up(nbuckets + 1, 64);
+    const size_t misc_words = nb1 * 6 + 2 * (DE_SCAN_THREADS * DE_SCAN_ITEMS) + 64;
+    DE_WS(ctx, misc, unsigned int, WS_MSM_COUNTS, sizeof(unsigned int) * misc_words);
+    unsigned int* counts = misc;
+    unsigned int* offsets = counts + nb1;
+    unsigned int* cursor = offsets + nb1;
+    unsigned int* ntasks = cursor + nb1;
+    unsigned int* task_off = ntasks + nb1;
+    unsigned int* multi_list = task_off + nb1;
+    unsigned int* block_sums = multi_list + nb1;
+    unsigned int* block_sums2 = block_sums + DE_SCAN_THREADS * DE_SCAN_ITEMS;
+    unsigned int* scalars_u32 = block_sums2 + DE_SCAN_THREADS * DE_SCAN_ITEMS;  // [0] total entries, [1] total tasks, [2] multi_count
+    DE_WS(ctx, buckets, XYZZ, WS_MSM_BUCKETS, sizeof(XYZZ) * nbuckets);
+    DE_WS(ctx, partials, XYZZ, WS_MSM_PARTIALS, sizeof(XYZZ) * max_tasks);
+    DE_WS(ctx, red, XYZZ, WS_MSM_MISC, sizeof(XYZZ) * ((size_t)chunks_per_set * nsets_total + nsets_total));
+    XYZZ* chunk_out = red;
+    XYZZ* set_out = red + (size_t)chunks_per_set * nsets_total;
+    DE_WS(ctx, d_out, Jac, WS_MSM_OUT, sizeof(Jac) * count);
+
+    cudaStream_t st = ctx->stream;
+    DE_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(unsigned int) * nb1, st));
+    DE_CUDA(ctx, cudaMemsetAsync(ntasks, 0, sizeof(unsigned int) * nb1, st));
+    DE_CUDA(ctx, cudaMemsetAsync(scalars_u32, 0, sizeof(unsigned int) * 64, st));
+    DE_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * nbuckets, st));
+
+    const unsigned long long nscal = (unsigned long long)n * count;
+    k_msm_digits<<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals);
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_hist<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, E, counts);
+    DE_CHECK_LAUNCH(ctx);
+    DE_TRY(scan_u32(ctx, counts, nbuckets + 1, offsets, block_sums, &scalars_u32[0]));
+    DE_CUDA(ctx, cudaMemcpyAsync(cursor, offsets, sizeof(unsigned int) * (nbuckets + 1), cudaMemcpyDeviceToDevice, st));
+    k_msm_scatter<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, vals, E, cursor, sorted);
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_task_counts<<<(unsigned int)((nbuckets + 255) / 256), 256, 0, st>>>(counts, (unsigned int)nbuckets, CH, ntasks, multi_list,
+                                                                             &scalars_u32[2]);
+    DE_CHECK_LAUNCH(ctx);
+    DE_TRY(scan_u32(ctx, ntasks, nbuckets + 1, task_off, block_sums2, &scalars_u32[1]));
+    k_msm_accumulate<<<(unsigned int)((max_tasks + 127) / 128), 128, 0, st>>>(sorted, offsets, counts, task_off, (unsigned int)nbuckets, CH,
+                                                                              d_tables, buckets, partials);
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_merge<<<ctx->sm_count * 2, 128, 0, st>>>(multi_list, &scalars_u32[2], task_off, partials, buckets);
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_reduce_chunks<<<(chunks_per_set * nsets_total + 127) / 128, 128, 0, st>>>(buckets, sh.NB, CK, nsets_total, chunk_out);
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_reduce_sets<<<nsets_total, 256, 0, st>>>(chunk_out, chunks_per_set, set_out);
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_combine<<<(unsigned int)count, 32, 0, st>>>(set_out, sh.nsets, sh.c, d_out);
+    DE_CHECK_LAUNCH(ctx);
+    DE_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));
+    DE_CUDA(ctx, cudaStreamSynchronize(st));
+    return DE_OK;
+}
+
+}  // namespace de
+
+using namespace de;
+
+struct de_params {
+    de_ctx* ctx;
+    uint32_t k;
+    size_t n;
+    MsmCfg cfg;
+    Affine* tables[2];  // [0] g, [1] g_lagrange; each cfg.ntables tables of n points
+};
+
+extern "C" {
+
+int de_msm_dev(de_ctx* ctx, const de_fr* d_scalars, const de_g1_affine* d_bases, size_t n, de_g1* out) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!out || (n && (!d_scalars || !d_bases))) return fail(ctx, DE_ERR_ARG, "de_msm_dev: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    MsmCfg cfg = choose_cfg(n, false, 1);
+    return msm_core(ctx, (const Fr*)d_scalars, n, n, 1, (const Affine*)d_bases, n, 0, cfg, out);
+}
+
+int de_msm(de_ctx* ctx, const de_fr* scalars, const de_g1_affine* bases, size_t n, de_g1* out) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!out || (n && (!scalars || !bases))) return fail(ctx, DE_ERR_ARG, "de_msm: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) {
+        memset(out, 0, sizeof(*out));
+        return DE_OK;
+    }
+    DE_WS(ctx, ds, Fr, WS_IO_A, sizeof(Fr) * n);
+    DE_WS(ctx, db, Affine, WS_IO_B, sizeof(Affine) * n);
+    DE_CUDA(ctx, cudaMemcpyAsync(ds, scalars, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaMemcpyAsync(db, bases, sizeof(Affine) * n, cudaMemcpyHostToDevice, ctx->stream));
+    return de_msm_dev(ctx, (const de_fr*)ds, (const de_g1_affine*)db, n, out);
+}
+
+int de_params_upload(de_ctx* ctx, uint32_t k, const de_g1_affine* g, const de_g1_affine* g_lagrange, de_params** out) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!out) return fail(ctx, DE_ERR_ARG, "de_params_upload: out is NULL");
+    *out = nullptr;
+    if (k > 26) return fail(ctx, DE_ERR_ARG, "de_params_upload: k > 26 not supported");
+    if (!g && !g_lagrange) return fail(ctx, DE_ERR_ARG, "de_params_upload: both bases NULL");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << k;
+    // table budget per basis: 4 GiB (override with DE_MSM_TABLE_MB)
+    size_t budget = (size_t)4 << 30;
+    if (const char* e = getenv("DE_MSM_TABLE_MB")) budget = (size_t)atoll(e) << 20;
+    unsigned long long max_tables = budget / (sizeof(Affine) * n);
+    if (max_tables < 1) max_tables = 1;
+    de_params* p = new de_params();
+    p->ctx = ctx;
+    p->k = k;
+    p->n = n;
+    p->cfg = choose_cfg(n, true, max_tables);
+    p->tables[0] = p->tables[1] = nullptr;
+    const de_g1_affine* src[2] = {g, g_lagrange};
+    for (int b = 0; b < 2; b++) {
+        if (!src[b]) continue;
+        cudaError_t e = cudaMalloc((void**)&p->tables[b], sizeof(Affine) * n * p->cfg.ntables);
+        Affine* staging = nullptr;
+        if (e == cudaSuccess) staging = (Affine*)ctx->ws[WS_IO_B].ensure(sizeof(Affine) * n);
+        if (e != cudaSuccess || !staging) {
+            cudaGetLastError();
+            de_params_free(p);
+            return fail(ctx, DE_ERR_OOM, "de_params_upload: device allocation failed");
+        }
+        e = cudaMemcpyAsync(staging, src[b], sizeof(Affine) * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            k_msm_precompute<<<(unsigned int)((n + 127) / 128), 128, 0, ctx->stream>>>(staging, n, p->cfg.c * p->cfg.nsets, p->cfg.ntables, n,
+                                                                                     p->tables[b]);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            de_params_free(p);
+            return fail(ctx, DE_ERR_CUDA, std::string("de_params_upload: ") + cudaGetErrorString(e));
+        }
+    }
+    *out = p;
+    return DE_OK;
+}
+
+int de_params_free(de_params* p) {
+    if (!p) return DE_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    for (int b = 0; b < 2; b++)
+        if (p->tables[b]) cudaFree(p->tables[b]);
+    delete p;
+    return DE_OK;
+}
+
+int de_commit_batch_dev(de_params* p, int basis, const de_fr* d_scalars, size_t stride, size_t n, size_t count, de_g1* out) {
+    if (!p) return DE_ERR_ARG;
+    de_ctx* ctx = p->ctx;
+    if (basis < 0 || basis > 1 || !p->tables[basis]) return fail(ctx, DE_ERR_ARG, "de_commit: basis not uploaded");
+    if (n > p->n) return fail(ctx, DE_ERR_ARG, "de_commit: polynomial longer than the SRS (n > 2^k)");
+    if (!out || (n && count && !d_scalars)) return fail(ctx, DE_ERR_ARG, "de_commit: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return msm_core(ctx, (const Fr*)d_scalars, stride, n, count, p->tables[basis], p->n, 0, p->cfg, out);
+}
+
+int de_commit_batch(de_params* p, int basis, const de_fr* const* scalars, size_t n, size_t count, de_g1* out) {
+    if (!p) return DE_ERR_ARG;
+    de_ctx* ctx = p->ctx;
+    if (!out || (count && !scalars)) return fail(ctx, DE_ERR_ARG, "de_commit_batch: null pointer");
+    if (n > p->n) return fail(ctx, DE_ERR_ARG, "de_commit: polynomial longer than the SRS (n > 2^k)");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (count == 0) return DE_OK;
+    if (n == 0) {
+        memset(out, 0, sizeof(de_g1) * count);
+        return DE_OK;
+    }
+    DE_WS(ctx, ds, Fr, WS_IO_A, sizeof(Fr) * n * count);
+    for (size_t i = 0; i < count; i++) {
+        if (!scalars[i]) return fail(ctx, DE_ERR_ARG, "de_commit_batch: null polynomial");
+        DE_CUDA(ctx, cudaMemcpyAsync(ds + i * n, scalars[i], sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return de_commit_batch_dev(p, basis, (const de_fr*)ds, n, n, count, out);
+}
+
+int de_commit(de_params* p, int basis, const de_fr* scalars, size_t n, de_g1* out) {
+    const de_fr* arr[1] = {scalars};
+    return de_commit_batch(p, basis, arr, n, 1, out);
+}
+
+int de_commit_range(de_params* p, int basis, const de_fr* scalars, size_t lo, size_t hi, de_g1* out_partial) {
+    if (!p) return DE_ERR_ARG;
+    de_ctx* ctx = p->ctx;
+    if (basis < 0 || basis > 1 || !p->tables[basis]) return fail(ctx, DE_ERR_ARG, "de_commit_range: basis not uploaded");
+    if (lo > hi || hi > p->n) return fail(ctx, DE_ERR_ARG, "de_commit_range: bad range");
+    if (!out_partial || (hi > lo && !scalars)) return fail(ctx, DE_ERR_ARG, "de_commit_range: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t n = hi - lo;
+    if (n == 0) {
+        memset(out_partial, 0, sizeof(de_g1));
+        return DE_OK;
+    }
+    DE_WS(ctx, ds, Fr, WS_IO_A, sizeof(Fr) * n);
+    DE_CUDA(ctx, cudaMemcpyAsync(ds, scalars + lo, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_core(ctx, ds, n, n, 1, p->tables[basis], p->n, lo, p->cfg, out_partial);
+}
+
+int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!out || (count && !points)) return fail(ctx, DE_ERR_ARG, "de_g1_sum: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (count == 0) {
+        memset(out, 0, sizeof(*out));
+        return DE_OK;
+    }
+    DE_WS(ctx, d, Jac, WS_MSM_OUT, sizeof(Jac) * (count + 1));
+    DE_CUDA(ctx, cudaMemcpyAsync(d + 1, points, sizeof(Jac) * count, cudaMemcpyHostToDevice, ctx->stream));
+    k_g1_sum<<<1, 32, 0, ctx->stream>>>(d + 1, (unsigned int)count, d);
+    DE_CHECK_LAUNCH(ctx);
+    DE_CUDA(ctx, cudaMemcpyAsync(out, d, sizeof(Jac), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// msm.cuh — Pippenger multi-scalar multiplication over BN254 G1 for sm_100a (replaces
+// halo2_proofs::arithmetic::best_multiexp and ParamsKZG::commit / commit_lagrange; SURVEY.md section 8 rows a3, a8;
+// reference behaviour Appendix B.1).  The result is the unique group element sum_i s_i * P_i, so any window layout
+// gives the reference's answer; this one is chosen for the GPU:
+//
+//   1. k_msm_digits     canonical scalar (one Montgomery reduction) -> signed c-bit digits; one (key, value) entry per
+//                       non-zero digit: key = bucket id, value = base-table index | sign
+//   2. counting sort    histogram (k_msm_hist) -> exclusive scan -> scatter (k_msm_scatter): entries grouped by bucket
+//   3. k_msm_accumulate one thread per task (a run of <= CH entries of one bucket): gathers 64-byte affine bases with
+//                       16-byte loads and adds them into an XYZZ accumulator (8M + 2S per point); heavy buckets are
+//                       split into several tasks whose partial sums are merged warp-cooperatively (k_msm_merge)
+//   4. k_msm_reduce_*   sum_b (b+1) * B_b per bucket set by chunked running sums
+//   5. k_msm_combine    sum over bucket sets of 2^(c*u) * R_u
+//
+// With tables 2^(c*nsets*t) * P_i precomputed per ParamsKZG (k_msm_precompute) all windows of a scalar share one
+// bucket set (nsets = 1): one reduction, no doublings.
+#pragma once
+#include "ec.cuh"
+
+namespace de {
+
+#define DE_MSM_INVALID 0xffffffffu
+
+struct MsmShape {
+    unsigned int c;         // window bits
+    unsigned int W;         // number of windows, c * W >= 255
+    unsigned int nsets;     // bucket sets per polynomial; window w uses set w % nsets and table w / nsets
+    unsigned int NB;        // buckets per set = 2^(c-1)
+    unsigned int count;     // polynomials in the batch
+    unsigned long long n;   // scalars per polynomial
+    unsigned long long table_stride;  // elements between consecutive base tables
+    unsigned long long base_offset;   // first base of this (sharded) range inside each table
+};
+
+// ---- 1. digits -------------------------------------------------------------------------------------------------
+__global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmShape sh, unsigned int* keys, unsigned int* vals) {
+    unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= sh.n * sh.count) return;
+    unsigned int b = (unsigned int)(gid / sh.n);
+    unsigned long long i = gid % sh.n;
+    Fr s = from_mont(load(&scalars[b * stride + i]));
+    const unsigned int c = sh.c;
+    const unsigned int half = 1u << (c - 1);
+    unsigned int carry = 0;
+    for (unsigned int w = 0; w < sh.W; w++) {
+        unsigned int bit = w * c;
+        unsigned int limb = bit >> 5, off = bit & 31;
+        unsigned long long lo = limb < 8 ? s.l[limb] : 0;
+        unsigned long long hi = (limb + 1) < 8 ? s.l[limb + 1] : 0;
+        unsigned int raw = (unsigned int)(((lo | (hi << 32)) >> off) & ((1ull << c) - 1));
+        unsigned int v = raw + carry;
+        unsigned int neg = 0, mag = v;
+        carry = 0;
+        if (v > half) {
+            mag = (1u << c) - v;
+            neg = 1;
+            carry = 1;
+        }
+        unsigned long long e = ((unsigned long long)b * sh.W + w) * sh.n + i;
+        unsigned int set = w % sh.nsets, table = w / sh.nsets;
+        if (mag == 0) {
+            keys[e] = DE_MSM_INVALID;
+        } else {
+            keys[e] = (b * sh.nsets + set) * sh.NB + (mag - 1);
+            vals[e] = (unsigned int)(table * sh.table_stride + sh.base_offset + i) | (neg << 31);
+        }
+    }
+}
+
+// ---- 2. counting sort ------------------------------------------------------------------------------------------
+__global__ void k_msm_hist(const unsigned int* keys, unsigned long long E, unsigned int* counts) {
+    unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    unsigned int k = keys[e];
+    if (k != DE_MSM_INVALID) atomicAdd(&counts[k], 1u);
+}
+__global__ void k_msm_scatter(const unsigned int* keys, const unsigned int* vals, unsigned long long E, unsigned int* cursor,
+                              unsigned int* sorted) {
+    unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    unsigned int k = keys[e];
+    if (k == DE_MSM_INVALID) return;
+    unsigned int pos = atomicAdd(&cursor[k], 1u);
+    sorted[pos] = vals[e];
+}
+
+// exclusive scan of n u32 values in three kernels (4096 items per block; n <= 4096 * 4096).  out has n + 1 entries.
+#define DE_SCAN_ITEMS 4
+#define DE_SCAN_THREADS 1024
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* total, unsigned int* sm) {
+    // sm: 32 words
+    const unsigned int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) sm[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int s = sm[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned int y = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += y;
+        }
+        sm[lane] = s;
+    }
+    __syncthreads();
+    unsigned int base = wid ? sm[wid - 1] : 0;
+    *total = sm[31];
+    __syncthreads();
+    return base + x - v;
+}
+__global__ void __launch_bounds__(DE_SCAN_THREADS) k_scan_blocks(const unsigned int* in, unsigned long long n, unsigned int* out,
+                                                                   unsigned int* block_sums) {
+    __shared__ unsigned int sm[32];
+    unsigned long long base = ((unsigned long long)blockIdx.x * DE_SCAN_THREADS + threadIdx.x) * DE_SCAN_ITEMS;
+    unsigned int v[DE_SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < DE_SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    unsigned int total;
+    unsigned int ex = block_exclusive_scan(sum, &total, sm);
+#pragma unroll
+    for (int k = 0; k < DE_SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(DE_SCAN_THREADS) k_scan_tops(unsigned int* block_sums, unsigned int nblocks, unsigned int* grand_total) {
+    __shared__ unsigned int sm[32];
+    unsigned int base = threadIdx.x * DE_SCAN_ITEMS;
+    unsigned int v[DE_SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < DE_SCAN_ITEMS; k++) {
+        v[k] = (base + k < nblocks) ? block_sums[base + k] : 0;
+        sum += v[k];
+    }
+    unsigned int total;
+    unsigned int ex = block_exclusive_scan(sum, &total, sm);
+#pragma unroll
+    for (int k = 0; k < DE_SCAN_ITEMS; k++) {
+        if (base + k < nblocks) block_sums[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) *grand_total = total;
+}
+__global__ void k_scan_add(unsigned int* out, unsigned long long n, const unsigned int* block_sums) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] += block_sums[i / (DE_SCAN_THREADS * DE_SCAN_ITEMS)];
+}
+
+// ---- 3. bucket accumulation ------------------------------------------------------------------------------------
+// tasks per bucket = ceil(count / CH); buckets that need more than one task are appended to multi_list
+__global__ void k_msm_task_counts(const unsigned int* counts, unsigned int nbuckets, unsigned int CH, unsigned int* ntasks,
+                                  unsigned int* multi_list, unsigned int* multi_count) {
+    unsigned int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    unsigned int t = (counts[b] + CH - 1) / CH;
+    ntasks[b] = t;
+    if (t > 1) multi_list[atomicAdd(multi_count, 1u)] = b;
+}
+
+__device__ __forceinline__ Affine msm_fetch(const Affine* bases, unsigned int v) {
+    Affine p = load_affine(&bases[v & 0x7fffffffu]);
+    if (v >> 31) p.y = neg(p.y);
+    return p;
+}
+
+__global__ void __launch_bounds__(128) k_msm_accumulate(const unsigned int* sorted, const unsigned int* offsets, const unsigned int* counts,
+                                                        const unsigned int* task_off, unsigned int nbuckets, unsigned int CH,
+                                                        const Affine* bases, XYZZ* buckets, XYZZ* partials) {
+    unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int ntasks_total = task_off[nbuckets];
+    if (t >= ntasks_total) return;
+    // largest b with task_off[b] <= t
+    unsigned int lo = 0, hi = nbuckets;
+    while (hi - lo > 1) {
+        unsigned int mid = (lo + hi) >> 1;
+        if (task_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const unsigned int b = lo;
+    const unsigned int local = t - task_off[b];
+    const unsigned int cnt = counts[b];
+    const unsigned int start = offsets[b] + local * CH;
+    unsigned int len = cnt - local * CH;
+    if (len > CH) len = CH;
+    XYZZ acc = xyzz_identity();
+    Affine next = msm_fetch(bases, sorted[start]);
+    for (unsigned int k = 0; k < len; k++) {
+        Affine cur = next;
+        if (k + 1 < len) next = msm_fetch(bases, sorted[start + k + 1]);
+        xyzz_madd(acc, cur);
+    }
+    if (cnt <= CH) store_xyzz(&buckets[b], acc);
+    else store_xyzz(&partials[t], acc);
+}
+
+__device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
+    XYZZ r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], delta);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], delta);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], delta);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], delta);
+    }
+    return r;
+}
+
+// one warp per multi-task bucket: lanes stride over the bucket's partial sums, then a shuffle tree
+__global__ void __launch_bounds__(128) k_msm_merge(const unsigned int* multi_list, const unsigned int* multi_count, const unsigned int* task_off,
+                                                   const XYZZ* partials, XYZZ* buckets) {
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned int total = *multi_count;
+    for (unsigned int m = warp; m < total; m += nwarps) {
+        const unsigned int b = multi_list[m];
+        const unsigned int first = task_off[b], last = task_off[b + 1];
+        XYZZ acc = xyzz_identity();
+        for (unsigned int p = first + lane; p < last; p += 32) {
+            XYZZ v = load_xyzz(&partials[p]);
+            xyzz_add(acc, v);
+        }
+        const unsigned int np = (last - first) < 32 ? (last - first) : 32;  // lanes >= np hold the identity
+        for (unsigned int d = 16; d >= 1; d >>= 1) {
+            if (d >= np) continue;  // warp-uniform: nothing but identities above lane d
+            XYZZ o = shfl_down_xyzz(acc, (int)d);
+            if (lane + d < 32) xyzz_add(acc, o);
+        }
+        if (lane == 0) store_xyzz(&buckets[b], acc);
+    }
+}
+
+// ---- 4. bucket reduction ---------------------------------------------------------------------------------------
+// k * P for a small scalar k (double-and-add, MSB first)
+__device__ __forceinline__ XYZZ xyzz_mul_small(const XYZZ& p, unsigned int k) {
+    XYZZ acc = xyzz_identity();
+    for (int i = 31 - __clz(k | 1); i >= 0; i--) {
+        acc = xyzz_dbl(acc);
+        if ((k >> i) & 1) xyzz_add(acc, p);
+    }
+    return acc;
+}
+// thread per chunk of CK buckets: T_k = sum_{b in chunk} (b + 1) * B_b, via running sums plus lo * S
+__global__ void __launch_bounds__(128) k_msm_reduce_chunks(const XYZZ* buckets, unsigned int NB, unsigned int CK, unsigned int nsets_total,
+                                                           XYZZ* chunk_out) {
+    const unsigned int chunks_per_set = NB / CK;
+    unsigned int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= chunks_per_set * nsets_total) return;
+    const unsigned int set = gid / chunks_per_set, k = gid % chunks_per_set;
+    const XYZZ* B = buckets + (unsigned long long)set * NB + (unsigned long long)k * CK;
+    XYZZ run = xyzz_identity(), acc = xyzz_identity();
+    for (int b = (int)CK - 1; b >= 0; b--) {
+        XYZZ v = load_xyzz(&B[b]);
+        xyzz_add(run, v);
+        xyzz_add(acc, run);
+    }
+    if (k > 0) {
+        XYZZ w = xyzz_mul_small(run, k * CK);
+        xyzz_add(acc, w);
+    }
+    store_xyzz(&chunk_out[gid], acc);
+}
+// one CTA per bucket set: tree-sum of the chunk results
+__global__ void __launch_bounds__(256) k_msm_reduce_sets(const XYZZ* chunk_in, unsigned int chunks_per_set, XYZZ* set_out) {
+    __shared__ XYZZ sm[256];
+    const unsigned int set = blockIdx.x, tid = threadIdx.x;
+    XYZZ acc = xyzz_identity();
+    for (unsigned int k = tid; k < chunks_per_set; k += blockDim.x) {
+        XYZZ v = load_xyzz(&chunk_in[(unsigned long long)set * chunks_per_set + k]);
+        xyzz_add(acc, v);
+    }
+    sm[tid] = acc;
+    __syncthreads();
+    for (unsigned int d = blockDim.x >> 1; d >= 1; d >>= 1) {
+        if (tid < d) {
+            XYZZ o = sm[tid + d];
+            xyzz_add(acc, o);
+            sm[tid] = acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_xyzz(&set_out[set], acc);
+}
+
+// ---- 5. combine bucket sets: out[b] = sum_u 2^(c*u) * R[b][u], written as Jacobian -------------------------------
+__global__ void __launch_bounds__(32) k_msm_combine(const XYZZ* set_in, unsigned int nsets, unsigned int c, Jac* out) {
+    const unsigned int b = blockIdx.x, lane = threadIdx.x;
+    // nsets <= 32 (c >= 8): lane u scales set u by 2^(c*u), then a shuffle tree adds the lanes
+    XYZZ acc = xyzz_identity();
+    if (lane < nsets) {
+        acc = load_xyzz(&set_in[(unsigned long long)b * nsets + lane]);
+        for (unsigned int d = 0; d < c * lane; d++) acc = xyzz_dbl(acc);
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        XYZZ o = shfl_down_xyzz(acc, d);
+        if (lane + d < 32) xyzz_add(acc, o);
+    }
+    if (lane == 0) {
+        Jac j = xyzz_to_jac(acc);
+        store(&out[b].x, j.x);
+        store(&out[b].y, j.y);
+        store(&out[b].z, j.z);
+    }
+}
+
+// ---- one-time per ParamsKZG: tables[t][i] = 2^(shift * t) * base[i], affine --------------------------------------
+__global__ void __launch_bounds__(128) k_msm_precompute(const Affine* bases, unsigned long long n, unsigned int shift, unsigned int ntables,
+                                                        unsigned long long table_stride, Affine* tables) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine p = load_affine(&bases[i]);
+    store_affine(&tables[i], p);
+    XYZZ cur = xyzz_from_affine(p);
+    for (unsigned int t = 1; t < ntables; t++) {
+        for (unsigned int d = 0; d < shift; d++) cur = xyzz_dbl(cur);
+        Affine a;
+        if (is_identity(cur)) {
+            a.x = Fq::zero();
+            a.y = Fq::zero();
+        } else {
+            // 1/ZZZ by Fermat; 1/ZZ = ZZ^2 / ZZZ^2
+            Fq iz3 = inv(cur.zzz);
+            Fq iz2 = mul(sqr(cur.zz), sqr(iz3));
+            a.x = mul(cur.x, iz2);
+            a.y = mul(cur.y, iz3);
+        }
+        store_affine(&tables[t * table_stride + i], a);
+    }
+}
+
+// sum of `count` Jacobian points (multi-GPU partial combine); single warp
+__global__ void __launch_bounds__(32) k_g1_sum(const Jac* pts, unsigned int count, Jac* out) {
+    const unsigned int lane = threadIdx.x;
+    XYZZ acc = xyzz_identity();
+    for (unsigned int i = lane; i < count; i += 32) {
+        Jac p;
+        p.x = load(&pts[i].x); p.y = load(&pts[i].y); p.z = load(&pts[i].z);
+        if (!p.z.is_zero()) {
+            // Jacobian (X, Y, Z) -> XYZZ (X, Y, Z^2, Z^3)
+            XYZZ v;
+            v.x = p.x; v.y = p.y; v.zz = sqr(p.z); v.zzz = mul(v.zz, p.z);
+            xyzz_add(acc, v);
+        }
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        XYZZ o = shfl_down_xyzz(acc, d);
+        if (lane + d < 32) xyzz_add(acc, o);
+    }
+    if (lane == 0) {
+        Jac j = xyzz_to_jac(acc);
+        store(&out->x, j.x); store(&out->y, j.y); store(&out->z, j.z);
+    }
+}
+
+}  // namespace de

@@ -1,0 +1,620 @@
+// ntt.cu — host side of the NTT / EvaluationDomain entry points: transform plans (pass geometry + twiddle tables
+// resident in HBM), kernel dispatch, and the C ABI functions de_ntt*, de_domain_*, de_coeff_to_extended*, ...
+// Reference semantics: halo2_proofs::arithmetic::best_fft and poly::EvaluationDomain.
+#include <string.h>
+
+#include "common.cuh"
+#include "ntt.cuh"
+
+namespace de {
+
+thread_local std::string g_create_error;
+
+struct NttPlan {
+    uint32_t log_n = 0;
+    de_fr omega;
+    int npass = 0;
+    int S[3] = {0, 0, 0};
+    Fr* wl[3] = {nullptr, nullptr, nullptr};
+    Fr* tw_full = nullptr;
+    Fr* tw_hi = nullptr;
+    Fr* tw_lo = nullptr;
+    uint32_t tw_lo_bits = 0;
+    ~NttPlan() {
+        for (int i = 0; i < 3; i++)
+            if (wl[i]) cudaFree(wl[i]);
+        if (tw_full) cudaFree(tw_full);
+        if (tw_hi) cudaFree(tw_hi);
+        if (tw_lo) cudaFree(tw_lo);
+    }
+};
+
+void ntt_free_plans(de_ctx* ctx) {
+    for (auto* p : ctx->plans) delete p;
+    ctx->plans.clear();
+}
+
+static int pow_table(de_ctx* ctx, Fr** out, unsigned long long n, const Fr& base, unsigned long long step) {
+    DE_CUDA(ctx, cudaMalloc((void**)out, sizeof(Fr) * (n ? n : 1)));
+    unsigned int threads = 256;
+    unsigned long long blocks = (n + threads - 1) / threads;
+    k_pow_table<<<(unsigned int)blocks, threads, 0, ctx->stream>>>(*out, n, base, step);
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
+static int get_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, NttPlan** out) {
+    for (auto* p : ctx->plans)
+        if (p->log_n == log_n && memcmp(&p->omega, &omega, sizeof(de_fr)) == 0) {
+            *out = p;
+            return DE_OK;
+        }
+    if (log_n < 1 || log_n > 28) return fail(ctx, DE_ERR_ARG, "ntt: log_n must be in 1..28");
+    NttPlan* p = new NttPlan();
+    p->log_n = log_n;
+    p->omega = omega;
+    if (log_n <= 10) {
+        p->npass = 1;
+        p->S[0] = (int)log_n;
+    } else if (log_n <= 20) {
+        p->npass = 2;
+        p->S[0] = (int)(log_n + 1) / 2;
+        p->S[1] = (int)log_n - p->S[0];
+    } else {
+        p->npass = 3;
+        p->S[0] = (int)(log_n + 2) / 3;
+        p->S[1] = (int)(log_n - p->S[0] + 1) / 2;
+        p->S[2] = (int)log_n - p->S[0] - p->S[1];
+    }
+    Fr w = fr_from_host(omega);
+    unsigned long long N = 1ull << log_n;
+    int rc = DE_OK;
+    for (int k = 0; k < p->npass && rc == DE_OK; k++) {
+        unsigned long long L = 1ull << p->S[k];
+        rc = pow_table(ctx, &p->wl[k], L / 2, w, N / L);
+    }
+    if (rc == DE_OK && p->npass > 1) {
+        if (log_n <= 22) {
+            rc = pow_table(ctx, &p->tw_full, N, w, 1);
+        } else {
+            p->tw_lo_bits = 12;
+            rc = pow_table(ctx, &p->tw_lo, 1ull << p->tw_lo_bits, w, 1);
+            if (rc == DE_OK) rc = pow_table(ctx, &p->tw_hi, N >> p->tw_lo_bits, w, 1ull << p->tw_lo_bits);
+        }
+    }
+    if (rc != DE_OK) {
+        delete p;
+        return rc;
+    }
+    ctx->plans.push_back(p);
+    *out = p;
+    return DE_OK;
+}
+
+template <int S, int LT>
+static int launch_pass_t(de_ctx* ctx, const NttPassParams& prm, unsigned int blocks, unsigned int batch) {
+    using Sh = NttShape<S, LT>;
+    static bool configured[16] = {false};
+    int dev = ctx->device & 15;
+    if (!configured[dev]) {
+        DE_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<S, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::SMEM));
+        configured[dev] = true;
+    }
+    dim3 grid(blocks, batch);
+    k_ntt_pass<S, LT><<<grid, Sh::NTHREADS, Sh::SMEM, ctx->stream>>>(prm);
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
+// tile width used for sub-transform size 2^S when tiling is on
+static int tile_log(int S) {
+    int lt = 11 - S;
+    if (lt > 3) lt = 3;
+    if (lt < 0) lt = 0;
+    return lt;
+}
+
+static int launch_pass(de_ctx* ctx, int S, int LT, const NttPassParams& prm, unsigned int blocks, unsigned int batch) {
+#define CASE(s, lt) \
+    if (S == s && LT == lt) return launch_pass_t<s, lt>(ctx, prm, blocks, batch);
+    CASE(1, 0) CASE(2, 0) CASE(3, 0) CASE(4, 0) CASE(5, 0) CASE(6, 0) CASE(7, 0) CASE(8, 0) CASE(9, 0) CASE(10, 0)
+    CASE(1, 3) CASE(2, 3) CASE(3, 3) CASE(4, 3) CASE(5, 3) CASE(6, 3) CASE(7, 3) CASE(8, 3) CASE(9, 2) CASE(10, 1)
+#undef CASE
+    return fail(ctx, DE_ERR_UNSUPPORTED, "ntt: no kernel for this pass shape");
+}
+
+int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, size_t src_stride, Fr* d_dst, size_t dst_stride,
+            size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3) {
+    if (batch == 0) return DE_OK;
+    if (batch > 65535) return fail(ctx, DE_ERR_ARG, "ntt: batch too large");
+    if (log_n == 0) {
+        if (in_mode != 0 || out_mode != 0) return fail(ctx, DE_ERR_ARG, "ntt: fused scaling needs log_n >= 1");
+        if (d_src != d_dst)
+            DE_CUDA(ctx, cudaMemcpy2DAsync(d_dst, dst_stride * sizeof(Fr), d_src, src_stride * sizeof(Fr), sizeof(Fr), batch,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+        return DE_OK;
+    }
+    NttPlan* plan = nullptr;
+    DE_TRY(get_plan(ctx, omega, log_n, &plan));
+    const unsigned long long N = 1ull << log_n;
+    const int P = plan->npass;
+    Fr* scratch = nullptr;
+    if (P > 1) {
+        scratch = (Fr*)ctx->ws[WS_NTT_SCRATCH].ensure(sizeof(Fr) * N * batch);
+        if (!scratch) return fail(ctx, DE_ERR_OOM, "ntt: scratch allocation failed");
+    }
+    unsigned long long Lprod = 1;  // L_1 * ... * L_{k-1}
+    for (int k = 0; k < P; k++) {
+        const int S = plan->S[k];
+        const unsigned long long L = 1ull << S;
+        const bool last = (k == P - 1);
+        NttPassParams prm;
+        memset(&prm, 0, sizeof(prm));
+        prm.wl = plan->wl[k];
+        // source / destination of this pass
+        if (k == 0) {
+            prm.in = d_src;
+            prm.in_batch_stride = src_stride;
+            prm.in_mode = in_mode;
+            prm.n_in = n_in;
+            if (in_mode == 1) {
+                prm.zeta[0] = zeta2[0];
+                prm.zeta[1] = zeta2[1];
+            }
+        } else {
+            prm.in = scratch;
+            prm.in_batch_stride = N;
+        }
+        if (last) {
+            prm.out = d_dst;
+            prm.out_batch_stride = dst_stride;
+            prm.out_mode = out_mode;
+            if (out_mode == 1)
+                for (int i = 0; i < 3; i++) prm.oscale[i] = oscale3[i];
+        } else {
+            prm.out = scratch;
+            prm.out_batch_stride = N;
+        }
+        int LT;
+        unsigned long long blocks;
+        if (!last) {
+            // strided-column pass over segments of length L * M
+            const unsigned long long M = N / (Lprod * L);
+            LT = tile_log(S);
+            const unsigned long long T = 1ull << LT;
+            prm.G = (unsigned int)(M / T);
+            prm.in_grp = prm.out_grp = L * M;
+            prm.in_blk = prm.out_blk = T;
+            prm.in_tt = prm.out_tt = 1;
+            prm.in_el = prm.out_el = M;
+            prm.tw_mul = Lprod;  // w_{L*M} = w_N^(N / (L*M)) = w_N^(L_1..L_{k-1})
+            if (plan->tw_full) {
+                prm.tw_mode = 1;
+                prm.tw_full = plan->tw_full;
+            } else {
+                prm.tw_mode = 2;
+                prm.tw_hi = plan->tw_hi;
+                prm.tw_lo = plan->tw_lo;
+                prm.tw_lo_bits = plan->tw_lo_bits;
+            }
+            blocks = N / (T * L);
+        } else if (P == 1) {
+            LT = 0;
+            prm.G = 1;
+            prm.in_el = prm.out_el = 1;
+            blocks = 1;
+        } else {
+            // contiguous rows of length L; tile over j1 so the transposed store is T*32 B contiguous
+            const unsigned long long L1 = 1ull << plan->S[0];
+            const unsigned long long M1 = N / L1;
+            LT = tile_log(S);
+            const unsigned long long T = 1ull << LT;
+            prm.G = (unsigned int)(L1 / T);
+            prm.in_grp = L;
+            prm.in_blk = T * M1;
+            prm.in_tt = M1;
+            prm.in_el = 1;
+            prm.out_grp = L1;
+            prm.out_blk = T;
+            prm.out_tt = 1;
+            prm.out_el = N / L;
+            blocks = N / (T * L);
+        }
+        DE_TRY(launch_pass(ctx, S, LT, prm, (unsigned int)blocks, (unsigned int)batch));
+        Lprod *= L;
+    }
+    return DE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small device helpers (one-time constants; keeps every field operation of the library on the GPU)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_fr_pow(Fr base, unsigned long long e, Fr* out) {
+    Fr acc = Fr::one(), cur = base;
+    while (e) {
+        if (e & 1) acc = mul(acc, cur);
+        cur = sqr(cur);
+        e >>= 1;
+    }
+    store(out, acc);
+}
+
+template <class P>
+__device__ Fp<P> dev_inv(const Fp<P>& a) {
+    Fp<P> acc = Fp<P>::one();
+    for (int i = 7; i >= 0; i--) {
+        uint32_t w = P::p(i);
+        if (i == 0) w -= 2;
+        for (int b = 31; b >= 0; b--) {
+            acc = sqr(acc);
+            if ((w >> b) & 1) acc = mul(acc, a);
+        }
+    }
+    return acc;
+}
+
+// EvaluationDomain::new constants.  out: [0] ext_omega [1] ext_omega_inv [2] omega [3] omega_inv [4] zeta [5] zeta^2
+// [6] 1/n [7] 1/ext_n [8..8+2^(ek-k)) t_evaluations.  One thread per constant.
+__global__ void k_domain_consts(unsigned int k, unsigned int ek, Fr* out) {
+    const unsigned int t = threadIdx.x;
+    const unsigned int nt = 1u << (ek - k);
+    if (t >= 8 + nt) return;
+    Fr root = Fr::zero();  // ROOT_OF_UNITY = 7^((r-1)/2^28), canonical limbs -> Montgomery
+    {
+        const uint32_t c[8] = {0x60c37c9cu, 0xd34f1ed9u, 0xd39329c8u, 0x3215cf6du, 0x3dd31f74u, 0x98865ea9u, 0x166d18b7u, 0x03ddb9f5u};
+        for (int i = 0; i < 8; i++) root.l[i] = c[i];
+        root = to_mont(root);
+    }
+    Fr zeta = Fr::zero();
+    {
+        const uint32_t c[8] = {0x36636f23u, 0xb8ca0b2du, 0xec2bc5e9u, 0xcc37a73fu, 0x3fd84104u, 0x048b6e19u, 0xe131a029u, 0x30644e72u};
+        for (int i = 0; i < 8; i++) zeta.l[i] = c[i];
+        zeta = to_mont(zeta);
+    }
+    Fr ext_omega = root;
+    for (unsigned int i = ek; i < 28; i++) ext_omega = sqr(ext_omega);
+    Fr omega = ext_omega;
+    for (unsigned int i = k; i < ek; i++) omega = sqr(omega);
+    Fr r;
+    if (t == 0) r = ext_omega;
+    else if (t == 1) r = dev_inv(ext_omega);
+    else if (t == 2) r = omega;
+    else if (t == 3) r = dev_inv(omega);
+    else if (t == 4) r = zeta;
+    else if (t == 5) r = sqr(zeta);
+    else if (t == 6 || t == 7) {
+        // 1 / 2^m = (1/2)^m
+        Fr two = add(Fr::one(), Fr::one());
+        Fr half = dev_inv(two);
+        unsigned int m = (t == 6) ? k : ek;
+        r = Fr::one();
+        for (unsigned int i = 0; i < m; i++) r = mul(r, half);
+    } else {
+        // t_evaluations[i] = 1 / ((zeta * ext_omega^i)^n - 1)
+        unsigned int i = t - 8;
+        Fr cur = zeta;
+        for (unsigned int s = 0; s < i; s++) cur = mul(cur, ext_omega);
+        for (unsigned int s = 0; s < k; s++) cur = sqr(cur);
+        r = dev_inv(sub(cur, Fr::one()));
+    }
+    store(&out[t], r);
+}
+
+template <class F>
+__global__ void k_vec_op(int op, const F* a, const F* b, F* out, unsigned long long n) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = load(&a[i]);
+    F r;
+    if (op == DE_OP_MUL) r = mul(x, load(&b[i]));
+    else if (op == DE_OP_ADD) r = add(x, load(&b[i]));
+    else if (op == DE_OP_SUB) r = sub(x, load(&b[i]));
+    else if (op == DE_OP_FROM_MONT) r = from_mont(x);
+    else r = to_mont(x);
+    store(&out[i], r);
+}
+
+template <class F>
+static int vec_op(de_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n) {
+    if (!ctx) return DE_ERR_ARG;
+    if (op < DE_OP_MUL || op > DE_OP_TO_MONT) return fail(ctx, DE_ERR_ARG, "vec_op: unknown op");
+    if (n == 0) return DE_OK;
+    bool binary = op <= DE_OP_SUB;
+    if (!a || !out || (binary && !b)) return fail(ctx, DE_ERR_ARG, "vec_op: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DE_WS(ctx, da, F, WS_IO_A, sizeof(F) * n * 2);
+    DE_WS(ctx, dout, F, WS_IO_B, sizeof(F) * n);
+    F* db = da + n;
+    DE_CUDA(ctx, cudaMemcpyAsync(da, a, sizeof(F) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (binary) DE_CUDA(ctx, cudaMemcpyAsync(db, b, sizeof(F) * n, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned int threads = 128;
+    k_vec_op<F><<<(unsigned int)((n + threads - 1) / threads), threads, 0, ctx->stream>>>(op, da, db, dout, n);
+    DE_CHECK_LAUNCH(ctx);
+    DE_CUDA(ctx, cudaMemcpyAsync(out, dout, sizeof(F) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+}  // namespace de
+
+using namespace de;
+
+struct de_domain {
+    de_ctx* ctx;
+    uint32_t j, k, ek;
+    size_t n, ext_n, qdeg;
+    de_fr omega, omega_inv, ext_omega, ext_omega_inv;
+    Fr zeta[2];          // zeta, zeta^2
+    Fr ifft_scale[3];    // 1/n three times
+    Fr ext_out_scale[3]; // (1/ext_n) * {1, zeta^2, zeta}
+    Fr* d_t_evals;       // 2^(ek-k) entries
+    uint32_t t_len;
+};
+
+extern "C" {
+
+const char* de_version(void) { return "de_b200 0.1 (sm_100a)"; }
+
+int de_ctx_create(int device, de_ctx** out) {
+    if (!out) return fail(nullptr, DE_ERR_ARG, "de_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, DE_ERR_CUDA, std::string("no CUDA device available (") +
+                                              (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                              "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, DE_ERR_ARG, "de_ctx_create: device index out of range");
+    de_ctx* ctx = new de_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        std::string msg = cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return fail(nullptr, DE_ERR_CUDA, "de_ctx_create: " + msg);
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return DE_OK;
+}
+
+int de_ctx_destroy(de_ctx* ctx) {
+    if (!ctx) return DE_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ntt_free_plans(ctx);
+    for (auto& w : ctx->ws) w.release();
+    ctx->pinned.release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return DE_OK;
+}
+
+int de_ctx_set_stream(de_ctx* ctx, void* s) {
+    if (!ctx) return DE_ERR_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return DE_OK;
+}
+
+int de_ctx_sync(de_ctx* ctx) {
+    if (!ctx) return DE_ERR_ARG;
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+const char* de_last_error(de_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+uint64_t de_launch_count(de_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int de_fr_vec_op(de_ctx* ctx, int op, const de_fr* a, const de_fr* b, de_fr* out, size_t n) { return vec_op<Fr>(ctx, op, a, b, out, n); }
+int de_fq_vec_op(de_ctx* ctx, int op, const de_fq* a, const de_fq* b, de_fq* out, size_t n) { return vec_op<Fq>(ctx, op, a, b, out, n); }
+
+// ---- best_fft -------------------------------------------------------------------------------------------------
+int de_ntt_dev(de_ctx* ctx, de_fr* d_a, const de_fr* omega, uint32_t log_n, size_t batch, size_t stride) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!d_a || !omega) return fail(ctx, DE_ERR_ARG, "de_ntt_dev: null pointer");
+    if (log_n > 28) return fail(ctx, DE_ERR_ARG, "de_ntt_dev: log_n > 28 exceeds the 2-adicity of Fr");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_run(ctx, *omega, log_n, (const Fr*)d_a, stride, (Fr*)d_a, stride, batch, 0, 0, nullptr, 0, nullptr);
+}
+
+int de_ntt(de_ctx* ctx, de_fr* a, const de_fr* omega, uint32_t log_n) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!a || !omega) return fail(ctx, DE_ERR_ARG, "de_ntt: null pointer");
+    if (log_n > 28) return fail(ctx, DE_ERR_ARG, "de_ntt: log_n > 28 exceeds the 2-adicity of Fr");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t n = (size_t)1 << log_n;
+    DE_WS(ctx, d, Fr, WS_IO_A, sizeof(Fr) * n);
+    DE_CUDA(ctx, cudaMemcpyAsync(d, a, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    DE_TRY(ntt_run(ctx, *omega, log_n, d, n, d, n, 1, 0, 0, nullptr, 0, nullptr));
+    DE_CUDA(ctx, cudaMemcpyAsync(a, d, sizeof(Fr) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+// ---- EvaluationDomain -----------------------------------------------------------------------------------------
+int de_domain_create(de_ctx* ctx, uint32_t j, uint32_t k, de_domain** out) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!out) return fail(ctx, DE_ERR_ARG, "de_domain_create: out is NULL");
+    *out = nullptr;
+    if (j < 2) return fail(ctx, DE_ERR_ARG, "de_domain_create: cs.degree() must be >= 2");
+    uint32_t ek = k;
+    while (ek < 64 && ((uint64_t)1 << ek) < ((uint64_t)1 << k) * (j - 1)) ek++;
+    if (k < 1 || ek > 28) return fail(ctx, DE_ERR_ARG, "de_domain_create: need 1 <= k and extended_k <= 28 (Fr::S)");
+    if (ek - k > 4) return fail(ctx, DE_ERR_ARG, "de_domain_create: extension factor above 16 is not supported");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t t_len = 1u << (ek - k);
+    Fr* d_consts = nullptr;
+    DE_CUDA(ctx, cudaMalloc((void**)&d_consts, sizeof(Fr) * (8 + t_len)));
+    k_domain_consts<<<1, 32, 0, ctx->stream>>>(k, ek, d_consts);
+    ctx->launches++;
+    Fr h[8 + 16];
+    cudaError_t e = cudaMemcpyAsync(h, d_consts, sizeof(Fr) * (8 + t_len), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d_consts);
+        return fail(ctx, DE_ERR_CUDA, std::string("de_domain_create: ") + cudaGetErrorString(e));
+    }
+    de_domain* d = new de_domain();
+    d->ctx = ctx;
+    d->j = j; d->k = k; d->ek = ek;
+    d->n = (size_t)1 << k;
+    d->ext_n = (size_t)1 << ek;
+    d->qdeg = j - 1;
+    d->ext_omega = fr_to_host(h[0]);
+    d->ext_omega_inv = fr_to_host(h[1]);
+    d->omega = fr_to_host(h[2]);
+    d->omega_inv = fr_to_host(h[3]);
+    d->zeta[0] = h[4];
+    d->zeta[1] = h[5];
+    d->t_len = t_len;
+    // keep t_evaluations on the device; reuse the constants buffer
+    d->d_t_evals = d_consts;  // entries [8, 8 + t_len)
+    for (int i = 0; i < 3; i++) d->ifft_scale[i] = h[6];
+    // extended_to_coeff multiplies by ext_ifft_divisor and zeta^-(i mod 3) = {1, zeta^2, zeta}; done on the device
+    // by a 3-thread kernel to keep host code free of field arithmetic
+    {
+        Fr* tmp = d_consts;  // overwrite slots 0..2 (already copied to host)
+        Fr a3[3] = {Fr::one(), h[5], h[4]};
+        Fr b3[3] = {h[7], h[7], h[7]};
+        Fr* d_ab = nullptr;
+        if (cudaMalloc((void**)&d_ab, sizeof(Fr) * 6) != cudaSuccess) {
+            cudaFree(d_consts);
+            delete d;
+            return fail(ctx, DE_ERR_OOM, "de_domain_create: allocation failed");
+        }
+        cudaMemcpyAsync(d_ab, a3, sizeof(a3), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_ab + 3, b3, sizeof(b3), cudaMemcpyHostToDevice, ctx->stream);
+        k_vec_op<Fr><<<1, 32, 0, ctx->stream>>>(DE_OP_MUL, d_ab, d_ab + 3, tmp, 3);
+        ctx->launches++;
+        cudaMemcpyAsync(d->ext_out_scale, tmp, sizeof(Fr) * 3, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_ab);
+        if (e != cudaSuccess) {
+            cudaFree(d_consts);
+            delete d;
+            return fail(ctx, DE_ERR_CUDA, std::string("de_domain_create: ") + cudaGetErrorString(e));
+        }
+    }
+    *out = d;
+    return DE_OK;
+}
+
+int de_domain_free(de_domain* d) {
+    if (!d) return DE_OK;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    if (d->d_t_evals) cudaFree(d->d_t_evals);
+    delete d;
+    return DE_OK;
+}
+
+int de_domain_info(de_domain* d, uint32_t* extended_k, de_fr consts[4]) {
+    if (!d) return DE_ERR_ARG;
+    if (extended_k) *extended_k = d->ek;
+    if (consts) {
+        consts[0] = d->omega;
+        consts[1] = d->omega_inv;
+        consts[2] = d->ext_omega;
+        consts[3] = d->ext_omega_inv;
+    }
+    return DE_OK;
+}
+
+int de_coeff_to_extended_dev(de_domain* d, const de_fr* d_coeff, size_t in_stride, de_fr* d_ext, size_t out_stride, size_t batch) {
+    if (!d) return DE_ERR_ARG;
+    de_ctx* ctx = d->ctx;
+    if (!d_coeff || !d_ext) return fail(ctx, DE_ERR_ARG, "de_coeff_to_extended_dev: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_run(ctx, d->ext_omega, d->ek, (const Fr*)d_coeff, in_stride, (Fr*)d_ext, out_stride, batch, 1, d->n, d->zeta, 0, nullptr);
+}
+int de_extended_to_coeff_dev(de_domain* d, de_fr* d_ext, size_t stride, size_t batch, size_t* out_len) {
+    if (!d) return DE_ERR_ARG;
+    de_ctx* ctx = d->ctx;
+    if (!d_ext) return fail(ctx, DE_ERR_ARG, "de_extended_to_coeff_dev: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (out_len) *out_len = d->n * d->qdeg;
+    return ntt_run(ctx, d->ext_omega_inv, d->ek, (const Fr*)d_ext, stride, (Fr*)d_ext, stride, batch, 0, 0, nullptr, 1, d->ext_out_scale);
+}
+int de_lagrange_to_coeff_dev(de_domain* d, de_fr* d_a, size_t stride, size_t batch) {
+    if (!d) return DE_ERR_ARG;
+    de_ctx* ctx = d->ctx;
+    if (!d_a) return fail(ctx, DE_ERR_ARG, "de_lagrange_to_coeff_dev: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_run(ctx, d->omega_inv, d->k, (const Fr*)d_a, stride, (Fr*)d_a, stride, batch, 0, 0, nullptr, 1, d->ifft_scale);
+}
+int de_coeff_to_lagrange_dev(de_domain* d, de_fr* d_a, size_t stride, size_t batch) {
+    if (!d) return DE_ERR_ARG;
+    de_ctx* ctx = d->ctx;
+    if (!d_a) return fail(ctx, DE_ERR_ARG, "de_coeff_to_lagrange_dev: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_run(ctx, d->omega, d->k, (const Fr*)d_a, stride, (Fr*)d_a, stride, batch, 0, 0, nullptr, 0, nullptr);
+}
+int de_divide_by_vanishing_dev(de_domain* d, de_fr* d_ext, size_t stride, size_t batch) {
+    if (!d) return DE_ERR_ARG;
+    de_ctx* ctx = d->ctx;
+    if (!d_ext) return fail(ctx, DE_ERR_ARG, "de_divide_by_vanishing_dev: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (size_t b = 0; b < batch; b++) {
+        unsigned int threads = 256;
+        k_scale_periodic<<<(unsigned int)((d->ext_n + threads - 1) / threads), threads, 0, ctx->stream>>>(
+            (Fr*)d_ext + b * stride, d->ext_n, d->d_t_evals + 8, d->t_len - 1);
+        DE_CHECK_LAUNCH(ctx);
+    }
+    return DE_OK;
+}
+
+// host-pointer wrappers: stage through the context's I/O workspace
+static int host_roundtrip(de_domain* d, const de_fr* in, size_t n_in, de_fr* out, size_t n_out, int which) {
+    de_ctx* ctx = d->ctx;
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t cap = n_in > n_out ? n_in : n_out;
+    if (which == 0) cap = d->n + d->ext_n;
+    DE_WS(ctx, buf, Fr, WS_IO_A, sizeof(Fr) * cap);
+    DE_CUDA(ctx, cudaMemcpyAsync(buf, in, sizeof(Fr) * n_in, cudaMemcpyHostToDevice, ctx->stream));
+    Fr* res = buf;
+    switch (which) {
+        case 0:
+            res = buf + d->n;
+            DE_TRY(de_coeff_to_extended_dev(d, (const de_fr*)buf, d->n, (de_fr*)res, d->ext_n, 1));
+            break;
+        case 1: DE_TRY(de_extended_to_coeff_dev(d, (de_fr*)buf, d->ext_n, 1, nullptr)); break;
+        case 2: DE_TRY(de_lagrange_to_coeff_dev(d, (de_fr*)buf, d->n, 1)); break;
+        case 3: DE_TRY(de_coeff_to_lagrange_dev(d, (de_fr*)buf, d->n, 1)); break;
+        case 4: DE_TRY(de_divide_by_vanishing_dev(d, (de_fr*)buf, d->ext_n, 1)); break;
+    }
+    DE_CUDA(ctx, cudaMemcpyAsync(out, res, sizeof(Fr) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+int de_coeff_to_extended(de_domain* d, const de_fr* coeff_n, de_fr* ext_out) {
+    if (!d) return DE_ERR_ARG;
+    if (!coeff_n || !ext_out) return fail(d->ctx, DE_ERR_ARG, "de_coeff_to_extended: null pointer");
+    return host_roundtrip(d, coeff_n, d->n, ext_out, d->ext_n, 0);
+}
+int de_extended_to_coeff(de_domain* d, de_fr* a, size_t* out_len) {
+    if (!d) return DE_ERR_ARG;
+    if (!a) return fail(d->ctx, DE_ERR_ARG, "de_extended_to_coeff: null pointer");
+    if (out_len) *out_len = d->n * d->qdeg;
+    return host_roundtrip(d, a, d->ext_n, a, d->ext_n, 1);
+}
+int de_lagrange_to_coeff(de_domain* d, de_fr* a) {
+    if (!d) return DE_ERR_ARG;
+    if (!a) return fail(d->ctx, DE_ERR_ARG, "de_lagrange_to_coeff: null pointer");
+    return host_roundtrip(d, a, d->n, a, d->n, 2);
+}
+int de_coeff_to_lagrange(de_domain* d, de_fr* a) {
+    if (!d) return DE_ERR_ARG;
+    if (!a) return fail(d->ctx, DE_ERR_ARG, "de_coeff_to_lagrange: null pointer");
+    return host_roundtrip(d, a, d->n, a, d->n, 3);
+}
+int de_divide_by_vanishing(de_domain* d, de_fr* a) {
+    if (!d) return DE_ERR_ARG;
+    if (!a) return fail(d->ctx, DE_ERR_ARG, "de_divide_by_vanishing: null pointer");
+    return host_roundtrip(d, a, d->ext_n, a, d->ext_n, 4);
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+// ntt.cuh — Fr number-theoretic transform for sm_100a (replaces halo2_proofs::arithmetic::best_fft and the
+// transforms inside poly::EvaluationDomain; SURVEY.md section 8 rows a4-a7, behavioural spec Appendix B.2/B.3).
+//
+// Algorithm: natural order in, natural order out, A[j] = sum_i a[i] w^(ij), computed as a 1-, 2- or 3-pass
+// "four-step" decomposition N = L1*L2*L3 (every Lk = 2^Sk <= 1024).  A pass is ONE kernel: a CTA stages a tile of
+// T independent Lk-point sub-transforms in shared memory (T chosen so that the T*32 B they share in global memory
+// are contiguous), runs radix-8 decimation-in-frequency rounds on registers with a shared-memory exchange between
+// rounds, and writes the tile back transposed, multiplying by the inter-pass twiddle w^(c*j) on the way out.
+// Passes 1..p-1 work on strided columns in place; the last pass reads contiguous rows and scatters them to natural
+// order.  The zeta-coset scaling and zero padding of coeff_to_extended are fused into the first pass' load, the
+// 1/N and zeta^-i scalings of lagrange_to_coeff / extended_to_coeff into the last pass' store.
+#pragma once
+#include "field.cuh"
+
+namespace de {
+
+struct NttPassParams {
+    const Fr* in;
+    Fr* out;
+    unsigned long long in_batch_stride, out_batch_stride;  // elements between consecutive polynomials of a batch
+    unsigned int G;                                         // tiles per group
+    unsigned long long in_grp, in_blk, in_tt, in_el;        // element strides: group, tile, tile member, sub-transform index
+    unsigned long long out_grp, out_blk, out_tt, out_el;
+    const Fr* wl;  // powers of the Lk-th root of unity: wl[i] = w_L^i, i < L/2
+    int tw_mode;   // 0: none, 1: full table tw_full[e] = w_N^e (e < N), 2: two-level tw_hi[e >> lo_bits] * tw_lo[e & mask]
+    const Fr* tw_full;
+    const Fr* tw_hi;
+    const Fr* tw_lo;
+    unsigned int tw_lo_bits;
+    unsigned long long tw_mul;  // exponent = column * j * tw_mul
+    int in_mode;                // 0: plain, 1: element i is a[i] * zeta^(i mod 3) for i < n_in and 0 beyond (coeff_to_extended)
+    unsigned long long n_in;
+    int out_mode;               // 0: none, 1: multiply output j by oscale[j mod 3]
+    Fr zeta[2];                 // zeta, zeta^2
+    Fr oscale[3];
+};
+
+__device__ __forceinline__ void sm_put(uint4* lo, uint4* hi, int slot, const Fr& v) {
+    lo[slot] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[slot] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ Fr sm_get(const uint4* lo, const uint4* hi, int slot) {
+    uint4 a = lo[slot], b = hi[slot];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+template <int LT>
+__device__ __forceinline__ int ntt_slot(int pos, int tt) {
+    int i = (pos << LT) | tt;
+    return i + ((i >> (3 + LT)) << LT);  // one tile-row of padding every 8 rows: keeps the last round conflict-free
+}
+template <int S, int LT>
+struct NttShape {
+    static constexpr int L = 1 << S;
+    static constexpr int T = 1 << LT;
+    static constexpr int M = L * T;
+    static constexpr int MPAD = M + (M >> 3);
+    static constexpr int NTHREADS = (M / 8) < 32 ? 32 : (M / 8);
+    static constexpr int WN = (L / 2) < 1 ? 1 : (L / 2);
+    static constexpr size_t SMEM = (size_t)(2 * MPAD + 2 * WN) * sizeof(uint4);
+    static constexpr int MINBLOCKS = 512 / NTHREADS;  // two 256-thread CTAs (16 warps) per SM: caps registers at 128
+};
+
+// One radix-2^R decimation-in-frequency round starting at stage Q of an L = 2^S point transform.
+template <int S, int LT, int Q, int R>
+__device__ __forceinline__ void ntt_round(uint4* lo, uint4* hi, const uint4* wlo, const uint4* whi, int tid, int nthreads) {
+    constexpr int T = 1 << LT;
+    constexpr int LOWBITS = S - Q - R;
+    constexpr int NG = (T << S) >> R;
+    for (int g = tid; g < NG; g += nthreads) {
+        int tt = g & (T - 1);
+        int gg = g >> LT;
+        int base_low = gg & ((1 << LOWBITS) - 1);
+        int base = ((gg >> LOWBITS) << (LOWBITS + R)) | base_low;
+        Fr x[1 << R];
+#pragma unroll
+        for (int e = 0; e < (1 << R); e++) x[e] = sm_get(lo, hi, ntt_slot<LT>(base + (e << LOWBITS), tt));
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int half = 1 << (R - 1 - u);
+#pragma unroll
+            for (int e = 0; e < (1 << R); e++) {
+                if (e & half) continue;
+                Fr a = x[e], b = x[e + half];
+                x[e] = add(a, b);
+                Fr d = sub(a, b);
+                const int e_low = e & (half - 1);
+                if (LOWBITS == 0 && e_low == 0) {
+                    x[e + half] = d;  // twiddle is w^0
+                } else {
+                    int ex = (base_low << (Q + u)) + (e_low << (S - R + u));
+                    x[e + half] = mul(d, sm_get(wlo, whi, ex));
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < (1 << R); e++) sm_put(lo, hi, ntt_slot<LT>(base + (e << LOWBITS), tt), x[e]);
+    }
+    __syncthreads();
+}
+
+template <int S, int LT, int Q>
+__device__ __forceinline__ void ntt_rounds(uint4* lo, uint4* hi, const uint4* wlo, const uint4* whi, int tid, int nthreads) {
+    if constexpr (Q < S) {
+        constexpr int R = (S - Q) >= 3 ? 3 : (S - Q);
+        ntt_round<S, LT, Q, R>(lo, hi, wlo, whi, tid, nthreads);
+        ntt_rounds<S, LT, Q + R>(lo, hi, wlo, whi, tid, nthreads);
+    }
+}
+
+__device__ __forceinline__ Fr ntt_twiddle(const NttPassParams& p, unsigned long long e) {
+    if (p.tw_mode == 1) return load(&p.tw_full[e]);
+    Fr h = load(&p.tw_hi[e >> p.tw_lo_bits]);
+    Fr l = load(&p.tw_lo[e & ((1ull << p.tw_lo_bits) - 1)]);
+    return mul(h, l);
+}
+
+template <int S, int LT>
+__global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MINBLOCKS) k_ntt_pass(const __grid_constant__ NttPassParams p) {
+    using Sh = NttShape<S, LT>;
+    constexpr int T = Sh::T, M = Sh::M, L = Sh::L;
+    extern __shared__ uint4 smem[];
+    uint4* lo = smem;
+    uint4* hi = lo + Sh::MPAD;
+    uint4* wlo = hi + Sh::MPAD;
+    uint4* whi = wlo + Sh::WN;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const unsigned int grp = blockIdx.x / p.G, tile = blockIdx.x % p.G;
+    const Fr* in = p.in + (unsigned long long)blockIdx.y * p.in_batch_stride;
+    Fr* out = p.out + (unsigned long long)blockIdx.y * p.out_batch_stride;
+    const unsigned long long in_base = grp * p.in_grp + tile * p.in_blk;
+    const unsigned long long out_base = grp * p.out_grp + tile * p.out_blk;
+
+    for (int i = tid; i < L / 2; i += nthreads) {
+        Fr w = load(&p.wl[i]);
+        sm_put(wlo, whi, i, w);
+    }
+    for (int idx = tid; idx < M; idx += nthreads) {
+        int tt = idx & (T - 1), t = idx >> LT;
+        unsigned long long gi = in_base + tt * p.in_tt + t * p.in_el;
+        Fr v;
+        if (p.in_mode == 1) {
+            if (gi < p.n_in) {
+                v = load(&in[gi]);
+                unsigned int r3 = (unsigned int)(gi % 3ull);
+                if (r3 != 0) v = mul(v, p.zeta[r3 - 1]);
+            } else {
+                v = Fr::zero();
+            }
+        } else {
+            v = load(&in[gi]);
+        }
+        sm_put(lo, hi, ntt_slot<LT>(t, tt), v);
+    }
+    __syncthreads();
+
+    ntt_rounds<S, LT, 0>(lo, hi, wlo, whi, tid, nthreads);
+
+    for (int idx = tid; idx < M; idx += nthreads) {
+        int tt = idx & (T - 1), j = idx >> LT;
+        int pos = (S == 0) ? 0 : (int)(__brev((unsigned)j) >> (32 - (S == 0 ? 1 : S)));
+        Fr v = sm_get(lo, hi, ntt_slot<LT>(pos, tt));
+        if (p.tw_mode != 0) {
+            unsigned long long c = (unsigned long long)tile * T + tt;
+            unsigned long long e = c * (unsigned long long)j * p.tw_mul;
+            if (e != 0) v = mul(v, ntt_twiddle(p, e));
+        }
+        unsigned long long go = out_base + tt * p.out_tt + (unsigned long long)j * p.out_el;
+        if (p.out_mode == 1) v = mul(v, p.oscale[(unsigned int)(go % 3ull)]);
+        store(&out[go], v);
+    }
+}
+
+// out[i] = base^(i * step) for i < n  (twiddle tables; one-time per plan)
+__global__ void k_pow_table(Fr* out, unsigned long long n, Fr base, unsigned long long step) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // exponent i*step can exceed 64 bits only if the caller misuses it; tables here keep it < 2^60
+    unsigned long long e = i * step;
+    Fr acc = Fr::one(), cur = base;
+    while (e) {
+        if (e & 1) acc = mul(acc, cur);
+        cur = sqr(cur);
+        e >>= 1;
+    }
+    store(&out[i], acc);
+}
+
+// element-wise helpers used by the domain operations
+__global__ void k_scale_periodic(Fr* a, unsigned long long n, const Fr* table, unsigned int period_mask) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    store(&a[i], mul(load(&a[i]), load(&table[i & period_mask])));
+}
+
+}  // namespace de

@@ -1,0 +1,280 @@
+"""de_b200 — host-side mirror (Python) of the halo2_proofs arithmetic / poly surface that the delay-encryption circuits'
+prover reaches, backed by libde_b200.so (hand-written sm_100a CUDA behind the C ABI of
+include/de_b200.h).  Names and argument meaning follow halo2_proofs @ v2023_04_20:
+
+    best_multiexp(coeffs, bases)                    arithmetic::best_multiexp
+    best_fft(a, omega, log_n)                       arithmetic::best_fft (in place in Rust; returns the result here)
+    EvaluationDomain(j, k)                          poly::EvaluationDomain::new
+        .coeff_to_extended / .extended_to_coeff / .lagrange_to_coeff / .coeff_to_lagrange / .divide_by_vanishing_poly
+    ParamsKZG(k, g, g_lagrange)                     poly::kzg::commitment::ParamsKZG (bases staged in HBM once)
+        .commit(poly) / .commit_lagrange(poly)
+
+Field elements are numpy uint64 arrays of shape (n, 4) (Montgomery limbs, halo2curves' memory layout); points are
+(n, 8) affine / (12,) Jacobian.  `*_dev` methods take torch CUDA tensors (uint64/int64 storage) and stay on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DeError
+
+__all__ = ["Context", "EvaluationDomain", "ParamsKZG", "best_multiexp", "best_fft", "DeError", "default_context"]
+
+
+def _np(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if cols is not None:
+        assert a.size % cols == 0
+    return a
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+class Context:
+    """de_ctx: one device, one stream.  Not thread-safe (one per host thread / GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        rc = self.L.de_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise DeError(rc, self.L.de_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise DeError(rc, self.L.de_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream: int | None):
+        self.check(self.L.de_ctx_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        self.check(self.L.de_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.de_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.de_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- a1 ----
+    def _vec(self, fn, op, a, b):
+        a = _np(a)
+        out = np.empty_like(a)
+        bb = _np(b) if b is not None else None
+        self.check(fn(self.h, op, _ptr(a), _ptr(bb), _ptr(out), a.size // 4))
+        return out
+
+    def fr_mul(self, a, b): return self._vec(self.L.de_fr_vec_op, _lib.OP_MUL, a, b)
+    def fr_add(self, a, b): return self._vec(self.L.de_fr_vec_op, _lib.OP_ADD, a, b)
+    def fr_sub(self, a, b): return self._vec(self.L.de_fr_vec_op, _lib.OP_SUB, a, b)
+    def fr_from_mont(self, a): return self._vec(self.L.de_fr_vec_op, _lib.OP_FROM_MONT, a, None)
+    def fr_to_mont(self, a): return self._vec(self.L.de_fr_vec_op, _lib.OP_TO_MONT, a, None)
+    def fq_mul(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_MUL, a, b)
+    def fq_add(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_ADD, a, b)
+    def fq_sub(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_SUB, a, b)
+
+    # ---- a3 / a4 ----
+    def best_multiexp(self, coeffs, bases):
+        coeffs, bases = _np(coeffs), _np(bases)
+        n = coeffs.size // 4
+        if bases.size // 8 != n:
+            raise ValueError("best_multiexp: coeffs.len() != bases.len()")  # assert_eq! in the reference
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.L.de_msm(self.h, _ptr(coeffs), _ptr(bases), n, _ptr(out)))
+        return out
+
+    def best_multiexp_dev(self, d_coeffs, d_bases, n: int):
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.L.de_msm_dev(self.h, _ptr(d_coeffs), _ptr(d_bases), n, _ptr(out)))
+        return out
+
+    def best_fft(self, a, omega, log_n: int):
+        a = _np(a).copy()
+        if a.size // 4 != (1 << log_n):
+            raise ValueError("best_fft: a.len() != 1 << log_n")  # assert_eq! in the reference
+        omega = _np(omega)
+        self.check(self.L.de_ntt(self.h, _ptr(a), _ptr(omega), log_n))
+        return a
+
+    def best_fft_dev(self, d_a, omega, log_n: int, batch: int = 1, stride: int | None = None):
+        omega = _np(omega)
+        self.check(self.L.de_ntt_dev(self.h, _ptr(d_a), _ptr(omega), log_n, batch, stride or (1 << log_n)))
+
+    def g1_sum(self, points):
+        points = _np(points)
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.L.de_g1_sum(self.h, _ptr(points), points.size // 12, _ptr(out)))
+        return out
+
+
+_default = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]
+
+
+def best_multiexp(coeffs, bases, ctx: Context | None = None):
+    return (ctx or default_context()).best_multiexp(coeffs, bases)
+
+
+def best_fft(a, omega, log_n: int, ctx: Context | None = None):
+    return (ctx or default_context()).best_fft(a, omega, log_n)
+
+
+class EvaluationDomain:
+    """poly::EvaluationDomain::new(j, k) with j = cs.degree()."""
+
+    def __init__(self, j: int, k: int, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        L = self.ctx.L
+        h = C.c_void_p()
+        self.ctx.check(L.de_domain_create(self.ctx.h, j, k, C.byref(h)))
+        self.h = h
+        ek = C.c_uint32()
+        consts = np.zeros((4, 4), dtype=np.uint64)
+        self.ctx.check(L.de_domain_info(h, C.byref(ek), _ptr(consts)))
+        self.j, self.k, self.extended_k = j, k, int(ek.value)
+        self.n, self.extended_n = 1 << k, 1 << self.extended_k
+        self.omega, self.omega_inv, self.extended_omega, self.extended_omega_inv = consts
+        self.quotient_poly_degree = j - 1
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.de_domain_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk_len(self, a, n, what):
+        a = _np(a)
+        if a.size // 4 != n:
+            raise ValueError(f"{what}: wrong length {a.size // 4}, expected {n}")
+        return a
+
+    def coeff_to_extended(self, a):
+        a = self._chk_len(a, self.n, "coeff_to_extended")
+        out = np.empty((self.extended_n, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.de_coeff_to_extended(self.h, _ptr(a), _ptr(out)))
+        return out
+
+    def extended_to_coeff(self, a):
+        a = self._chk_len(a, self.extended_n, "extended_to_coeff").copy()
+        m = C.c_size_t()
+        self.ctx.check(self.ctx.L.de_extended_to_coeff(self.h, _ptr(a), C.byref(m)))
+        return a.reshape(-1, 4)[: m.value].copy()
+
+    def lagrange_to_coeff(self, a):
+        a = self._chk_len(a, self.n, "lagrange_to_coeff").copy()
+        self.ctx.check(self.ctx.L.de_lagrange_to_coeff(self.h, _ptr(a)))
+        return a
+
+    def coeff_to_lagrange(self, a):
+        a = self._chk_len(a, self.n, "coeff_to_lagrange").copy()
+        self.ctx.check(self.ctx.L.de_coeff_to_lagrange(self.h, _ptr(a)))
+        return a
+
+    def divide_by_vanishing_poly(self, a):
+        a = self._chk_len(a, self.extended_n, "divide_by_vanishing_poly").copy()
+        self.ctx.check(self.ctx.L.de_divide_by_vanishing(self.h, _ptr(a)))
+        return a
+
+    # device-resident, batched
+    def coeff_to_extended_dev(self, d_coeff, d_ext, batch=1, in_stride=None, out_stride=None):
+        self.ctx.check(self.ctx.L.de_coeff_to_extended_dev(self.h, _ptr(d_coeff), in_stride or self.n, _ptr(d_ext),
+                                                           out_stride or self.extended_n, batch))
+
+    def extended_to_coeff_dev(self, d_ext, batch=1, stride=None):
+        m = C.c_size_t()
+        self.ctx.check(self.ctx.L.de_extended_to_coeff_dev(self.h, _ptr(d_ext), stride or self.extended_n, batch, C.byref(m)))
+        return m.value
+
+    def lagrange_to_coeff_dev(self, d_a, batch=1, stride=None):
+        self.ctx.check(self.ctx.L.de_lagrange_to_coeff_dev(self.h, _ptr(d_a), stride or self.n, batch))
+
+    def coeff_to_lagrange_dev(self, d_a, batch=1, stride=None):
+        self.ctx.check(self.ctx.L.de_coeff_to_lagrange_dev(self.h, _ptr(d_a), stride or self.n, batch))
+
+    def divide_by_vanishing_poly_dev(self, d_ext, batch=1, stride=None):
+        self.ctx.check(self.ctx.L.de_divide_by_vanishing_dev(self.h, _ptr(d_ext), stride or self.extended_n, batch))
+
+
+class ParamsKZG:
+    """poly::kzg::commitment::ParamsKZG: g / g_lagrange staged (with window tables) in HBM once."""
+
+    def __init__(self, k: int, g=None, g_lagrange=None, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.k, self.n = k, 1 << k
+        g = _np(g) if g is not None else None
+        gl = _np(g_lagrange) if g_lagrange is not None else None
+        for b in (g, gl):
+            if b is not None and b.size // 8 != self.n:
+                raise ValueError("ParamsKZG: basis length != 2^k")
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.de_params_upload(self.ctx.h, k, _ptr(g), _ptr(gl), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.de_params_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _commit(self, basis, poly):
+        poly = _np(poly)
+        out = np.zeros(12, dtype=np.uint64)
+        self.ctx.check(self.ctx.L.de_commit(self.h, basis, _ptr(poly), poly.size // 4, _ptr(out)))
+        return out
+
+    def commit(self, poly): return self._commit(0, poly)
+    def commit_lagrange(self, poly): return self._commit(1, poly)
+
+    def commit_batch(self, basis: int, polys):
+        polys = [_np(p) for p in polys]
+        n = polys[0].size // 4
+        arr = (C.c_void_p * len(polys))(*[p.ctypes.data for p in polys])
+        out = np.zeros((len(polys), 12), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.de_commit_batch(self.h, basis, arr, n, len(polys), _ptr(out)))
+        return out
+
+    def commit_batch_dev(self, basis: int, d_scalars, n: int, count: int, stride: int | None = None):
+        out = np.zeros((count, 12), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.de_commit_batch_dev(self.h, basis, _ptr(d_scalars), stride or n, n, count, _ptr(out)))
+        return out
+
+    def commit_range(self, basis: int, poly, lo: int, hi: int):
+        poly = _np(poly)
+        out = np.zeros(12, dtype=np.uint64)
+        self.ctx.check(self.ctx.L.de_commit_range(self.h, basis, _ptr(poly), lo, hi, _ptr(out)))
+        return out

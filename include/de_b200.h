@@ -1,0 +1,170 @@
+/*
+ * de_b200.h — C ABI of libde_b200.so, the B200 (sm_100a) backend for the proving hot path under the halo2 circuits
+ * of radiusxyz/delay-encryption-in-halo2.
+ *
+ * The reference has no FFI today: the path is reached through plain Rust generics of the un-vendored dependency
+ * halo2_proofs (tag v2023_04_20, /root/reference/Cargo.toml:17) from create_proof / keygen_vk / keygen_pk
+ * (/root/reference/benches/delay_enc.rs:86,103,123; benches/mod_pow.rs:163,180,201; benches/pose_enc.rs:89,106,127).
+ * Each entry point below names the halo2_proofs function a patched crate would forward to it (INTEGRATION.md shows
+ * the Rust `extern "C"` block and the [patch] wiring).
+ *
+ * Data conventions (zero-copy with halo2curves' in-memory layout):
+ *   de_fr / de_fq   4 x u64 little-endian limbs, MONTGOMERY form (R = 2^256)       = halo2curves::bn256::{Fr,Fq}
+ *   de_g1_affine    {x, y}, identity = all zero                                      = halo2curves::bn256::G1Affine
+ *   de_g1           {x, y, z} Jacobian, identity z = 0; any valid representative     = halo2curves::bn256::G1
+ * Every function returns 0 on success or a negative de_status; de_last_error() gives the message.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with DE_ERR_CUDA.
+ * Pointers named d_* are device pointers (e.g. torch tensors' data_ptr()); all others are host pointers that are
+ * not retained past the call.  A context is bound to one device and one stream and is not thread-safe; use one
+ * context per host thread / GPU (proof-batch sharding uses one per GPU).
+ */
+#ifndef DE_B200_H
+#define DE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } de_fr;
+typedef struct { uint64_t l[4]; } de_fq;
+typedef struct { de_fq x, y; } de_g1_affine;
+typedef struct { de_fq x, y, z; } de_g1;
+
+typedef struct de_ctx de_ctx;
+typedef struct de_params de_params;
+typedef struct de_domain de_domain;
+typedef struct de_pk de_pk;
+
+enum de_status {
+    DE_OK = 0,
+    DE_ERR_ARG = -1,     /* bad argument (the Rust originals would panic on an assert) */
+    DE_ERR_CUDA = -2,    /* CUDA runtime error, including "no device" */
+    DE_ERR_OOM = -3,     /* device or pinned-host allocation failed */
+    DE_ERR_UNSUPPORTED = -4
+};
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+int de_ctx_create(int device, de_ctx** out);
+int de_ctx_destroy(de_ctx* ctx);
+/* bind an existing CUDA stream (cudaStream_t as void*); NULL restores the context's own stream */
+int de_ctx_set_stream(de_ctx* ctx, void* cuda_stream);
+int de_ctx_sync(de_ctx* ctx);
+const char* de_last_error(de_ctx* ctx); /* ctx may be NULL: returns the last error of a failed de_ctx_create */
+const char* de_version(void);
+/* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
+uint64_t de_launch_count(de_ctx* ctx);
+
+/* ---- a1: halo2curves Fr / Fq element-wise arithmetic (parity surface for the field kernels) ---------------- */
+enum de_field_op { DE_OP_MUL = 0, DE_OP_ADD = 1, DE_OP_SUB = 2, DE_OP_FROM_MONT = 3, DE_OP_TO_MONT = 4 };
+int de_fr_vec_op(de_ctx* ctx, int op, const de_fr* a, const de_fr* b, de_fr* out, size_t n);
+int de_fq_vec_op(de_ctx* ctx, int op, const de_fq* a, const de_fq* b, de_fq* out, size_t n);
+
+/* ---- a3: halo2_proofs::arithmetic::best_multiexp(coeffs, bases) -> G1 ------------------------------------- */
+int de_msm(de_ctx* ctx, const de_fr* scalars, const de_g1_affine* bases, size_t n, de_g1* out);
+/* same with device-resident inputs; result written to host */
+int de_msm_dev(de_ctx* ctx, const de_fr* d_scalars, const de_g1_affine* d_bases, size_t n, de_g1* out);
+
+/* ---- a8: halo2_proofs::poly::kzg::commitment::ParamsKZG --------------------------------------------------- */
+/* Stage g[0..2^k) and g_lagrange[0..2^k) in HBM once per ParamsKZG (either may be NULL).  Window tables
+ * 2^(c*t) * base are precomputed on the device so every later commit is a single-bucket-set Pippenger. */
+int de_params_upload(de_ctx* ctx, uint32_t k, const de_g1_affine* g, const de_g1_affine* g_lagrange, de_params** out);
+int de_params_free(de_params* p);
+/* ParamsKZG::commit (basis 0, uses g[..n]) / ParamsKZG::commit_lagrange (basis 1, uses g_lagrange[..n]); the Blind
+ * argument of the Rust API is unused for KZG and has no counterpart here. */
+int de_commit(de_params* p, int basis, const de_fr* scalars, size_t n, de_g1* out);
+/* `count` polynomials of n scalars each in one launch sequence (the 5/10/5 same-round commitments of create_proof) */
+int de_commit_batch(de_params* p, int basis, const de_fr* const* scalars, size_t n, size_t count, de_g1* out);
+/* device-resident: d_scalars holds count polynomials, `stride` elements apart */
+int de_commit_batch_dev(de_params* p, int basis, const de_fr* d_scalars, size_t stride, size_t n, size_t count, de_g1* out);
+
+/* ---- a4: halo2_proofs::arithmetic::best_fft(a, omega, log_n) for Scalar = Fr ------------------------------ */
+int de_ntt(de_ctx* ctx, de_fr* a, const de_fr* omega, uint32_t log_n);
+/* device-resident, `batch` vectors `stride` elements apart, in place */
+int de_ntt_dev(de_ctx* ctx, de_fr* d_a, const de_fr* omega, uint32_t log_n, size_t batch, size_t stride);
+
+/* ---- a5-a7: halo2_proofs::poly::EvaluationDomain ---------------------------------------------------------- */
+int de_domain_create(de_ctx* ctx, uint32_t j /* cs.degree() */, uint32_t k, de_domain** out); /* EvaluationDomain::new */
+int de_domain_free(de_domain* d);
+/* consts = {omega, omega_inv, extended_omega, extended_omega_inv} */
+int de_domain_info(de_domain* d, uint32_t* extended_k, de_fr consts[4]);
+int de_coeff_to_extended(de_domain* d, const de_fr* coeff_n, de_fr* ext_out);     /* coeff_to_extended */
+int de_extended_to_coeff(de_domain* d, de_fr* ext_inout, size_t* out_len);         /* extended_to_coeff: first out_len entries */
+int de_lagrange_to_coeff(de_domain* d, de_fr* a);                                  /* lagrange_to_coeff */
+int de_coeff_to_lagrange(de_domain* d, de_fr* a);                                  /* coeff_to_lagrange */
+int de_divide_by_vanishing(de_domain* d, de_fr* ext_inout);                        /* divide_by_vanishing_poly */
+/* device-resident, batched variants (vectors `stride` elements apart) */
+int de_coeff_to_extended_dev(de_domain* d, const de_fr* d_coeff, size_t in_stride, de_fr* d_ext, size_t out_stride, size_t batch);
+int de_extended_to_coeff_dev(de_domain* d, de_fr* d_ext, size_t stride, size_t batch, size_t* out_len);
+int de_lagrange_to_coeff_dev(de_domain* d, de_fr* d_a, size_t stride, size_t batch);
+int de_coeff_to_lagrange_dev(de_domain* d, de_fr* d_a, size_t stride, size_t batch);
+int de_divide_by_vanishing_dev(de_domain* d, de_fr* d_ext, size_t stride, size_t batch);
+
+/* ---- a9: halo2_proofs::plonk::evaluation::Evaluator::evaluate_h ------------------------------------------- */
+/* A compiled GraphEvaluator (constants / rotations / calculations) plus the permutation and lookup arguments'
+ * shapes; mirrors the structures evaluate_h walks. */
+enum de_calc_op { DE_CALC_ADD = 0, DE_CALC_SUB = 1, DE_CALC_MUL = 2, DE_CALC_SQUARE = 3, DE_CALC_DOUBLE = 4,
+                  DE_CALC_NEGATE = 5, DE_CALC_HORNER = 6, DE_CALC_STORE = 7 };
+enum de_value_kind { DE_VAL_CONSTANT = 0, DE_VAL_INTERMEDIATE = 1, DE_VAL_FIXED = 2, DE_VAL_ADVICE = 3,
+                     DE_VAL_INSTANCE = 4, DE_VAL_CHALLENGE = 5, DE_VAL_BETA = 6, DE_VAL_GAMMA = 7, DE_VAL_THETA = 8,
+                     DE_VAL_Y = 9, DE_VAL_PREVIOUS = 10 };
+typedef struct { uint32_t kind; uint32_t index; uint32_t rotation; /* index into rotations[] */ } de_value_source;
+typedef struct {
+    uint32_t op;            /* de_calc_op */
+    de_value_source a, b;   /* operands (b unused for unary ops; HORNER: a = start value, b = multiplier) */
+    uint32_t horner_first;  /* HORNER: parts are horner_parts[horner_first .. horner_first + horner_len) */
+    uint32_t horner_len;
+    uint32_t target;        /* intermediate slot written */
+} de_calculation;
+typedef struct {
+    const de_fr* constants; uint32_t n_constants;
+    const int32_t* rotations; uint32_t n_rotations;
+    const de_calculation* calcs; uint32_t n_calcs;
+    const de_value_source* horner_parts; uint32_t n_horner_parts;
+    uint32_t n_intermediates;
+    de_value_source result;  /* value of the expression after the last calculation */
+} de_graph;
+typedef struct {
+    de_graph graph;          /* evaluates the theta-compressed table and input; result = table, result_input = input */
+    de_value_source result_input;
+} de_lookup_graph;
+typedef struct {
+    uint32_t n_fixed, n_advice, n_instance;
+    const de_fr* const* fixed_coeff;   /* fixed column polynomials, coefficient form, n each */
+    /* permutation argument */
+    uint32_t n_perm_columns;           /* columns in the permutation, in order */
+    const uint32_t* perm_column_kind;  /* de_value_kind (FIXED / ADVICE / INSTANCE) per column */
+    const uint32_t* perm_column_index;
+    const de_fr* const* sigma_coeff;   /* permutation polynomials, coefficient form */
+    uint32_t chunk_len;                /* cs.degree() - 2 */
+    uint32_t blinding_factors;         /* cs.blinding_factors() */
+    de_fr delta;                       /* Fr::DELTA */
+    /* custom gates: value = value * y + gate, in order */
+    de_graph gates;
+    /* lookups */
+    uint32_t n_lookups;
+    const de_lookup_graph* lookups;
+} de_pk_desc;
+typedef struct { de_fr y, beta, gamma, theta; const de_fr* challenges; uint32_t n_challenges; } de_challenges;
+
+/* ProvingKey staging: fixed / sigma / l0 / l_last / l_active cosets are computed on the device once and stay in HBM */
+int de_pk_upload(de_domain* d, const de_pk_desc* desc, de_pk** out);
+int de_pk_free(de_pk* pk);
+/* advice / instance polynomials in coefficient form (n each); permutation z polys (ceil(n_perm_columns/chunk_len)),
+ * lookup polys per lookup in order {product z, permuted input a', permuted table s'}: all coefficient form, n each.
+ * Output: h evaluations over the extended domain, BEFORE divide_by_vanishing_poly (as evaluate_h returns them). */
+int de_evaluate_h(de_pk* pk, const de_fr* const* advice_coeff, const de_fr* const* instance_coeff,
+                  const de_challenges* ch, const de_fr* const* perm_z_coeff, const de_fr* const* lookup_coeff,
+                  de_fr* h_ext_out);
+
+/* ---- multi-GPU: MSM base-range sharding -------------------------------------------- */
+/* shard s of n_shards: commits scalars[lo..hi) against the matching base range of p and returns the partial sum;
+ * the host (or de_g1_sum) adds the n_shards partial points. */
+int de_commit_range(de_params* p, int basis, const de_fr* scalars, size_t lo, size_t hi, de_g1* out_partial);
+int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DE_B200_H */

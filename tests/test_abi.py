@@ -1,0 +1,47 @@
+"""The C-ABI boundary: every function include/de_b200.h declares is exported by libde_b200.so and bound by the Python
+host layer; without a GPU the library must refuse to create a context (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "de_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(de_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_library_agree():
+    import __graft_entry__ as g
+    from de_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        g.build()
+    L = C.CDLL(_lib.LIB_PATH)
+    fns = header_functions()
+    assert len(fns) >= 30
+    assert sorted(_lib.SYMBOLS) == fns
+    for f in fns:
+        assert hasattr(L, f), f"libde_b200.so does not export {f}"
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import de_b200
+    with pytest.raises(de_b200.DeError) as e:
+        de_b200.Context(0)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_oracle_is_not_imported_by_the_product():
+    pkg = os.path.join(ROOT, "delay-encryption-in-halo2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f == "NOTES", f"{f} mentions the oracle: the product path must not use it"

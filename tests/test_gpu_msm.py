@@ -1,0 +1,108 @@
+"""a3 / a8 parity (GPU): best_multiexp and ParamsKZG::commit / commit_lagrange through the C ABI == oracle (compared as
+affine points, bit-exact), including the exceptional cases of the group law and skewed (witness-like) scalars."""
+import numpy as np
+import pytest
+
+import de_b200
+import orc
+import pyoracle as po
+from util import affine_ints, fr, golden, points
+
+pytestmark = pytest.mark.gpu
+
+
+def same_point(a, b):
+    return (orc.g1_to_affine(a.reshape(1, 12)) == orc.g1_to_affine(b.reshape(1, 12))).all()
+
+
+def test_golden_msm(ctx):
+    for case in golden()["msm"]:
+        got = ctx.best_multiexp(fr(case["scalars"]), points(case["bases"]))
+        want = None if case["result"] is None else (int(case["result"][0], 16), int(case["result"][1], 16))
+        assert affine_ints(got) == want
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 1000, 4096, 1 << 14, (1 << 16) + 17])
+def test_best_multiexp_matches_oracle(ctx, n):
+    s = orc.uniform_fr(0xDE04 + n, n)
+    b = orc.gen_bases(n)
+    assert same_point(ctx.best_multiexp(s, b), orc.best_multiexp(s, b))
+
+
+def test_best_multiexp_length_mismatch(ctx):
+    with pytest.raises(ValueError):
+        ctx.best_multiexp(orc.uniform_fr(1, 4), orc.gen_bases(5))
+
+
+def test_exceptional_cases(ctx):
+    n = 256
+    bases = orc.gen_bases(n)
+    ones = orc.fr_mont_from_ints([1] * n)
+    # sum of (i+1)G hits acc == next base (doubling) inside a bucket
+    assert affine_ints(ctx.best_multiexp(ones, bases)) == po.g1_mul(po.G1_GEN, n * (n + 1) // 2)
+    # all zero scalars -> identity
+    assert affine_ints(ctx.best_multiexp(np.zeros((n, 4), dtype=np.uint64), bases)) is None
+    # the same base n times -> repeated doubling
+    same = np.repeat(bases[:1], n, axis=0)
+    assert affine_ints(ctx.best_multiexp(ones, same)) == po.g1_mul(po.G1_GEN, n)
+    # P + (-P) -> identity; identity bases are skipped
+    pair = bases[:4].copy()
+    pair[1, :4] = pair[0, :4]
+    y = orc.fq_ints_from_mont(pair[0, 4:].reshape(1, 4))[0]
+    pair[1, 4:] = orc.fq_mont_from_ints([po.FQ - y])[0]
+    pair[2] = 0
+    s = orc.fr_mont_from_ints([5, 5, 9, 0])
+    assert affine_ints(ctx.best_multiexp(s, pair)) is None
+    # scalars r-1, r-2 (maximal signed-digit carries)
+    big = orc.fr_mont_from_ints([po.FR - 1, po.FR - 2, 1 << 253, (1 << 128) - 1])
+    assert same_point(ctx.best_multiexp(big, bases[:4]), orc.best_multiexp(big, bases[:4]))
+
+
+def test_witness_like_scalars(ctx):
+    # SURVEY.md 8d distribution "W": many zeros and small values -> heavy buckets, split tasks and the warp merge
+    n = 1 << 15
+    s = orc.witness_fr(0xDE05, n, used=int(n * 0.77))
+    b = orc.gen_bases(n)
+    assert same_point(ctx.best_multiexp(s, b), orc.best_multiexp(s, b))
+    # one value repeated everywhere: a single bucket per window holds every point
+    s2 = np.repeat(orc.fr_mont_from_ints([0x1234567]), n, axis=0)
+    assert same_point(ctx.best_multiexp(s2, b), orc.best_multiexp(s2, b))
+
+
+@pytest.mark.parametrize("k", [4, 10, 13])
+def test_params_commit_matches_oracle(ctx, k):
+    n = 1 << k
+    g = orc.gen_bases(n)
+    gl = orc.gen_bases(n, start=n)
+    params = de_b200.ParamsKZG(k, g, gl, ctx)
+    s = orc.uniform_fr(k, n)
+    assert same_point(params.commit(s), orc.best_multiexp(s, g))
+    assert same_point(params.commit_lagrange(s), orc.best_multiexp(s, gl))
+    # shorter polynomial: uses g[..len]
+    assert same_point(params.commit(s[: n // 2 + 1]), orc.best_multiexp(s[: n // 2 + 1], g[: n // 2 + 1]))
+    w = orc.witness_fr(k + 1, n, used=n // 2)
+    assert same_point(params.commit_lagrange(w), orc.best_multiexp(w, gl))
+
+
+def test_commit_batch_and_ranges(ctx):
+    k = 12
+    n = 1 << k
+    gl = orc.gen_bases(n)
+    params = de_b200.ParamsKZG(k, None, gl, ctx)
+    polys = [orc.uniform_fr(50 + i, n) for i in range(4)] + [orc.witness_fr(60, n, n // 3)]
+    got = params.commit_batch(1, polys)
+    for i, p in enumerate(polys):
+        assert same_point(got[i], orc.best_multiexp(p, gl))
+    # base-range sharding: partial commitments over disjoint ranges sum to the commitment (multi-GPU row 8e)
+    parts = np.stack([params.commit_range(1, polys[0], lo, hi) for lo, hi in ((0, 1000), (1000, 1000), (1000, 3000), (3000, n))])
+    assert same_point(ctx.g1_sum(parts), orc.best_multiexp(polys[0], gl))
+
+
+def test_commit_delay_enc_size(ctx):
+    # the bench configuration: k = 16 commit_lagrange, uniform and witness-like columns
+    k = 16
+    n = 1 << k
+    gl = orc.gen_bases(n)
+    params = de_b200.ParamsKZG(k, None, gl, ctx)
+    for s in (orc.uniform_fr(0xDE03, n), orc.witness_fr(0xDE03, n, 50400)):
+        assert same_point(params.commit_lagrange(s), orc.best_multiexp(s, gl))
