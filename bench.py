@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 proving backend on the reference's delay_enc configuration.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is ONE pass of the proving hot path for one delay_enc proof (BASELINE.json configs[2]: the DelayEncryptCircuit
+at its bench k = 16, /root/reference/benches/delay_enc.rs:181): 31 MSMs of 2^16, 23 iNTTs of 2^16, 23 coset NTTs and one
+iNTT of 2^18, and the quotient evaluator over 2^18 rows, issued in create_proof's order (de_b200/prover.py).
+Inputs are synthetic columns of the circuit's shape (seed 0xDE03).
+
+  value      proofs/s with every input already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e        the same schedule through the host-buffer API: pinned host columns are copied to the device inside the timed
+             region and the commitments are read back every step
+  roofline   dominant kernel (k_msm_accumulate): algorithmic bytes per launch / measured launch time, against the measured
+             HBM copy bandwidth (MEASURED_PEAKS.json); the kernel is integer-pipe bound, so `int_pipe` gives the fraction of
+             the measured Montgomery-multiply peak as well
+  cpu_baseline   the restated reference algorithms (oracle/liboracle.so: best_multiexp / best_fft / evaluate_h as halo2_proofs
+             v2023_04_20 implements them, C + pthreads) on this box's host cores, one proof
+
+--impl reference times that CPU restatement alone (the Rust prover cannot be built: no cargo/rustc, un-vendored crates).
+N > 1 (torchrun): independent proofs are sharded one stream of proofs per GPU, no collective on the data path (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "delay-encryption-in-halo2_b200"))
+
+K = 16
+USED_ROWS = 50400
+SEED = 0xDE03
+WORKLOAD = ("delay_enc k=16 hot-path schedule: 31 MSM 2^16 (KZG bases resident), 23 iNTT 2^16, 23 coset-NTT 2^18, "
+            "evaluate_h over 2^18 rows (15 fixed, 5 lookups, 6 permutation columns), 1 iNTT 2^18")
+METRIC = "delay_enc_hot_path_proofs_per_s"
+UNIT = "proofs/s"
+MUL_PEAK_GMULS = 65.9   # measured on this pool's B200 by tools/int_peak (profiles/r01_int_peak.jsonl): Fr Montgomery mul/s
+MULS_PER_POINT = 160    # SURVEY.md 8d convention: 16 windows x (8M + 2S) per point
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def build_inputs():
+    """Host-side synthetic proof inputs + key material for the delay_enc shape."""
+    import numpy as np
+    from de_b200 import plonk, prover, synth
+    shape = plonk.main_gate_shape(True)
+    w = prover.Workload(shape, K)
+    n = w.n
+    o = w.offsets()
+    cols = np.empty((w.n_cols, n, 4), dtype=np.uint64)
+    for i in range(shape.n_advice):
+        cols[o["advice"] + i] = synth.witness_fr(SEED + i, n, USED_ROWS)
+    cols[o["instance"]] = 0  # the bench circuits have an empty instance column
+    for i in range(o["permz"], w.n_cols):
+        cols[i] = synth.uniform_fr(SEED + 100 + i, n)
+    random_poly = synth.uniform_fr(SEED + 200, n).reshape(1, n, 4)
+    openings = synth.uniform_fr(SEED + 201, n * prover.N_OPENING_POINTS).reshape(prover.N_OPENING_POINTS, n, 4)
+    fixed = [synth.uniform_fr(SEED + 300 + i, n) for i in range(shape.n_fixed)]
+    sigma = [synth.uniform_fr(SEED + 400 + i, n) for i in range(len(shape.perm_columns))]
+    g = synth.gen_bases(n, start=0)
+    g_lagrange = synth.gen_bases(n, start=n)
+    challenges = (0x1D2C3B4A59687766, 0x0F1E2D3C4B5A6978, 0x1122334455667788, 0x99AABBCCDDEEFF00)
+    return dict(shape=shape, w=w, cols=cols, random=random_poly, openings=openings, fixed=fixed, sigma=sigma, g=g,
+                g_lagrange=g_lagrange, challenges=challenges)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx, self.proc, self.lines = device_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_setup(inp, state):
+    """CPU 'ProvingKey' (fixed / sigma / l0 / l_last / l_active cosets), as keygen_pk builds it once in the reference."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from de_b200 import plonk
+    shape = inp["shape"]
+    state["dom"] = orc.Domain(shape.degree(), K)
+    desc, keep = plonk.marshal_pk_desc(shape, inp["fixed"], inp["sigma"])
+    state["pk"] = orc.Pk(state["dom"], desc, keep)
+    state["ch"], state["chkeep"] = plonk.marshal_challenges(*inp["challenges"])
+
+
+def cpu_reference_step(inp, state):
+    """One proof's hot path on the host cores with the restated reference algorithms (the only place the oracle is executed
+    by bench.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import orc
+    from de_b200 import prover
+    shape, w = inp["shape"], inp["w"]
+    n, o, L = w.n, w.offsets(), w.n_lookups
+    if "pk" not in state:
+        cpu_reference_setup(inp, state)
+    dom, pk = state["dom"], state["pk"]
+    cols = inp["cols"]
+    pts = []
+    for i in range(shape.n_advice):
+        pts.append(orc.best_multiexp(cols[o["advice"] + i], inp["g_lagrange"]))
+    for i in range(2 * L):
+        pts.append(orc.best_multiexp(cols[o["lookup_a"] + i], inp["g_lagrange"]))
+    for i in range(shape.n_perm_sets + L):
+        pts.append(orc.best_multiexp(cols[o["permz"] + i], inp["g_lagrange"]))
+    pts.append(orc.best_multiexp(inp["random"][0], inp["g"]))
+    coeff = [dom.lagrange_to_coeff(cols[i]) for i in range(w.n_cols)]
+    h = pk.evaluate_h(coeff[o["advice"]:o["advice"] + shape.n_advice], coeff[o["instance"]:o["instance"] + shape.n_instance],
+                      state["ch"], coeff[o["permz"]:o["permz"] + shape.n_perm_sets], coeff[o["lookup_z"]:])
+    h = dom.divide_by_vanishing(h)
+    hc = dom.extended_to_coeff(h)
+    for i in range(shape.degree() - 1):
+        pts.append(orc.best_multiexp(np.ascontiguousarray(hc[i * n:(i + 1) * n]), inp["g"]))
+    for i in range(prover.N_OPENING_POINTS):
+        pts.append(orc.best_multiexp(inp["openings"][i], inp["g"]))
+    return np.stack(pts)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    orc.build()
+    inp = build_inputs()
+    state = {}
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_step(inp, state)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(inp, state)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    cores = orc.ncpu()
+    sample = "one delay_enc k=16 hot-path schedule per step (restated reference algorithm in C, not the Rust binary)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery limbs)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3  # timing hygiene: at least three untimed steps
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import de_b200
+    from de_b200 import prover
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    inp = build_inputs()
+    w, shape = inp["w"], inp["shape"]
+    stream = torch.cuda.Stream()
+    ctx = de_b200.Context(local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        hp = prover.HotPathProver(ctx, w, inp["g"], inp["g_lagrange"], inp["fixed"], inp["sigma"])
+        as_i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
+        cols_h, random_h, openings_h = (as_i64(inp[k]).pin_memory() for k in ("cols", "random", "openings"))
+        cols_d, random_d, openings_d = cols_h.cuda(), random_h.cuda(), openings_h.cuda()
+        staging = {"cols": torch.empty_like(cols_d), "random": torch.empty_like(random_d), "openings": torch.empty_like(openings_d)}
+        ch = inp["challenges"]
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(fn, steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record(stream)
+            for _ in range(steps):
+                out = fn()
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, out
+
+        run_dev = lambda: hp.prove_dev(cols_d, random_d, openings_d, ch)
+        run_host = lambda: hp.prove_host(cols_h, random_h, openings_h, ch, staging)
+        for _ in range(args.warmup):
+            first = run_dev()
+        # ---- device-resident arm (value) with per-kernel event timing and clock sampling
+        ctx.timing_reset()
+        ctx.timing_enable(True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = ctx.launches
+        ms_dev, out_dev = timed(run_dev, args.steps)
+        launches = ctx.launches - launches0
+        clocks = sampler.stop()
+        acc_ms, acc_pts, acc_n = ctx.timing_get("k_msm_accumulate")
+        ntt_ms, ntt_el, ntt_n = ctx.timing_get("k_ntt_pass")
+        ev_ms, ev_rows, ev_n = ctx.timing_get("k_eval_h")
+        red_ms, _, red_n = ctx.timing_get("k_msm_reduce_chunks")
+        ctx.timing_enable(False)
+        assert (out_dev == first).all(), "commitments changed between steps"
+        # ---- end-to-end arm: host buffers in, commitments out, every step
+        for _ in range(2):
+            run_host()
+        ms_e2e, out_e2e = timed(run_host, args.steps)
+        assert (out_e2e == first).all(), "host-buffer path disagrees with the device-resident path"
+    h2d = cols_h.numel() * 8 + random_h.numel() * 8 + openings_h.numel() * 8
+    d2h = w.n_msm * 96
+    peaks, peak_kind = _peaks()
+    value = world * args.steps / (ms_dev / 1000.0)
+    e2e_value = world * args.steps / (ms_e2e / 1000.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE carry chains)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proofs_per_step_per_gpu": 1,
+                   "l2": "per-step working set ~0.7 GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
+                   "sharding": "independent proofs, one per GPU per step, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "create_proof_hot_path_s": ms_dev / args.steps / 1000.0,
+    }
+    if acc_n:
+        pts_per_launch = acc_pts / acc_n
+        avg_ms = acc_ms / acc_n
+        achieved = 96.0 * pts_per_launch / (avg_ms * 1e-3) / 1e9
+        line["roofline"] = {"kernel": "k_msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                            "share_of_step": acc_ms / ms_dev, "launches": acc_n, "avg_launch_ms": avg_ms,
+                            "int_pipe": {"achieved_gmuls": MULS_PER_POINT * pts_per_launch / (avg_ms * 1e-3) / 1e9,
+                                         "peak_gmuls": MUL_PEAK_GMULS,
+                                         "frac": MULS_PER_POINT * pts_per_launch / (avg_ms * 1e-3) / 1e9 / MUL_PEAK_GMULS,
+                                         "note": "160 field muls per point (16 windows x 8M+2S); peak = measured Fr mul/s (tools/int_peak)"}}
+        line["msm_gpts_s"] = acc_pts / (acc_ms * 1e-3) / 1e9
+    if ntt_n:
+        line["ntt_gb_s"] = 64.0 * ntt_el / (ntt_ms * 1e-3) / 1e9 / 2.0  # two passes per transform at these sizes
+        line["kernel_share"] = {"k_msm_accumulate": acc_ms / ms_dev, "k_msm_reduce_chunks": red_ms / ms_dev,
+                                "k_ntt_pass": ntt_ms / ms_dev, "k_eval_h": ev_ms / ms_dev}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        state = {}
+        cpu_reference_setup(inp, state)  # keygen_pk's cosets: one-time in the reference too, not timed
+        t0 = time.perf_counter()
+        cpu_out = cpu_reference_step(inp, state)
+        dt = time.perf_counter() - t0
+        import orc
+        same = (orc.g1_to_affine(cpu_out) == orc.g1_to_affine(out_dev)).all()
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": orc.ncpu(), "kind": "port",
+                                "sample": "one full delay_enc k=16 hot-path schedule (pk cosets precomputed, untimed); "
+                                          "restated reference algorithm in C, not the Rust binary",
+                                "commitments_match_gpu": bool(same)}
+    if rank == 0:
+        print(json.dumps(line))
+    hp.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,24 @@ enum { WS_IO_A = 0, WS_IO_B, WS_NTT_SCRATCH, WS_MSM_KEYS, WS_MSM_VALS, WS_MSM_SO
 
 }  // namespace de
 
+namespace de {
+// optional per-kernel CUDA-event timing on the context's stream (bench.py's roofline section)
+struct TimedLaunch {
+    const char* name;
+    cudaEvent_t e0, e1;
+    double units;  // algorithmic units processed by this launch (points, elements, rows)
+};
+struct KernelStat {
+    std::string name;
+    double ms = 0, units = 0;
+    uint64_t launches = 0;
+};
+}  // namespace de
+
 struct de_ctx {
+    bool timing = false;
+    std::vector<de::TimedLaunch> timed;
+    std::vector<de::KernelStat> stats;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
@@ -108,6 +125,22 @@ inline int fail(de_ctx* ctx, int code, const std::string& msg) {
         if (e__ != cudaSuccess)                                                                             \
             return de::fail((ctx), DE_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__) +  \
                                                     " at " + __FILE__ + ":" + std::to_string(__LINE__));    \
+    } while (0)
+
+// DE_TIMED(ctx, "kernel", units, launch-statement): wraps the launch in a CUDA event pair when timing is enabled
+#define DE_TIMED(ctx, kname, nunits, stmt)                                      \
+    do {                                                                        \
+        de::TimedLaunch tl__ = {kname, nullptr, nullptr, (double)(nunits)};     \
+        if ((ctx)->timing) {                                                    \
+            cudaEventCreate(&tl__.e0);                                          \
+            cudaEventCreate(&tl__.e1);                                          \
+            cudaEventRecord(tl__.e0, (ctx)->stream);                            \
+        }                                                                       \
+        stmt;                                                                   \
+        if ((ctx)->timing) {                                                    \
+            cudaEventRecord(tl__.e1, (ctx)->stream);                            \
+            (ctx)->timed.push_back(tl__);                                       \
+        }                                                                       \
     } while (0)
 
 #define DE_TRY(expr)                 \

@@ -1,18 +1,452 @@
-// eval.cu — quotient-polynomial evaluator (halo2_proofs::plonk::evaluation::Evaluator::evaluate_h), SURVEY.md row a9.
+// eval.cu — quotient-polynomial evaluator on the extended domain (replaces
+// halo2_proofs::plonk::evaluation::Evaluator::evaluate_h; reached from the
+// reference through create_proof at benches/delay_enc.rs:123, benches/mod_pow.rs:201, benches/pose_enc.rs:127).
+//
+// ProvingKey staging (de_pk_upload): fixed, sigma, l0, l_last, l_active_row cosets and the coset points are computed on
+// the device once and stay resident.  Per proof: ONE batched coeff_to_extended for advice / instance / z / lookup
+// polynomials, then ONE fused kernel: each thread owns an extended-domain row, keeps `value` in registers and runs
+//   custom gates (compiled GraphEvaluator program, interpreted; intermediates in thread-local memory)
+//   -> permutation argument constraints -> every lookup's five constraints
+// folding with y exactly in the reference's order, so the output equals evaluate_h's bit for bit.
+#include <string.h>
+
+#include <vector>
+
 #include "common.cuh"
+
+struct de_domain_view {  // layout prefix of de_domain (ntt.cu) that this unit reads
+    de_ctx* ctx;
+    uint32_t j, k, ek;
+    size_t n, ext_n, qdeg;
+    de_fr omega, omega_inv, ext_omega, ext_omega_inv;
+};
+
+namespace de {
+
+#define DE_MAX_INTER 96
+#define DE_MAX_ROT 16
+
+struct DevSrc { uint32_t kind, index, rot; };
+struct DevCalc { uint32_t op; DevSrc a, b; uint32_t hfirst, hlen, target; };
+struct DevGraph {
+    const Fr* constants;
+    const int* rotations;
+    const DevCalc* calcs;
+    const DevSrc* hparts;
+    uint32_t n_rot, n_calcs;
+};
+
+struct EvalParams {
+    uint32_t ext_mask, rot_scale;
+    unsigned long long ext_n;
+    // resident pk cosets (column-major, ext_n apart)
+    const Fr* fixed; const Fr* sigma; const Fr* l0; const Fr* l_last; const Fr* l_active; const Fr* omega_pows;
+    // per-proof cosets
+    const Fr* advice; const Fr* instance; const Fr* permz; const Fr* lookup;
+    const Fr* challenges;
+    Fr y, beta, gamma, theta, delta, delta_start;  // delta_start holds ZETA (Montgomery)
+    DevGraph gates;
+    const DevGraph* lookups;
+    uint32_t n_lookups;
+    // permutation
+    uint32_t n_perm_cols, chunk_len, n_sets;
+    int last_rotation;
+    const uint32_t* perm_kind; const uint32_t* perm_index;
+    Fr* out;
+};
+
+struct RowCtx {
+    const EvalParams* p;
+    unsigned int idx;
+    unsigned int rot_idx[DE_MAX_ROT];
+    Fr inter[DE_MAX_INTER];
+    Fr prev;
+};
+
+__device__ __forceinline__ unsigned int rot_index(unsigned int idx, int rot, unsigned int rot_scale, unsigned int mask) {
+    return (unsigned int)((int)idx + rot * (int)rot_scale) & mask;
+}
+
+__device__ __forceinline__ Fr fetch(const RowCtx& c, const DevGraph& g, const DevSrc& s) {
+    const EvalParams& p = *c.p;
+    switch (s.kind) {
+        case DE_VAL_CONSTANT: return load(&g.constants[s.index]);
+        case DE_VAL_INTERMEDIATE: return c.inter[s.index];
+        case DE_VAL_FIXED: return load(&p.fixed[(unsigned long long)s.index * p.ext_n + c.rot_idx[s.rot]]);
+        case DE_VAL_ADVICE: return load(&p.advice[(unsigned long long)s.index * p.ext_n + c.rot_idx[s.rot]]);
+        case DE_VAL_INSTANCE: return load(&p.instance[(unsigned long long)s.index * p.ext_n + c.rot_idx[s.rot]]);
+        case DE_VAL_CHALLENGE: return load(&p.challenges[s.index]);
+        case DE_VAL_BETA: return p.beta;
+        case DE_VAL_GAMMA: return p.gamma;
+        case DE_VAL_THETA: return p.theta;
+        case DE_VAL_Y: return p.y;
+        default: return c.prev;  // DE_VAL_PREVIOUS
+    }
+}
+
+__device__ Fr run_graph(RowCtx& c, const DevGraph& g) {
+    const EvalParams& p = *c.p;
+    for (uint32_t r = 0; r < g.n_rot; r++) c.rot_idx[r] = rot_index(c.idx, g.rotations[r], p.rot_scale, p.ext_mask);
+    Fr last = Fr::zero();
+    for (uint32_t i = 0; i < g.n_calcs; i++) {
+        const DevCalc cc = g.calcs[i];
+        Fr a = fetch(c, g, cc.a);
+        Fr r;
+        switch (cc.op) {
+            case DE_CALC_ADD: r = add(a, fetch(c, g, cc.b)); break;
+            case DE_CALC_SUB: r = sub(a, fetch(c, g, cc.b)); break;
+            case DE_CALC_MUL: r = mul(a, fetch(c, g, cc.b)); break;
+            case DE_CALC_SQUARE: r = sqr(a); break;
+            case DE_CALC_DOUBLE: r = dbl(a); break;
+            case DE_CALC_NEGATE: r = neg(a); break;
+            case DE_CALC_HORNER: {
+                Fr f = fetch(c, g, cc.b);
+                r = a;
+                for (uint32_t k = 0; k < cc.hlen; k++) r = add(mul(r, f), fetch(c, g, g.hparts[cc.hfirst + k]));
+                break;
+            }
+            default: r = a; break;  // DE_CALC_STORE
+        }
+        c.inter[cc.target] = r;
+        last = r;
+    }
+    return last;
+}
+
+__device__ __forceinline__ const Fr* perm_column(const EvalParams& p, uint32_t col) {
+    const uint32_t kind = p.perm_kind[col], index = p.perm_index[col];
+    const Fr* base = kind == DE_VAL_ADVICE ? p.advice : (kind == DE_VAL_FIXED ? p.fixed : p.instance);
+    return base + (unsigned long long)index * p.ext_n;
+}
+
+__global__ void __launch_bounds__(128) k_eval_h(const __grid_constant__ EvalParams p) {
+    const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.ext_n) return;
+    RowCtx c;
+    c.p = &p;
+    c.idx = idx;
+    const Fr one = Fr::one();
+    const Fr y = p.y;
+    // ---- custom gates: value = Horner(previous = 0, gate polynomials, y) inside the compiled program
+    c.prev = Fr::zero();
+    Fr value = run_graph(c, p.gates);
+    const Fr l0 = load(&p.l0[idx]), l_last = load(&p.l_last[idx]), l_active = load(&p.l_active[idx]);
+    const unsigned int r_next = rot_index(idx, 1, p.rot_scale, p.ext_mask);
+    const unsigned int r_prev = rot_index(idx, -1, p.rot_scale, p.ext_mask);
+    // ---- permutation argument
+    if (p.n_sets > 0) {
+        const unsigned int r_last = rot_index(idx, p.last_rotation, p.rot_scale, p.ext_mask);
+        const Fr z_first = load(&p.permz[idx]);
+        value = add(mul(value, y), mul(sub(one, z_first), l0));
+        const Fr z_lastset = load(&p.permz[(unsigned long long)(p.n_sets - 1) * p.ext_n + idx]);
+        value = add(mul(value, y), mul(sub(sqr(z_lastset), z_lastset), l_last));
+        for (uint32_t s = 1; s < p.n_sets; s++) {
+            Fr zi = load(&p.permz[(unsigned long long)s * p.ext_n + idx]);
+            Fr zp = load(&p.permz[(unsigned long long)(s - 1) * p.ext_n + r_last]);
+            value = add(mul(value, y), mul(sub(zi, zp), l0));
+        }
+        Fr current_delta = mul(mul(p.beta, p.delta_start), load(&p.omega_pows[idx]));  // beta * ZETA * extended_omega^idx
+        for (uint32_t s = 0; s < p.n_sets; s++) {
+            const uint32_t c0 = s * p.chunk_len;
+            const uint32_t c1 = (c0 + p.chunk_len < p.n_perm_cols) ? c0 + p.chunk_len : p.n_perm_cols;
+            Fr left = load(&p.permz[(unsigned long long)s * p.ext_n + r_next]);
+            Fr right = load(&p.permz[(unsigned long long)s * p.ext_n + idx]);
+            for (uint32_t col = c0; col < c1; col++) {
+                Fr v = load(&perm_column(p, col)[idx]);
+                Fr sg = load(&p.sigma[(unsigned long long)col * p.ext_n + idx]);
+                left = mul(left, add(add(v, mul(p.beta, sg)), p.gamma));
+                right = mul(right, add(add(v, current_delta), p.gamma));
+                current_delta = mul(current_delta, p.delta);
+            }
+            value = add(mul(value, y), mul(sub(left, right), l_active));
+        }
+    }
+    // ---- lookups
+    for (uint32_t n = 0; n < p.n_lookups; n++) {
+        c.prev = Fr::zero();
+        const Fr table_value = run_graph(c, p.lookups[n]);
+        const Fr* zc = p.lookup + (unsigned long long)n * p.ext_n;  // block order: all z | all a' | all s'
+        const Fr* ac = zc + (unsigned long long)p.n_lookups * p.ext_n;
+        const Fr* sc = ac + (unsigned long long)p.n_lookups * p.ext_n;
+        const Fr z = load(&zc[idx]), a = load(&ac[idx]), s = load(&sc[idx]);
+        const Fr a_minus_s = sub(a, s);
+        value = add(mul(value, y), mul(sub(one, z), l0));
+        value = add(mul(value, y), mul(sub(sqr(z), z), l_last));
+        Fr t = sub(mul(mul(load(&zc[r_next]), add(a, p.beta)), add(s, p.gamma)), mul(z, table_value));
+        value = add(mul(value, y), mul(t, l_active));
+        value = add(mul(value, y), mul(a_minus_s, l0));
+        value = add(mul(value, y), mul(mul(a_minus_s, sub(a, load(&ac[r_prev]))), l_active));
+    }
+    store(&p.out[idx], value);
+}
+
+// lagrange indicator columns for l0 / l_last / l_blind (written in lagrange form, then iNTT + coset NTT)
+__global__ void k_fill_indicators(Fr* l0, Fr* l_last, Fr* l_blind, unsigned long long n, unsigned int blinding) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr one = Fr::one(), zero = Fr::zero();
+    store(&l0[i], i == 0 ? one : zero);
+    store(&l_last[i], i == n - blinding - 1 ? one : zero);
+    store(&l_blind[i], i >= n - blinding ? one : zero);
+}
+// l_active = 1 - (l_last + l_blind) on the extended domain
+__global__ void k_l_active(const Fr* l_last, const Fr* l_blind, Fr* out, unsigned long long n) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    store(&out[i], sub(Fr::one(), add(load(&l_last[i]), load(&l_blind[i]))));
+}
+__global__ void k_pow_seq(Fr* out, unsigned long long n, Fr base) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long e = i;
+    Fr acc = Fr::one(), cur = base;
+    while (e) {
+        if (e & 1) acc = mul(acc, cur);
+        cur = sqr(cur);
+        e >>= 1;
+    }
+    store(&out[i], acc);
+}
+
+struct HostGraph {
+    DevGraph dev;
+    std::vector<void*> allocs;
+};
+
+}  // namespace de
 
 using namespace de;
 
-extern "C" {
-int de_pk_upload(de_domain* d, const de_pk_desc* desc, de_pk** out) {
-    (void)d; (void)desc;
-    if (out) *out = nullptr;
-    return DE_ERR_UNSUPPORTED;
+struct de_pk {
+    de_domain* dom;
+    de_ctx* ctx;
+    uint32_t n_fixed, n_advice, n_instance, n_perm_cols, chunk_len, n_sets, n_lookups, blinding;
+    size_t n, ext_n;
+    uint32_t k, ek;
+    Fr* resident;  // fixed | sigma | l0 | l_last | l_active | omega_pows, ext_n apart
+    Fr* work;      // advice | instance | permz | lookup (3 per lookup) cosets, ext_n apart
+    Fr* d_challenges;
+    uint32_t challenges_cap;
+    uint32_t *d_perm_kind, *d_perm_index;
+    DevGraph gates;
+    DevGraph* d_lookups;
+    std::vector<void*> allocs;
+    Fr delta, zeta;
+};
+
+static int upload_graph(de_ctx* ctx, const de_graph& g, DevGraph* out, std::vector<void*>& allocs) {
+    if (g.n_intermediates > DE_MAX_INTER) return fail(ctx, DE_ERR_UNSUPPORTED, "evaluator: too many intermediates in a graph");
+    if (g.n_rotations > DE_MAX_ROT) return fail(ctx, DE_ERR_UNSUPPORTED, "evaluator: too many distinct rotations in a graph");
+    std::vector<DevCalc> calcs(g.n_calcs);
+    auto conv = [](const de_value_source& s) { return DevSrc{s.kind, s.index, s.rotation}; };
+    for (uint32_t i = 0; i < g.n_calcs; i++) {
+        const de_calculation& c = g.calcs[i];
+        if (c.target >= g.n_intermediates) return fail(ctx, DE_ERR_ARG, "evaluator: calculation target out of range");
+        if (c.op > DE_CALC_STORE) return fail(ctx, DE_ERR_ARG, "evaluator: unknown calculation");
+        if (c.op == DE_CALC_HORNER && (uint64_t)c.horner_first + c.horner_len > g.n_horner_parts)
+            return fail(ctx, DE_ERR_ARG, "evaluator: horner parts out of range");
+        calcs[i] = DevCalc{c.op, conv(c.a), conv(c.b), c.horner_first, c.horner_len, c.target};
+    }
+    std::vector<DevSrc> parts(g.n_horner_parts);
+    for (uint32_t i = 0; i < g.n_horner_parts; i++) parts[i] = conv(g.horner_parts[i]);
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+        void* d = nullptr;
+        DE_CUDA(ctx, cudaMalloc(&d, bytes ? bytes : 16));
+        allocs.push_back(d);
+        if (bytes) DE_CUDA(ctx, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        *dst = d;
+        return DE_OK;
+    };
+    DE_TRY(up(g.constants, sizeof(Fr) * g.n_constants, (const void**)&out->constants));
+    DE_TRY(up(g.rotations, sizeof(int) * g.n_rotations, (const void**)&out->rotations));
+    DE_TRY(up(calcs.data(), sizeof(DevCalc) * calcs.size(), (const void**)&out->calcs));
+    DE_TRY(up(parts.data(), sizeof(DevSrc) * parts.size(), (const void**)&out->hparts));
+    out->n_rot = g.n_rotations;
+    out->n_calcs = g.n_calcs;
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    return DE_OK;
 }
-int de_pk_free(de_pk* pk) { (void)pk; return DE_OK; }
+
+extern "C" {
+
+int de_pk_free(de_pk* pk) {
+    if (!pk) return DE_OK;
+    cudaSetDevice(pk->ctx->device);
+    cudaStreamSynchronize(pk->ctx->stream);
+    for (void* a : pk->allocs) cudaFree(a);
+    delete pk;
+    return DE_OK;
+}
+
+int de_pk_upload(de_domain* dom, const de_pk_desc* desc, de_pk** out) {
+    if (!dom) return DE_ERR_ARG;
+    const de_domain_view* dv = (const de_domain_view*)dom;
+    de_ctx* ctx = dv->ctx;
+    if (!desc || !out) return fail(ctx, DE_ERR_ARG, "de_pk_upload: null pointer");
+    *out = nullptr;
+    if (desc->chunk_len == 0 && desc->n_perm_columns) return fail(ctx, DE_ERR_ARG, "de_pk_upload: chunk_len is 0");
+    if (desc->blinding_factors + 1 >= dv->n) return fail(ctx, DE_ERR_ARG, "de_pk_upload: blinding_factors too large for n");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    de_pk* pk = new de_pk();
+    pk->dom = dom; pk->ctx = ctx;
+    pk->n_fixed = desc->n_fixed; pk->n_advice = desc->n_advice; pk->n_instance = desc->n_instance;
+    pk->n_perm_cols = desc->n_perm_columns; pk->chunk_len = desc->chunk_len; pk->n_lookups = desc->n_lookups;
+    pk->n_sets = desc->n_perm_columns ? (desc->n_perm_columns + desc->chunk_len - 1) / desc->chunk_len : 0;
+    pk->blinding = desc->blinding_factors;
+    pk->n = dv->n; pk->ext_n = dv->ext_n; pk->k = dv->k; pk->ek = dv->ek;
+    pk->delta = fr_from_host(desc->delta);
+    pk->d_challenges = nullptr; pk->challenges_cap = 0;
+    const size_t n = dv->n, ext_n = dv->ext_n;
+    const size_t n_res = (size_t)desc->n_fixed + desc->n_perm_columns + 4;  // + l0, l_last, l_active, omega_pows
+    const size_t n_work = (size_t)desc->n_advice + desc->n_instance + pk->n_sets + 3 * (size_t)desc->n_lookups;
+    auto bail = [&](int rc) { de_pk_free(pk); return rc; };
+    auto dmalloc = [&](void** p, size_t bytes) -> int {
+        DE_CUDA(ctx, cudaMalloc(p, bytes ? bytes : 16));
+        pk->allocs.push_back(*p);
+        return DE_OK;
+    };
+    int rc;
+    if ((rc = dmalloc((void**)&pk->resident, sizeof(Fr) * ext_n * n_res)) != DE_OK) return bail(rc);
+    if ((rc = dmalloc((void**)&pk->work, sizeof(Fr) * ext_n * (n_work ? n_work : 1))) != DE_OK) return bail(rc);
+    // stage coefficient-form fixed + sigma polynomials, then one batched coeff_to_extended into the resident block
+    const size_t n_polys = (size_t)desc->n_fixed + desc->n_perm_columns;
+    Fr* staging = (Fr*)ctx->ws[WS_EVAL_A].ensure(sizeof(Fr) * n * (n_polys + 3));
+    if (!staging) return bail(fail(ctx, DE_ERR_OOM, "de_pk_upload: staging allocation failed"));
+    for (size_t i = 0; i < n_polys; i++) {
+        const de_fr* src = i < desc->n_fixed ? desc->fixed_coeff[i] : desc->sigma_coeff[i - desc->n_fixed];
+        if (!src) return bail(fail(ctx, DE_ERR_ARG, "de_pk_upload: null polynomial"));
+        cudaError_t e = cudaMemcpyAsync(staging + i * n, src, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) return bail(fail(ctx, DE_ERR_CUDA, cudaGetErrorString(e)));
+    }
+    Fr* ind = staging + n_polys * n;  // l0, l_last, l_blind in lagrange form
+    k_fill_indicators<<<(unsigned int)((n + 255) / 256), 256, 0, ctx->stream>>>(ind, ind + n, ind + 2 * n, n, desc->blinding_factors);
+    ctx->launches++;
+    if ((rc = de_lagrange_to_coeff_dev(dom, (de_fr*)ind, n, 3)) != DE_OK) return bail(rc);
+    Fr* res_fixed = pk->resident;
+    Fr* res_l0 = pk->resident + n_polys * ext_n;
+    Fr* res_l_last = res_l0 + ext_n;
+    Fr* res_l_active = res_l_last + ext_n;
+    Fr* res_omega = res_l_active + ext_n;
+    if (n_polys && (rc = de_coeff_to_extended_dev(dom, (const de_fr*)staging, n, (de_fr*)res_fixed, ext_n, n_polys)) != DE_OK) return bail(rc);
+    // l0, l_last -> their slots; l_blind -> the omega slot temporarily
+    if ((rc = de_coeff_to_extended_dev(dom, (const de_fr*)ind, n, (de_fr*)res_l0, ext_n, 2)) != DE_OK) return bail(rc);
+    if ((rc = de_coeff_to_extended_dev(dom, (const de_fr*)(ind + 2 * n), n, (de_fr*)res_omega, ext_n, 1)) != DE_OK) return bail(rc);
+    k_l_active<<<(unsigned int)((ext_n + 255) / 256), 256, 0, ctx->stream>>>(res_l_last, res_omega, res_l_active, ext_n);
+    ctx->launches++;
+    k_pow_seq<<<(unsigned int)((ext_n + 255) / 256), 256, 0, ctx->stream>>>(res_omega, ext_n, fr_from_host(dv->ext_omega));
+    ctx->launches++;
+    // permutation column descriptors
+    if (desc->n_perm_columns) {
+        if ((rc = dmalloc((void**)&pk->d_perm_kind, sizeof(uint32_t) * desc->n_perm_columns)) != DE_OK) return bail(rc);
+        if ((rc = dmalloc((void**)&pk->d_perm_index, sizeof(uint32_t) * desc->n_perm_columns)) != DE_OK) return bail(rc);
+        for (uint32_t i = 0; i < desc->n_perm_columns; i++) {
+            uint32_t kind = desc->perm_column_kind[i], index = desc->perm_column_index[i];
+            uint32_t lim = kind == DE_VAL_ADVICE ? desc->n_advice : kind == DE_VAL_FIXED ? desc->n_fixed : kind == DE_VAL_INSTANCE ? desc->n_instance : 0;
+            if (index >= lim) return bail(fail(ctx, DE_ERR_ARG, "de_pk_upload: permutation column out of range"));
+        }
+        cudaMemcpyAsync(pk->d_perm_kind, desc->perm_column_kind, sizeof(uint32_t) * desc->n_perm_columns, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(pk->d_perm_index, desc->perm_column_index, sizeof(uint32_t) * desc->n_perm_columns, cudaMemcpyHostToDevice, ctx->stream);
+    } else {
+        pk->d_perm_kind = pk->d_perm_index = nullptr;
+    }
+    if ((rc = upload_graph(ctx, desc->gates, &pk->gates, pk->allocs)) != DE_OK) return bail(rc);
+    std::vector<DevGraph> lg(desc->n_lookups);
+    for (uint32_t i = 0; i < desc->n_lookups; i++)
+        if ((rc = upload_graph(ctx, desc->lookups[i], &lg[i], pk->allocs)) != DE_OK) return bail(rc);
+    if ((rc = dmalloc((void**)&pk->d_lookups, sizeof(DevGraph) * (lg.size() ? lg.size() : 1))) != DE_OK) return bail(rc);
+    if (!lg.empty()) cudaMemcpyAsync(pk->d_lookups, lg.data(), sizeof(DevGraph) * lg.size(), cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return bail(fail(ctx, DE_ERR_CUDA, std::string("de_pk_upload: ") + cudaGetErrorString(e)));
+    *out = pk;
+    return DE_OK;
+}
+
+int de_evaluate_h_dev(de_pk* pk, const de_fr* d_advice, const de_fr* d_instance, const de_challenges* ch, const de_fr* d_permz,
+                      const de_fr* d_lookup, size_t stride, de_fr* d_h_ext) {
+    if (!pk) return DE_ERR_ARG;
+    de_ctx* ctx = pk->ctx;
+    if (!ch || !d_h_ext) return fail(ctx, DE_ERR_ARG, "de_evaluate_h: null pointer");
+    if ((pk->n_advice && !d_advice) || (pk->n_instance && !d_instance) || (pk->n_sets && !d_permz) || (pk->n_lookups && !d_lookup))
+        return fail(ctx, DE_ERR_ARG, "de_evaluate_h: missing polynomial block");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t ext_n = pk->ext_n;
+    Fr* w_adv = pk->work;
+    Fr* w_inst = w_adv + (size_t)pk->n_advice * ext_n;
+    Fr* w_permz = w_inst + (size_t)pk->n_instance * ext_n;
+    Fr* w_lookup = w_permz + (size_t)pk->n_sets * ext_n;
+    if (pk->n_advice) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_advice, stride, (de_fr*)w_adv, ext_n, pk->n_advice));
+    if (pk->n_instance) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_instance, stride, (de_fr*)w_inst, ext_n, pk->n_instance));
+    if (pk->n_sets) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_permz, stride, (de_fr*)w_permz, ext_n, pk->n_sets));
+    if (pk->n_lookups) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_lookup, stride, (de_fr*)w_lookup, ext_n, 3 * (size_t)pk->n_lookups));
+    if (ch->n_challenges > pk->challenges_cap) {
+        Fr* d = nullptr;
+        DE_CUDA(ctx, cudaMalloc((void**)&d, sizeof(Fr) * ch->n_challenges));
+        pk->allocs.push_back(d);
+        pk->d_challenges = d;
+        pk->challenges_cap = ch->n_challenges;
+    }
+    if (ch->n_challenges) DE_CUDA(ctx, cudaMemcpyAsync(pk->d_challenges, ch->challenges, sizeof(Fr) * ch->n_challenges, cudaMemcpyHostToDevice, ctx->stream));
+    EvalParams p;
+    memset(&p, 0, sizeof(p));
+    p.ext_mask = (uint32_t)(ext_n - 1);
+    p.rot_scale = 1u << (pk->ek - pk->k);
+    p.ext_n = ext_n;
+    const size_t n_polys = (size_t)pk->n_fixed + pk->n_perm_cols;
+    p.fixed = pk->resident;
+    p.sigma = pk->resident + (size_t)pk->n_fixed * ext_n;
+    p.l0 = pk->resident + n_polys * ext_n;
+    p.l_last = p.l0 + ext_n;
+    p.l_active = p.l_last + ext_n;
+    p.omega_pows = p.l_active + ext_n;
+    p.advice = w_adv; p.instance = w_inst; p.permz = w_permz; p.lookup = w_lookup;
+    p.challenges = pk->d_challenges;
+    p.y = fr_from_host(ch->y); p.beta = fr_from_host(ch->beta); p.gamma = fr_from_host(ch->gamma); p.theta = fr_from_host(ch->theta);
+    p.delta = pk->delta;
+    p.gates = pk->gates;
+    p.lookups = pk->d_lookups;
+    p.n_lookups = pk->n_lookups;
+    p.n_perm_cols = pk->n_perm_cols; p.chunk_len = pk->chunk_len; p.n_sets = pk->n_sets;
+    p.last_rotation = -((int)pk->blinding + 1);
+    p.perm_kind = pk->d_perm_kind; p.perm_index = pk->d_perm_index;
+    p.out = (Fr*)d_h_ext;
+    {
+        // ZETA in Montgomery form (a field constant); delta_start = beta * ZETA is formed per thread in the kernel
+        const uint32_t zm[8] = {0x55fcd653u, 0x0363f299u, 0x5fc1e200u, 0x73e7950bu, 0x576d9d24u, 0xc5fce83eu, 0xa1c3a4d4u, 0x059c805du};
+        for (int i = 0; i < 8; i++) p.delta_start.l[i] = zm[i];
+    }
+    DE_TIMED(ctx, "k_eval_h", (double)ext_n, (k_eval_h<<<(unsigned int)((ext_n + 127) / 128), 128, 0, ctx->stream>>>(p)));
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
 int de_evaluate_h(de_pk* pk, const de_fr* const* advice_coeff, const de_fr* const* instance_coeff, const de_challenges* ch,
                   const de_fr* const* perm_z_coeff, const de_fr* const* lookup_coeff, de_fr* h_ext_out) {
-    (void)pk; (void)advice_coeff; (void)instance_coeff; (void)ch; (void)perm_z_coeff; (void)lookup_coeff; (void)h_ext_out;
-    return DE_ERR_UNSUPPORTED;
+    if (!pk) return DE_ERR_ARG;
+    de_ctx* ctx = pk->ctx;
+    if (!ch || !h_ext_out) return fail(ctx, DE_ERR_ARG, "de_evaluate_h: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = pk->n, ext_n = pk->ext_n;
+    const size_t counts[4] = {pk->n_advice, pk->n_instance, pk->n_sets, 3 * (size_t)pk->n_lookups};
+    const de_fr* const* srcs[4] = {advice_coeff, instance_coeff, perm_z_coeff, lookup_coeff};
+    const size_t total = counts[0] + counts[1] + counts[2] + counts[3];
+    DE_WS(ctx, staging, Fr, WS_EVAL_A, sizeof(Fr) * n * (total ? total : 1));
+    DE_WS(ctx, d_h, Fr, WS_EVAL_C, sizeof(Fr) * ext_n);
+    Fr* blocks[4];
+    size_t off = 0;
+    for (int b = 0; b < 4; b++) {
+        blocks[b] = staging + off * n;
+        if (counts[b] && !srcs[b]) return fail(ctx, DE_ERR_ARG, "de_evaluate_h: missing polynomial array");
+        for (size_t i = 0; i < counts[b]; i++) {
+            if (!srcs[b][i]) return fail(ctx, DE_ERR_ARG, "de_evaluate_h: null polynomial");
+            DE_CUDA(ctx, cudaMemcpyAsync(blocks[b] + i * n, srcs[b][i], sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        off += counts[b];
+    }
+    DE_TRY(de_evaluate_h_dev(pk, (const de_fr*)blocks[0], (const de_fr*)blocks[1], ch, (const de_fr*)blocks[2], (const de_fr*)blocks[3], n,
+                             (de_fr*)d_h));
+    DE_CUDA(ctx, cudaMemcpyAsync(h_ext_out, d_h, sizeof(Fr) * ext_n, cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
 }
-}
+
+}  // extern "C"

@@ -123,12 +123,14 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
                                                                              &scalars_u32[2]);
     DE_CHECK_LAUNCH(ctx);
     DE_TRY(scan_u32(ctx, ntasks, nbuckets + 1, task_off, block_sums2, &scalars_u32[1]));
-    k_msm_accumulate<<<(unsigned int)((max_tasks + 127) / 128), 128, 0, st>>>(sorted, offsets, counts, task_off, (unsigned int)nbuckets, CH,
-                                                                              d_tables, buckets, partials);
+    DE_TIMED(ctx, "k_msm_accumulate", (double)n * count,
+             (k_msm_accumulate<<<(unsigned int)((max_tasks + 127) / 128), 128, 0, st>>>(sorted, offsets, counts, task_off, (unsigned int)nbuckets,
+                                                                                       CH, d_tables, buckets, partials)));
     DE_CHECK_LAUNCH(ctx);
     k_msm_merge<<<ctx->sm_count * 2, 128, 0, st>>>(multi_list, &scalars_u32[2], task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    k_msm_reduce_chunks<<<(chunks_per_set * nsets_total + 127) / 128, 128, 0, st>>>(buckets, sh.NB, CK, nsets_total, chunk_out);
+    DE_TIMED(ctx, "k_msm_reduce_chunks", (double)n * count,
+             (k_msm_reduce_chunks<<<(chunks_per_set * nsets_total + 127) / 128, 128, 0, st>>>(buckets, sh.NB, CK, nsets_total, chunk_out)));
     DE_CHECK_LAUNCH(ctx);
     k_msm_reduce_sets<<<nsets_total, 256, 0, st>>>(chunk_out, chunks_per_set, set_out);
     DE_CHECK_LAUNCH(ctx);

@@ -101,7 +101,7 @@ static int launch_pass_t(de_ctx* ctx, const NttPassParams& prm, unsigned int blo
         configured[dev] = true;
     }
     dim3 grid(blocks, batch);
-    k_ntt_pass<S, LT><<<grid, Sh::NTHREADS, Sh::SMEM, ctx->stream>>>(prm);
+    DE_TIMED(ctx, "k_ntt_pass", (double)blocks * batch * Sh::M, (k_ntt_pass<S, LT><<<grid, Sh::NTHREADS, Sh::SMEM, ctx->stream>>>(prm)));
     DE_CHECK_LAUNCH(ctx);
     return DE_OK;
 }
@@ -406,6 +406,58 @@ int de_ctx_sync(de_ctx* ctx) {
 }
 
 const char* de_last_error(de_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+// ---- per-kernel timing (CUDA events on the context's stream) ------------------------------------------------
+static void timing_collect(de_ctx* ctx) {
+    for (auto& t : ctx->timed) {
+        float ms = 0;
+        if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+            KernelStat* st = nullptr;
+            for (auto& s : ctx->stats)
+                if (s.name == t.name) st = &s;
+            if (!st) {
+                ctx->stats.push_back(KernelStat());
+                st = &ctx->stats.back();
+                st->name = t.name;
+            }
+            st->ms += ms;
+            st->units += t.units;
+            st->launches++;
+        }
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    cudaGetLastError();
+    ctx->timed.clear();
+}
+int de_timing_enable(de_ctx* ctx, int on) {
+    if (!ctx) return DE_ERR_ARG;
+    timing_collect(ctx);
+    ctx->timing = on != 0;
+    return DE_OK;
+}
+int de_timing_reset(de_ctx* ctx) {
+    if (!ctx) return DE_ERR_ARG;
+    timing_collect(ctx);
+    ctx->stats.clear();
+    return DE_OK;
+}
+int de_timing_get(de_ctx* ctx, const char* kernel, double* total_ms, double* total_units, uint64_t* launches) {
+    if (!ctx || !kernel) return DE_ERR_ARG;
+    timing_collect(ctx);
+    double ms = 0, units = 0;
+    uint64_t n = 0;
+    for (auto& s : ctx->stats)
+        if (s.name == kernel) {
+            ms = s.ms;
+            units = s.units;
+            n = s.launches;
+        }
+    if (total_ms) *total_ms = ms;
+    if (total_units) *total_units = units;
+    if (launches) *launches = n;
+    return DE_OK;
+}
 uint64_t de_launch_count(de_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int de_fr_vec_op(de_ctx* ctx, int op, const de_fr* a, const de_fr* b, de_fr* out, size_t n) { return vec_op<Fr>(ctx, op, a, b, out, n); }

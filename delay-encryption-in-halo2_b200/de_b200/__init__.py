@@ -65,6 +65,18 @@ class Context:
     def launches(self) -> int:
         return int(self.L.de_launch_count(self.h))
 
+    def timing_enable(self, on: bool = True):
+        self.check(self.L.de_timing_enable(self.h, 1 if on else 0))
+
+    def timing_reset(self):
+        self.check(self.L.de_timing_reset(self.h))
+
+    def timing_get(self, kernel: str):
+        """(total_ms, total_units, launches) of a named kernel since the last reset"""
+        ms, units, n = C.c_double(), C.c_double(), C.c_uint64()
+        self.check(self.L.de_timing_get(self.h, kernel.encode(), C.byref(ms), C.byref(units), C.byref(n)))
+        return ms.value, units.value, int(n.value)
+
     def close(self):
         if getattr(self, "h", None):
             self.L.de_ctx_destroy(self.h)

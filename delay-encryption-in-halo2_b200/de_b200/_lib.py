@@ -14,11 +14,12 @@ OP_MUL, OP_ADD, OP_SUB, OP_FROM_MONT, OP_TO_MONT = 0, 1, 2, 3, 4
 # every symbol include/de_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [
     "de_ctx_create", "de_ctx_destroy", "de_ctx_set_stream", "de_ctx_sync", "de_last_error", "de_version", "de_launch_count",
+    "de_timing_enable", "de_timing_reset", "de_timing_get",
     "de_fr_vec_op", "de_fq_vec_op", "de_msm", "de_msm_dev", "de_params_upload", "de_params_free", "de_commit",
     "de_commit_batch", "de_commit_batch_dev", "de_ntt", "de_ntt_dev", "de_domain_create", "de_domain_free", "de_domain_info",
     "de_coeff_to_extended", "de_extended_to_coeff", "de_lagrange_to_coeff", "de_coeff_to_lagrange", "de_divide_by_vanishing",
     "de_coeff_to_extended_dev", "de_extended_to_coeff_dev", "de_lagrange_to_coeff_dev", "de_coeff_to_lagrange_dev",
-    "de_divide_by_vanishing_dev", "de_pk_upload", "de_pk_free", "de_evaluate_h", "de_commit_range", "de_g1_sum",
+    "de_divide_by_vanishing_dev", "de_pk_upload", "de_pk_free", "de_evaluate_h", "de_evaluate_h_dev", "de_commit_range", "de_g1_sum",
 ]
 
 
@@ -49,6 +50,9 @@ def load():
     L.de_version.restype = C.c_char_p
     L.de_launch_count.argtypes = [P]
     L.de_launch_count.restype = C.c_uint64
+    L.de_timing_enable.argtypes = [P, I]
+    L.de_timing_reset.argtypes = [P]
+    L.de_timing_get.argtypes = [P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.de_fr_vec_op.argtypes = [P, I, P, P, P, SZ]
     L.de_fq_vec_op.argtypes = [P, I, P, P, P, SZ]
     L.de_msm.argtypes = [P, P, P, SZ, P]
@@ -76,6 +80,7 @@ def load():
     L.de_pk_upload.argtypes = [P, P, C.POINTER(P)]
     L.de_pk_free.argtypes = [P]
     L.de_evaluate_h.argtypes = [P, P, P, P, P, P, P]
+    L.de_evaluate_h_dev.argtypes = [P, P, P, P, P, P, SZ, P]
     L.de_commit_range.argtypes = [P, I, P, SZ, SZ, P]
     L.de_g1_sum.argtypes = [P, P, SZ, P]
     for s in SYMBOLS:

@@ -56,6 +56,12 @@ const char* de_version(void);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
 uint64_t de_launch_count(de_ctx* ctx);
 
+/* per-kernel device timing: CUDA events recorded around the named kernels on the context's stream.
+ * Known names: "k_msm_accumulate", "k_msm_reduce_chunks", "k_ntt_pass", "k_eval_h".  units = points / elements / rows. */
+int de_timing_enable(de_ctx* ctx, int on);
+int de_timing_reset(de_ctx* ctx);
+int de_timing_get(de_ctx* ctx, const char* kernel, double* total_ms, double* total_units, uint64_t* launches);
+
 /* ---- a1: halo2curves Fr / Fq element-wise arithmetic (parity surface for the field kernels) ---------------- */
 enum de_field_op { DE_OP_MUL = 0, DE_OP_ADD = 1, DE_OP_SUB = 2, DE_OP_FROM_MONT = 3, DE_OP_TO_MONT = 4 };
 int de_fr_vec_op(de_ctx* ctx, int op, const de_fr* a, const de_fr* b, de_fr* out, size_t n);
@@ -122,13 +128,8 @@ typedef struct {
     const int32_t* rotations; uint32_t n_rotations;
     const de_calculation* calcs; uint32_t n_calcs;
     const de_value_source* horner_parts; uint32_t n_horner_parts;
-    uint32_t n_intermediates;
-    de_value_source result;  /* value of the expression after the last calculation */
+    uint32_t n_intermediates;  /* result of the graph = intermediate written by the last calculation (zero if none) */
 } de_graph;
-typedef struct {
-    de_graph graph;          /* evaluates the theta-compressed table and input; result = table, result_input = input */
-    de_value_source result_input;
-} de_lookup_graph;
 typedef struct {
     uint32_t n_fixed, n_advice, n_instance;
     const de_fr* const* fixed_coeff;   /* fixed column polynomials, coefficient form, n each */
@@ -143,8 +144,10 @@ typedef struct {
     /* custom gates: value = value * y + gate, in order */
     de_graph gates;
     /* lookups */
+    /* lookups: one compiled graph each, whose result is (compressed_input + beta) * (compressed_table + gamma) as
+     * Evaluator::new builds it */
     uint32_t n_lookups;
-    const de_lookup_graph* lookups;
+    const de_graph* lookups;
 } de_pk_desc;
 typedef struct { de_fr y, beta, gamma, theta; const de_fr* challenges; uint32_t n_challenges; } de_challenges;
 
@@ -152,11 +155,17 @@ typedef struct { de_fr y, beta, gamma, theta; const de_fr* challenges; uint32_t 
 int de_pk_upload(de_domain* d, const de_pk_desc* desc, de_pk** out);
 int de_pk_free(de_pk* pk);
 /* advice / instance polynomials in coefficient form (n each); permutation z polys (ceil(n_perm_columns/chunk_len)),
- * lookup polys per lookup in order {product z, permuted input a', permuted table s'}: all coefficient form, n each.
+ * lookup polys in block order {all product z | all permuted inputs a' | all permuted tables s'} (3 * n_lookups entries;
+ * the order create_proof commits them in): all coefficient form, n each.
  * Output: h evaluations over the extended domain, BEFORE divide_by_vanishing_poly (as evaluate_h returns them). */
 int de_evaluate_h(de_pk* pk, const de_fr* const* advice_coeff, const de_fr* const* instance_coeff,
                   const de_challenges* ch, const de_fr* const* perm_z_coeff, const de_fr* const* lookup_coeff,
                   de_fr* h_ext_out);
+/* device-resident: each d_* block holds its polynomials `stride` elements apart (coefficient form, n valid entries);
+ * the extended cosets are produced in the pk's HBM workspace by one batched coeff_to_extended, then one fused kernel
+ * walks the extended domain. */
+int de_evaluate_h_dev(de_pk* pk, const de_fr* d_advice_coeff, const de_fr* d_instance_coeff, const de_challenges* ch,
+                      const de_fr* d_perm_z_coeff, const de_fr* d_lookup_coeff, size_t stride, de_fr* d_h_ext);
 
 /* ---- multi-GPU: MSM base-range sharding -------------------------------------------- */
 /* shard s of n_shards: commits scalars[lo..hi) against the matching base range of p and returns the partial sum;

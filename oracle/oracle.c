@@ -716,3 +716,249 @@ void orc_gen_bases(size_t start, size_t n, u64* out, int threads) {
     gen_ctx c = {(aff*)out, n, start};
     parallel_for(n, threads, gen_job, &c);
 }
+
+/* ---------------------------------------------------------------- Evaluator::evaluate_h (a9; Appendix B.5)
+ * Restates halo2_proofs::plonk::evaluation::{GraphEvaluator::evaluate, Evaluator::evaluate_h} and the l0 / l_last /
+ * l_active_row construction of plonk::keygen.  Uses only the STRUCT LAYOUTS of include/de_b200.h (the descriptor a
+ * ProvingKey is marshalled into); no product code is linked. */
+#include "../include/de_b200.h"
+
+typedef struct {
+    const orc_domain* d;
+    const de_pk_desc* desc;
+    fe **fixed, **sigma, **advice, **instance, **permz, **lookup;
+    fe *l0, *l_last, *l_active;
+    fe y, beta, gamma, theta, delta;
+    const fe* challenges;
+    fe* out;
+    size_t n_sets;
+} evalh_ctx;
+
+static inline size_t rot_idx(size_t idx, int rot, size_t rot_scale, size_t size) {
+    long long v = (long long)idx + (long long)rot * (long long)rot_scale;
+    long long m = (long long)size;
+    v %= m;
+    if (v < 0) v += m;
+    return (size_t)v;
+}
+static fe graph_fetch(const evalh_ctx* c, const de_graph* g, const de_value_source* s, const fe* inter, const size_t* rots, const fe* prev) {
+    switch (s->kind) {
+        case DE_VAL_CONSTANT: return *(const fe*)&g->constants[s->index];
+        case DE_VAL_INTERMEDIATE: return inter[s->index];
+        case DE_VAL_FIXED: return c->fixed[s->index][rots[s->rotation]];
+        case DE_VAL_ADVICE: return c->advice[s->index][rots[s->rotation]];
+        case DE_VAL_INSTANCE: return c->instance[s->index][rots[s->rotation]];
+        case DE_VAL_CHALLENGE: return c->challenges[s->index];
+        case DE_VAL_BETA: return c->beta;
+        case DE_VAL_GAMMA: return c->gamma;
+        case DE_VAL_THETA: return c->theta;
+        case DE_VAL_Y: return c->y;
+        default: return *prev;
+    }
+}
+static fe graph_eval(const evalh_ctx* c, const de_graph* g, fe* inter, size_t idx, size_t rot_scale, size_t size, const fe* prev) {
+    const field_t* F = &FRF;
+    size_t rots[64];
+    for (uint32_t r = 0; r < g->n_rotations; r++) rots[r] = rot_idx(idx, g->rotations[r], rot_scale, size);
+    fe last;
+    memset(&last, 0, sizeof(last));
+    for (uint32_t i = 0; i < g->n_calcs; i++) {
+        const de_calculation* k = &g->calcs[i];
+        fe a = graph_fetch(c, g, &k->a, inter, rots, prev), b, r;
+        switch (k->op) {
+            case DE_CALC_ADD: b = graph_fetch(c, g, &k->b, inter, rots, prev); f_add(F, &r, &a, &b); break;
+            case DE_CALC_SUB: b = graph_fetch(c, g, &k->b, inter, rots, prev); f_sub(F, &r, &a, &b); break;
+            case DE_CALC_MUL: b = graph_fetch(c, g, &k->b, inter, rots, prev); f_mul(F, &r, &a, &b); break;
+            case DE_CALC_SQUARE: f_sqr(F, &r, &a); break;
+            case DE_CALC_DOUBLE: f_dbl(F, &r, &a); break;
+            case DE_CALC_NEGATE: f_neg(F, &r, &a); break;
+            case DE_CALC_HORNER:
+                b = graph_fetch(c, g, &k->b, inter, rots, prev);
+                r = a;
+                for (uint32_t h = 0; h < k->horner_len; h++) {
+                    fe part = graph_fetch(c, g, &g->horner_parts[k->horner_first + h], inter, rots, prev);
+                    f_mul(F, &r, &r, &b);
+                    f_add(F, &r, &r, &part);
+                }
+                break;
+            default: r = a; break;
+        }
+        inter[k->target] = r;
+        last = r;
+    }
+    return last;
+}
+#define FOLD(expr_fe)                              \
+    do {                                           \
+        f_mul(F, &value, &value, &c->y);           \
+        fe t__ = (expr_fe);                        \
+        f_add(F, &value, &value, &t__);            \
+    } while (0)
+static inline fe fe_mul2(const fe* a, const fe* b) { fe r; f_mul(&FRF, &r, a, b); return r; }
+static inline fe fe_sub2(const fe* a, const fe* b) { fe r; f_sub(&FRF, &r, a, b); return r; }
+static inline fe fe_add2(const fe* a, const fe* b) { fe r; f_add(&FRF, &r, a, b); return r; }
+
+static void evalh_job(void* v, size_t lo, size_t hi, int tid) {
+    const evalh_ctx* c = (const evalh_ctx*)v;
+    const field_t* F = &FRF;
+    const de_pk_desc* desc = c->desc;
+    const orc_domain* d = c->d;
+    (void)tid;
+    if (lo >= hi) return;
+    const size_t size = d->ext_n, rot_scale = (size_t)1 << (d->extended_k - d->k);
+    uint32_t max_inter = desc->gates.n_intermediates;
+    for (uint32_t i = 0; i < desc->n_lookups; i++)
+        if (desc->lookups[i].n_intermediates > max_inter) max_inter = desc->lookups[i].n_intermediates;
+    fe* inter = (fe*)malloc(sizeof(fe) * (max_inter + 1));
+    const fe one = F->r;
+    fe zero;
+    memset(&zero, 0, sizeof(zero));
+    const int last_rotation = -((int)desc->blinding_factors + 1);
+    fe delta_start = fe_mul2(&c->beta, &d->zeta);
+    u64 e[4] = {lo, 0, 0, 0};
+    fe beta_term;
+    f_pow(F, &beta_term, &d->ext_omega, e);
+    for (size_t idx = lo; idx < hi; idx++) {
+        /* custom gates */
+        fe value = graph_eval(c, &desc->gates, inter, idx, rot_scale, size, &zero);
+        const size_t r_next = rot_idx(idx, 1, rot_scale, size), r_prev = rot_idx(idx, -1, rot_scale, size);
+        const size_t r_last = rot_idx(idx, last_rotation, rot_scale, size);
+        /* permutation */
+        if (c->n_sets) {
+            fe t = fe_sub2(&one, &c->permz[0][idx]);
+            FOLD(fe_mul2(&t, &c->l0[idx]));
+            const fe* zl = &c->permz[c->n_sets - 1][idx];
+            t = fe_mul2(zl, zl);
+            t = fe_sub2(&t, zl);
+            FOLD(fe_mul2(&t, &c->l_last[idx]));
+            for (size_t s = 1; s < c->n_sets; s++) {
+                t = fe_sub2(&c->permz[s][idx], &c->permz[s - 1][r_last]);
+                FOLD(fe_mul2(&t, &c->l0[idx]));
+            }
+            fe current_delta = fe_mul2(&delta_start, &beta_term);
+            for (size_t s = 0; s < c->n_sets; s++) {
+                size_t c0 = s * desc->chunk_len, c1 = c0 + desc->chunk_len;
+                if (c1 > desc->n_perm_columns) c1 = desc->n_perm_columns;
+                fe left = c->permz[s][r_next], right = c->permz[s][idx];
+                for (size_t col = c0; col < c1; col++) {
+                    uint32_t kind = desc->perm_column_kind[col], index = desc->perm_column_index[col];
+                    fe** src = kind == DE_VAL_ADVICE ? c->advice : (kind == DE_VAL_FIXED ? c->fixed : c->instance);
+                    const fe* val = &src[index][idx];
+                    fe u = fe_mul2(&c->beta, &c->sigma[col][idx]);
+                    u = fe_add2(val, &u);
+                    u = fe_add2(&u, &c->gamma);
+                    left = fe_mul2(&left, &u);
+                    u = fe_add2(val, &current_delta);
+                    u = fe_add2(&u, &c->gamma);
+                    right = fe_mul2(&right, &u);
+                    current_delta = fe_mul2(&current_delta, &c->delta);
+                }
+                t = fe_sub2(&left, &right);
+                FOLD(fe_mul2(&t, &c->l_active[idx]));
+            }
+        }
+        f_mul(F, &beta_term, &beta_term, &d->ext_omega);
+        /* lookups */
+        for (uint32_t n = 0; n < desc->n_lookups; n++) {
+            fe table_value = graph_eval(c, &desc->lookups[n], inter, idx, rot_scale, size, &zero);
+            fe *zc = c->lookup[n], *ac = c->lookup[desc->n_lookups + n], *sc = c->lookup[2 * desc->n_lookups + n];
+            fe a_minus_s = fe_sub2(&ac[idx], &sc[idx]);
+            fe t = fe_sub2(&one, &zc[idx]);
+            FOLD(fe_mul2(&t, &c->l0[idx]));
+            t = fe_mul2(&zc[idx], &zc[idx]);
+            t = fe_sub2(&t, &zc[idx]);
+            FOLD(fe_mul2(&t, &c->l_last[idx]));
+            fe u = fe_add2(&ac[idx], &c->beta), w = fe_add2(&sc[idx], &c->gamma);
+            t = fe_mul2(&zc[r_next], &u);
+            t = fe_mul2(&t, &w);
+            u = fe_mul2(&zc[idx], &table_value);
+            t = fe_sub2(&t, &u);
+            FOLD(fe_mul2(&t, &c->l_active[idx]));
+            FOLD(fe_mul2(&a_minus_s, &c->l0[idx]));
+            u = fe_sub2(&ac[idx], &ac[r_prev]);
+            t = fe_mul2(&a_minus_s, &u);
+            FOLD(fe_mul2(&t, &c->l_active[idx]));
+        }
+        c->out[idx] = value;
+    }
+    free(inter);
+}
+static fe** cosets_of(const orc_domain* d, const de_fr* const* polys, size_t count) {
+    fe** out = (fe**)calloc(count ? count : 1, sizeof(fe*));
+    for (size_t i = 0; i < count; i++) {
+        out[i] = (fe*)malloc(sizeof(fe) * d->ext_n);
+        orc_coeff_to_extended(d, (const u64*)polys[i], (u64*)out[i]);
+    }
+    return out;
+}
+static void free_cosets(fe** c, size_t count) {
+    for (size_t i = 0; i < count; i++) free(c[i]);
+    free(c);
+}
+static fe* indicator_coset(const orc_domain* d, size_t lo, size_t hi) {
+    fe* lag = (fe*)calloc(d->n, sizeof(fe));
+    for (size_t i = lo; i < hi; i++) lag[i] = FRF.r;
+    orc_lagrange_to_coeff(d, (u64*)lag);
+    fe* ext = (fe*)malloc(sizeof(fe) * d->ext_n);
+    orc_coeff_to_extended(d, (const u64*)lag, (u64*)ext);
+    free(lag);
+    return ext;
+}
+typedef struct {
+    const orc_domain* d;
+    const de_pk_desc* desc; /* borrowed: must outlive the pk */
+    fe **fixed, **sigma;
+    fe *l0, *l_last, *l_active;
+} orc_pk;
+/* keygen_pk's resident part: fixed / sigma / l0 / l_last / l_active_row cosets, computed once */
+orc_pk* orc_pk_new(const orc_domain* d, const de_pk_desc* desc) {
+    orc_pk* pk = (orc_pk*)calloc(1, sizeof(*pk));
+    pk->d = d;
+    pk->desc = desc;
+    pk->fixed = cosets_of(d, desc->fixed_coeff, desc->n_fixed);
+    pk->sigma = cosets_of(d, desc->sigma_coeff, desc->n_perm_columns);
+    const size_t bf = desc->blinding_factors;
+    pk->l0 = indicator_coset(d, 0, 1);
+    pk->l_last = indicator_coset(d, d->n - bf - 1, d->n - bf);
+    fe* l_blind = indicator_coset(d, d->n - bf, d->n);
+    pk->l_active = (fe*)malloc(sizeof(fe) * d->ext_n);
+    for (size_t i = 0; i < d->ext_n; i++) {
+        fe t;
+        f_add(&FRF, &t, &pk->l_last[i], &l_blind[i]);
+        f_sub(&FRF, &pk->l_active[i], &FRF.r, &t);
+    }
+    free(l_blind);
+    return pk;
+}
+void orc_pk_free(orc_pk* pk) {
+    if (!pk) return;
+    free_cosets(pk->fixed, pk->desc->n_fixed);
+    free_cosets(pk->sigma, pk->desc->n_perm_columns);
+    free(pk->l0); free(pk->l_last); free(pk->l_active);
+    free(pk);
+}
+int orc_evaluate_h(const orc_pk* pk, const de_fr* const* advice_coeff, const de_fr* const* instance_coeff,
+                   const de_challenges* ch, const de_fr* const* perm_z_coeff, const de_fr* const* lookup_coeff, u64* h_ext_out) {
+    const orc_domain* d = pk->d;
+    const de_pk_desc* desc = pk->desc;
+    evalh_ctx c;
+    memset(&c, 0, sizeof(c));
+    c.d = d;
+    c.desc = desc;
+    c.n_sets = desc->n_perm_columns ? (desc->n_perm_columns + desc->chunk_len - 1) / desc->chunk_len : 0;
+    c.fixed = pk->fixed;
+    c.sigma = pk->sigma;
+    c.advice = cosets_of(d, advice_coeff, desc->n_advice);
+    c.instance = cosets_of(d, instance_coeff, desc->n_instance);
+    c.permz = cosets_of(d, perm_z_coeff, c.n_sets);
+    c.lookup = cosets_of(d, lookup_coeff, 3 * (size_t)desc->n_lookups);
+    c.l0 = pk->l0; c.l_last = pk->l_last; c.l_active = pk->l_active;
+    memcpy(&c.y, &ch->y, 32); memcpy(&c.beta, &ch->beta, 32); memcpy(&c.gamma, &ch->gamma, 32); memcpy(&c.theta, &ch->theta, 32);
+    memcpy(&c.delta, &desc->delta, 32);
+    c.challenges = (const fe*)ch->challenges;
+    c.out = (fe*)h_ext_out;
+    parallel_for(d->ext_n, d->threads, evalh_job, &c);
+    free_cosets(c.advice, desc->n_advice);
+    free_cosets(c.instance, desc->n_instance); free_cosets(c.permz, c.n_sets); free_cosets(c.lookup, 3 * (size_t)desc->n_lookups);
+    return 0;
+}

@@ -56,6 +56,11 @@ def lib():
         L.orc_g1_add.argtypes = [P, P, P]
         L.orc_g1_on_curve.argtypes = [P]
         L.orc_g1_on_curve.restype = C.c_int
+        L.orc_pk_new.argtypes = [P, P]
+        L.orc_pk_new.restype = P
+        L.orc_pk_free.argtypes = [P]
+        L.orc_evaluate_h.argtypes = [P, P, P, P, P, P, P]
+        L.orc_evaluate_h.restype = C.c_int
     return _LIB
 
 
@@ -224,3 +229,36 @@ class Domain:
         out = np.ascontiguousarray(a).copy()
         lib().orc_divide_by_vanishing(self.h, _p(out))
         return out
+
+
+class Pk:
+    """keygen_pk's resident cosets (oracle.c: orc_pk_new).  desc_struct is the ctypes image of de_pk_desc."""
+
+    def __init__(self, domain: "Domain", desc_struct, keepalive=None):
+        self.domain, self.desc, self.keep = domain, desc_struct, keepalive
+        self.h = lib().orc_pk_new(domain.h, C.byref(desc_struct))
+
+    def __del__(self):
+        try:
+            lib().orc_pk_free(self.h)
+        except Exception:
+            pass
+
+    def evaluate_h(self, advice, instance, challenges_struct, permz, lookup):
+        """lookup: [all z | all a' | all s']; polynomial lists are (n, 4) uint64 Montgomery arrays in coefficient form."""
+        def arr(polys):
+            polys = [np.ascontiguousarray(p, dtype=np.uint64) for p in polys]
+            a = (C.c_void_p * max(len(polys), 1))(*[p.ctypes.data for p in polys])
+            return a, polys
+        a, k1 = arr(advice)
+        i, k2 = arr(instance)
+        z, k3 = arr(permz)
+        l, k4 = arr(lookup)
+        out = np.empty((self.domain.ext_n, 4), dtype=np.uint64)
+        rc = lib().orc_evaluate_h(self.h, a, i, C.byref(challenges_struct), z, l, _p(out))
+        assert rc == 0
+        return out
+
+
+def evaluate_h(domain: "Domain", desc_struct, advice, instance, challenges_struct, permz, lookup):
+    return Pk(domain, desc_struct).evaluate_h(advice, instance, challenges_struct, permz, lookup)

@@ -446,3 +446,93 @@ def eval_poly(coeffs: Sequence[int], x: int) -> int:
     for c in reversed(coeffs):
         acc = (acc * x + c) % FR
     return acc
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluate_h by the DEFINITION: every polynomial is evaluated with Horner at the coset point
+# x = zeta * extended_omega^idx (rotations multiply x by omega^rot); expressions are walked as trees, not as the compiled
+# GraphEvaluator program.  Independent of the NTT, of rotation index arithmetic and of the graph compiler.
+# Expressions are the plain tuples ("const", v) / ("fixed"|"advice"|"instance", col, rot) / ("challenge", i) /
+# ("neg", e) / ("sum", a, b) / ("prod", a, b) / ("scaled", e, v).
+# ----------------------------------------------------------------------------------------------
+def evaluate_h_definition(dom: "EvaluationDomain", gates, lookups, perm_columns, chunk_len, blinding_factors, fixed, sigma,
+                          advice, instance, permz, lookup_polys, y, beta, gamma, theta, challenges=(), rows=None):
+    """All polynomials are coefficient lists of canonical ints.  perm_columns: [(kind, index)] with kind 2=fixed,
+    3=advice, 4=instance.  lookup_polys: [all z | all a' | all s'].  Returns {idx: h(idx)} for idx in rows (default all)."""
+    n = dom.n
+
+    def lag_poly(lo, hi):
+        return dom.lagrange_to_coeff([1 if lo <= i < hi else 0 for i in range(n)])
+
+    l0p = lag_poly(0, 1)
+    l_lastp = lag_poly(n - blinding_factors - 1, n - blinding_factors)
+    l_blindp = lag_poly(n - blinding_factors, n)
+    cols = {2: fixed, 3: advice, 4: instance}
+    n_sets = -(-len(perm_columns) // chunk_len) if perm_columns else 0
+    out = {}
+    for idx in (rows if rows is not None else range(dom.extended_n)):
+        x = FR_ZETA * pow(dom.extended_omega, idx, FR) % FR
+
+        def at(poly, rot=0):
+            return eval_poly(poly, x * pow(dom.omega, rot, FR) % FR)
+
+        def ev(e):
+            t = e[0]
+            if t == "const":
+                return e[1] % FR
+            if t == "fixed":
+                return at(fixed[e[1]], e[2])
+            if t == "advice":
+                return at(advice[e[1]], e[2])
+            if t == "instance":
+                return at(instance[e[1]], e[2])
+            if t == "challenge":
+                return challenges[e[1]]
+            if t == "neg":
+                return (-ev(e[1])) % FR
+            if t == "sum":
+                return (ev(e[1]) + ev(e[2])) % FR
+            if t == "prod":
+                return ev(e[1]) * ev(e[2]) % FR
+            if t == "scaled":
+                return ev(e[1]) * e[2] % FR
+            raise ValueError(t)
+
+        l0, l_last = at(l0p), at(l_lastp)
+        l_active = (1 - (l_last + at(l_blindp))) % FR
+        value = 0
+        for g in gates:
+            value = (value * y + ev(g)) % FR
+        if n_sets:
+            last_rot = -(blinding_factors + 1)
+            value = (value * y + (1 - at(permz[0])) * l0) % FR
+            zl = at(permz[-1])
+            value = (value * y + (zl * zl - zl) * l_last) % FR
+            for s in range(1, n_sets):
+                value = (value * y + (at(permz[s]) - at(permz[s - 1], last_rot)) * l0) % FR
+            col_no = 0
+            for s in range(n_sets):
+                left, right = at(permz[s], 1), at(permz[s])
+                for kind, index in perm_columns[s * chunk_len:(s + 1) * chunk_len]:
+                    v = at(cols[kind][index])
+                    left = left * (v + beta * at(sigma[col_no]) + gamma) % FR
+                    right = right * (v + pow(FR_DELTA, col_no, FR) * beta % FR * x + gamma) % FR
+                    col_no += 1
+                value = (value * y + (left - right) * l_active) % FR
+        for li, (inp, tab) in enumerate(lookups):
+            nl = len(lookups)
+            z, a, s = lookup_polys[li], lookup_polys[nl + li], lookup_polys[2 * nl + li]
+            ci = 0
+            for e in inp:
+                ci = (ci * theta + ev(e)) % FR
+            ct = 0
+            for e in tab:
+                ct = (ct * theta + ev(e)) % FR
+            zv, av, sv = at(z), at(a), at(s)
+            value = (value * y + (1 - zv) * l0) % FR
+            value = (value * y + (zv * zv - zv) * l_last) % FR
+            value = (value * y + (at(z, 1) * (av + beta) * (sv + gamma) - zv * (ci + beta) * (ct + gamma)) * l_active) % FR
+            value = (value * y + (av - sv) * l0) % FR
+            value = (value * y + (av - sv) * (av - at(a, -1)) * l_active) % FR
+        out[idx] = value % FR
+    return out
