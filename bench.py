@@ -41,7 +41,11 @@ WORKLOAD = ("delay_enc k=16 hot-path schedule: 31 MSM 2^16 (KZG bases resident),
 METRIC = "delay_enc_hot_path_proofs_per_s"
 UNIT = "proofs/s"
 MUL_PEAK_GMULS = 65.9   # measured on this pool's B200 by tools/int_peak (profiles/r01_int_peak.jsonl): Fr Montgomery mul/s
-MULS_PER_POINT = 160    # SURVEY.md 8d convention: 16 windows x (8M + 2S) per point
+MULS_PER_POINT = 160    # SURVEY.md 8d convention: 16 windows x (8M + 2S) per point (a uniform scalar)
+MULS_PER_ADD = 10       # XYZZ mixed addition: 8M + 2S
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_msm_accumulate launch (10 polynomials x 2^16 points), from the
+# `ncu --set full` capture summarised in profiles/r01_accumulate_ncu.md
+TRAFFIC_PER_LAUNCH = 298.2e6
 
 
 def _peaks():
@@ -203,6 +207,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=8, help="independent proofs in flight per GPU (one stream each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,96 +231,138 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     inp = build_inputs()
     w, shape = inp["w"], inp["shape"]
-    stream = torch.cuda.Stream()
-    ctx = de_b200.Context(local_rank)
-    ctx.set_stream(stream.cuda_stream)
-    with torch.cuda.stream(stream):
-        hp = prover.HotPathProver(ctx, w, inp["g"], inp["g_lagrange"], inp["fixed"], inp["sigma"])
-        as_i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
-        cols_h, random_h, openings_h = (as_i64(inp[k]).pin_memory() for k in ("cols", "random", "openings"))
-        cols_d, random_d, openings_d = cols_h.cuda(), random_h.cuda(), openings_h.cuda()
-        staging = {"cols": torch.empty_like(cols_d), "random": torch.empty_like(random_d), "openings": torch.empty_like(openings_d)}
-        ch = inp["challenges"]
+    B = max(1, args.inflight)
+    as_i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
+    cols_h, random_h, openings_h = (as_i64(inp[k]).pin_memory() for k in ("cols", "random", "openings"))
+    cols_d, random_d, openings_d = cols_h.cuda(), random_h.cuda(), openings_h.cuda()
+    ch = inp["challenges"]
+    main_stream = torch.cuda.current_stream()
 
-        def barrier():
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
+    class Worker:
+        """one in-flight proof: its own context, stream, ParamsKZG / ProvingKey handles and scratch"""
 
-        def timed(fn, steps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            e0.record(stream)
-            for _ in range(steps):
-                out = fn()
-            e1.record(stream)
-            barrier()
-            ms = e0.elapsed_time(e1)
-            if world > 1:
-                t = torch.tensor([ms], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
-            return ms, out
+        def __init__(self):
+            self.stream = torch.cuda.Stream()
+            self.ctx = de_b200.Context(local_rank)
+            self.ctx.set_stream(self.stream.cuda_stream)
+            with torch.cuda.stream(self.stream):
+                self.hp = prover.HotPathProver(self.ctx, w, inp["g"], inp["g_lagrange"], inp["fixed"], inp["sigma"])
+                self.staging = {"cols": torch.empty_like(cols_d), "random": torch.empty_like(random_d),
+                                "openings": torch.empty_like(openings_d)}
+            self.out = None
 
-        run_dev = lambda: hp.prove_dev(cols_d, random_d, openings_d, ch)
-        run_host = lambda: hp.prove_host(cols_h, random_h, openings_h, ch, staging)
-        for _ in range(args.warmup):
-            first = run_dev()
-        # ---- device-resident arm (value) with per-kernel event timing and clock sampling
-        ctx.timing_reset()
-        ctx.timing_enable(True)
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        launches0 = ctx.launches
-        ms_dev, out_dev = timed(run_dev, args.steps)
-        launches = ctx.launches - launches0
-        clocks = sampler.stop()
-        acc_ms, acc_pts, acc_n = ctx.timing_get("k_msm_accumulate")
-        ntt_ms, ntt_el, ntt_n = ctx.timing_get("k_ntt_pass")
-        ev_ms, ev_rows, ev_n = ctx.timing_get("k_eval_h")
-        red_ms, _, red_n = ctx.timing_get("k_msm_reduce_chunks")
-        ctx.timing_enable(False)
-        assert (out_dev == first).all(), "commitments changed between steps"
-        # ---- end-to-end arm: host buffers in, commitments out, every step
-        for _ in range(2):
-            run_host()
-        ms_e2e, out_e2e = timed(run_host, args.steps)
-        assert (out_e2e == first).all(), "host-buffer path disagrees with the device-resident path"
+        def run(self, steps, host):
+            with torch.cuda.stream(self.stream):
+                for _ in range(steps):
+                    if host:
+                        self.out = self.hp.prove_host(cols_h, random_h, openings_h, ch, self.staging)
+                    else:
+                        self.out = self.hp.prove_dev(cols_d, random_d, openings_d, ch)
+
+    workers = [Worker() for _ in range(B)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(active, steps, host):
+        """K steps on every active worker concurrently; device time between two events on the main stream that fence all
+        worker streams; max over ranks"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(main_stream)
+        for wk in active:
+            wk.stream.wait_event(e0)
+        threads = [threading.Thread(target=wk.run, args=(steps, host)) for wk in active]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for wk in active:
+            main_stream.wait_stream(wk.stream)
+        e1.record(main_stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    ctx = workers[0].ctx
+    timed(workers, args.warmup, False)
+    first_aff = ctx.batch_normalize(workers[0].out)
+    # ---- throughput arm (value): B proofs in flight per GPU, inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sum(wk.ctx.launches for wk in workers)
+    ms_dev = timed(workers, args.steps, False)
+    launches = sum(wk.ctx.launches for wk in workers) - launches0
+    clocks = sampler.stop()
+    for wk in workers:
+        assert (wk.ctx.batch_normalize(wk.out) == first_aff).all(), "commitments differ between workers / steps"
+    # ---- end-to-end arm: pinned host columns in, commitments out, every proof
+    timed(workers, 2, True)
+    ms_e2e = timed(workers, args.steps, True)
+    for wk in workers:
+        assert (wk.ctx.batch_normalize(wk.out) == first_aff).all(), "host-buffer path disagrees with the device-resident path"
+    # ---- latency arm: ONE proof in flight; per-kernel CUDA-event timing is taken here (no overlapping streams)
+    timed(workers[:1], 2, False)
+    ctx.timing_reset()
+    ctx.timing_enable(True)
+    lat_steps = max(5, min(args.steps, 20))
+    ms_lat = timed(workers[:1], lat_steps, False)
+    acc_ms, acc_pts, acc_n = ctx.timing_get("k_msm_accumulate")
+    ntt_ms, ntt_el, ntt_n = ctx.timing_get("k_ntt_pass")
+    ev_ms, ev_rows, ev_n = ctx.timing_get("k_eval_h")
+    red_ms, _, red_n = ctx.timing_get("k_msm_digit_sums")
+    _, bucket_adds, _ = ctx.timing_get("msm_bucket_adds")
+    ctx.timing_enable(False)
+    out_dev = workers[0].out
+
     h2d = cols_h.numel() * 8 + random_h.numel() * 8 + openings_h.numel() * 8
     d2h = w.n_msm * 96
     peaks, peak_kind = _peaks()
-    value = world * args.steps / (ms_dev / 1000.0)
-    e2e_value = world * args.steps / (ms_e2e / 1000.0)
+    value = world * args.steps * B / (ms_dev / 1000.0)
+    e2e_value = world * args.steps * B / (ms_e2e / 1000.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE carry chains)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proofs_per_step_per_gpu": 1,
-                   "l2": "per-step working set ~0.7 GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
-                   "sharding": "independent proofs, one per GPU per step, no data-path collective"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proofs_per_step_per_gpu": B,
+                   "in_flight": f"{B} independent proofs per GPU, one host thread + CUDA stream each (BASELINE config 5: 64 proofs over "
+                                "8 GPUs = 8 per GPU)",
+                   "l2": f"per-step working set ~{0.7 * B:.1f} GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
+                   "sharding": "independent proofs across GPUs, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "create_proof_hot_path_s": ms_dev / args.steps / 1000.0,
+        "latency": {"create_proof_hot_path_s": ms_lat / lat_steps / 1000.0, "proofs_in_flight": 1, "steps": lat_steps},
     }
+    ms_ref = ms_lat  # kernel shares are relative to the single-stream latency pass they were measured in
     if acc_n:
         pts_per_launch = acc_pts / acc_n
         avg_ms = acc_ms / acc_n
         achieved = 96.0 * pts_per_launch / (avg_ms * 1e-3) / 1e9
         line["roofline"] = {"kernel": "k_msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
-                            "share_of_step": acc_ms / ms_dev, "launches": acc_n, "avg_launch_ms": avg_ms,
-                            "int_pipe": {"achieved_gmuls": MULS_PER_POINT * pts_per_launch / (avg_ms * 1e-3) / 1e9,
+                            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_PER_LAUNCH, "peak_source": peak_kind,
+                            "measured_in": "latency arm (one proof in flight, CUDA events around every launch on its stream)",
+                            "share_of_step": acc_ms / ms_ref, "launches": acc_n, "avg_launch_ms": avg_ms,
+                            "int_pipe": {"achieved_gmuls": MULS_PER_ADD * bucket_adds / (acc_ms * 1e-3) / 1e9,
                                          "peak_gmuls": MUL_PEAK_GMULS,
-                                         "frac": MULS_PER_POINT * pts_per_launch / (avg_ms * 1e-3) / 1e9 / MUL_PEAK_GMULS,
-                                         "note": "160 field muls per point (16 windows x 8M+2S); peak = measured Fr mul/s (tools/int_peak)"}}
+                                         "frac": MULS_PER_ADD * bucket_adds / (acc_ms * 1e-3) / 1e9 / MUL_PEAK_GMULS,
+                                         "bucket_adds_per_step": bucket_adds / lat_steps,
+                                         "note": "field muls actually executed by the bucket fill (10 per mixed add, zero digits of "
+                                                 "witness-like columns skipped) / time in k_msm_accumulate; peak = measured Fr "
+                                                 "Montgomery mul/s of this chip (tools/int_peak, 99% of the IMAD.WIDE issue limit)"}}
         line["msm_gpts_s"] = acc_pts / (acc_ms * 1e-3) / 1e9
     if ntt_n:
         line["ntt_gb_s"] = 64.0 * ntt_el / (ntt_ms * 1e-3) / 1e9 / 2.0  # two passes per transform at these sizes
-        line["kernel_share"] = {"k_msm_accumulate": acc_ms / ms_dev, "k_msm_reduce_chunks": red_ms / ms_dev,
-                                "k_ntt_pass": ntt_ms / ms_dev, "k_eval_h": ev_ms / ms_dev}
+        line["kernel_share"] = {"k_msm_accumulate": acc_ms / ms_ref, "k_msm_digit_sums": red_ms / ms_ref,
+                                "k_ntt_pass": ntt_ms / ms_ref, "k_eval_h": ev_ms / ms_ref}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         state = {}
         cpu_reference_setup(inp, state)  # keygen_pk's cosets: one-time in the reference too, not timed
@@ -323,15 +370,16 @@ def main():
         cpu_out = cpu_reference_step(inp, state)
         dt = time.perf_counter() - t0
         import orc
-        same = (orc.g1_to_affine(cpu_out) == orc.g1_to_affine(out_dev)).all()
+        same = (orc.g1_to_affine(cpu_out) == first_aff).all()
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": orc.ncpu(), "kind": "port",
                                 "sample": "one full delay_enc k=16 hot-path schedule (pk cosets precomputed, untimed); "
                                           "restated reference algorithm in C, not the Rust binary",
                                 "commitments_match_gpu": bool(same)}
     if rank == 0:
         print(json.dumps(line))
-    hp.close()
-    ctx.close()
+    for wk in workers:
+        wk.hp.close()
+        wk.ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -74,40 +74,53 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     const unsigned long long E = (unsigned long long)count * sh.W * n;
     const unsigned long long nbuckets = (unsigned long long)count * sh.nsets * sh.NB;
     if (E >= (1ull << 32) || nbuckets >= (1ull << 31)) return fail(ctx, DE_ERR_UNSUPPORTED, "msm: batch too large for 32-bit entry indices");
-    unsigned int CH = (unsigned int)(4 * ((E + nbuckets - 1) / nbuckets));
-    if (CH < 32) CH = 32;
+    // task length: enough tasks to fill the chip twice over, but never longer than DE_MSM_MAX_CH entries
+    unsigned int CH = 8;
+    {
+        const unsigned long long target_tasks = (unsigned long long)ctx->sm_count * 1024;
+        while (CH < DE_MSM_MAX_CH && E / (CH * 2) >= target_tasks) CH *= 2;
+        // when the buckets alone already give enough tasks, make a task hold a whole bucket (twice the mean size covers the
+        // Poisson tail of uniform scalars), so that almost no bucket needs a merge
+        const unsigned long long avg = (E + nbuckets - 1) / nbuckets;
+        if (nbuckets >= target_tasks / 2)
+            while (CH < DE_MSM_MAX_CH && CH < 2 * avg) CH *= 2;
+    }
     const unsigned long long max_tasks = E / CH + nbuckets + 1;
-    const unsigned int CK = sh.NB >= 4096 ? 32 : (sh.NB >= 256 ? 8 : 1);
-    const unsigned int chunks_per_set = sh.NB / CK;
+    const unsigned int ndigits = (sh.c - 1 + 4) / 5;
     const unsigned int nsets_total = (unsigned int)(count * sh.nsets);
 
     DE_WS(ctx, keys, unsigned int, WS_MSM_KEYS, sizeof(unsigned int) * E);
     DE_WS(ctx, vals, unsigned int, WS_MSM_VALS, sizeof(unsigned int) * E);
-    DE_WS(ctx, sorted, unsigned int, WS_MSM_SORTED, sizeof(unsigned int) * E);
-    // u32 arrays of nbuckets + 1 entries each: counts, offsets, cursor, ntasks, task_off, multi_list; then block sums + scalars
+    DE_WS(ctx, sorted, unsigned int, WS_MSM_SORTED, sizeof(unsigned int) * (E + 2) + sizeof(uint2) * max_tasks);
+    uint2* task_list = (uint2*)(sorted + ((E + 1) & ~1ull));
+    // u32 arrays of nbuckets + 1 entries each: counts, offsets, cursor, ntasks, task_off, multi_small, multi_large; then scan
+    // block sums, scalars and the task-length bins
     const size_t nb1 = align_up(nbuckets + 1, 64);
-    const size_t misc_words = nb1 * 6 + 2 * (DE_SCAN_THREADS * DE_SCAN_ITEMS) + 64;
+    const size_t misc_words = nb1 * 7 + 2 * (DE_SCAN_THREADS * DE_SCAN_ITEMS) + 64 + 2 * 256;
     DE_WS(ctx, misc, unsigned int, WS_MSM_COUNTS, sizeof(unsigned int) * misc_words);
     unsigned int* counts = misc;
     unsigned int* offsets = counts + nb1;
     unsigned int* cursor = offsets + nb1;
     unsigned int* ntasks = cursor + nb1;
     unsigned int* task_off = ntasks + nb1;
-    unsigned int* multi_list = task_off + nb1;
-    unsigned int* block_sums = multi_list + nb1;
+    unsigned int* multi_small = task_off + nb1;
+    unsigned int* multi_large = multi_small + nb1;
+    unsigned int* block_sums = multi_large + nb1;
     unsigned int* block_sums2 = block_sums + DE_SCAN_THREADS * DE_SCAN_ITEMS;
-    unsigned int* scalars_u32 = block_sums2 + DE_SCAN_THREADS * DE_SCAN_ITEMS;  // [0] total entries, [1] total tasks, [2] multi_count
+    unsigned int* scalars_u32 = block_sums2 + DE_SCAN_THREADS * DE_SCAN_ITEMS;  // [0] entries, [1] tasks, [2] multi_small, [3] multi_large
+    unsigned int* len_bins = scalars_u32 + 64;  // 256 words
+    unsigned int* bin_cursor = len_bins + 256;  // 256 words
     DE_WS(ctx, buckets, XYZZ, WS_MSM_BUCKETS, sizeof(XYZZ) * nbuckets);
     DE_WS(ctx, partials, XYZZ, WS_MSM_PARTIALS, sizeof(XYZZ) * max_tasks);
-    DE_WS(ctx, red, XYZZ, WS_MSM_MISC, sizeof(XYZZ) * ((size_t)chunks_per_set * nsets_total + nsets_total));
-    XYZZ* chunk_out = red;
-    XYZZ* set_out = red + (size_t)chunks_per_set * nsets_total;
+    DE_WS(ctx, red, XYZZ, WS_MSM_MISC, sizeof(XYZZ) * ((size_t)ndigits * 32 * nsets_total + nsets_total));
+    XYZZ* dsums = red;
+    XYZZ* set_out = red + (size_t)ndigits * 32 * nsets_total;
     DE_WS(ctx, d_out, Jac, WS_MSM_OUT, sizeof(Jac) * count);
 
     cudaStream_t st = ctx->stream;
     DE_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(unsigned int) * nb1, st));
     DE_CUDA(ctx, cudaMemsetAsync(ntasks, 0, sizeof(unsigned int) * nb1, st));
-    DE_CUDA(ctx, cudaMemsetAsync(scalars_u32, 0, sizeof(unsigned int) * 64, st));
+    DE_CUDA(ctx, cudaMemsetAsync(scalars_u32, 0, sizeof(unsigned int) * (64 + 512), st));
     DE_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * nbuckets, st));
 
     const unsigned long long nscal = (unsigned long long)n * count;
@@ -119,25 +132,46 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CUDA(ctx, cudaMemcpyAsync(cursor, offsets, sizeof(unsigned int) * (nbuckets + 1), cudaMemcpyDeviceToDevice, st));
     k_msm_scatter<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, vals, E, cursor, sorted);
     DE_CHECK_LAUNCH(ctx);
-    k_msm_task_counts<<<(unsigned int)((nbuckets + 255) / 256), 256, 0, st>>>(counts, (unsigned int)nbuckets, CH, ntasks, multi_list,
-                                                                             &scalars_u32[2]);
+    k_msm_task_counts<<<(unsigned int)((nbuckets + 255) / 256), 256, 0, st>>>(counts, (unsigned int)nbuckets, CH, ntasks, multi_small,
+                                                                             multi_large, scalars_u32, len_bins);
     DE_CHECK_LAUNCH(ctx);
     DE_TRY(scan_u32(ctx, ntasks, nbuckets + 1, task_off, block_sums2, &scalars_u32[1]));
+    k_msm_bin_starts<<<1, 32, 0, st>>>(len_bins, CH, bin_cursor);
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_task_fill<<<(unsigned int)((nbuckets + 255) / 256), 256, 0, st>>>(counts, (unsigned int)nbuckets, CH, bin_cursor, task_list);
+    DE_CHECK_LAUNCH(ctx);
     DE_TIMED(ctx, "k_msm_accumulate", (double)n * count,
-             (k_msm_accumulate<<<(unsigned int)((max_tasks + 127) / 128), 128, 0, st>>>(sorted, offsets, counts, task_off, (unsigned int)nbuckets,
-                                                                                       CH, d_tables, buckets, partials)));
+             (k_msm_accumulate<<<(unsigned int)((max_tasks + 127) / 128), 128, 0, st>>>(sorted, offsets, counts, task_off, task_list,
+                                                                                       &scalars_u32[1], CH, d_tables, buckets, partials)));
     DE_CHECK_LAUNCH(ctx);
-    k_msm_merge<<<ctx->sm_count * 2, 128, 0, st>>>(multi_list, &scalars_u32[2], task_off, partials, buckets);
+    k_msm_merge_small<<<ctx->sm_count * 4, 128, 0, st>>>(multi_small, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    DE_TIMED(ctx, "k_msm_reduce_chunks", (double)n * count,
-             (k_msm_reduce_chunks<<<(chunks_per_set * nsets_total + 127) / 128, 128, 0, st>>>(buckets, sh.NB, CK, nsets_total, chunk_out)));
+    k_msm_merge_large<<<ctx->sm_count * 2, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    k_msm_reduce_sets<<<nsets_total, 256, 0, st>>>(chunk_out, chunks_per_set, set_out);
+    DE_TIMED(ctx, "k_msm_digit_sums", (double)n * count,
+             (k_msm_digit_sums<<<dim3(ndigits * 32, nsets_total), 128, 0, st>>>(buckets, sh.NB, sh.c - 1, dsums)));
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_digit_final<<<nsets_total, 128, 0, st>>>(dsums, ndigits, set_out);
     DE_CHECK_LAUNCH(ctx);
     k_msm_combine<<<(unsigned int)count, 32, 0, st>>>(set_out, sh.nsets, sh.c, d_out);
     DE_CHECK_LAUNCH(ctx);
     DE_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));
+    unsigned int total_entries = 0;
+    if (ctx->timing) DE_CUDA(ctx, cudaMemcpyAsync(&total_entries, &scalars_u32[0], sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     DE_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ctx->timing) {
+        // bucket additions actually performed (non-zero signed digits): the work figure behind the int-pipe fraction
+        KernelStat* stat = nullptr;
+        for (auto& k : ctx->stats)
+            if (k.name == "msm_bucket_adds") stat = &k;
+        if (!stat) {
+            ctx->stats.push_back(KernelStat());
+            stat = &ctx->stats.back();
+            stat->name = "msm_bucket_adds";
+        }
+        stat->units += total_entries;
+        stat->launches++;
+    }
     return DE_OK;
 }
 
@@ -299,6 +333,21 @@ int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out) {
     k_g1_sum<<<1, 32, 0, ctx->stream>>>(d + 1, (unsigned int)count, d);
     DE_CHECK_LAUNCH(ctx);
     DE_CUDA(ctx, cudaMemcpyAsync(out, d, sizeof(Jac), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_affine* out) {
+    if (!ctx) return DE_ERR_ARG;
+    if (count && (!points || !out)) return fail(ctx, DE_ERR_ARG, "de_g1_batch_normalize: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (count == 0) return DE_OK;
+    DE_WS(ctx, d, Jac, WS_MSM_OUT, sizeof(Jac) * count + sizeof(Affine) * count);
+    Affine* da = (Affine*)(d + count);
+    DE_CUDA(ctx, cudaMemcpyAsync(d, points, sizeof(Jac) * count, cudaMemcpyHostToDevice, ctx->stream));
+    k_g1_normalize<<<(unsigned int)((count + 63) / 64), 64, 0, ctx->stream>>>(d, (unsigned int)count, da);
+    DE_CHECK_LAUNCH(ctx);
+    DE_CUDA(ctx, cudaMemcpyAsync(out, da, sizeof(Affine) * count, cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DE_OK;
 }

@@ -157,14 +157,69 @@ __global__ void k_scan_add(unsigned int* out, unsigned long long n, const unsign
 }
 
 // ---- 3. bucket accumulation ------------------------------------------------------------------------------------
-// tasks per bucket = ceil(count / CH); buckets that need more than one task are appended to multi_list
-__global__ void k_msm_task_counts(const unsigned int* counts, unsigned int nbuckets, unsigned int CH, unsigned int* ntasks,
-                                  unsigned int* multi_list, unsigned int* multi_count) {
+// A task is a run of <= CH entries of one bucket.  Tasks are binned by exact length and laid out longest-first, so that
+// the 32 tasks of a warp have (almost always) the same trip count and the longest tasks start first (LPT order).
+#define DE_MSM_MAX_CH 128
+
+// pass 1: tasks per bucket, multi-task bucket lists (few partials: one thread merges; many: one warp), length histogram
+__global__ void __launch_bounds__(256) k_msm_task_counts(const unsigned int* counts, unsigned int nbuckets, unsigned int CH, unsigned int* ntasks,
+                                                         unsigned int* multi_small, unsigned int* multi_large, unsigned int* scal,
+                                                         unsigned int* len_bins) {
+    __shared__ unsigned int sbins[DE_MSM_MAX_CH + 1];
+    for (unsigned int i = threadIdx.x; i <= CH; i += blockDim.x) sbins[i] = 0;
+    __syncthreads();
     unsigned int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbuckets) return;
-    unsigned int t = (counts[b] + CH - 1) / CH;
-    ntasks[b] = t;
-    if (t > 1) multi_list[atomicAdd(multi_count, 1u)] = b;
+    if (b < nbuckets) {
+        unsigned int cnt = counts[b];
+        unsigned int full = cnt / CH, rem = cnt % CH;
+        unsigned int t = full + (rem ? 1 : 0);
+        ntasks[b] = t;
+        if (t > 1) {
+            if (t <= 8) multi_small[atomicAdd(&scal[2], 1u)] = b;
+            else multi_large[atomicAdd(&scal[3], 1u)] = b;
+        }
+        if (full) atomicAdd(&sbins[CH], full);
+        if (rem) atomicAdd(&sbins[rem], 1u);
+    }
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i <= CH; i += blockDim.x)
+        if (sbins[i]) atomicAdd(&len_bins[i], sbins[i]);
+}
+// bin start offsets, longest first: start[len] = sum of bins of greater length.  One block.
+__global__ void k_msm_bin_starts(const unsigned int* len_bins, unsigned int CH, unsigned int* bin_cursor) {
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int l = (int)CH; l >= 1; l--) {
+            bin_cursor[l] = run;
+            run += len_bins[l];
+        }
+        bin_cursor[0] = run;
+    }
+}
+// pass 2: every bucket writes its tasks (bucket, local index) into the slot range of their length bin
+__global__ void __launch_bounds__(256) k_msm_task_fill(const unsigned int* counts, unsigned int nbuckets, unsigned int CH,
+                                                       unsigned int* bin_cursor, uint2* task_list) {
+    __shared__ unsigned int scount[DE_MSM_MAX_CH + 1];
+    __shared__ unsigned int sbase[DE_MSM_MAX_CH + 1];
+    for (unsigned int i = threadIdx.x; i <= CH; i += blockDim.x) scount[i] = 0;
+    __syncthreads();
+    unsigned int b = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int cnt = 0, full = 0, rem = 0, off_full = 0, off_rem = 0;
+    if (b < nbuckets) {
+        cnt = counts[b];
+        full = cnt / CH;
+        rem = cnt % CH;
+        if (full) off_full = atomicAdd(&scount[CH], full);
+        if (rem) off_rem = atomicAdd(&scount[rem], 1u);
+    }
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i <= CH; i += blockDim.x)
+        if (scount[i]) sbase[i] = atomicAdd(&bin_cursor[i], scount[i]);
+    __syncthreads();
+    if (b < nbuckets) {
+        for (unsigned int k = 0; k < full; k++) task_list[sbase[CH] + off_full + k] = make_uint2(b, k);
+        if (rem) task_list[sbase[rem] + off_rem] = make_uint2(b, full);
+    }
 }
 
 __device__ __forceinline__ Affine msm_fetch(const Affine* bases, unsigned int v) {
@@ -174,19 +229,12 @@ __device__ __forceinline__ Affine msm_fetch(const Affine* bases, unsigned int v)
 }
 
 __global__ void __launch_bounds__(128) k_msm_accumulate(const unsigned int* sorted, const unsigned int* offsets, const unsigned int* counts,
-                                                        const unsigned int* task_off, unsigned int nbuckets, unsigned int CH,
-                                                        const Affine* bases, XYZZ* buckets, XYZZ* partials) {
+                                                        const unsigned int* task_off, const uint2* task_list, const unsigned int* n_tasks,
+                                                        unsigned int CH, const Affine* bases, XYZZ* buckets, XYZZ* partials) {
     unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int ntasks_total = task_off[nbuckets];
-    if (t >= ntasks_total) return;
-    // largest b with task_off[b] <= t
-    unsigned int lo = 0, hi = nbuckets;
-    while (hi - lo > 1) {
-        unsigned int mid = (lo + hi) >> 1;
-        if (task_off[mid] <= t) lo = mid; else hi = mid;
-    }
-    const unsigned int b = lo;
-    const unsigned int local = t - task_off[b];
+    if (t >= *n_tasks) return;
+    const uint2 task = task_list[t];
+    const unsigned int b = task.x, local = task.y;
     const unsigned int cnt = counts[b];
     const unsigned int start = offsets[b] + local * CH;
     unsigned int len = cnt - local * CH;
@@ -199,7 +247,7 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const unsigned int* sort
         xyzz_madd(acc, cur);
     }
     if (cnt <= CH) store_xyzz(&buckets[b], acc);
-    else store_xyzz(&partials[t], acc);
+    else store_xyzz(&partials[task_off[b] + local], acc);
 }
 
 __device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
@@ -214,15 +262,30 @@ __device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
     return r;
 }
 
-// one warp per multi-task bucket: lanes stride over the bucket's partial sums, then a shuffle tree
-__global__ void __launch_bounds__(128) k_msm_merge(const unsigned int* multi_list, const unsigned int* multi_count, const unsigned int* task_off,
-                                                   const XYZZ* partials, XYZZ* buckets) {
+// buckets split into 2..8 tasks: one thread adds the partial sums
+__global__ void __launch_bounds__(128) k_msm_merge_small(const unsigned int* multi_small, const unsigned int* scal, const unsigned int* task_off,
+                                                         const XYZZ* partials, XYZZ* buckets) {
+    const unsigned int total = scal[2];
+    for (unsigned int m = blockIdx.x * blockDim.x + threadIdx.x; m < total; m += gridDim.x * blockDim.x) {
+        const unsigned int b = multi_small[m];
+        const unsigned int first = task_off[b], last = task_off[b + 1];
+        XYZZ acc = load_xyzz(&partials[first]);
+        for (unsigned int p = first + 1; p < last; p++) {
+            XYZZ v = load_xyzz(&partials[p]);
+            xyzz_add(acc, v);
+        }
+        store_xyzz(&buckets[b], acc);
+    }
+}
+// heavy buckets (> 8 tasks): one warp per bucket, lanes stride over the partial sums, then a shuffle tree
+__global__ void __launch_bounds__(128) k_msm_merge_large(const unsigned int* multi_large, const unsigned int* scal, const unsigned int* task_off,
+                                                         const XYZZ* partials, XYZZ* buckets) {
     const unsigned int lane = threadIdx.x & 31;
     const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned int total = *multi_count;
+    const unsigned int total = scal[3];
     for (unsigned int m = warp; m < total; m += nwarps) {
-        const unsigned int b = multi_list[m];
+        const unsigned int b = multi_large[m];
         const unsigned int first = task_off[b], last = task_off[b + 1];
         XYZZ acc = xyzz_identity();
         for (unsigned int p = first + lane; p < last; p += 32) {
@@ -240,55 +303,79 @@ __global__ void __launch_bounds__(128) k_msm_merge(const unsigned int* multi_lis
 }
 
 // ---- 4. bucket reduction ---------------------------------------------------------------------------------------
-// k * P for a small scalar k (double-and-add, MSB first)
-__device__ __forceinline__ XYZZ xyzz_mul_small(const XYZZ& p, unsigned int k) {
+// sum_b (b + 1) * B_b without long serial chains: write b in radix-32 digits d_j (bit offset 5j, the top digit narrower).
+//   sum_b (b+1) B_b = sum_b B_b + sum_j 2^(5j) * sum_v v * D[j][v],   D[j][v] = sum of the buckets whose j-th digit is v.
+// Every D[j][v] is a PLAIN sum (a CTA: 8 serial adds per thread, then a tree), so the only dependent chain left is the
+// 32-element weighted sum per digit, done by one warp with two shuffle scans.
+__global__ void __launch_bounds__(128) k_msm_digit_sums(const XYZZ* buckets, unsigned int NB, unsigned int cm1 /* c - 1 */, XYZZ* dsums) {
+    // grid: x = digit slot (j * 32 + v), y = bucket set
+    __shared__ XYZZ sm[4];
+    const unsigned int j = blockIdx.x >> 5, v = blockIdx.x & 31;
+    const unsigned int off = 5 * j;
+    const unsigned int width = (cm1 - off) < 5 ? (cm1 - off) : 5;
+    const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     XYZZ acc = xyzz_identity();
-    for (int i = 31 - __clz(k | 1); i >= 0; i--) {
-        acc = xyzz_dbl(acc);
-        if ((k >> i) & 1) xyzz_add(acc, p);
-    }
-    return acc;
-}
-// thread per chunk of CK buckets: T_k = sum_{b in chunk} (b + 1) * B_b, via running sums plus lo * S
-__global__ void __launch_bounds__(128) k_msm_reduce_chunks(const XYZZ* buckets, unsigned int NB, unsigned int CK, unsigned int nsets_total,
-                                                           XYZZ* chunk_out) {
-    const unsigned int chunks_per_set = NB / CK;
-    unsigned int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= chunks_per_set * nsets_total) return;
-    const unsigned int set = gid / chunks_per_set, k = gid % chunks_per_set;
-    const XYZZ* B = buckets + (unsigned long long)set * NB + (unsigned long long)k * CK;
-    XYZZ run = xyzz_identity(), acc = xyzz_identity();
-    for (int b = (int)CK - 1; b >= 0; b--) {
-        XYZZ v = load_xyzz(&B[b]);
-        xyzz_add(run, v);
-        xyzz_add(acc, run);
-    }
-    if (k > 0) {
-        XYZZ w = xyzz_mul_small(run, k * CK);
-        xyzz_add(acc, w);
-    }
-    store_xyzz(&chunk_out[gid], acc);
-}
-// one CTA per bucket set: tree-sum of the chunk results
-__global__ void __launch_bounds__(256) k_msm_reduce_sets(const XYZZ* chunk_in, unsigned int chunks_per_set, XYZZ* set_out) {
-    __shared__ XYZZ sm[256];
-    const unsigned int set = blockIdx.x, tid = threadIdx.x;
-    XYZZ acc = xyzz_identity();
-    for (unsigned int k = tid; k < chunks_per_set; k += blockDim.x) {
-        XYZZ v = load_xyzz(&chunk_in[(unsigned long long)set * chunks_per_set + k]);
-        xyzz_add(acc, v);
-    }
-    sm[tid] = acc;
-    __syncthreads();
-    for (unsigned int d = blockDim.x >> 1; d >= 1; d >>= 1) {
-        if (tid < d) {
-            XYZZ o = sm[tid + d];
-            xyzz_add(acc, o);
-            sm[tid] = acc;
+    if (v < (1u << width)) {
+        const XYZZ* B = buckets + (unsigned long long)blockIdx.y * NB;
+        const unsigned int m_count = NB >> width;
+        for (unsigned int m = tid; m < m_count; m += blockDim.x) {
+            unsigned int lo = m & ((1u << off) - 1), hi = m >> off;
+            unsigned int b = (hi << (off + width)) | (v << off) | lo;
+            XYZZ x = load_xyzz(&B[b]);
+            xyzz_add(acc, x);
         }
-        __syncthreads();
     }
-    if (tid == 0) store_xyzz(&set_out[set], acc);
+    for (int d = 16; d >= 1; d >>= 1) {
+        XYZZ o = shfl_down_xyzz(acc, d);
+        if (lane + d < 32) xyzz_add(acc, o);
+    }
+    if (lane == 0) sm[wid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        for (unsigned int w = 1; w < (blockDim.x >> 5); w++) {
+            XYZZ o = sm[w];
+            xyzz_add(acc, o);
+        }
+        store_xyzz(&dsums[(unsigned long long)blockIdx.y * gridDim.x + blockIdx.x], acc);
+    }
+}
+// one CTA per bucket set, one warp per digit: W_j = sum_v v * D[j][v] by two shuffle scans (all digits in parallel), then
+// thread 0 folds the digits: result = (..(W_top * 32 + W_{top-1}) * 32 ..) + W_0 + total
+__global__ void __launch_bounds__(128) k_msm_digit_final(const XYZZ* dsums, unsigned int ndigits, XYZZ* set_out) {
+    __shared__ XYZZ sw[4];
+    __shared__ XYZZ stotal;
+    const unsigned int set = blockIdx.x, lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const XYZZ* D = dsums + (unsigned long long)set * ndigits * 32;
+    if (j < ndigits) {
+        XYZZ r = load_xyzz(&D[j * 32 + lane]);
+        // suffix sums R_v = sum_{u >= v} X_u
+        for (int d = 1; d < 32; d <<= 1) {
+            XYZZ o = shfl_down_xyzz(r, d);
+            if (lane + d < 32) xyzz_add(r, o);
+        }
+        if (lane == 0) {
+            if (j == 0) stotal = r;  // R_0 of digit 0 = sum of all buckets
+            r = xyzz_identity();
+        }
+        // sum_{v >= 1} R_v = sum_v v * X_v
+        for (int d = 16; d >= 1; d >>= 1) {
+            XYZZ o = shfl_down_xyzz(r, d);
+            if (lane + d < 32) xyzz_add(r, o);
+        }
+        if (lane == 0) sw[j] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XYZZ result = sw[ndigits - 1];
+        for (int k = (int)ndigits - 2; k >= 0; k--) {
+            for (int t = 0; t < 5; t++) result = xyzz_dbl(result);
+            XYZZ w = sw[k];
+            xyzz_add(result, w);
+        }
+        XYZZ tot = stotal;
+        xyzz_add(result, tot);
+        store_xyzz(&set_out[set], result);
+    }
 }
 
 // ---- 5. combine bucket sets: out[b] = sum_u 2^(c*u) * R[b][u], written as Jacobian -------------------------------
@@ -359,6 +446,25 @@ __global__ void __launch_bounds__(32) k_g1_sum(const Jac* pts, unsigned int coun
         Jac j = xyzz_to_jac(acc);
         store(&out->x, j.x); store(&out->y, j.y); store(&out->z, j.z);
     }
+}
+
+// Jacobian -> affine, one thread per point (Fermat inversion)
+__global__ void k_g1_normalize(const Jac* pts, unsigned int count, Affine* out) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Jac p;
+    p.x = load(&pts[i].x); p.y = load(&pts[i].y); p.z = load(&pts[i].z);
+    Affine a;
+    if (p.z.is_zero()) {
+        a.x = Fq::zero();
+        a.y = Fq::zero();
+    } else {
+        Fq zi = inv(p.z);
+        Fq zi2 = sqr(zi);
+        a.x = mul(p.x, zi2);
+        a.y = mul(p.y, mul(zi2, zi));
+    }
+    store_affine(&out[i], a);
 }
 
 }  // namespace de

@@ -132,6 +132,13 @@ class Context:
         omega = _np(omega)
         self.check(self.L.de_ntt_dev(self.h, _ptr(d_a), _ptr(omega), log_n, batch, stride or (1 << log_n)))
 
+    def batch_normalize(self, points):
+        """group::Curve::batch_normalize: (count, 12) Jacobian -> (count, 8) affine"""
+        points = _np(points).reshape(-1, 12)
+        out = np.zeros((points.shape[0], 8), dtype=np.uint64)
+        self.check(self.L.de_g1_batch_normalize(self.h, _ptr(points), points.shape[0], _ptr(out)))
+        return out
+
     def g1_sum(self, points):
         points = _np(points)
         out = np.zeros(12, dtype=np.uint64)

@@ -19,7 +19,7 @@ SYMBOLS = [
     "de_commit_batch", "de_commit_batch_dev", "de_ntt", "de_ntt_dev", "de_domain_create", "de_domain_free", "de_domain_info",
     "de_coeff_to_extended", "de_extended_to_coeff", "de_lagrange_to_coeff", "de_coeff_to_lagrange", "de_divide_by_vanishing",
     "de_coeff_to_extended_dev", "de_extended_to_coeff_dev", "de_lagrange_to_coeff_dev", "de_coeff_to_lagrange_dev",
-    "de_divide_by_vanishing_dev", "de_pk_upload", "de_pk_free", "de_evaluate_h", "de_evaluate_h_dev", "de_commit_range", "de_g1_sum",
+    "de_divide_by_vanishing_dev", "de_pk_upload", "de_pk_free", "de_evaluate_h", "de_evaluate_h_dev", "de_commit_range", "de_g1_sum", "de_g1_batch_normalize",
 ]
 
 
@@ -83,6 +83,7 @@ def load():
     L.de_evaluate_h_dev.argtypes = [P, P, P, P, P, P, SZ, P]
     L.de_commit_range.argtypes = [P, I, P, SZ, SZ, P]
     L.de_g1_sum.argtypes = [P, P, SZ, P]
+    L.de_g1_batch_normalize.argtypes = [P, P, SZ, P]
     for s in SYMBOLS:
         fn = getattr(L, s)
         if s not in ("de_last_error", "de_version", "de_launch_count"):

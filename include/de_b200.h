@@ -57,7 +57,7 @@ const char* de_version(void);
 uint64_t de_launch_count(de_ctx* ctx);
 
 /* per-kernel device timing: CUDA events recorded around the named kernels on the context's stream.
- * Known names: "k_msm_accumulate", "k_msm_reduce_chunks", "k_ntt_pass", "k_eval_h".  units = points / elements / rows. */
+ * Known names: "k_msm_accumulate", "k_msm_digit_sums", "k_ntt_pass", "k_eval_h".  units = points / elements / rows. */
 int de_timing_enable(de_ctx* ctx, int on);
 int de_timing_reset(de_ctx* ctx);
 int de_timing_get(de_ctx* ctx, const char* kernel, double* total_ms, double* total_units, uint64_t* launches);
@@ -172,6 +172,9 @@ int de_evaluate_h_dev(de_pk* pk, const de_fr* d_advice_coeff, const de_fr* d_ins
  * the host (or de_g1_sum) adds the n_shards partial points. */
 int de_commit_range(de_params* p, int basis, const de_fr* scalars, size_t lo, size_t hi, de_g1* out_partial);
 int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out);
+/* group::Curve::batch_normalize: Jacobian -> affine (identity -> all zero).  The Jacobian representative an MSM returns
+ * depends on the (atomic) accumulation order; the affine point does not. */
+int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_affine* out);
 
 #ifdef __cplusplus
 }

@@ -106,3 +106,11 @@ def test_commit_delay_enc_size(ctx):
     params = de_b200.ParamsKZG(k, None, gl, ctx)
     for s in (orc.uniform_fr(0xDE03, n), orc.witness_fr(0xDE03, n, 50400)):
         assert same_point(params.commit_lagrange(s), orc.best_multiexp(s, gl))
+
+
+def test_batch_normalize(ctx):
+    n = 300
+    s = orc.uniform_fr(5, n)
+    b = orc.gen_bases(n)
+    pts = np.stack([ctx.best_multiexp(s[: i + 1], b[: i + 1]) for i in (0, 7, 299)] + [np.zeros(12, dtype=np.uint64)])
+    assert (ctx.batch_normalize(pts) == orc.g1_to_affine(pts)).all()
