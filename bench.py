@@ -43,9 +43,9 @@ UNIT = "proofs/s"
 MUL_PEAK_GMULS = 65.9   # measured on this pool's B200 by tools/int_peak (profiles/r01_int_peak.jsonl): Fr Montgomery mul/s
 MULS_PER_POINT = 160    # SURVEY.md 8d convention: 16 windows x (8M + 2S) per point (a uniform scalar)
 MULS_PER_ADD = 10       # XYZZ mixed addition: 8M + 2S
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_msm_accumulate launch (10 polynomials x 2^16 points), from the
+# (dram__bytes_read.sum + dram__bytes_write.sum) / points of a k_msm_accumulate launch (298.2 MB for 10 x 2^16 points), from the
 # `ncu --set full` capture summarised in profiles/r01_accumulate_ncu.md
-TRAFFIC_PER_LAUNCH = 298.2e6
+TRAFFIC_BYTES_PER_POINT = 298.2e6 / 655360
 
 
 def _peaks():
@@ -222,7 +222,7 @@ def main():
     import torch
     import torch.distributed as dist
     import de_b200
-    from de_b200 import prover
+    from de_b200 import prover, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU path (use --impl reference for the CPU baseline)")
@@ -284,12 +284,7 @@ def main():
             main_stream.wait_stream(wk.stream)
         e1.record(main_stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return sharding.max_over_ranks(e0.elapsed_time(e1))
 
     ctx = workers[0].ctx
     timed(workers, args.warmup, False)
@@ -348,7 +343,7 @@ def main():
         avg_ms = acc_ms / acc_n
         achieved = 96.0 * pts_per_launch / (avg_ms * 1e-3) / 1e9
         line["roofline"] = {"kernel": "k_msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_PER_LAUNCH, "peak_source": peak_kind,
+                            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_BYTES_PER_POINT * pts_per_launch, "peak_source": peak_kind,
                             "measured_in": "latency arm (one proof in flight, CUDA events around every launch on its stream)",
                             "share_of_step": acc_ms / ms_ref, "launches": acc_n, "avg_launch_ms": avg_ms,
                             "int_pipe": {"achieved_gmuls": MULS_PER_ADD * bucket_adds / (acc_ms * 1e-3) / 1e9,

@@ -1,0 +1,128 @@
+// halo2_b200.hpp — header-only C++ host-side mirror of the halo2_proofs surface served by libde_b200.so.
+// The reference's host language is Rust, which this environment cannot compile; this mirror keeps the reference's names,
+// argument meaning and failure behaviour (the Rust functions panic on violated asserts; these throw std::runtime_error).
+//   halo2_proofs::arithmetic::best_multiexp / best_fft, poly::EvaluationDomain, poly::kzg::commitment::ParamsKZG
+// Element types are the C ABI's (include/de_b200.h): Montgomery limbs, byte-identical to halo2curves.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/de_b200.h"
+
+namespace halo2_b200 {
+
+class Context {
+public:
+    explicit Context(int device = 0) {
+        int rc = de_ctx_create(device, &h_);
+        if (rc != DE_OK) throw std::runtime_error(std::string("de_ctx_create: ") + de_last_error(nullptr));
+    }
+    ~Context() { de_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    de_ctx* handle() const { return h_; }
+    void check(int rc, const char* what) const {
+        if (rc != DE_OK) throw std::runtime_error(std::string(what) + ": " + de_last_error(h_));
+    }
+    std::vector<de_g1_affine> batch_normalize(const std::vector<de_g1>& pts) const {  // group::Curve::batch_normalize
+        std::vector<de_g1_affine> out(pts.size());
+        check(de_g1_batch_normalize(h_, pts.data(), pts.size(), out.data()), "batch_normalize");
+        return out;
+    }
+
+private:
+    de_ctx* h_ = nullptr;
+};
+
+// arithmetic::best_multiexp(coeffs, bases): assert_eq!(coeffs.len(), bases.len())
+inline de_g1 best_multiexp(const Context& ctx, const std::vector<de_fr>& coeffs, const std::vector<de_g1_affine>& bases) {
+    if (coeffs.size() != bases.size()) throw std::runtime_error("best_multiexp: coeffs.len() != bases.len()");
+    de_g1 out;
+    ctx.check(de_msm(ctx.handle(), coeffs.data(), bases.data(), coeffs.size(), &out), "best_multiexp");
+    return out;
+}
+// arithmetic::best_fft(a, omega, log_n): assert_eq!(a.len(), 1 << log_n); in place
+inline void best_fft(const Context& ctx, std::vector<de_fr>& a, const de_fr& omega, uint32_t log_n) {
+    if (a.size() != (size_t(1) << log_n)) throw std::runtime_error("best_fft: a.len() != 1 << log_n");
+    ctx.check(de_ntt(ctx.handle(), a.data(), &omega, log_n), "best_fft");
+}
+
+class EvaluationDomain {  // poly::EvaluationDomain::new(j, k)
+public:
+    EvaluationDomain(const Context& ctx, uint32_t j, uint32_t k) : ctx_(ctx), k_(k) {
+        ctx.check(de_domain_create(ctx.handle(), j, k, &h_), "EvaluationDomain::new");
+        de_fr c[4];
+        ctx.check(de_domain_info(h_, &extended_k_, c), "EvaluationDomain::new");
+        omega = c[0]; omega_inv = c[1]; extended_omega = c[2]; extended_omega_inv = c[3];
+    }
+    ~EvaluationDomain() { de_domain_free(h_); }
+    EvaluationDomain(const EvaluationDomain&) = delete;
+    uint32_t k() const { return k_; }
+    uint32_t extended_k() const { return extended_k_; }
+    size_t extended_len() const { return size_t(1) << extended_k_; }
+    std::vector<de_fr> coeff_to_extended(const std::vector<de_fr>& a) const {
+        need(a.size(), size_t(1) << k_, "coeff_to_extended");
+        std::vector<de_fr> out(extended_len());
+        ctx_.check(de_coeff_to_extended(h_, a.data(), out.data()), "coeff_to_extended");
+        return out;
+    }
+    std::vector<de_fr> extended_to_coeff(std::vector<de_fr> a) const {
+        need(a.size(), extended_len(), "extended_to_coeff");
+        size_t len = 0;
+        ctx_.check(de_extended_to_coeff(h_, a.data(), &len), "extended_to_coeff");
+        a.resize(len);
+        return a;
+    }
+    void lagrange_to_coeff(std::vector<de_fr>& a) const {
+        need(a.size(), size_t(1) << k_, "lagrange_to_coeff");
+        ctx_.check(de_lagrange_to_coeff(h_, a.data()), "lagrange_to_coeff");
+    }
+    void coeff_to_lagrange(std::vector<de_fr>& a) const {
+        need(a.size(), size_t(1) << k_, "coeff_to_lagrange");
+        ctx_.check(de_coeff_to_lagrange(h_, a.data()), "coeff_to_lagrange");
+    }
+    void divide_by_vanishing_poly(std::vector<de_fr>& a) const {
+        need(a.size(), extended_len(), "divide_by_vanishing_poly");
+        ctx_.check(de_divide_by_vanishing(h_, a.data()), "divide_by_vanishing_poly");
+    }
+    de_domain* handle() const { return h_; }
+    de_fr omega, omega_inv, extended_omega, extended_omega_inv;
+
+private:
+    static void need(size_t got, size_t want, const char* what) {
+        if (got != want) throw std::runtime_error(std::string(what) + ": wrong polynomial length");
+    }
+    const Context& ctx_;
+    de_domain* h_ = nullptr;
+    uint32_t k_, extended_k_ = 0;
+};
+
+class ParamsKZG {  // poly::kzg::commitment::ParamsKZG: g / g_lagrange staged in HBM once
+public:
+    ParamsKZG(const Context& ctx, uint32_t k, const de_g1_affine* g, const de_g1_affine* g_lagrange) : ctx_(ctx), k_(k) {
+        ctx.check(de_params_upload(ctx.handle(), k, g, g_lagrange, &h_), "ParamsKZG");
+    }
+    ~ParamsKZG() { de_params_free(h_); }
+    ParamsKZG(const ParamsKZG&) = delete;
+    uint32_t k() const { return k_; }
+    de_g1 commit(const de_fr* poly, size_t n) const { return commit_basis(0, poly, n); }           // Blind unused for KZG
+    de_g1 commit_lagrange(const de_fr* poly, size_t n) const { return commit_basis(1, poly, n); }
+    std::vector<de_g1> commit_lagrange_batch(const std::vector<const de_fr*>& polys, size_t n) const {
+        std::vector<de_g1> out(polys.size());
+        ctx_.check(de_commit_batch(h_, 1, polys.data(), n, polys.size(), out.data()), "commit_lagrange (batch)");
+        return out;
+    }
+
+private:
+    de_g1 commit_basis(int basis, const de_fr* poly, size_t n) const {
+        de_g1 out;
+        ctx_.check(de_commit(h_, basis, poly, n, &out), "commit");
+        return out;
+    }
+    const Context& ctx_;
+    de_params* h_ = nullptr;
+    uint32_t k_;
+};
+
+}  // namespace halo2_b200
