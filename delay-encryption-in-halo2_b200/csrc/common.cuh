@@ -65,7 +65,7 @@ struct PinnedBuf {
 };
 
 enum { WS_IO_A = 0, WS_IO_B, WS_NTT_SCRATCH, WS_MSM_KEYS, WS_MSM_VALS, WS_MSM_SORTED, WS_MSM_COUNTS, WS_MSM_BUCKETS,
-       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_COUNT };
+       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_RED, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_COUNT };
 
 }  // namespace de
 
@@ -142,6 +142,23 @@ inline int fail(de_ctx* ctx, int code, const std::string& msg) {
             (ctx)->timed.push_back(tl__);                                       \
         }                                                                       \
     } while (0)
+
+// the same for a sequence of launches: timing_begin / timing_end bracket them with one event pair
+inline TimedLaunch timing_begin(de_ctx* ctx, const char* name, double units) {
+    TimedLaunch tl = {name, nullptr, nullptr, units};
+    if (ctx->timing) {
+        cudaEventCreate(&tl.e0);
+        cudaEventCreate(&tl.e1);
+        cudaEventRecord(tl.e0, ctx->stream);
+    }
+    return tl;
+}
+inline void timing_end(de_ctx* ctx, TimedLaunch& tl) {
+    if (ctx->timing) {
+        cudaEventRecord(tl.e1, ctx->stream);
+        ctx->timed.push_back(tl);
+    }
+}
 
 #define DE_TRY(expr)                 \
     do {                             \

@@ -33,7 +33,7 @@ static MsmCfg choose_cfg(unsigned long long n, bool precomputed, unsigned long l
             nsets = (W + ntables - 1) / ntables;
             ntables = (W + nsets - 1) / nsets;
         }
-        double cost = 10.0 * (double)n * W + 40.0 * (double)nsets * (double)(1u << (c - 1));
+        double cost = 10.0 * (double)n * W + 30.0 * (double)nsets * (double)(1u << (c - 1));  // 2 full additions (14 muls) per bucket
         if (cost < best_cost) {
             best_cost = cost;
             best = {c, W, nsets, ntables};
@@ -116,6 +116,8 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     XYZZ* dsums = red;
     XYZZ* set_out = red + (size_t)ndigits * 32 * nsets_total;
     DE_WS(ctx, d_out, Jac, WS_MSM_OUT, sizeof(Jac) * count);
+    // scratch of the two-digit reduction: two ping-pong partial buffers, D0 / D1 and their digit sums
+    DE_WS(ctx, red2, XYZZ, WS_MSM_RED, sizeof(XYZZ) * ((size_t)nsets_total * sh.NB + 4096 + (size_t)nsets_total * 4 * 2048));
 
     cudaStream_t st = ctx->stream;
     DE_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(unsigned int) * nb1, st));
@@ -124,9 +126,7 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * nbuckets, st));
 
     const unsigned long long nscal = (unsigned long long)n * count;
-    k_msm_digits<<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals);
-    DE_CHECK_LAUNCH(ctx);
-    k_msm_hist<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, E, counts);
+    k_msm_digits<<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals, counts);
     DE_CHECK_LAUNCH(ctx);
     DE_TRY(scan_u32(ctx, counts, nbuckets + 1, offsets, block_sums, &scalars_u32[0]));
     DE_CUDA(ctx, cudaMemcpyAsync(cursor, offsets, sizeof(unsigned int) * (nbuckets + 1), cudaMemcpyDeviceToDevice, st));
@@ -148,11 +148,63 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CHECK_LAUNCH(ctx);
     k_msm_merge_large<<<ctx->sm_count * 2, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    DE_TIMED(ctx, "k_msm_digit_sums", (double)n * count,
-             (k_msm_digit_sums<<<dim3(ndigits * 32, nsets_total), 128, 0, st>>>(buckets, sh.NB, sh.c - 1, dsums)));
-    DE_CHECK_LAUNCH(ctx);
-    k_msm_digit_final<<<nsets_total, 128, 0, st>>>(dsums, ndigits, set_out);
-    DE_CHECK_LAUNCH(ctx);
+    if (sh.c >= 11) {
+        // two-digit reduction: row / column plain sums by segmented additions, then the short weighted sums
+        const unsigned int cm1 = sh.c - 1, w0 = (cm1 + 1) / 2, w1 = cm1 - w0;
+        const unsigned long long V0 = 1ull << w0, V1 = 1ull << w1;
+        const unsigned int nd0 = (w0 + 4) / 5, nd1 = (w1 + 4) / 5;
+        XYZZ* bufA = red2;
+        XYZZ* bufB = red2 + (size_t)nsets_total * sh.NB / 8 * 2;
+        XYZZ* D0 = bufB + (size_t)nsets_total * sh.NB / 64 * 2 + 64;
+        XYZZ* D1 = D0 + nsets_total * V0;
+        XYZZ* ds0 = D1 + nsets_total * V1;
+        XYZZ* ds1 = ds0 + (size_t)nsets_total * nd0 * 32;
+        auto segsum = [&](const XYZZ* in, XYZZ* out, unsigned long long n_out, unsigned int seg) -> int {
+            k_xyzz_segsum<<<(unsigned int)((n_out + 127) / 128), 128, 0, st>>>(in, out, n_out, seg);
+            DE_CHECK_LAUNCH(ctx);
+            return DE_OK;
+        };
+        // reduce `len` contiguous terms per sum down to 1, 8 (then whatever is left) at a time
+        auto reduce_rows = [&](const XYZZ* in, unsigned long long n_sums, unsigned long long len, XYZZ* final_out, XYZZ* t0, XYZZ* t1) -> int {
+            const XYZZ* cur = in;
+            XYZZ* tmp[2] = {t0, t1};
+            int flip = 0;
+            while (len > 1) {
+                unsigned int seg = len >= 8 ? 8 : (unsigned int)len;
+                unsigned long long nlen = len / seg;
+                XYZZ* dst = nlen == 1 ? final_out : tmp[flip];
+                DE_TRY(segsum(cur, dst, n_sums * nlen, seg));
+                cur = dst;
+                flip ^= 1;
+                len = nlen;
+            }
+            return DE_OK;
+        };
+        TimedLaunch tl = timing_begin(ctx, "k_msm_digit_sums", (double)n * count);
+        // D1[u] = sum over the V0 contiguous buckets of row u
+        DE_TRY(reduce_rows(buckets, nsets_total * V1, V0, D1, bufA, bufB));
+        // D0[v]: first level strided over the rows (8 at a time), then contiguous
+        const unsigned int seg = V1 >= 8 ? 8 : (unsigned int)V1;
+        const unsigned int Q = (unsigned int)(V1 / seg);
+        const unsigned long long n_out = nsets_total * V0 * Q;
+        XYZZ* first = Q == 1 ? D0 : bufA;
+        k_xyzz_colsum<<<(unsigned int)((n_out + 127) / 128), 128, 0, st>>>(buckets, first, sh.NB, w0, Q, seg, n_out);
+        DE_CHECK_LAUNCH(ctx);
+        if (Q > 1) DE_TRY(reduce_rows(bufA, nsets_total * V0, Q, D0, bufB, bufA + n_out));
+        timing_end(ctx, tl);
+        k_msm_digit_sums<<<dim3(nd0 * 32, nsets_total), 128, 0, st>>>(D0, (unsigned int)V0, w0, ds0);
+        DE_CHECK_LAUNCH(ctx);
+        k_msm_digit_sums<<<dim3(nd1 * 32, nsets_total), 128, 0, st>>>(D1, (unsigned int)V1, w1, ds1);
+        DE_CHECK_LAUNCH(ctx);
+        k_msm_digit_final2<<<nsets_total, 128, 0, st>>>(ds0, nd0, ds1, nd1, w0, set_out);
+        DE_CHECK_LAUNCH(ctx);
+    } else {
+        DE_TIMED(ctx, "k_msm_digit_sums", (double)n * count,
+                 (k_msm_digit_sums<<<dim3(ndigits * 32, nsets_total), 128, 0, st>>>(buckets, sh.NB, sh.c - 1, dsums)));
+        DE_CHECK_LAUNCH(ctx);
+        k_msm_digit_final<<<nsets_total, 128, 0, st>>>(dsums, ndigits, set_out);
+        DE_CHECK_LAUNCH(ctx);
+    }
     k_msm_combine<<<(unsigned int)count, 32, 0, st>>>(set_out, sh.nsets, sh.c, d_out);
     DE_CHECK_LAUNCH(ctx);
     DE_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));

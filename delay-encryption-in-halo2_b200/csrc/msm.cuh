@@ -5,7 +5,7 @@
 //
 //   1. k_msm_digits     canonical scalar (one Montgomery reduction) -> signed c-bit digits; one (key, value) entry per
 //                       non-zero digit: key = bucket id, value = base-table index | sign
-//   2. counting sort    histogram (k_msm_hist) -> exclusive scan -> scatter (k_msm_scatter): entries grouped by bucket
+//   2. counting sort    histogram (fused into k_msm_digits) -> exclusive scan -> scatter (k_msm_scatter): entries grouped by bucket
 //   3. k_msm_accumulate one thread per task (a run of <= CH entries of one bucket): gathers 64-byte affine bases with
 //                       16-byte loads and adds them into an XYZZ accumulator (8M + 2S per point); heavy buckets are
 //                       split into several tasks whose partial sums are merged warp-cooperatively (k_msm_merge)
@@ -33,7 +33,8 @@ struct MsmShape {
 };
 
 // ---- 1. digits -------------------------------------------------------------------------------------------------
-__global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmShape sh, unsigned int* keys, unsigned int* vals) {
+__global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmShape sh, unsigned int* keys, unsigned int* vals,
+                             unsigned int* counts) {
     unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= sh.n * sh.count) return;
     unsigned int b = (unsigned int)(gid / sh.n);
@@ -61,19 +62,15 @@ __global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmSh
         if (mag == 0) {
             keys[e] = DE_MSM_INVALID;
         } else {
-            keys[e] = (b * sh.nsets + set) * sh.NB + (mag - 1);
+            const unsigned int key = (b * sh.nsets + set) * sh.NB + (mag - 1);
+            keys[e] = key;
             vals[e] = (unsigned int)(table * sh.table_stride + sh.base_offset + i) | (neg << 31);
+            atomicAdd(&counts[key], 1u);  // bucket histogram of the counting sort, fused here
         }
     }
 }
 
 // ---- 2. counting sort ------------------------------------------------------------------------------------------
-__global__ void k_msm_hist(const unsigned int* keys, unsigned long long E, unsigned int* counts) {
-    unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    unsigned int k = keys[e];
-    if (k != DE_MSM_INVALID) atomicAdd(&counts[k], 1u);
-}
 __global__ void k_msm_scatter(const unsigned int* keys, const unsigned int* vals, unsigned long long E, unsigned int* cursor,
                               unsigned int* sorted) {
     unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,6 +369,89 @@ __global__ void __launch_bounds__(128) k_msm_digit_final(const XYZZ* dsums, unsi
             XYZZ w = sw[k];
             xyzz_add(result, w);
         }
+        XYZZ tot = stotal;
+        xyzz_add(result, tot);
+        store_xyzz(&set_out[set], result);
+    }
+}
+
+// ---- 4b. two-digit reduction (c >= 11) ---------------------------------------------------------------------------
+// Split the bucket index b = u * V0 + v (v: low w0 bits, u: high w1 bits).  Then
+//   sum_b (b+1) B_b = T + sum_v v * D0[v] + 2^w0 * sum_u u * D1[u],   D0[v] = sum_u B[u][v],  D1[u] = sum_v B[u][v],  T = sum D0.
+// D0 / D1 are plain sums (2 additions per bucket in total instead of 3), formed by lane-efficient segmented sums: every
+// thread adds <= 8 terms serially, level after level; the two short weighted sums reuse the radix-32 digit kernels.
+// out[i] = sum_{k < seg} in[i * seg + k]
+__global__ void __launch_bounds__(128, 4) k_xyzz_segsum(const XYZZ* in, XYZZ* out, unsigned long long n_out, unsigned int seg) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const XYZZ* p = in + i * seg;
+    XYZZ acc = load_xyzz(&p[0]);
+    for (unsigned int k = 1; k < seg; k++) {
+        XYZZ v = load_xyzz(&p[k]);
+        xyzz_add(acc, v);
+    }
+    store_xyzz(&out[i], acc);
+}
+// column partial sums: out[(set * V0 + v) * Q + q] = sum_{k < seg} B[set][(q * seg + k) * V0 + v]
+__global__ void __launch_bounds__(128, 4) k_xyzz_colsum(const XYZZ* buckets, XYZZ* out, unsigned int NB, unsigned int w0, unsigned int Q,
+                                                         unsigned int seg, unsigned long long n_out) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    // consecutive threads take consecutive v (coalesced 128-byte bucket reads): decode i as (set, q, v) for the loads
+    const unsigned int V0 = 1u << w0;
+    const unsigned int v = (unsigned int)(i & (V0 - 1));
+    const unsigned int q = (unsigned int)((i >> w0) % Q);
+    const unsigned long long set = (i >> w0) / Q;
+    const XYZZ* B = buckets + set * NB + (unsigned long long)q * seg * V0 + v;
+    XYZZ acc = load_xyzz(&B[0]);
+    for (unsigned int k = 1; k < seg; k++) {
+        XYZZ x = load_xyzz(&B[(unsigned long long)k * V0]);
+        xyzz_add(acc, x);
+    }
+    store_xyzz(&out[(set * V0 + v) * Q + q], acc);
+}
+// one CTA per bucket set, warp (a, j) = weighted sum of digit j of array a; thread 0 folds:
+//   result = T + W0 + 2^w0 * W1,  W_a = W_{a,1} * 32 + W_{a,0}
+__global__ void __launch_bounds__(128) k_msm_digit_final2(const XYZZ* dsums0, unsigned int nd0, const XYZZ* dsums1, unsigned int nd1,
+                                                          unsigned int w0, XYZZ* set_out) {
+    __shared__ XYZZ sw[4];
+    __shared__ XYZZ stotal;
+    const unsigned int set = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int a = wid >> 1, j = wid & 1;
+    const unsigned int nd = a ? nd1 : nd0;
+    const XYZZ* D = (a ? dsums1 : dsums0) + (unsigned long long)set * nd * 32;
+    XYZZ r = xyzz_identity();
+    if (j < nd) r = load_xyzz(&D[j * 32 + lane]);
+    for (int d = 1; d < 32; d <<= 1) {
+        XYZZ o = shfl_down_xyzz(r, d);
+        if (lane + d < 32) xyzz_add(r, o);
+    }
+    if (lane == 0) {
+        if (wid == 0) stotal = r;
+        r = xyzz_identity();
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        XYZZ o = shfl_down_xyzz(r, d);
+        if (lane + d < 32) xyzz_add(r, o);
+    }
+    if (lane == 0) sw[wid] = r;
+    __syncthreads();
+    if (threadIdx.x < 64 && lane == 0) {
+        // warp 0 lane 0 folds array 0, warp 1 lane 0 folds array 1 (in parallel), results back through shared memory
+        const unsigned int arr = threadIdx.x >> 5;
+        XYZZ w = sw[arr * 2 + 1];
+        for (int t = 0; t < 5; t++) w = xyzz_dbl(w);
+        XYZZ lo = sw[arr * 2];
+        xyzz_add(w, lo);
+        if (arr == 1)
+            for (unsigned int t = 0; t < w0; t++) w = xyzz_dbl(w);
+        sw[arr * 2] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XYZZ result = sw[0];
+        XYZZ w1 = sw[2];
+        xyzz_add(result, w1);
         XYZZ tot = stotal;
         xyzz_add(result, tot);
         store_xyzz(&set_out[set], result);
