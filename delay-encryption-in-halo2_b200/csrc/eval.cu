@@ -361,13 +361,12 @@ int de_pk_upload(de_domain* dom, const de_pk_desc* desc, de_pk** out) {
     return DE_OK;
 }
 
-int de_evaluate_h_dev(de_pk* pk, const de_fr* d_advice, const de_fr* d_instance, const de_challenges* ch, const de_fr* d_permz,
-                      const de_fr* d_lookup, size_t stride, de_fr* d_h_ext) {
+int de_pk_extend_dev(de_pk* pk, const de_fr* d_advice, const de_fr* d_instance, const de_fr* d_permz, const de_fr* d_lookup,
+                     size_t stride) {
     if (!pk) return DE_ERR_ARG;
     de_ctx* ctx = pk->ctx;
-    if (!ch || !d_h_ext) return fail(ctx, DE_ERR_ARG, "de_evaluate_h: null pointer");
     if ((pk->n_advice && !d_advice) || (pk->n_instance && !d_instance) || (pk->n_sets && !d_permz) || (pk->n_lookups && !d_lookup))
-        return fail(ctx, DE_ERR_ARG, "de_evaluate_h: missing polynomial block");
+        return fail(ctx, DE_ERR_ARG, "de_pk_extend_dev: missing polynomial block");
     DE_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t ext_n = pk->ext_n;
     Fr* w_adv = pk->work;
@@ -378,6 +377,19 @@ int de_evaluate_h_dev(de_pk* pk, const de_fr* d_advice, const de_fr* d_instance,
     if (pk->n_instance) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_instance, stride, (de_fr*)w_inst, ext_n, pk->n_instance));
     if (pk->n_sets) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_permz, stride, (de_fr*)w_permz, ext_n, pk->n_sets));
     if (pk->n_lookups) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_lookup, stride, (de_fr*)w_lookup, ext_n, 3 * (size_t)pk->n_lookups));
+    return DE_OK;
+}
+
+int de_evaluate_h_rows_dev(de_pk* pk, const de_challenges* ch, de_fr* d_h_ext) {
+    if (!pk) return DE_ERR_ARG;
+    de_ctx* ctx = pk->ctx;
+    if (!ch || !d_h_ext) return fail(ctx, DE_ERR_ARG, "de_evaluate_h: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t ext_n = pk->ext_n;
+    Fr* w_adv = pk->work;
+    Fr* w_inst = w_adv + (size_t)pk->n_advice * ext_n;
+    Fr* w_permz = w_inst + (size_t)pk->n_instance * ext_n;
+    Fr* w_lookup = w_permz + (size_t)pk->n_sets * ext_n;
     if (ch->n_challenges > pk->challenges_cap) {
         Fr* d = nullptr;
         DE_CUDA(ctx, cudaMalloc((void**)&d, sizeof(Fr) * ch->n_challenges));
@@ -417,6 +429,14 @@ int de_evaluate_h_dev(de_pk* pk, const de_fr* d_advice, const de_fr* d_instance,
     DE_TIMED(ctx, "k_eval_h", (double)ext_n, (k_eval_h<<<(unsigned int)((ext_n + 127) / 128), 128, 0, ctx->stream>>>(p)));
     DE_CHECK_LAUNCH(ctx);
     return DE_OK;
+}
+
+int de_evaluate_h_dev(de_pk* pk, const de_fr* d_advice, const de_fr* d_instance, const de_challenges* ch, const de_fr* d_permz,
+                      const de_fr* d_lookup, size_t stride, de_fr* d_h_ext) {
+    if (!pk) return DE_ERR_ARG;
+    if (!ch || !d_h_ext) return fail(pk->ctx, DE_ERR_ARG, "de_evaluate_h: null pointer");
+    DE_TRY(de_pk_extend_dev(pk, d_advice, d_instance, d_permz, d_lookup, stride));
+    return de_evaluate_h_rows_dev(pk, ch, d_h_ext);
 }
 
 int de_evaluate_h(de_pk* pk, const de_fr* const* advice_coeff, const de_fr* const* instance_coeff, const de_challenges* ch,

@@ -19,7 +19,7 @@ SYMBOLS = [
     "de_commit_batch", "de_commit_batch_dev", "de_ntt", "de_ntt_dev", "de_domain_create", "de_domain_free", "de_domain_info",
     "de_coeff_to_extended", "de_extended_to_coeff", "de_lagrange_to_coeff", "de_coeff_to_lagrange", "de_divide_by_vanishing",
     "de_coeff_to_extended_dev", "de_extended_to_coeff_dev", "de_lagrange_to_coeff_dev", "de_coeff_to_lagrange_dev",
-    "de_divide_by_vanishing_dev", "de_pk_upload", "de_pk_free", "de_evaluate_h", "de_evaluate_h_dev", "de_commit_range", "de_g1_sum", "de_g1_batch_normalize",
+    "de_divide_by_vanishing_dev", "de_pk_upload", "de_pk_free", "de_evaluate_h", "de_evaluate_h_dev", "de_pk_extend_dev", "de_evaluate_h_rows_dev", "de_commit_range", "de_g1_sum", "de_g1_batch_normalize",
 ]
 
 
@@ -81,6 +81,8 @@ def load():
     L.de_pk_free.argtypes = [P]
     L.de_evaluate_h.argtypes = [P, P, P, P, P, P, P]
     L.de_evaluate_h_dev.argtypes = [P, P, P, P, P, P, SZ, P]
+    L.de_pk_extend_dev.argtypes = [P, P, P, P, P, SZ]
+    L.de_evaluate_h_rows_dev.argtypes = [P, P, P]
     L.de_commit_range.argtypes = [P, I, P, SZ, SZ, P]
     L.de_g1_sum.argtypes = [P, P, SZ, P]
     L.de_g1_batch_normalize.argtypes = [P, P, SZ, P]

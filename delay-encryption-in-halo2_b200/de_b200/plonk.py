@@ -395,3 +395,15 @@ class ProvingKey:
 
         self.ctx.check(self.ctx.L.de_evaluate_h_dev(self.h, p(d_advice), p(d_instance), C.byref(ch), p(d_perm_z), p(d_lookup),
                                                     stride or self.domain.n, p(d_h_ext)))
+
+    def extend_dev(self, d_advice, d_instance, d_perm_z, d_lookup, stride=None):
+        """first half of evaluate_h: coeff_to_extended of every per-proof polynomial into the pk's HBM workspace"""
+        def p(t):
+            return C.c_void_p(t.data_ptr()) if t is not None else None
+
+        self.ctx.check(self.ctx.L.de_pk_extend_dev(self.h, p(d_advice), p(d_instance), p(d_perm_z), p(d_lookup), stride or self.domain.n))
+
+    def evaluate_h_rows_dev(self, y, beta, gamma, theta, d_h_ext, challenges=()):
+        """second half: the fused row kernel over the extended domain"""
+        ch, k1 = marshal_challenges(y, beta, gamma, theta, challenges)
+        self.ctx.check(self.ctx.L.de_evaluate_h_rows_dev(self.h, C.byref(ch), C.c_void_p(d_h_ext.data_ptr())))

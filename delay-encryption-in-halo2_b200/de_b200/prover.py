@@ -60,14 +60,29 @@ class Workload:
 
 
 class HotPathProver:
-    """Holds the per-(ParamsKZG, ProvingKey) state resident in HBM and runs the per-proof schedule."""
+    """Holds the per-(ParamsKZG, ProvingKey) state resident in HBM and runs the per-proof schedule.
+
+    Two CUDA streams per prover: the commitments run on the context's stream, the transforms and the quotient evaluator on
+    a second context / stream.  lagrange_to_coeff and coeff_to_extended of a column do not depend on any transcript
+    challenge, so they overlap the same rounds' MSMs; the row kernel of evaluate_h is issued only after the last
+    pre-`y` commitment has been read back (create_proof's order), and the h-piece commitments wait for the quotient."""
 
     def __init__(self, ctx, workload: Workload, g, g_lagrange, fixed_coeff, sigma_coeff):
+        import os
+        import torch
+        from . import Context
         self.ctx, self.w = ctx, workload
         s = workload.shape
         self.params = ParamsKZG(workload.k, g, g_lagrange, ctx)
-        self.domain = EvaluationDomain(s.degree(), workload.k, ctx)
-        self.pk = ProvingKey(self.domain, s, fixed_coeff, sigma_coeff)
+        # DE_PROVER_OVERLAP=0 puts the transforms on the commitments' stream (A/B switch for measurements)
+        self.overlap = os.environ.get("DE_PROVER_OVERLAP", "1") != "0"
+        self.stream_b = torch.cuda.Stream() if self.overlap else torch.cuda.current_stream()
+        self.ctx_b = Context(ctx.device)
+        self.ctx_b.set_stream(self.stream_b.cuda_stream)
+        with torch.cuda.stream(self.stream_b):
+            self.domain = EvaluationDomain(s.degree(), workload.k, self.ctx_b)
+            self.pk = ProvingKey(self.domain, s, fixed_coeff, sigma_coeff)
+        self.stream_b.synchronize()
         self._work = None
         self._h = None
 
@@ -80,22 +95,31 @@ class HotPathProver:
         y, beta, gamma, theta = challenges
         out = []
         P = self.params
+        stream_a = torch.cuda.current_stream()
+        if self._work is None or self._work.shape != cols.shape:
+            self._work = torch.empty_like(cols)
+            self._h = torch.empty((self.domain.extended_n, 4), dtype=cols.dtype, device=cols.device)
+        work = self._work
+        # stream B: every column to coefficient form and onto the extended coset (challenge-independent)
+        self.stream_b.wait_stream(stream_a)
+        with torch.cuda.stream(self.stream_b):
+            work.copy_(cols)
+            self.domain.lagrange_to_coeff_dev(work, batch=w.n_cols)
+            self.pk.extend_dev(work[o["advice"]:], work[o["instance"]:] if s.n_instance else None,
+                               work[o["permz"]:] if s.n_perm_sets else None, work[o["lookup_z"]:] if L else None)
+        # stream A: the commitment rounds, each read back before the next (the transcript needs them)
         out.append(P.commit_batch_dev(1, cols[o["advice"]:], n, s.n_advice))
         if L:
             out.append(P.commit_batch_dev(1, cols[o["lookup_a"]:], n, 2 * L))
         if s.n_perm_sets + L:
             out.append(P.commit_batch_dev(1, cols[o["permz"]:], n, s.n_perm_sets + L))
         out.append(P.commit_batch_dev(0, random_poly, n, 1))
-        if self._work is None or self._work.shape != cols.shape:
-            self._work = torch.empty_like(cols)
-            self._h = torch.empty((self.domain.extended_n, 4), dtype=cols.dtype, device=cols.device)
-        work = self._work
-        work.copy_(cols)
-        self.domain.lagrange_to_coeff_dev(work, batch=w.n_cols)
-        self.pk.evaluate_h_dev(work[o["advice"]:], work[o["instance"]:] if s.n_instance else None, y, beta, gamma, theta,
-                               work[o["permz"]:] if s.n_perm_sets else None, work[o["lookup_z"]:] if L else None, self._h)
-        self.domain.divide_by_vanishing_poly_dev(self._h)
-        self.domain.extended_to_coeff_dev(self._h)
+        # y is known from here on: row kernel, division by the vanishing polynomial, back to coefficients
+        with torch.cuda.stream(self.stream_b):
+            self.pk.evaluate_h_rows_dev(y, beta, gamma, theta, self._h)
+            self.domain.divide_by_vanishing_poly_dev(self._h)
+            self.domain.extended_to_coeff_dev(self._h)
+        stream_a.wait_stream(self.stream_b)
         out.append(P.commit_batch_dev(0, self._h, n, s.degree() - 1))
         out.append(P.commit_batch_dev(0, openings, n, N_OPENING_POINTS))
         return np.concatenate(out, axis=0)
@@ -112,3 +136,8 @@ class HotPathProver:
         self.pk.close()
         self.domain.close()
         self.params.close()
+        self.ctx_b.close()
+
+    @property
+    def launches(self) -> int:
+        return self.ctx.launches + self.ctx_b.launches

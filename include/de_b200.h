@@ -167,6 +167,12 @@ int de_evaluate_h(de_pk* pk, const de_fr* const* advice_coeff, const de_fr* cons
 int de_evaluate_h_dev(de_pk* pk, const de_fr* d_advice_coeff, const de_fr* d_instance_coeff, const de_challenges* ch,
                       const de_fr* d_perm_z_coeff, const de_fr* d_lookup_coeff, size_t stride, de_fr* d_h_ext);
 
+/* the two halves of de_evaluate_h_dev, so that a prover can run the coset transforms on a second stream while the same
+ * round's commitments are computed (they do not depend on any challenge), and only the row kernel after y is known */
+int de_pk_extend_dev(de_pk* pk, const de_fr* d_advice_coeff, const de_fr* d_instance_coeff, const de_fr* d_perm_z_coeff,
+                     const de_fr* d_lookup_coeff, size_t stride);
+int de_evaluate_h_rows_dev(de_pk* pk, const de_challenges* ch, de_fr* d_h_ext);
+
 /* ---- multi-GPU: MSM base-range sharding -------------------------------------------- */
 /* shard s of n_shards: commits scalars[lo..hi) against the matching base range of p and returns the partial sum;
  * the host (or de_g1_sum) adds the n_shards partial points. */
