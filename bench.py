@@ -71,7 +71,7 @@ def build_inputs():
     for i in range(o["permz"], w.n_cols):
         cols[i] = synth.uniform_fr(SEED + 100 + i, n)
     random_poly = synth.uniform_fr(SEED + 200, n).reshape(1, n, 4)
-    openings = synth.uniform_fr(SEED + 201, n * prover.N_OPENING_POINTS).reshape(prover.N_OPENING_POINTS, n, 4)
+    openings = synth.uniform_fr(SEED + 201, n * w.n_openings).reshape(w.n_openings, n, 4)
     fixed = [synth.uniform_fr(SEED + 300 + i, n) for i in range(shape.n_fixed)]
     sigma = [synth.uniform_fr(SEED + 400 + i, n) for i in range(len(shape.perm_columns))]
     g = synth.gen_bases(n, start=0)
@@ -168,7 +168,7 @@ def cpu_reference_step(inp, state):
     hc = dom.extended_to_coeff(h)
     for i in range(shape.degree() - 1):
         pts.append(orc.best_multiexp(np.ascontiguousarray(hc[i * n:(i + 1) * n]), inp["g"]))
-    for i in range(prover.N_OPENING_POINTS):
+    for i in range(w.n_openings):
         pts.append(orc.best_multiexp(inp["openings"][i], inp["g"]))
     return np.stack(pts)
 

@@ -19,7 +19,7 @@ import numpy as np
 from . import EvaluationDomain, ParamsKZG
 from .plonk import ConstraintSystemShape, ProvingKey
 
-N_OPENING_POINTS = 4  # distinct rotation sets of the reference circuits: x, omega x, omega^-1 x, omega^last x (GWC)
+N_OPENING_POINTS = 4  # upper bound; see Workload.n_openings
 
 
 @dataclass
@@ -42,9 +42,15 @@ class Workload:
         return s.n_advice + s.n_instance + s.n_perm_sets + 3 * self.n_lookups
 
     @property
+    def n_openings(self):
+        """distinct evaluation points of the GWC multi-open: x, omega x, omega^last x, plus omega^-1 x when lookups exist
+        (31 = 27 + 4 commitments with RangeChip, 17 = 14 + 3 without)"""
+        return 4 if self.n_lookups else 3
+
+    @property
     def n_msm(self):
         s = self.shape
-        return s.n_advice + 3 * self.n_lookups + s.n_perm_sets + 1 + (s.degree() - 1) + N_OPENING_POINTS
+        return s.n_advice + 3 * self.n_lookups + s.n_perm_sets + 1 + (s.degree() - 1) + self.n_openings
 
     def offsets(self):
         """row offsets inside the column block: advice | instance | perm z | lookup z | lookup a' | lookup s'"""
@@ -121,7 +127,7 @@ class HotPathProver:
             self.domain.extended_to_coeff_dev(self._h)
         stream_a.wait_stream(self.stream_b)
         out.append(P.commit_batch_dev(0, self._h, n, s.degree() - 1))
-        out.append(P.commit_batch_dev(0, openings, n, N_OPENING_POINTS))
+        out.append(P.commit_batch_dev(0, openings, n, w.n_openings))
         return np.concatenate(out, axis=0)
 
     # -- host inputs (pinned CPU tensors or numpy arrays of the same shapes): every step copies them to the device
