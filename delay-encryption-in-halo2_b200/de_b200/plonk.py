@@ -229,6 +229,38 @@ def main_gate_shape(with_range_lookups: bool) -> ConstraintSystemShape:
     return ConstraintSystemShape(n_fixed, 5, 1, [gate], lookups, perm)
 
 
+def collect_queries(shape: "ConstraintSystemShape"):
+    """cs.advice_queries / cs.fixed_queries / cs.instance_queries as (column, rotation) lists in first-query order:
+    enable_equality queries every permutation column at Rotation::cur() first (ConstraintSystem::query_any_index), then the
+    gates' and the lookups' expressions are walked left to right.  A Rust integration passes the real lists of its
+    ConstraintSystem instead (their order is fixed by the circuit's configure(), which is not restated here)."""
+    q = {"advice": [], "fixed": [], "instance": []}
+
+    def add(kind, col, rot):
+        if (col, rot) not in q[kind]:
+            q[kind].append((col, rot))
+
+    for kind, index in shape.perm_columns:
+        add({ADVICE: "advice", FIXED: "fixed", INSTANCE: "instance"}[kind], index, 0)
+
+    def walk(e):
+        t = e[0]
+        if t in q:
+            add(t, e[1], e[2])
+        elif t in ("neg", "scaled"):
+            walk(e[1])
+        elif t in ("sum", "prod"):
+            walk(e[1])
+            walk(e[2])
+
+    for g in shape.gates:
+        walk(g)
+    for inp, tab in shape.lookups:
+        for e in list(inp) + list(tab):
+            walk(e)
+    return q["advice"], q["fixed"], q["instance"]
+
+
 # ---- marshalling to the C ABI (include/de_b200.h) -----------------------------------------------------------------
 class _ValueSource(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("index", C.c_uint32), ("rotation", C.c_uint32)]

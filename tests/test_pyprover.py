@@ -1,0 +1,81 @@
+"""The restated create_proof / verify_proof (oracle/pyprover.py) and the pairing under it (oracle/pairing.py).
+
+Pins available without the Rust crate: a single proof of the MainGate + RangeChip shape is
+31 points + 58 scalars = 2848 bytes and one of the Poseidon-only shape 17 + 39 = 1792 bytes — the sizes the reference's
+README |pi| figures decompose into (/root/reference/benches/README.md:56-63,89-99) — and the proofs
+must be accepted by the verifier's final pairing check while any corrupted proof is rejected.
+"""
+import pytest
+
+import pairing
+import pyoracle as po
+import pyprover as pp
+from de_b200 import circuits, plonk
+
+
+def test_pairing_bilinear_and_nondegenerate():
+    assert pairing.g2_is_on_curve(pairing.G2_GEN)
+    assert pairing.g2_mul(pairing.G2_GEN, po.FR - 1) == (pairing.G2_GEN[0], pairing.f2_neg(pairing.G2_GEN[1]))
+    e1 = pairing.pairing(pairing.G2_GEN, po.G1_GEN)
+    assert e1 != pairing.Fq12.one() and e1 ** po.FR == pairing.Fq12.one()
+    a, b = 0x1234567, 0x7654321
+    e2 = pairing.pairing(pairing.g2_mul(pairing.G2_GEN, b), po.g1_mul(po.G1_GEN, a))
+    assert e2 == e1 ** (a * b)
+    assert pairing.pairing_check([(pairing.G2_GEN, po.g1_mul(po.G1_GEN, a)),
+                                  (pairing.g2_mul(pairing.G2_GEN, a), po.g1_neg(po.G1_GEN))])
+
+
+def test_point_encoding_round_trip():
+    for i in (1, 2, 3, 0xDEADBEEF):
+        p = po.g1_mul(po.G1_GEN, i)
+        assert pp.g1_from_bytes(pp.g1_to_bytes(p)) == p
+        assert pp.g1_from_bytes(pp.g1_to_bytes(po.g1_neg(p))) == po.g1_neg(p)
+    assert pp.g1_to_bytes(None) == bytes(32) and pp.g1_from_bytes(bytes(32)) is None
+
+
+def test_permute_expression_pair_rule():
+    inp = [5, 3, 5, 0, 0, 3, 5, 9]
+    tab = [0, 3, 5, 9, 7, 7, 1, 2]
+    a, s = pp.permute_expression_pair(inp, tab, 8)
+    assert a == sorted(inp)
+    assert sorted(s) == sorted(tab)
+    for i in range(8):
+        assert a[i] == s[i] or (i > 0 and a[i] == a[i - 1])
+    # leftover table values (ascending: 1, 2, 7, 7) fill the repeated rows from the LAST repeated row backwards
+    assert s == [0, 7, 3, 7, 5, 2, 1, 9]
+    with pytest.raises(ValueError):
+        pp.permute_expression_pair([4], [0], 1)
+
+
+def test_kate_division_is_exact_quotient():
+    rng = po.Xoshiro(5)
+    a = [rng.uniform_fr() for _ in range(33)]
+    b = rng.uniform_fr()
+    a[0] = (a[0] - po.eval_poly(a, b)) % po.FR  # make b a root
+    q = pp.kate_division(a, b)
+    z = rng.uniform_fr()
+    assert po.eval_poly(q, z) * (z - b) % po.FR == po.eval_poly(a, z)
+
+
+@pytest.mark.parametrize("with_lookups,k,used,size", [(False, 5, 20, 1792), (True, 6, 40, 2848)])
+def test_create_proof_verifies(with_lookups, k, used, size):
+    asg = circuits.satisfied_assignment(with_lookups, k, 0xDE00 + k, used)
+    circuits.check_assignment(asg)
+    params = pp.setup(k, 0x1234567)
+    q = pp.Queries(*plonk.collect_queries(asg.shape))
+    assert len(q.advice) == 6 and len(q.fixed) == asg.shape.n_fixed and q.instance == [(0, 0)]
+    pk = pp.keygen(params, asg.shape, q, asg.fixed, asg.copies, 0xABCDEF)
+    proof = pp.create_proof(params, pk, asg.advice, asg.instances, po.Xoshiro(99).uniform_fr)
+    assert len(proof) == size
+    assert pp.verify_proof(params, pk.vk, asg.instances, proof)
+    bad = bytearray(proof)
+    bad[-40] ^= 1  # one of the opening evaluations... any bit flip must be rejected
+    assert not pp.verify_proof(params, pk.vk, asg.instances, bytes(bad))
+    # an unsatisfied witness gives a proof the verifier rejects
+    adv = [list(c) for c in asg.advice]
+    adv[0][1] = (adv[0][1] + 1) % po.FR
+    try:
+        proof2 = pp.create_proof(params, pk, adv, asg.instances, po.Xoshiro(99).uniform_fr)
+    except ValueError:
+        return  # a broken lookup input is caught by permute_expression_pair already
+    assert not pp.verify_proof(params, pk.vk, asg.instances, proof2)
