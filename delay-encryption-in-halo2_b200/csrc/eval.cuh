@@ -1,0 +1,169 @@
+// eval.cuh — pieces of the quotient evaluator shared with the prover (prover.cu): the device image of a compiled
+// GraphEvaluator, its interpreter, and the ProvingKey object (see eval.cu for the reference mapping).
+#pragma once
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+struct de_domain_view {  // layout prefix of de_domain (ntt.cu) that this unit reads
+    de_ctx* ctx;
+    uint32_t j, k, ek;
+    size_t n, ext_n, qdeg;
+    de_fr omega, omega_inv, ext_omega, ext_omega_inv;
+};
+
+namespace de {
+
+#define DE_MAX_INTER 96
+#define DE_MAX_ROT 16
+
+struct DevSrc { uint32_t kind, index, rot; };
+struct DevCalc { uint32_t op; DevSrc a, b; uint32_t hfirst, hlen, target; };
+struct DevGraph {
+    const Fr* constants;
+    const int* rotations;
+    const DevCalc* calcs;
+    const DevSrc* hparts;
+    uint32_t n_rot, n_calcs;
+};
+
+struct EvalParams {
+    uint32_t ext_mask, rot_scale;
+    unsigned long long ext_n;
+    // resident pk cosets (column-major, ext_n apart)
+    const Fr* fixed; const Fr* sigma; const Fr* l0; const Fr* l_last; const Fr* l_active; const Fr* omega_pows;
+    // per-proof cosets
+    const Fr* advice; const Fr* instance; const Fr* permz; const Fr* lookup;
+    const Fr* challenges;
+    Fr y, beta, gamma, theta, delta, delta_start;  // delta_start holds ZETA (Montgomery)
+    DevGraph gates;
+    const DevGraph* lookups;
+    uint32_t n_lookups;
+    // permutation
+    uint32_t n_perm_cols, chunk_len, n_sets;
+    int last_rotation;
+    const uint32_t* perm_kind; const uint32_t* perm_index;
+    Fr* out;
+};
+
+struct RowCtx {
+    const EvalParams* p;
+    unsigned int idx;
+    unsigned int rot_idx[DE_MAX_ROT];
+    Fr inter[DE_MAX_INTER];
+    Fr prev;
+};
+
+__device__ __forceinline__ unsigned int rot_index(unsigned int idx, int rot, unsigned int rot_scale, unsigned int mask) {
+    return (unsigned int)((int)idx + rot * (int)rot_scale) & mask;
+}
+
+__device__ __forceinline__ Fr fetch(const RowCtx& c, const DevGraph& g, const DevSrc& s) {
+    const EvalParams& p = *c.p;
+    switch (s.kind) {
+        case DE_VAL_CONSTANT: return load(&g.constants[s.index]);
+        case DE_VAL_INTERMEDIATE: return c.inter[s.index];
+        case DE_VAL_FIXED: return load(&p.fixed[(unsigned long long)s.index * p.ext_n + c.rot_idx[s.rot]]);
+        case DE_VAL_ADVICE: return load(&p.advice[(unsigned long long)s.index * p.ext_n + c.rot_idx[s.rot]]);
+        case DE_VAL_INSTANCE: return load(&p.instance[(unsigned long long)s.index * p.ext_n + c.rot_idx[s.rot]]);
+        case DE_VAL_CHALLENGE: return load(&p.challenges[s.index]);
+        case DE_VAL_BETA: return p.beta;
+        case DE_VAL_GAMMA: return p.gamma;
+        case DE_VAL_THETA: return p.theta;
+        case DE_VAL_Y: return p.y;
+        default: return c.prev;  // DE_VAL_PREVIOUS
+    }
+}
+
+__device__ inline Fr run_graph(RowCtx& c, const DevGraph& g) {
+    const EvalParams& p = *c.p;
+    for (uint32_t r = 0; r < g.n_rot; r++) c.rot_idx[r] = rot_index(c.idx, g.rotations[r], p.rot_scale, p.ext_mask);
+    Fr last = Fr::zero();
+    for (uint32_t i = 0; i < g.n_calcs; i++) {
+        const DevCalc cc = g.calcs[i];
+        Fr a = fetch(c, g, cc.a);
+        Fr r;
+        switch (cc.op) {
+            case DE_CALC_ADD: r = add(a, fetch(c, g, cc.b)); break;
+            case DE_CALC_SUB: r = sub(a, fetch(c, g, cc.b)); break;
+            case DE_CALC_MUL: r = mul(a, fetch(c, g, cc.b)); break;
+            case DE_CALC_SQUARE: r = sqr(a); break;
+            case DE_CALC_DOUBLE: r = dbl(a); break;
+            case DE_CALC_NEGATE: r = neg(a); break;
+            case DE_CALC_HORNER: {
+                Fr f = fetch(c, g, cc.b);
+                r = a;
+                for (uint32_t k = 0; k < cc.hlen; k++) r = add(mul(r, f), fetch(c, g, g.hparts[cc.hfirst + k]));
+                break;
+            }
+            default: r = a; break;  // DE_CALC_STORE
+        }
+        c.inter[cc.target] = r;
+        last = r;
+    }
+    return last;
+}
+
+__device__ __forceinline__ const Fr* perm_column(const EvalParams& p, uint32_t col) {
+    const uint32_t kind = p.perm_kind[col], index = p.perm_index[col];
+    const Fr* base = kind == DE_VAL_ADVICE ? p.advice : (kind == DE_VAL_FIXED ? p.fixed : p.instance);
+    return base + (unsigned long long)index * p.ext_n;
+}
+
+}  // namespace de
+
+using namespace de;  // internal header of libde_b200.so
+
+struct de_pk {
+    de_domain* dom;
+    de_ctx* ctx;
+    uint32_t n_fixed, n_advice, n_instance, n_perm_cols, chunk_len, n_sets, n_lookups, blinding;
+    size_t n, ext_n;
+    uint32_t k, ek;
+    Fr* resident;  // fixed | sigma | l0 | l_last | l_active | omega_pows, ext_n apart
+    Fr* coeff;     // fixed | sigma polynomials in coefficient form, n apart (the prover opens and evaluates them)
+    Fr* work;      // advice | instance | permz | lookup (3 per lookup) cosets, ext_n apart
+    Fr* d_challenges;
+    uint32_t challenges_cap;
+    uint32_t *d_perm_kind, *d_perm_index;
+    DevGraph gates;
+    DevGraph* d_lookups;
+    std::vector<void*> allocs;
+    Fr delta, zeta;
+};
+
+inline int upload_graph(de_ctx* ctx, const de_graph& g, DevGraph* out, std::vector<void*>& allocs) {
+    if (g.n_intermediates > DE_MAX_INTER) return fail(ctx, DE_ERR_UNSUPPORTED, "evaluator: too many intermediates in a graph");
+    if (g.n_rotations > DE_MAX_ROT) return fail(ctx, DE_ERR_UNSUPPORTED, "evaluator: too many distinct rotations in a graph");
+    std::vector<DevCalc> calcs(g.n_calcs);
+    auto conv = [](const de_value_source& s) { return DevSrc{s.kind, s.index, s.rotation}; };
+    for (uint32_t i = 0; i < g.n_calcs; i++) {
+        const de_calculation& c = g.calcs[i];
+        if (c.target >= g.n_intermediates) return fail(ctx, DE_ERR_ARG, "evaluator: calculation target out of range");
+        if (c.op > DE_CALC_STORE) return fail(ctx, DE_ERR_ARG, "evaluator: unknown calculation");
+        if (c.op == DE_CALC_HORNER && (uint64_t)c.horner_first + c.horner_len > g.n_horner_parts)
+            return fail(ctx, DE_ERR_ARG, "evaluator: horner parts out of range");
+        calcs[i] = DevCalc{c.op, conv(c.a), conv(c.b), c.horner_first, c.horner_len, c.target};
+    }
+    std::vector<DevSrc> parts(g.n_horner_parts);
+    for (uint32_t i = 0; i < g.n_horner_parts; i++) parts[i] = conv(g.horner_parts[i]);
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+        void* d = nullptr;
+        DE_CUDA(ctx, cudaMalloc(&d, bytes ? bytes : 16));
+        allocs.push_back(d);
+        if (bytes) DE_CUDA(ctx, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        *dst = d;
+        return DE_OK;
+    };
+    DE_TRY(up(g.constants, sizeof(Fr) * g.n_constants, (const void**)&out->constants));
+    DE_TRY(up(g.rotations, sizeof(int) * g.n_rotations, (const void**)&out->rotations));
+    DE_TRY(up(calcs.data(), sizeof(DevCalc) * calcs.size(), (const void**)&out->calcs));
+    DE_TRY(up(parts.data(), sizeof(DevSrc) * parts.size(), (const void**)&out->hparts));
+    out->n_rot = g.n_rotations;
+    out->n_calcs = g.n_calcs;
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    return DE_OK;
+}
+

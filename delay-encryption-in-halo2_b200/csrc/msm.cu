@@ -60,11 +60,12 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 // d_scalars: `count` polynomials of n Montgomery scalars, `stride` elements apart.  d_tables: cfg.ntables base tables,
 // table_stride elements apart.  Writes `count` Jacobian points to host_out.
+// out_mode 0: Jacobian points (de_g1, Montgomery); 1: canonical affine x || y, 64 bytes per point (transcript form)
 static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, size_t count, const Affine* d_tables,
-                    size_t table_stride, size_t base_offset, const MsmCfg& cfg, de_g1* host_out) {
+                    size_t table_stride, size_t base_offset, const MsmCfg& cfg, void* host_out, int out_mode = 0) {
     if (count == 0) return DE_OK;
     if (n == 0) {
-        memset(host_out, 0, sizeof(de_g1) * count);
+        memset(host_out, 0, (out_mode ? sizeof(de_g1_affine) : sizeof(de_g1)) * count);
         return DE_OK;
     }
     if ((unsigned long long)cfg.ntables * table_stride >= (1ull << 31)) return fail(ctx, DE_ERR_UNSUPPORTED, "msm: base table exceeds 2^31 points");
@@ -115,7 +116,7 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_WS(ctx, red, XYZZ, WS_MSM_MISC, sizeof(XYZZ) * ((size_t)ndigits * 32 * nsets_total + nsets_total));
     XYZZ* dsums = red;
     XYZZ* set_out = red + (size_t)ndigits * 32 * nsets_total;
-    DE_WS(ctx, d_out, Jac, WS_MSM_OUT, sizeof(Jac) * count);
+    DE_WS(ctx, d_out, Jac, WS_MSM_OUT, (sizeof(Jac) + sizeof(Affine)) * count);
     // scratch of the two-digit reduction: two ping-pong partial buffers, D0 / D1 and their digit sums
     DE_WS(ctx, red2, XYZZ, WS_MSM_RED, sizeof(XYZZ) * ((size_t)nsets_total * sh.NB + 4096 + (size_t)nsets_total * 4 * 2048));
 
@@ -207,7 +208,14 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     }
     k_msm_combine<<<(unsigned int)count, 32, 0, st>>>(set_out, sh.nsets, sh.c, d_out);
     DE_CHECK_LAUNCH(ctx);
-    DE_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));
+    if (out_mode == 1) {
+        Affine* d_aff = (Affine*)(d_out + count);
+        k_g1_normalize_canonical<<<(unsigned int)((count + 31) / 32), 32, 0, st>>>(d_out, (unsigned int)count, d_aff);
+        DE_CHECK_LAUNCH(ctx);
+        DE_CUDA(ctx, cudaMemcpyAsync(host_out, d_aff, sizeof(Affine) * count, cudaMemcpyDeviceToHost, st));
+    } else {
+        DE_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));
+    }
     unsigned int total_entries = 0;
     if (ctx->timing) DE_CUDA(ctx, cudaMemcpyAsync(&total_entries, &scalars_u32[0], sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     DE_CUDA(ctx, cudaStreamSynchronize(st));
@@ -331,6 +339,16 @@ int de_commit_batch_dev(de_params* p, int basis, const de_fr* d_scalars, size_t 
     return msm_core(ctx, (const Fr*)d_scalars, stride, n, count, p->tables[basis], p->n, 0, p->cfg, out);
 }
 
+int de_commit_batch_canonical_dev(de_params* p, int basis, const de_fr* d_scalars, size_t stride, size_t n, size_t count, uint8_t* out_xy) {
+    if (!p) return DE_ERR_ARG;
+    de_ctx* ctx = p->ctx;
+    if (basis < 0 || basis > 1 || !p->tables[basis]) return fail(ctx, DE_ERR_ARG, "de_commit: basis not uploaded");
+    if (n > p->n) return fail(ctx, DE_ERR_ARG, "de_commit: polynomial longer than the SRS (n > 2^k)");
+    if (!out_xy || (n && count && !d_scalars)) return fail(ctx, DE_ERR_ARG, "de_commit: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return msm_core(ctx, (const Fr*)d_scalars, stride, n, count, p->tables[basis], p->n, 0, p->cfg, out_xy, 1);
+}
+
 int de_commit_batch(de_params* p, int basis, const de_fr* const* scalars, size_t n, size_t count, de_g1* out) {
     if (!p) return DE_ERR_ARG;
     de_ctx* ctx = p->ctx;
@@ -405,3 +423,12 @@ int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_
 }
 
 }  // extern "C"
+
+// internal entry points for prover.cu
+namespace de {
+int commit_canonical_dev(de_params* p, int basis, const Fr* d_scalars, size_t stride, size_t n, size_t count, uint8_t* out_xy) {
+    return de_commit_batch_canonical_dev(p, basis, (const de_fr*)d_scalars, stride, n, count, out_xy);
+}
+de_ctx* params_ctx(de_params* p) { return p->ctx; }
+size_t params_n(de_params* p) { return p->n; }
+}  // namespace de

@@ -1,0 +1,225 @@
+// poly.cu — opening-phase polynomial kernels (the callers' side of the hot path):
+//   halo2_proofs::arithmetic::eval_polynomial(poly, point)   -> de_eval_polynomial      (k_eval_polynomial)
+//   halo2_proofs::arithmetic::kate_division(a, b)            -> de_kate_division        (k_kate_*)
+// create_proof evaluates every queried polynomial at x * omega^rot (58 Horner evaluations for the RSA shape,
+// benches/delay_enc.rs:123 -> plonk::prover) and the GWC multi-open divides the combined polynomial of each point by
+// (X - point) before committing to the quotient.  prover.cu drives the batched device-side entry points declared in
+// poly.cuh; the C ABI functions here are the single-polynomial parity surface.
+#include "poly.cuh"
+
+#include "transcript.hpp"
+
+namespace de {
+
+#define DE_POLY_THREADS 256
+#define DE_KATE_CHUNK 32
+#define DE_KATE_SCAN 512
+
+// tree sum of Fr values in shared memory (adds only); result in sm[0]
+__device__ __forceinline__ void block_sum(Fr* sm, int tid, int nthreads) {
+    for (int d = nthreads >> 1; d >= 1; d >>= 1) {
+        __syncthreads();
+        if (tid < d) store(&sm[tid], add(load(&sm[tid]), load(&sm[tid + d])));
+    }
+    __syncthreads();
+}
+
+// one CTA per (polynomial, point) pair: thread t Horner-evaluates its contiguous chunk, scales by x^(t * chunk), tree sum.
+// polys[e] points at n coefficients; the result is written in Montgomery form and, when out_canonical != nullptr, also as
+// the canonical integer (Fr::to_repr), which is what the transcript hashes.
+__global__ void __launch_bounds__(DE_POLY_THREADS) k_eval_polynomial(const Fr* const* polys, unsigned long long n, const unsigned int* point_index,
+                                                                     const Fr* points, Fr* out, Fr* out_canonical) {
+    __shared__ Fr sm[DE_POLY_THREADS];
+    const int tid = threadIdx.x;
+    const Fr* p = polys[blockIdx.x];
+    const Fr x = load(&points[point_index ? point_index[blockIdx.x] : blockIdx.x]);
+    const unsigned long long chunk = (n + DE_POLY_THREADS - 1) / DE_POLY_THREADS;
+    const unsigned long long lo = (unsigned long long)tid * chunk;
+    unsigned long long hi = lo + chunk;
+    if (hi > n) hi = n;
+    Fr acc = Fr::zero();
+    for (unsigned long long i = hi; i > lo; i--) acc = add(mul(acc, x), load(&p[i - 1]));
+    if (lo < n && lo > 0) acc = mul(acc, pow_u64(x, lo));
+    store(&sm[tid], (lo < n) ? acc : Fr::zero());
+    block_sum(sm, tid, DE_POLY_THREADS);
+    if (tid == 0) {
+        const Fr r = load(&sm[0]);
+        if (out) store(&out[blockIdx.x], r);
+        if (out_canonical) store(&out_canonical[blockIdx.x], from_mont(r));
+    }
+}
+
+// kate_division: with t_i = q[i-1] the quotient satisfies t_i = a[i] + b * t_(i+1), t_n = 0.
+// pass 1: per chunk c = [lo, hi) of a: V_c = sum_{i in chunk} a[i] * b^(i - lo), so that t_lo = V_c + b^(hi-lo) * t_hi.
+// grid.y = polynomial of the batch; b per polynomial.
+__global__ void k_kate_chunk_values(const Fr* const* as, unsigned long long n, const Fr* bs, Fr* vals, unsigned long long nchunks) {
+    unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const Fr* a = as[blockIdx.y];
+    const Fr b = load(&bs[blockIdx.y]);
+    unsigned long long lo = c * DE_KATE_CHUNK, hi = lo + DE_KATE_CHUNK;
+    if (hi > n) hi = n;
+    Fr acc = Fr::zero();
+    for (unsigned long long i = hi; i > lo; i--) acc = add(mul(acc, b), load(&a[i - 1]));
+    store(&vals[blockIdx.y * nchunks + c], acc);
+}
+// pass 2 (one CTA per polynomial): carry[c] = t_(hi_c) = V_(c+1) + b^CHUNK * carry[c+1], carry[last] = 0: a suffix scan of
+// affine maps (Hillis-Steele), DE_KATE_SCAN chunks per sweep from the top of the polynomial down.
+__global__ void __launch_bounds__(DE_KATE_SCAN) k_kate_carries(const Fr* vals, unsigned long long nchunks, const Fr* b_pow_chunks, Fr* carries) {
+    __shared__ Fr s_add[DE_KATE_SCAN];
+    __shared__ Fr s_mul[DE_KATE_SCAN];
+    __shared__ Fr s_carry;
+    const int tid = threadIdx.x;
+    vals += blockIdx.x * nchunks;
+    carries += blockIdx.x * nchunks;
+    const Fr b_pow_chunk = load(&b_pow_chunks[blockIdx.x]);
+    if (tid == 0) store(&s_carry, Fr::zero());
+    __syncthreads();
+    for (long long top = (long long)nchunks; top > 0; top -= DE_KATE_SCAN) {
+        // element t of this sweep is chunk c = top - 1 - t (descending) with the map f_c(y) = V_(c+1) + m * y applied to the
+        // carry of chunk c + 1
+        const long long c = top - 1 - tid;
+        const bool live = c >= 0;
+        Fr addend = Fr::zero(), mult = Fr::one();
+        if (live) {
+            const bool has_above = c + 1 < (long long)nchunks;
+            addend = has_above ? load(&vals[c + 1]) : Fr::zero();
+            mult = has_above ? b_pow_chunk : Fr::zero();
+        }
+        store(&s_add[tid], addend);
+        store(&s_mul[tid], mult);
+        __syncthreads();
+        // inclusive scan: afterwards (s_mul[t], s_add[t]) maps the carry ENTERING element 0 of the sweep to the carry of element t
+        for (int d = 1; d < DE_KATE_SCAN; d <<= 1) {
+            Fr pa = Fr::zero(), pm = Fr::one();
+            const bool has = tid >= d;
+            if (has) {
+                pa = load(&s_add[tid - d]);
+                pm = load(&s_mul[tid - d]);
+            }
+            __syncthreads();
+            if (has) {
+                // f_t o f_(t-d): y -> add_t + mul_t * (add_p + mul_p * y)
+                const Fr mt = load(&s_mul[tid]);
+                store(&s_add[tid], add(load(&s_add[tid]), mul(mt, pa)));
+                store(&s_mul[tid], mul(mt, pm));
+            }
+            __syncthreads();
+        }
+        const Fr carry_in = load(&s_carry);
+        const Fr mine = add(load(&s_add[tid]), mul(load(&s_mul[tid]), carry_in));
+        if (live) store(&carries[c], mine);
+        __syncthreads();
+        // the carry entering the next sweep is the carry of the lowest chunk of this one
+        const long long last_t = (top >= DE_KATE_SCAN) ? DE_KATE_SCAN - 1 : top - 1;
+        if (tid == last_t) store(&s_carry, mine);
+        __syncthreads();
+    }
+}
+// pass 3: per chunk, run the recurrence downwards from the incoming carry and write q (n - 1 coefficients; q[n-1] := 0 is
+// also written so that the quotient can be committed as an n-coefficient polynomial)
+__global__ void k_kate_write(const Fr* const* as, unsigned long long n, const Fr* bs, const Fr* carries, Fr* q, unsigned long long q_stride,
+                             unsigned long long nchunks) {
+    unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const Fr* a = as[blockIdx.y];
+    const Fr b = load(&bs[blockIdx.y]);
+    Fr* qq = q + blockIdx.y * q_stride;
+    unsigned long long lo = c * DE_KATE_CHUNK, hi = lo + DE_KATE_CHUNK;
+    if (hi > n) hi = n;
+    Fr cur = load(&carries[blockIdx.y * nchunks + c]);  // = t_hi = q[hi - 1] (zero for the top chunk)
+    for (unsigned long long i = hi; i > lo; i--) {
+        store(&qq[i - 1], cur);
+        cur = add(load(&a[i - 1]), mul(cur, b));
+    }
+}
+
+int eval_polynomials_dev(de_ctx* ctx, const Fr* const* d_polys, size_t n, const unsigned int* d_point_index, const Fr* d_points, size_t count,
+                         Fr* d_out, Fr* d_out_canonical) {
+    if (count == 0) return DE_OK;
+    k_eval_polynomial<<<(unsigned int)count, DE_POLY_THREADS, 0, ctx->stream>>>(d_polys, n, d_point_index, d_points, d_out, d_out_canonical);
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
+size_t kate_scratch_elems(size_t n, size_t count) {
+    const size_t nchunks = (n + DE_KATE_CHUNK - 1) / DE_KATE_CHUNK;
+    return 2 * nchunks * count + 2 * count;
+}
+
+// d_as[i]: n coefficients; host_bs[i]: the divisor points (Montgomery); d_q: count quotients, q_stride apart, n entries each
+// (the top one zero); d_scratch: kate_scratch_elems(n, count) elements.
+int kate_division_dev(de_ctx* ctx, const Fr* const* d_as, size_t n, const de_fr* host_bs, size_t count, Fr* d_q, size_t q_stride,
+                      Fr* d_scratch) {
+    if (count == 0) return DE_OK;
+    if (count > 64) return fail(ctx, DE_ERR_UNSUPPORTED, "kate_division: batch larger than 64");
+    const size_t nchunks = (n + DE_KATE_CHUNK - 1) / DE_KATE_CHUNK;
+    Fr* vals = d_scratch;
+    Fr* carries = vals + nchunks * count;
+    Fr* d_b = carries + nchunks * count;
+    Fr* d_bpow = d_b + count;
+    Fr hb[128];
+    for (size_t i = 0; i < count; i++) {
+        host::HFr b;
+        memcpy(b.l, host_bs[i].l, 32);
+        host::HFr bp = host::fr_pow(b, DE_KATE_CHUNK);
+        de_fr t;
+        memcpy(t.l, bp.l, 32);
+        hb[i] = fr_from_host(host_bs[i]);
+        hb[count + i] = fr_from_host(t);
+    }
+    // small pageable copy: staged by the runtime before the call returns, so the stack buffer may go out of scope
+    DE_CUDA(ctx, cudaMemcpyAsync(d_b, hb, sizeof(Fr) * 2 * count, cudaMemcpyHostToDevice, ctx->stream));
+    const dim3 grid((unsigned int)((nchunks + 127) / 128), (unsigned int)count);
+    k_kate_chunk_values<<<grid, 128, 0, ctx->stream>>>(d_as, n, d_b, vals, nchunks);
+    DE_CHECK_LAUNCH(ctx);
+    k_kate_carries<<<(unsigned int)count, DE_KATE_SCAN, 0, ctx->stream>>>(vals, nchunks, d_bpow, carries);
+    DE_CHECK_LAUNCH(ctx);
+    k_kate_write<<<grid, 128, 0, ctx->stream>>>(d_as, n, d_b, carries, d_q, q_stride, nchunks);
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
+}  // namespace de
+
+using namespace de;
+
+extern "C" {
+
+int de_eval_polynomial(de_ctx* ctx, const de_fr* poly, size_t n, const de_fr* point, de_fr* out) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!point || !out || (n && !poly)) return fail(ctx, DE_ERR_ARG, "de_eval_polynomial: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DE_WS(ctx, d, Fr, WS_IO_A, sizeof(Fr) * (n + 4) + 64);
+    Fr* d_point = d + n;
+    Fr* d_out = d + n + 1;
+    const Fr** d_ptr = (const Fr**)(d + n + 2);
+    const Fr* hp = d;
+    if (n) DE_CUDA(ctx, cudaMemcpyAsync(d, poly, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaMemcpyAsync(d_point, point, sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaMemcpyAsync((void*)d_ptr, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+    DE_TRY(eval_polynomials_dev(ctx, d_ptr, n, nullptr, d_point, 1, d_out, nullptr));
+    DE_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+int de_kate_division(de_ctx* ctx, const de_fr* a, size_t n, const de_fr* b, de_fr* q) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!a || !b || !q) return fail(ctx, DE_ERR_ARG, "de_kate_division: null pointer");
+    if (n < 2) return fail(ctx, DE_ERR_ARG, "de_kate_division: polynomial needs at least 2 coefficients");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DE_WS(ctx, d, Fr, WS_IO_A, sizeof(Fr) * (2 * n + kate_scratch_elems(n, 1) + 2));
+    Fr* d_q = d + n;
+    Fr* scratch = d_q + n;
+    const Fr** d_ptr = (const Fr**)(scratch + kate_scratch_elems(n, 1));
+    const Fr* hp = d;
+    DE_CUDA(ctx, cudaMemcpyAsync(d, a, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaMemcpyAsync((void*)d_ptr, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+    DE_TRY(kate_division_dev(ctx, d_ptr, n, b, 1, d_q, n, scratch));
+    DE_CUDA(ctx, cudaMemcpyAsync(q, d_q, sizeof(Fr) * (n - 1), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+}  // extern "C"

@@ -132,6 +132,21 @@ class Context:
         omega = _np(omega)
         self.check(self.L.de_ntt_dev(self.h, _ptr(d_a), _ptr(omega), log_n, batch, stride or (1 << log_n)))
 
+    def eval_polynomial(self, poly, point):
+        """arithmetic::eval_polynomial: poly (n, 4) coefficients, point (4,) -> (4,) (all Montgomery)"""
+        poly, point = _np(poly), _np(point)
+        out = np.zeros(4, dtype=np.uint64)
+        self.check(self.L.de_eval_polynomial(self.h, _ptr(poly), poly.size // 4, _ptr(point), _ptr(out)))
+        return out
+
+    def kate_division(self, a, b):
+        """arithmetic::kate_division: quotient of a(X) by (X - b), len(a) - 1 coefficients"""
+        a, b = _np(a), _np(b)
+        n = a.size // 4
+        out = np.zeros((max(n - 1, 0), 4), dtype=np.uint64)
+        self.check(self.L.de_kate_division(self.h, _ptr(a), n, _ptr(b), _ptr(out)))
+        return out
+
     def batch_normalize(self, points):
         """group::Curve::batch_normalize: (count, 12) Jacobian -> (count, 8) affine"""
         points = _np(points).reshape(-1, 12)
@@ -290,6 +305,13 @@ class ParamsKZG:
     def commit_batch_dev(self, basis: int, d_scalars, n: int, count: int, stride: int | None = None):
         out = np.zeros((count, 12), dtype=np.uint64)
         self.ctx.check(self.ctx.L.de_commit_batch_dev(self.h, basis, _ptr(d_scalars), stride or n, n, count, _ptr(out)))
+        return out
+
+    def commit_batch_canonical_dev(self, basis: int, d_scalars, n: int, count: int, stride: int | None = None):
+        """commitments as (count, 64) bytes: canonical little-endian x || y (the transcript's encoding)"""
+        out = np.zeros((count, 64), dtype=np.uint8)
+        self.ctx.check(self.ctx.L.de_commit_batch_canonical_dev(self.h, basis, _ptr(d_scalars), stride or n, n, count,
+                                                                out.ctypes.data_as(C.c_void_p)))
         return out
 
     def commit_range(self, basis: int, poly, lo: int, hi: int):

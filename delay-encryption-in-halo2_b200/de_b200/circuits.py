@@ -14,7 +14,7 @@ properties whose every constraint holds:
     four composition lookups find (tag, sub-limb) in the fixed table; overflow rows look e up under the overflow tag;
   * copy constraints between cells holding equal values (cycles of length 2 and 3) across all five advice columns.
 
-Everything is seeded and pure Python integers (canonical field values); nothing here touches the GPU or the oracle.
+Everything is seeded and pure Python integers (canonical field values); nothing here touches the GPU or any checker code.
 """
 from __future__ import annotations
 

@@ -179,6 +179,15 @@ def compile_lookup(input_exprs: Sequence, table_exprs: Sequence) -> GraphEvaluat
     return g
 
 
+def compile_compress(exprs: Sequence) -> GraphEvaluator:
+    """lookup::prover::commit_permuted's compress_expressions: fold(0, |acc, e| acc * theta + e) over the argument's
+    expressions, as a graph whose result is the compressed value of a row."""
+    g = GraphEvaluator()
+    parts = [g.add_expression(e) for e in exprs]
+    g.add_calculation(HORNER, (CONSTANT, 0, 0), (THETA, 0, 0), parts)
+    return g
+
+
 @dataclass
 class ConstraintSystemShape:
     n_fixed: int
@@ -366,6 +375,12 @@ def marshal_pk_desc(shape: ConstraintSystemShape, fixed_coeff: Sequence[np.ndarr
     return d, keep
 
 
+class _ProverDesc(C.Structure):
+    _fields_ = [("n_advice_queries", C.c_uint32), ("advice_query_column", C.c_void_p), ("advice_query_rotation", C.c_void_p),
+                ("n_fixed_queries", C.c_uint32), ("fixed_query_column", C.c_void_p), ("fixed_query_rotation", C.c_void_p),
+                ("lookup_input_graphs", C.c_void_p), ("lookup_table_graphs", C.c_void_p), ("transcript_repr", _Fr)]
+
+
 def marshal_challenges(y: int, beta: int, gamma: int, theta: int, challenges: Sequence[int] = ()):
     ch = _Challenges()
     ch.y, ch.beta, ch.gamma, ch.theta = _fr_struct(y), _fr_struct(beta), _fr_struct(gamma), _fr_struct(theta)
@@ -439,3 +454,65 @@ class ProvingKey:
         """second half: the fused row kernel over the extended domain"""
         ch, k1 = marshal_challenges(y, beta, gamma, theta, challenges)
         self.ctx.check(self.ctx.L.de_evaluate_h_rows_dev(self.h, C.byref(ch), C.c_void_p(d_h_ext.data_ptr())))
+
+
+class Prover:
+    """plonk::create_proof behind the C ABI (de_prover_create / de_create_proof): KZG + ProverGWC + Blake2bWrite.
+
+    params: de_b200.ParamsKZG, pk: ProvingKey (same Context).  advice_queries / fixed_queries: the ConstraintSystem's query
+    lists (collect_queries(shape) for the synthetic shapes).  transcript_repr: vk.transcript_repr as an integer."""
+
+    def __init__(self, params, pk: ProvingKey, advice_queries, fixed_queries, transcript_repr: int):
+        self.params, self.pk, self.ctx = params, pk, pk.ctx
+        shape = pk.shape
+        keep: list = []
+        aq_c = np.array([c for c, _ in advice_queries], dtype=np.uint32)
+        aq_r = np.array([r for _, r in advice_queries], dtype=np.int32)
+        fq_c = np.array([c for c, _ in fixed_queries], dtype=np.uint32)
+        fq_r = np.array([r for _, r in fixed_queries], dtype=np.int32)
+        nl = len(shape.lookups)
+        gi = (_Graph * max(nl, 1))()
+        gt = (_Graph * max(nl, 1))()
+        for i, (inp, tab) in enumerate(shape.lookups):
+            gi[i] = _marshal_graph(compile_compress(inp), keep)
+            gt[i] = _marshal_graph(compile_compress(tab), keep)
+        d = _ProverDesc()
+        d.n_advice_queries, d.n_fixed_queries = len(aq_c), len(fq_c)
+        d.advice_query_column = aq_c.ctypes.data if len(aq_c) else None
+        d.advice_query_rotation = aq_r.ctypes.data if len(aq_r) else None
+        d.fixed_query_column = fq_c.ctypes.data if len(fq_c) else None
+        d.fixed_query_rotation = fq_r.ctypes.data if len(fq_r) else None
+        d.lookup_input_graphs = C.addressof(gi)
+        d.lookup_table_graphs = C.addressof(gt)
+        d.transcript_repr = _fr_struct(transcript_repr)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.de_prover_create(params.h, pk.h, C.byref(d), C.byref(h)))
+        self.h = h
+        self.random_count = int(self.ctx.L.de_prover_random_count(h))
+        self.proof_size = int(self.ctx.L.de_prover_proof_size(h))
+        self._proof = np.zeros(self.proof_size, dtype=np.uint8)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.de_prover_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def create_proof(self, advice, instances, randoms) -> bytes:
+        """advice: list of (n, 4) uint64 Montgomery columns; instances: list of (len, 4) arrays (may be empty);
+        randoms: (>= random_count, 4) Montgomery field elements = the Fr::random draws in order."""
+        adv = [np.ascontiguousarray(a, dtype=np.uint64) for a in advice]
+        ins = [np.ascontiguousarray(np.asarray(i, dtype=np.uint64).reshape(-1, 4)) for i in instances]
+        rnd = np.ascontiguousarray(randoms, dtype=np.uint64)
+        ap = (C.c_void_p * max(len(adv), 1))(*[a.ctypes.data for a in adv])
+        ip = (C.c_void_p * max(len(ins), 1))(*[i.ctypes.data for i in ins])
+        il = (C.c_size_t * max(len(ins), 1))(*[i.shape[0] for i in ins])
+        m = C.c_size_t()
+        self.ctx.check(self.ctx.L.de_create_proof(self.h, ap, ip, il, rnd.ctypes.data_as(C.c_void_p), rnd.size // 4,
+                                                  self._proof.ctypes.data_as(C.c_void_p), self._proof.size, C.byref(m)))
+        return self._proof[: m.value].tobytes()

@@ -173,6 +173,41 @@ int de_pk_extend_dev(de_pk* pk, const de_fr* d_advice_coeff, const de_fr* d_inst
                      const de_fr* d_lookup_coeff, size_t stride);
 int de_evaluate_h_rows_dev(de_pk* pk, const de_challenges* ch, de_fr* d_h_ext);
 
+/* ---- a8 (transcript form): commitments as canonical affine coordinates ------------------------------------ */
+/* like de_commit_batch_dev, but each result is written as 64 bytes: x || y, little-endian CANONICAL integers (what
+ * Fq::to_repr returns and the Blake2b transcript hashes); the identity is 64 zero bytes */
+int de_commit_batch_canonical_dev(de_params* p, int basis, const de_fr* d_scalars, size_t stride, size_t n, size_t count, uint8_t* out_xy);
+
+/* ---- section 8f row 4: halo2_proofs::arithmetic::{eval_polynomial, kate_division} -------------------------- */
+int de_eval_polynomial(de_ctx* ctx, const de_fr* poly, size_t n, const de_fr* point, de_fr* out);
+/* q = a / (X - b), n - 1 coefficients written; n >= 2 */
+int de_kate_division(de_ctx* ctx, const de_fr* a, size_t n, const de_fr* b, de_fr* q);
+
+/* ---- section 8f rows 1-2: halo2_proofs::plonk::create_proof (KZG, ProverGWC, Blake2bWrite / Challenge255) --- */
+typedef struct de_prover de_prover;
+typedef struct {
+    /* cs.advice_queries / cs.fixed_queries in the ConstraintSystem's order: (column index, rotation) */
+    uint32_t n_advice_queries; const uint32_t* advice_query_column; const int32_t* advice_query_rotation;
+    uint32_t n_fixed_queries; const uint32_t* fixed_query_column; const int32_t* fixed_query_rotation;
+    /* per lookup of the pk: compiled graphs of the theta-compressed input / table expressions
+     * (Horner over theta of the argument's expressions; evaluated on the n rows of the lagrange domain) */
+    const de_graph* lookup_input_graphs;
+    const de_graph* lookup_table_graphs;
+    de_fr transcript_repr;   /* vk.transcript_repr */
+} de_prover_desc;
+/* params and pk must live on the same context.  Allocates every per-proof buffer once. */
+int de_prover_create(de_params* params, de_pk* pk, const de_prover_desc* desc, de_prover** out);
+int de_prover_free(de_prover* p);
+/* number of Fr::random(rng) draws one proof consumes, and the proof size in bytes */
+size_t de_prover_random_count(de_prover* p);
+size_t de_prover_proof_size(de_prover* p);
+/* advice: n_advice columns of n values as synthesize leaves them (lagrange form; the last blinding_factors + 1 rows are
+ * overwritten with blinding values); instances: the public inputs per instance column; randoms: the draws of
+ * Fr::random(rng) in create_proof's order - the library never touches an RNG.
+ * Writes the proof (the bytes Blake2bWrite::finalize returns). */
+int de_create_proof(de_prover* p, const de_fr* const* advice, const de_fr* const* instances, const size_t* instance_lens,
+                    const de_fr* randoms, size_t n_randoms, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
 /* ---- multi-GPU: MSM base-range sharding -------------------------------------------- */
 /* shard s of n_shards: commits scalars[lo..hi) against the matching base range of p and returns the partial sum;
  * the host (or de_g1_sum) adds the n_shards partial points. */

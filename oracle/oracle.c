@@ -335,6 +335,24 @@ static void parallel_for(size_t n, int threads, range_fn fn, void* ctx) {
     free(jobs);
 }
 
+/* out[i] = [scalars[i]] base as affine points (ParamsKZG::setup's g / g_lagrange for a known secret), threaded */
+typedef struct { const aff* base; const fe* scalars; aff* out; } mulmany_ctx;
+static void mulmany_job(void* v, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    mulmany_ctx* c = (mulmany_ctx*)v;
+    for (size_t i = lo; i < hi; i++) {
+        fe k;
+        jac r;
+        f_from_mont(&FRF, &k, &c->scalars[i]);
+        jac_mul_canon(&r, c->base, k.l);
+        jac_to_aff(&c->out[i], &r);
+    }
+}
+void orc_g1_mul_many(const u64* base_aff, const u64* scalars_mont, size_t n, u64* out_aff, int threads) {
+    mulmany_ctx c = {(const aff*)base_aff, (const fe*)scalars_mont, (aff*)out_aff};
+    parallel_for(n, threads, mulmany_job, &c);
+}
+
 /* ---------------------------------------------------------------- best_multiexp (a3; Appendix B.1) */
 enum { B_NONE = 0, B_AFFINE = 1, B_PROJ = 2 };
 typedef struct { int tag; jac p; } bucket_t; /* Affine keeps x,y in p.x,p.y */

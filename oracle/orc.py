@@ -54,6 +54,7 @@ def lib():
         L.orc_gen_bases.argtypes = [C.c_size_t, C.c_size_t, P, C.c_int]
         L.orc_g1_mul.argtypes = [P, P, P]
         L.orc_g1_add.argtypes = [P, P, P]
+        L.orc_g1_mul_many.argtypes = [P, P, C.c_size_t, P, C.c_int]
         L.orc_g1_on_curve.argtypes = [P]
         L.orc_g1_on_curve.restype = C.c_int
         L.orc_pk_new.argtypes = [P, P]
@@ -160,6 +161,15 @@ def g1_to_affine(j: np.ndarray) -> np.ndarray:
     j = np.ascontiguousarray(j, dtype=np.uint64).reshape(-1, 12)
     out = np.empty((j.shape[0], 8), dtype=np.uint64)
     lib().orc_g1_to_affine(_p(j), _p(out), j.shape[0])
+    return out
+
+
+def g1_mul_many(base_aff: np.ndarray, scalars: np.ndarray, threads: int | None = None) -> np.ndarray:
+    """[scalars[i]] base for every i: affine Montgomery (n, 8)."""
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    n = scalars.size // 4
+    out = np.empty((n, 8), dtype=np.uint64)
+    lib().orc_g1_mul_many(_p(np.ascontiguousarray(base_aff, dtype=np.uint64)), _p(scalars), n, _p(out), threads or ncpu())
     return out
 
 

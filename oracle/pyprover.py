@@ -197,12 +197,7 @@ class Params:
 
 def fixed_base_mul_many(scalars: Sequence[int]) -> np.ndarray:
     """[scalars[i]] G for the generator G = (1, 2): affine Montgomery (n, 8)."""
-    gen = points_to_mont([po.G1_GEN])[0]
-    sm = to_mont(scalars)
-    out = np.empty((len(scalars), 12), dtype=np.uint64)
-    for i in range(len(scalars)):
-        orc.lib().orc_g1_mul(orc._p(gen), orc._p(sm[i]), orc._p(out[i]))
-    return orc.g1_to_affine(out)
+    return orc.g1_mul_many(points_to_mont([po.G1_GEN])[0], to_mont(scalars))
 
 
 def setup(k: int, s: int) -> Params:
