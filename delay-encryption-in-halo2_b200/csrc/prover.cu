@@ -669,15 +669,10 @@ int de_prover_create(de_params* params, de_pk* pk, const de_prover_desc* desc, d
     return DE_OK;
 }
 
-int de_create_proof(de_prover* p, const de_fr* const* advice, const de_fr* const* instances, const size_t* instance_lens, const de_fr* randoms,
-                    size_t n_randoms, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
-    if (!p) return DE_ERR_ARG;
+// the proof once the advice columns and the random stream are in p->lag / p->randoms
+static int prove_core(de_prover* p, const de_fr* const* instances, const size_t* instance_lens, uint8_t* proof_out, size_t proof_cap,
+                      size_t* proof_len) {
     de_ctx* ctx = p->ctx;
-    if ((p->A && !advice) || (p->I && (!instances || !instance_lens)) || !randoms || !proof_out || !proof_len)
-        return fail(ctx, DE_ERR_ARG, "de_create_proof: null pointer");
-    if (n_randoms < p->n_random) return fail(ctx, DE_ERR_ARG, "de_create_proof: not enough random field elements (see de_prover_random_count)");
-    if (proof_cap < de_prover_proof_size(p)) return fail(ctx, DE_ERR_ARG, "de_create_proof: proof buffer too small (see de_prover_proof_size)");
-    DE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t n = p->n, bf = p->bf, usable = p->usable;
     const uint32_t A = p->A, I = p->I, Z = p->Z, L = p->L;
@@ -685,12 +680,6 @@ int de_create_proof(de_prover* p, const de_fr* const* advice, const de_fr* const
     host::TranscriptWriter tr;
     std::vector<uint8_t> xy(64 * 64);
 
-    // ---- inputs to the device; vk and public inputs into the transcript
-    DE_CUDA(ctx, cudaMemcpyAsync(p->randoms, randoms, sizeof(Fr) * p->n_random, cudaMemcpyHostToDevice, st));
-    for (uint32_t a = 0; a < A; a++) {
-        if (!advice[a]) return fail(ctx, DE_ERR_ARG, "de_create_proof: null advice column");
-        DE_CUDA(ctx, cudaMemcpyAsync(p->lag + (off_advice(p) + a) * n, advice[a], sizeof(Fr) * n, cudaMemcpyHostToDevice, st));
-    }
     tr.common_scalar(p->transcript_repr);
     for (uint32_t i = 0; i < I; i++) {
         if (instance_lens[i] > usable) return fail(ctx, DE_ERR_ARG, "de_create_proof: InstanceTooLarge");
@@ -908,6 +897,41 @@ int de_create_proof(de_prover* p, const de_fr* const* advice, const de_fr* const
     memcpy(proof_out, tr.proof.data(), tr.proof.size());
     *proof_len = tr.proof.size();
     return DE_OK;
+}
+
+static int check_args(de_prover* p, const void* advice, const de_fr* const* instances, const size_t* instance_lens, const void* randoms,
+                      size_t n_randoms, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    de_ctx* ctx = p->ctx;
+    if ((p->A && !advice) || (p->I && (!instances || !instance_lens)) || !randoms || !proof_out || !proof_len)
+        return fail(ctx, DE_ERR_ARG, "de_create_proof: null pointer");
+    if (n_randoms < p->n_random) return fail(ctx, DE_ERR_ARG, "de_create_proof: not enough random field elements (see de_prover_random_count)");
+    if (proof_cap < de_prover_proof_size(p)) return fail(ctx, DE_ERR_ARG, "de_create_proof: proof buffer too small (see de_prover_proof_size)");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return DE_OK;
+}
+
+int de_create_proof(de_prover* p, const de_fr* const* advice, const de_fr* const* instances, const size_t* instance_lens, const de_fr* randoms,
+                    size_t n_randoms, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!p) return DE_ERR_ARG;
+    de_ctx* ctx = p->ctx;
+    DE_TRY(check_args(p, advice, instances, instance_lens, randoms, n_randoms, proof_out, proof_cap, proof_len));
+    DE_CUDA(ctx, cudaMemcpyAsync(p->randoms, randoms, sizeof(Fr) * p->n_random, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t a = 0; a < p->A; a++) {
+        if (!advice[a]) return fail(ctx, DE_ERR_ARG, "de_create_proof: null advice column");
+        DE_CUDA(ctx, cudaMemcpyAsync(p->lag + (off_advice(p) + a) * p->n, advice[a], sizeof(Fr) * p->n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return prove_core(p, instances, instance_lens, proof_out, proof_cap, proof_len);
+}
+
+int de_create_proof_dev(de_prover* p, const de_fr* d_advice, size_t advice_stride, const de_fr* const* instances, const size_t* instance_lens,
+                        const de_fr* d_randoms, size_t n_randoms, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!p) return DE_ERR_ARG;
+    de_ctx* ctx = p->ctx;
+    DE_TRY(check_args(p, d_advice, instances, instance_lens, d_randoms, n_randoms, proof_out, proof_cap, proof_len));
+    DE_CUDA(ctx, cudaMemcpyAsync(p->randoms, d_randoms, sizeof(Fr) * p->n_random, cudaMemcpyDeviceToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaMemcpy2DAsync(p->lag + off_advice(p) * p->n, sizeof(Fr) * p->n, d_advice, sizeof(Fr) * advice_stride, sizeof(Fr) * p->n, p->A,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    return prove_core(p, instances, instance_lens, proof_out, proof_cap, proof_len);
 }
 
 }  // extern "C"

@@ -504,15 +504,34 @@ class Prover:
             pass
 
     def create_proof(self, advice, instances, randoms) -> bytes:
-        """advice: list of (n, 4) uint64 Montgomery columns; instances: list of (len, 4) arrays (may be empty);
-        randoms: (>= random_count, 4) Montgomery field elements = the Fr::random draws in order."""
-        adv = [np.ascontiguousarray(a, dtype=np.uint64) for a in advice]
+        """advice: list of (n, 4) uint64 Montgomery columns (numpy, or pinned torch tensors); instances: list of (len, 4)
+        arrays (may be empty); randoms: (>= random_count, 4) Montgomery field elements = the Fr::random draws in order."""
+        def addr(a):
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+
+        adv = [a if hasattr(a, "data_ptr") else np.ascontiguousarray(a, dtype=np.uint64) for a in advice]
         ins = [np.ascontiguousarray(np.asarray(i, dtype=np.uint64).reshape(-1, 4)) for i in instances]
-        rnd = np.ascontiguousarray(randoms, dtype=np.uint64)
-        ap = (C.c_void_p * max(len(adv), 1))(*[a.ctypes.data for a in adv])
+        while len(ins) < self.pk.shape.n_instance:
+            ins.append(np.zeros((0, 4), dtype=np.uint64))
+        rnd = randoms if hasattr(randoms, "data_ptr") else np.ascontiguousarray(randoms, dtype=np.uint64)
+        n_rnd = (rnd.numel() if hasattr(rnd, "numel") else rnd.size) // 4
+        ap = (C.c_void_p * max(len(adv), 1))(*[addr(a) for a in adv])
         ip = (C.c_void_p * max(len(ins), 1))(*[i.ctypes.data for i in ins])
         il = (C.c_size_t * max(len(ins), 1))(*[i.shape[0] for i in ins])
         m = C.c_size_t()
-        self.ctx.check(self.ctx.L.de_create_proof(self.h, ap, ip, il, rnd.ctypes.data_as(C.c_void_p), rnd.size // 4,
+        self.ctx.check(self.ctx.L.de_create_proof(self.h, ap, ip, il, C.c_void_p(addr(rnd)), n_rnd,
                                                   self._proof.ctypes.data_as(C.c_void_p), self._proof.size, C.byref(m)))
+        return self._proof[: m.value].tobytes()
+
+    def create_proof_dev(self, d_advice, d_randoms, instances=(), advice_stride=None) -> bytes:
+        """advice columns (n_advice, n, 4) and random draws (>= random_count, 4) as CUDA tensors already in HBM"""
+        ins = [np.ascontiguousarray(np.asarray(i, dtype=np.uint64).reshape(-1, 4)) for i in instances]
+        while len(ins) < self.pk.shape.n_instance:
+            ins.append(np.zeros((0, 4), dtype=np.uint64))
+        ip = (C.c_void_p * max(len(ins), 1))(*[i.ctypes.data for i in ins])
+        il = (C.c_size_t * max(len(ins), 1))(*[i.shape[0] for i in ins])
+        m = C.c_size_t()
+        self.ctx.check(self.ctx.L.de_create_proof_dev(self.h, C.c_void_p(d_advice.data_ptr()), advice_stride or self.pk.domain.n, ip, il,
+                                                      C.c_void_p(d_randoms.data_ptr()), d_randoms.numel() // 4,
+                                                      self._proof.ctypes.data_as(C.c_void_p), self._proof.size, C.byref(m)))
         return self._proof[: m.value].tobytes()

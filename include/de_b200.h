@@ -207,6 +207,11 @@ size_t de_prover_proof_size(de_prover* p);
  * Writes the proof (the bytes Blake2bWrite::finalize returns). */
 int de_create_proof(de_prover* p, const de_fr* const* advice, const de_fr* const* instances, const size_t* instance_lens,
                     const de_fr* randoms, size_t n_randoms, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+/* the same with the advice columns (advice_stride elements apart) and the random draws already resident in HBM; the
+ * public inputs stay host pointers (they are hashed into the transcript on the host) */
+int de_create_proof_dev(de_prover* p, const de_fr* d_advice, size_t advice_stride, const de_fr* const* instances,
+                        const size_t* instance_lens, const de_fr* d_randoms, size_t n_randoms, uint8_t* proof_out,
+                        size_t proof_cap, size_t* proof_len);
 
 /* ---- multi-GPU: MSM base-range sharding -------------------------------------------- */
 /* shard s of n_shards: commits scalars[lo..hi) against the matching base range of p and returns the partial sum;
