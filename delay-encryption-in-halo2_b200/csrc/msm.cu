@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "msm.cuh"
+#include "transcript.hpp"
 
 namespace de {
 
@@ -116,7 +117,7 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_WS(ctx, red, XYZZ, WS_MSM_MISC, sizeof(XYZZ) * ((size_t)ndigits * 32 * nsets_total + nsets_total));
     XYZZ* dsums = red;
     XYZZ* set_out = red + (size_t)ndigits * 32 * nsets_total;
-    DE_WS(ctx, d_out, Jac, WS_MSM_OUT, (sizeof(Jac) + sizeof(Affine)) * count);
+    DE_WS(ctx, d_out, Jac, WS_MSM_OUT, sizeof(Jac) * count);
     // scratch of the two-digit reduction: two ping-pong partial buffers, D0 / D1 and their digit sums
     DE_WS(ctx, red2, XYZZ, WS_MSM_RED, sizeof(XYZZ) * ((size_t)nsets_total * sh.NB + 4096 + (size_t)nsets_total * 4 * 2048));
 
@@ -208,17 +209,14 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     }
     k_msm_combine<<<(unsigned int)count, 32, 0, st>>>(set_out, sh.nsets, sh.c, d_out);
     DE_CHECK_LAUNCH(ctx);
-    if (out_mode == 1) {
-        Affine* d_aff = (Affine*)(d_out + count);
-        k_g1_normalize_canonical<<<(unsigned int)((count + 31) / 32), 32, 0, st>>>(d_out, (unsigned int)count, d_aff);
-        DE_CHECK_LAUNCH(ctx);
-        DE_CUDA(ctx, cudaMemcpyAsync(host_out, d_aff, sizeof(Affine) * count, cudaMemcpyDeviceToHost, st));
-    } else {
-        DE_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));
-    }
+    std::vector<de_g1> jac_tmp;
+    if (out_mode == 1) jac_tmp.resize(count);
+    DE_CUDA(ctx, cudaMemcpyAsync(out_mode == 1 ? (void*)jac_tmp.data() : host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));
     unsigned int total_entries = 0;
     if (ctx->timing) DE_CUDA(ctx, cudaMemcpyAsync(&total_entries, &scalars_u32[0], sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     DE_CUDA(ctx, cudaStreamSynchronize(st));
+    // transcript form: one batched inversion on the host for the round's handful of points
+    if (out_mode == 1) host::g1_jacobian_to_canonical((const uint64_t*)jac_tmp.data(), count, (uint8_t*)host_out);
     if (ctx->timing) {
         // bucket additions actually performed (non-zero signed digits): the work figure behind the int-pipe fraction
         KernelStat* stat = nullptr;

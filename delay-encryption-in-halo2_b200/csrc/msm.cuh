@@ -547,24 +547,4 @@ __global__ void k_g1_normalize(const Jac* pts, unsigned int count, Affine* out) 
     store_affine(&out[i], a);
 }
 
-// Jacobian -> affine with CANONICAL (non-Montgomery) coordinates: the 64 bytes x || y that the transcript hashes and that
-// G1Affine::to_bytes compresses (identity -> all zero).  One thread per point.
-__global__ void k_g1_normalize_canonical(const Jac* pts, unsigned int count, Affine* out) {
-    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    Jac p;
-    p.x = load(&pts[i].x); p.y = load(&pts[i].y); p.z = load(&pts[i].z);
-    Affine a;
-    if (p.z.is_zero()) {
-        a.x = Fq::zero();
-        a.y = Fq::zero();
-    } else {
-        Fq zi = inv(p.z);
-        Fq zi2 = sqr(zi);
-        a.x = from_mont(mul(p.x, zi2));
-        a.y = from_mont(mul(p.y, mul(zi2, zi)));
-    }
-    store_affine(&out[i], a);
-}
-
 }  // namespace de

@@ -15,6 +15,8 @@
 // The order of commitments, challenges, evaluations, opening queries and RNG draws follows create_proof as recorded in
 // SURVEY.md Appendix B / E; tests/test_gpu_prover.py compares the proof bytes with the CPU restatement of the same algorithm.
 // Fr::random(rng) draws are an INPUT (`randoms`, in draw order): the GPU never touches an RNG.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -420,7 +422,20 @@ struct de_prover {
     size_t n_random;
     std::vector<void*> allocs;
     std::string err;
+    // second stream: lagrange -> coefficient -> coset transforms of a column block run while the block is being committed
+    cudaStream_t st_b = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    bool overlap = true;
 };
+
+namespace {
+struct StreamSwap {  // the NTT / evaluator entry points launch on ctx->stream
+    de_ctx* c;
+    cudaStream_t old;
+    StreamSwap(de_ctx* ctx, cudaStream_t s) : c(ctx), old(ctx->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = old; }
+};
+}  // namespace
 
 namespace {
 
@@ -475,6 +490,9 @@ int de_prover_free(de_prover* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     for (void* a : p->allocs) cudaFree(a);
+    if (p->st_b) cudaStreamDestroy(p->st_b);
+    if (p->ev_a) cudaEventDestroy(p->ev_a);
+    if (p->ev_b) cudaEventDestroy(p->ev_b);
     delete p;
     return DE_OK;
 }
@@ -512,6 +530,14 @@ int de_prover_create(de_params* params, de_pk* pk, const de_prover_desc* desc, d
         memcpy(p->transcript_repr, c.l, 32);
     }
     auto bail = [&](int rc) { de_prover_free(p); return rc; };
+    {
+        const char* e = getenv("DE_PROVER_OVERLAP");
+        p->overlap = !(e && e[0] == '0');
+        if (cudaStreamCreateWithFlags(&p->st_b, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_b, cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(ctx, DE_ERR_CUDA, "de_prover_create: stream / event creation failed"));
+    }
     for (uint32_t i = 0; i < desc->n_advice_queries; i++) {
         if (desc->advice_query_column[i] >= p->A) return bail(fail(ctx, DE_ERR_ARG, "de_prover_create: advice query column out of range"));
         p->aq_col.push_back(desc->advice_query_column[i]);
@@ -719,10 +745,27 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         return DE_OK;
     };
 
+    // columns [c0, c0 + cnt) are final in lagrange form on `st`: coefficient form and extended coset on the second stream
+    // (neither depends on a transcript challenge), overlapping the same columns' commitment
+    auto to_cosets = [&](size_t c0, size_t cnt) -> int {
+        if (!cnt) return DE_OK;
+        cudaStream_t sb = p->overlap ? p->st_b : st;
+        if (p->overlap) {
+            DE_CUDA(ctx, cudaEventRecord(p->ev_a, st));
+            DE_CUDA(ctx, cudaStreamWaitEvent(sb, p->ev_a, 0));
+        }
+        StreamSwap sw(ctx, sb);
+        DE_CUDA(ctx, cudaMemcpyAsync(p->coef + c0 * n, p->lag + c0 * n, sizeof(Fr) * n * cnt, cudaMemcpyDeviceToDevice, sb));
+        DE_TRY(de_lagrange_to_coeff_dev(p->dom, (de_fr*)(p->coef + c0 * n), n, cnt));
+        DE_TRY(de_coeff_to_extended_dev(p->dom, (const de_fr*)(p->coef + c0 * n), n, (de_fr*)(pk->work + c0 * p->ext_n), p->ext_n, cnt));
+        return DE_OK;
+    };
+
     // ---- advice: blinding rows, commitments
     for (uint32_t a = 0; a < A; a++) add_tail(p->lag + (off_advice(p) + a) * n + usable, bf + 1);
     rpos += A;  // advice blinds
     DE_TRY(flush_tails());
+    DE_TRY(to_cosets(off_advice(p), (size_t)A + I));
     DE_TRY(commit(1, p->lag + off_advice(p) * n, A));
     const HFr theta = tr.squeeze_challenge();
 
@@ -764,13 +807,14 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         DE_TRY(flush_tails());
         int h_err = 0;
         DE_CUDA(ctx, cudaMemcpyAsync(&h_err, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-        // commitments are written a'_0, s'_0, a'_1, s'_1, ...: commit the two blocks, then interleave
-        std::vector<uint8_t> pa(64 * (size_t)L), ps(64 * (size_t)L);
-        DE_TRY(commit_canonical_dev(p->params, 1, a_perm, n, n, L, pa.data()));
+        DE_TRY(to_cosets(off_lookup_a(p), 2 * (size_t)L));
+        // one launch sequence for the 2L permuted columns (a' block then s' block, adjacent in HBM); the transcript takes
+        // them interleaved: a'_0, s'_0, a'_1, s'_1, ...
+        std::vector<uint8_t> pas(64 * 2 * (size_t)L);
+        DE_TRY(commit_canonical_dev(p->params, 1, a_perm, n, n, 2 * (size_t)L, pas.data()));
         if (h_err) return fail(ctx, DE_ERR_ARG, "de_create_proof: a lookup input is not in its table (ConstraintSystemFailure)");
-        DE_TRY(commit_canonical_dev(p->params, 1, s_perm, n, n, L, ps.data()));
         for (uint32_t l = 0; l < L; l++)
-            if (!tr.write_point(pa.data() + 64 * l) || !tr.write_point(ps.data() + 64 * l))
+            if (!tr.write_point(pas.data() + 64 * l) || !tr.write_point(pas.data() + 64 * ((size_t)L + l)))
                 return fail(ctx, DE_ERR_ARG, "de_create_proof: a commitment is the point at infinity");
     }
     const HFr beta = tr.squeeze_challenge();
@@ -833,6 +877,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
             rpos += 1;
         }
         DE_TRY(flush_tails());
+        DE_TRY(to_cosets(off_permz(p), zl));
         DE_TRY(commit(1, p->lag + off_permz(p) * n, zl));
     }
 
@@ -842,11 +887,11 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     DE_TRY(commit(0, random_poly, 1));
     const HFr y = tr.squeeze_challenge();
 
-    // ---- coefficient forms, cosets, quotient
-    DE_CUDA(ctx, cudaMemcpyAsync(p->coef, p->lag, sizeof(Fr) * n * p->n_cols, cudaMemcpyDeviceToDevice, st));
-    DE_TRY(de_lagrange_to_coeff_dev(p->dom, (de_fr*)p->coef, n, p->n_cols));
-    DE_TRY(de_pk_extend_dev(pk, (const de_fr*)(p->coef + off_advice(p) * n), I ? (const de_fr*)(p->coef + off_instance(p) * n) : nullptr,
-                            Z ? (const de_fr*)(p->coef + off_permz(p) * n) : nullptr, L ? (const de_fr*)(p->coef + off_lookup_z(p) * n) : nullptr, n));
+    // ---- quotient: every coset is (being) produced on the second stream
+    if (p->overlap) {
+        DE_CUDA(ctx, cudaEventRecord(p->ev_b, p->st_b));
+        DE_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_b, 0));
+    }
     de_challenges ch;
     memset(&ch, 0, sizeof(ch));
     ch.y = to_defr(y); ch.beta = to_defr(beta); ch.gamma = to_defr(gamma); ch.theta = to_defr(theta);

@@ -16,33 +16,42 @@ namespace host {
 
 typedef unsigned __int128 u128;
 
-// ---- BN254 Fr, 4 x 64-bit Montgomery limbs (R = 2^256), the in-memory form of halo2curves::bn256::Fr ------------------
+// ---- BN254 Fr / Fq, 4 x 64-bit Montgomery limbs (R = 2^256), the in-memory form of halo2curves::bn256::{Fr, Fq} -------
 struct HFr {
     uint64_t l[4];
     bool operator==(const HFr& o) const { return memcmp(l, o.l, 32) == 0; }
 };
-static const uint64_t FR_MOD[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
-static const uint64_t FR_INV = 0xc2e1f593efffffffull;  // -r^-1 mod 2^64
-static const HFr FR_R = {{0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full}};
-static const HFr FR_R2 = {{0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull}};
+struct HField {
+    uint64_t mod[4];
+    uint64_t inv;  // -p^-1 mod 2^64
+    HFr r, r2;     // R mod p, R^2 mod p
+};
+static const HField FR_FIELD = {{0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull},
+                                0xc2e1f593efffffffull,
+                                {{0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full}},
+                                {{0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull}}};
+static const HField FQ_FIELD = {{0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull},
+                                0x87d20782e4866389ull,
+                                {{0xd35d438dc58f0d9dull, 0x0a78eb28f5c70b3dull, 0x666ea36f7879462cull, 0x0e0a77c19a07df2full}},
+                                {{0xf32cfc5b538afa89ull, 0xb5e71911d44501fbull, 0x47ab1eff0a417ff6ull, 0x06d89f71cab8351full}}};
 
-inline bool geq_mod(const uint64_t a[4]) {
+inline bool geq_mod(const HField& F, const uint64_t a[4]) {
     for (int i = 3; i >= 0; i--) {
-        if (a[i] > FR_MOD[i]) return true;
-        if (a[i] < FR_MOD[i]) return false;
+        if (a[i] > F.mod[i]) return true;
+        if (a[i] < F.mod[i]) return false;
     }
     return true;
 }
-inline void sub_mod(uint64_t a[4]) {
+inline void sub_mod(const HField& F, uint64_t a[4]) {
     u128 borrow = 0;
     for (int i = 0; i < 4; i++) {
-        u128 t = (u128)a[i] - FR_MOD[i] - borrow;
+        u128 t = (u128)a[i] - F.mod[i] - borrow;
         a[i] = (uint64_t)t;
         borrow = (t >> 64) & 1;
     }
 }
-// Montgomery product a * b / R mod r.  Requires b < r; a may be any 256-bit value (used by from_wide).
-inline HFr fr_mul(const HFr& a, const HFr& b) {
+// Montgomery product a * b / R mod p.  Requires b < p; a may be any 256-bit value (used by from_wide).
+inline HFr mont_mul(const HField& F, const HFr& a, const HFr& b) {
     uint64_t t[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
         u128 carry = 0;
@@ -54,10 +63,10 @@ inline HFr fr_mul(const HFr& a, const HFr& b) {
         u128 v = (u128)t[4] + carry;
         t[4] = (uint64_t)v;
         t[5] = (uint64_t)(v >> 64);
-        uint64_t m = t[0] * FR_INV;
-        carry = ((u128)m * FR_MOD[0] + t[0]) >> 64;
+        uint64_t m = t[0] * F.inv;
+        carry = ((u128)m * F.mod[0] + t[0]) >> 64;
         for (int j = 1; j < 4; j++) {
-            u128 w = (u128)m * FR_MOD[j] + t[j] + carry;
+            u128 w = (u128)m * F.mod[j] + t[j] + carry;
             t[j - 1] = (uint64_t)w;
             carry = w >> 64;
         }
@@ -67,10 +76,10 @@ inline HFr fr_mul(const HFr& a, const HFr& b) {
         t[5] = 0;
     }
     HFr r = {{t[0], t[1], t[2], t[3]}};
-    if (t[4] || geq_mod(r.l)) sub_mod(r.l);
+    if (t[4] || geq_mod(F, r.l)) sub_mod(F, r.l);
     return r;
 }
-inline HFr fr_add(const HFr& a, const HFr& b) {
+inline HFr mont_add(const HField& F, const HFr& a, const HFr& b) {
     HFr r;
     u128 carry = 0;
     for (int i = 0; i < 4; i++) {
@@ -78,10 +87,23 @@ inline HFr fr_add(const HFr& a, const HFr& b) {
         r.l[i] = (uint64_t)v;
         carry = v >> 64;
     }
-    if (geq_mod(r.l)) sub_mod(r.l);  // a + b < 2r < 2^255: no carry out
+    if (geq_mod(F, r.l)) sub_mod(F, r.l);  // a + b < 2p < 2^255: no carry out
     return r;
 }
-inline HFr fr_one() { return FR_R; }
+inline bool is_zero(const HFr& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+// a^(p - 2) (Fermat); a != 0
+inline HFr mont_inv(const HField& F, const HFr& a) {
+    uint64_t e[4] = {F.mod[0] - 2, F.mod[1], F.mod[2], F.mod[3]};  // both moduli end in a limb >= 2
+    HFr acc = F.r;
+    for (int i = 255; i >= 0; i--) {
+        acc = mont_mul(F, acc, acc);
+        if ((e[i / 64] >> (i % 64)) & 1) acc = mont_mul(F, acc, a);
+    }
+    return acc;
+}
+inline HFr fr_mul(const HFr& a, const HFr& b) { return mont_mul(FR_FIELD, a, b); }
+inline HFr fr_add(const HFr& a, const HFr& b) { return mont_add(FR_FIELD, a, b); }
+inline HFr fr_one() { return FR_FIELD.r; }
 inline HFr fr_pow(HFr base, uint64_t e) {
     HFr acc = fr_one();
     while (e) {
@@ -100,8 +122,42 @@ inline HFr fr_from_wide(const uint8_t b[64]) {
     HFr d0, d1;
     memcpy(d0.l, b, 32);
     memcpy(d1.l, b + 32, 32);
-    const HFr r3 = fr_mul(FR_R2, FR_R2);  // R^3
-    return fr_add(fr_mul(d0, FR_R2), fr_mul(d1, r3));
+    const HFr r3 = fr_mul(FR_FIELD.r2, FR_FIELD.r2);  // R^3
+    return fr_add(fr_mul(d0, FR_FIELD.r2), fr_mul(d1, r3));
+}
+
+// group::Curve::batch_normalize + Fq::to_repr on the host for the handful of commitments a proof hashes: `count` Jacobian
+// points (x, y, z as 12 Montgomery u64 limbs each) -> 64 bytes x || y of canonical little-endian coordinates per point
+// (identity -> zeros).  One shared inversion (Montgomery's trick).
+inline void g1_jacobian_to_canonical(const uint64_t* jac, size_t count, uint8_t* out_xy) {
+    const HField& F = FQ_FIELD;
+    std::vector<HFr> pre(count);
+    HFr acc = F.r;
+    for (size_t i = 0; i < count; i++) {
+        HFr z;
+        memcpy(z.l, jac + 12 * i + 8, 32);
+        pre[i] = acc;
+        if (!is_zero(z)) acc = mont_mul(F, acc, z);
+    }
+    HFr inv = count ? mont_inv(F, acc) : F.r;
+    const HFr one = {{1, 0, 0, 0}};
+    for (size_t i = count; i-- > 0;) {
+        HFr x, y, z;
+        memcpy(x.l, jac + 12 * i, 32);
+        memcpy(y.l, jac + 12 * i + 4, 32);
+        memcpy(z.l, jac + 12 * i + 8, 32);
+        if (is_zero(z)) {
+            memset(out_xy + 64 * i, 0, 64);
+            continue;
+        }
+        const HFr zi = mont_mul(F, inv, pre[i]);
+        inv = mont_mul(F, inv, z);
+        const HFr zi2 = mont_mul(F, zi, zi);
+        const HFr ax = mont_mul(F, mont_mul(F, x, zi2), one);
+        const HFr ay = mont_mul(F, mont_mul(F, mont_mul(F, y, zi2), zi), one);
+        memcpy(out_xy + 64 * i, ax.l, 32);
+        memcpy(out_xy + 64 * i + 32, ay.l, 32);
+    }
 }
 
 // ---- Blake2b-512 with a 16-byte personalisation string, no key ---------------------------------------------------------

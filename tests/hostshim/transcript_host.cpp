@@ -13,6 +13,7 @@ void h_fr_mul4(const uint64_t* a, const uint64_t* b, uint64_t* o) { HFr x, y; me
 void h_fr_add4(const uint64_t* a, const uint64_t* b, uint64_t* o) { HFr x, y; memcpy(x.l, a, 32); memcpy(y.l, b, 32); HFr r = fr_add(x, y); memcpy(o, r.l, 32); }
 void h_fr_pow4(const uint64_t* a, uint64_t e, uint64_t* o) { HFr x; memcpy(x.l, a, 32); HFr r = fr_pow(x, e); memcpy(o, r.l, 32); }
 void h_fr_from_wide(const uint8_t* b64, uint64_t* o) { HFr r = fr_from_wide(b64); memcpy(o, r.l, 32); }
+void h_g1_jacobian_to_canonical(const uint64_t* jac, size_t count, uint8_t* out) { g1_jacobian_to_canonical(jac, count, out); }
 // script: sequence of ops over a TranscriptWriter: 'p' + 64 bytes (write_point), 's' + 32 bytes (write_scalar),
 // 'c' + 32 bytes (common_scalar), 'q' (squeeze: appends the challenge, canonical 32 bytes, to `challenges`)
 size_t h_transcript_script(const uint8_t* script, size_t len, uint8_t* proof_out, uint8_t* challenges_out, size_t* n_challenges) {

@@ -92,3 +92,22 @@ def test_transcript_script_matches_python(shim):
     assert bytes(proof[:m]) == t.finalize()
     got = [int.from_bytes(bytes(ch[32 * i:32 * i + 32]), "little") for i in range(nc.value)]
     assert got == want_ch
+
+
+def test_host_batch_normalize_to_canonical(shim):
+    import orc
+    rng = po.Xoshiro(13)
+    pts = [po.g1_mul(po.G1_GEN, rng.uniform_fr()) for _ in range(6)] + [None]
+    jac = []
+    for p in pts:
+        if p is None:
+            jac += [5, 7, 0]
+            continue
+        z = rng.uniform_fr() % po.FQ or 1
+        jac += [p[0] * z * z % po.FQ, p[1] * z * z * z % po.FQ, z]
+    jm = orc.fq_mont_from_ints(jac).reshape(-1, 12)
+    out = (C.c_uint8 * (64 * len(pts)))()
+    shim.h_g1_jacobian_to_canonical(jm.ctypes.data_as(C.c_void_p), C.c_size_t(len(pts)), out)
+    for i, p in enumerate(pts):
+        want = bytes(64) if p is None else pp.fq_to_repr(p[0]) + pp.fq_to_repr(p[1])
+        assert bytes(out[64 * i:64 * i + 64]) == want
