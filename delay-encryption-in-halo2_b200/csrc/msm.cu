@@ -405,6 +405,18 @@ int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out) {
     return DE_OK;
 }
 
+int de_g1_mul_base_dev(de_ctx* ctx, const de_g1_affine* base, const de_fr* d_scalars, size_t n, de_g1_affine* d_out) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!base || (n && (!d_scalars || !d_out))) return fail(ctx, DE_ERR_ARG, "de_g1_mul_base_dev: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return DE_OK;
+    Affine b;
+    memcpy(&b, base, sizeof(b));
+    k_g1_mul_base<<<(unsigned int)((n + 127) / 128), 128, 0, ctx->stream>>>(b, (const Fr*)d_scalars, n, (Affine*)d_out);
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
 int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_affine* out) {
     if (!ctx) return DE_ERR_ARG;
     if (count && (!points || !out)) return fail(ctx, DE_ERR_ARG, "de_g1_batch_normalize: null pointer");

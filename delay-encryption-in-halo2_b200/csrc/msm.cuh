@@ -547,4 +547,30 @@ __global__ void k_g1_normalize(const Jac* pts, unsigned int count, Affine* out) 
     store_affine(&out[i], a);
 }
 
+// out[i] = [scalars[i]] base, affine (fixed-base scalar multiplication by double-and-add; ParamsKZG::setup's
+// g[i] = [s^i] G and synthetic SRS bases for the size sweeps).  One thread per scalar.
+__global__ void __launch_bounds__(128) k_g1_mul_base(Affine base, const Fr* scalars, unsigned long long n, Affine* out) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr s = from_mont(load(&scalars[i]));
+    int top = 255;
+    while (top >= 0 && !((s.l[top >> 5] >> (top & 31)) & 1)) top--;
+    XYZZ acc = xyzz_identity();
+    for (int b = top; b >= 0; b--) {
+        acc = xyzz_dbl(acc);
+        if ((s.l[b >> 5] >> (b & 31)) & 1) xyzz_madd(acc, base);
+    }
+    Affine a;
+    if (is_identity(acc)) {
+        a.x = Fq::zero();
+        a.y = Fq::zero();
+    } else {
+        Fq iz3 = inv(acc.zzz);
+        Fq iz2 = mul(sqr(acc.zz), sqr(iz3));
+        a.x = mul(acc.x, iz2);
+        a.y = mul(acc.y, iz3);
+    }
+    store_affine(&out[i], a);
+}
+
 }  // namespace de

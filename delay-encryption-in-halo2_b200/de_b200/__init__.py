@@ -147,6 +147,11 @@ class Context:
         self.check(self.L.de_kate_division(self.h, _ptr(a), n, _ptr(b), _ptr(out)))
         return out
 
+    def g1_mul_base_dev(self, base, d_scalars, n: int, d_out):
+        """d_out[i] = [d_scalars[i]] base: base (8,) affine Montgomery host array, scalars / out CUDA tensors"""
+        base = _np(base)
+        self.check(self.L.de_g1_mul_base_dev(self.h, _ptr(base), _ptr(d_scalars), n, _ptr(d_out)))
+
     def batch_normalize(self, points):
         """group::Curve::batch_normalize: (count, 12) Jacobian -> (count, 8) affine"""
         points = _np(points).reshape(-1, 12)

@@ -218,6 +218,9 @@ int de_create_proof_dev(de_prover* p, const de_fr* d_advice, size_t advice_strid
  * the host (or de_g1_sum) adds the n_shards partial points. */
 int de_commit_range(de_params* p, int basis, const de_fr* scalars, size_t lo, size_t hi, de_g1* out_partial);
 int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out);
+/* d_out[i] = [d_scalars[i]] base (affine, Montgomery), device-resident: the fixed-base multiplications of
+ * ParamsKZG::setup (g[i] = [s^i] G) and the generator of synthetic SRS bases for the size sweeps */
+int de_g1_mul_base_dev(de_ctx* ctx, const de_g1_affine* base, const de_fr* d_scalars, size_t n, de_g1_affine* d_out);
 /* group::Curve::batch_normalize: Jacobian -> affine (identity -> all zero).  The Jacobian representative an MSM returns
  * depends on the (atomic) accumulation order; the affine point does not. */
 int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_affine* out);

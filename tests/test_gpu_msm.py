@@ -114,3 +114,22 @@ def test_batch_normalize(ctx):
     b = orc.gen_bases(n)
     pts = np.stack([ctx.best_multiexp(s[: i + 1], b[: i + 1]) for i in (0, 7, 299)] + [np.zeros(12, dtype=np.uint64)])
     assert (ctx.batch_normalize(pts) == orc.g1_to_affine(pts)).all()
+
+
+def test_g1_mul_base_matches_oracle(ctx):
+    """de_g1_mul_base_dev (fixed-base multiplications of ParamsKZG::setup / synthetic SRS generation) vs the oracle"""
+    import torch
+    n = 300
+    s = orc.uniform_fr(0xBA5E, n)
+    s[0] = 0                                   # -> identity
+    s[1] = orc.fr_mont_from_ints([1])[0]       # -> the base itself
+    s[2] = orc.fr_mont_from_ints([po.FR - 1])[0]  # -> minus the base
+    s[3:40] = orc.fr_mont_from_ints(list(range(2, 39)))
+    base = orc.gen_bases(1)[0]
+    d_s = torch.from_numpy(s.view(np.int64)).cuda()
+    d_out = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    ctx.g1_mul_base_dev(base, d_s, n, d_out)
+    ctx.sync()
+    got = d_out.cpu().numpy().view(np.uint64)
+    assert (got == orc.g1_mul_many(base, s)).all()
+    assert not got[0].any() and (got[1] == base).all()

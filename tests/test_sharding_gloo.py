@@ -43,11 +43,11 @@ def _worker(rank, world, port, out_dir):
     bases = orc.gen_bases(n)
     lo, hi = sharding.base_range(n, rank, world)
     partial = orc.best_multiexp(np.ascontiguousarray(scalars[lo:hi]), np.ascontiguousarray(bases[lo:hi]), threads=1)
-    buf = [torch.zeros(12, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(buf, torch.from_numpy(partial.view(np.int64).copy()))
+    parts = sharding.gather_partials(partial)  # the product's exchange step (all_gather of 96 bytes per rank)
+    assert parts.shape == (world, 12) and (parts[rank] == partial).all()
     acc = np.zeros(12, dtype=np.uint64)
-    for p in buf:
-        acc = orc.g1_add(acc, p.numpy().view(np.uint64))
+    for p in parts:
+        acc = orc.g1_add(acc, np.ascontiguousarray(p))
     want = orc.best_multiexp(scalars, bases, threads=1)
     assert (orc.g1_to_affine(acc) == orc.g1_to_affine(want)).all()
     dist.barrier()
