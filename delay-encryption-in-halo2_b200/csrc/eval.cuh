@@ -16,7 +16,7 @@ struct de_domain_view {  // layout prefix of de_domain (ntt.cu) that this unit r
 
 namespace de {
 
-#define DE_MAX_INTER 96
+#define DE_MAX_INTER 24   // live intermediates per row AFTER slot allocation (upload_graph); local memory per thread
 #define DE_MAX_ROT 16
 
 struct DevSrc { uint32_t kind, index, rot; };
@@ -135,7 +135,6 @@ struct de_pk {
 };
 
 inline int upload_graph(de_ctx* ctx, const de_graph& g, DevGraph* out, std::vector<void*>& allocs) {
-    if (g.n_intermediates > DE_MAX_INTER) return fail(ctx, DE_ERR_UNSUPPORTED, "evaluator: too many intermediates in a graph");
     if (g.n_rotations > DE_MAX_ROT) return fail(ctx, DE_ERR_UNSUPPORTED, "evaluator: too many distinct rotations in a graph");
     std::vector<DevCalc> calcs(g.n_calcs);
     auto conv = [](const de_value_source& s) { return DevSrc{s.kind, s.index, s.rotation}; };
@@ -149,6 +148,73 @@ inline int upload_graph(de_ctx* ctx, const de_graph& g, DevGraph* out, std::vect
     }
     std::vector<DevSrc> parts(g.n_horner_parts);
     for (uint32_t i = 0; i < g.n_horner_parts; i++) parts[i] = conv(g.horner_parts[i]);
+    // ---- device-side program optimisation (results unchanged: same operations on the same values, in the same order)
+    // 1. Store(x) only copies a column / challenge value into an intermediate: forward x into the consumers instead, so that
+    //    the value is loaded where it is used and never parked in thread-local memory.
+    {
+        std::vector<int> store_of(g.n_intermediates, -1);
+        for (uint32_t i = 0; i < calcs.size(); i++)
+            if (calcs[i].op == DE_CALC_STORE && i + 1 != calcs.size()) store_of[calcs[i].target] = (int)i;
+        auto fwd = [&](DevSrc& s) {
+            int guard = 0;
+            while (s.kind == DE_VAL_INTERMEDIATE && s.index < store_of.size() && store_of[s.index] >= 0 && guard++ < 64) s = calcs[store_of[s.index]].a;
+        };
+        // a Store's own source may be an earlier Store's target: resolve in program order first
+        for (auto& c : calcs)
+            if (c.op == DE_CALC_STORE) fwd(c.a);
+        for (auto& c : calcs) {
+            if (c.op == DE_CALC_STORE) continue;
+            fwd(c.a);
+            fwd(c.b);
+        }
+        for (auto& s : parts) fwd(s);
+        std::vector<DevCalc> kept;
+        for (uint32_t i = 0; i < calcs.size(); i++)
+            if (!(calcs[i].op == DE_CALC_STORE && i + 1 != calcs.size())) kept.push_back(calcs[i]);
+        calcs.swap(kept);
+    }
+    // 2. slot allocation by liveness: an intermediate's slot is reused after its last consumer
+    {
+        const uint32_t nc = (uint32_t)calcs.size();
+        std::vector<int> last_use(g.n_intermediates, -1);
+        auto use = [&](const DevSrc& s, int at) {
+            if (s.kind == DE_VAL_INTERMEDIATE && s.index < last_use.size()) last_use[s.index] = at;
+        };
+        for (uint32_t i = 0; i < nc; i++) {
+            use(calcs[i].a, (int)i);
+            use(calcs[i].b, (int)i);
+            if (calcs[i].op == DE_CALC_HORNER)
+                for (uint32_t k = 0; k < calcs[i].hlen; k++) use(parts[calcs[i].hfirst + k], (int)i);
+        }
+        std::vector<int> slot_of(g.n_intermediates, -1);
+        std::vector<int> free_at(DE_MAX_INTER, -1);  // calc index after which the slot is free again; -1 = free now
+        auto remap = [&](DevSrc& s) {
+            if (s.kind == DE_VAL_INTERMEDIATE && s.index < slot_of.size() && slot_of[s.index] >= 0) s.index = (uint32_t)slot_of[s.index];
+        };
+        std::vector<char> part_done(parts.size(), 0);
+        for (uint32_t i = 0; i < nc; i++) {
+            remap(calcs[i].a);
+            remap(calcs[i].b);
+            if (calcs[i].op == DE_CALC_HORNER)
+                for (uint32_t k = 0; k < calcs[i].hlen; k++)
+                    if (!part_done[calcs[i].hfirst + k]) {
+                        remap(parts[calcs[i].hfirst + k]);
+                        part_done[calcs[i].hfirst + k] = 1;
+                    }
+            // operands were read before the target is written, so a slot whose last use is this very calculation may be reused
+            int slot = -1;
+            for (int s = 0; s < DE_MAX_INTER; s++)
+                if (free_at[s] <= (int)i) {
+                    slot = s;
+                    break;
+                }
+            if (slot < 0) return fail(ctx, DE_ERR_UNSUPPORTED, "evaluator: more live intermediates than DE_MAX_INTER");
+            const uint32_t t = calcs[i].target;
+            slot_of[t] = slot;
+            free_at[slot] = last_use[t] < 0 ? (int)i : last_use[t];  // never used again: free right after
+            calcs[i].target = (uint32_t)slot;
+        }
+    }
     auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
         void* d = nullptr;
         DE_CUDA(ctx, cudaMalloc(&d, bytes ? bytes : 16));
@@ -162,7 +228,7 @@ inline int upload_graph(de_ctx* ctx, const de_graph& g, DevGraph* out, std::vect
     DE_TRY(up(calcs.data(), sizeof(DevCalc) * calcs.size(), (const void**)&out->calcs));
     DE_TRY(up(parts.data(), sizeof(DevSrc) * parts.size(), (const void**)&out->hparts));
     out->n_rot = g.n_rotations;
-    out->n_calcs = g.n_calcs;
+    out->n_calcs = (uint32_t)calcs.size();
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     return DE_OK;
 }

@@ -63,31 +63,27 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // table_stride elements apart.  Writes `count` Jacobian points to host_out.
 // out_mode 0: Jacobian points (de_g1, Montgomery); 1: canonical affine x || y, 64 bytes per point (transcript form)
 static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, size_t count, const Affine* d_tables,
-                    size_t table_stride, size_t base_offset, const MsmCfg& cfg, void* host_out, int out_mode = 0) {
+                    size_t table_stride, size_t base_offset, const MsmCfg& cfg, void* host_out, int out_mode = 0,
+                    unsigned int alt_first = 0xffffffffu, long long alt_delta = 0) {
     if (count == 0) return DE_OK;
     if (n == 0) {
         memset(host_out, 0, (out_mode ? sizeof(de_g1_affine) : sizeof(de_g1)) * count);
         return DE_OK;
     }
-    if ((unsigned long long)cfg.ntables * table_stride >= (1ull << 31)) return fail(ctx, DE_ERR_UNSUPPORTED, "msm: base table exceeds 2^31 points");
+    if ((unsigned long long)cfg.ntables * table_stride >= (1ull << 31) ||
+        (alt_first != 0xffffffffu && 2ull * cfg.ntables * table_stride >= (1ull << 31)))
+        return fail(ctx, DE_ERR_UNSUPPORTED, "msm: base table exceeds 2^31 points");
     MsmShape sh;
     sh.c = cfg.c; sh.W = cfg.W; sh.nsets = cfg.nsets; sh.NB = 1u << (cfg.c - 1);
     sh.count = (unsigned int)count; sh.n = n; sh.table_stride = table_stride; sh.base_offset = base_offset;
+    sh.alt_first = alt_first; sh.alt_delta = alt_delta;
     const unsigned long long E = (unsigned long long)count * sh.W * n;
     const unsigned long long nbuckets = (unsigned long long)count * sh.nsets * sh.NB;
     if (E >= (1ull << 32) || nbuckets >= (1ull << 31)) return fail(ctx, DE_ERR_UNSUPPORTED, "msm: batch too large for 32-bit entry indices");
-    // task length: enough tasks to fill the chip twice over, but never longer than DE_MSM_MAX_CH entries
-    unsigned int CH = 8;
-    {
-        const unsigned long long target_tasks = (unsigned long long)ctx->sm_count * 1024;
-        while (CH < DE_MSM_MAX_CH && E / (CH * 2) >= target_tasks) CH *= 2;
-        // when the buckets alone already give enough tasks, make a task hold a whole bucket (twice the mean size covers the
-        // Poisson tail of uniform scalars), so that almost no bucket needs a merge
-        const unsigned long long avg = (E + nbuckets - 1) / nbuckets;
-        if (nbuckets >= target_tasks / 2)
-            while (CH < DE_MSM_MAX_CH && CH < 2 * avg) CH *= 2;
-    }
-    const unsigned long long max_tasks = E / CH + nbuckets + 1;
+    // task length CH is chosen on the device from the actual entry count (k_msm_choose_ch); the host only bounds the task
+    // count for the allocation and the grid: tasks <= E / 8 + nbuckets
+    const unsigned int target_tasks = (unsigned int)ctx->sm_count * 1024;
+    const unsigned long long max_tasks = E / 8 + nbuckets + 1;
     const unsigned int ndigits = (sh.c - 1 + 4) / 5;
     const unsigned int nsets_total = (unsigned int)(count * sh.nsets);
 
@@ -134,23 +130,39 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CUDA(ctx, cudaMemcpyAsync(cursor, offsets, sizeof(unsigned int) * (nbuckets + 1), cudaMemcpyDeviceToDevice, st));
     k_msm_scatter<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, vals, E, cursor, sorted);
     DE_CHECK_LAUNCH(ctx);
-    k_msm_task_counts<<<(unsigned int)((nbuckets + 255) / 256), 256, 0, st>>>(counts, (unsigned int)nbuckets, CH, ntasks, multi_small,
-                                                                             multi_large, scalars_u32, len_bins);
+    k_msm_choose_ch<<<1, 32, 0, st>>>(scalars_u32, (unsigned int)nbuckets, DE_MSM_MAX_CH, target_tasks);
+    DE_CHECK_LAUNCH(ctx);
+    k_msm_task_counts<<<(unsigned int)((nbuckets + 255) / 256), 256, 0, st>>>(counts, (unsigned int)nbuckets, ntasks, multi_small, multi_large,
+                                                                             scalars_u32, len_bins);
     DE_CHECK_LAUNCH(ctx);
     DE_TRY(scan_u32(ctx, ntasks, nbuckets + 1, task_off, block_sums2, &scalars_u32[1]));
-    k_msm_bin_starts<<<1, 32, 0, st>>>(len_bins, CH, bin_cursor);
+    k_msm_bin_starts<<<1, 32, 0, st>>>(len_bins, scalars_u32, bin_cursor);
     DE_CHECK_LAUNCH(ctx);
-    k_msm_task_fill<<<(unsigned int)((nbuckets + 255) / 256), 256, 0, st>>>(counts, (unsigned int)nbuckets, CH, bin_cursor, task_list);
+    k_msm_task_fill<<<(unsigned int)((nbuckets + 255) / 256), 256, 0, st>>>(counts, (unsigned int)nbuckets, scalars_u32, bin_cursor, task_list);
     DE_CHECK_LAUNCH(ctx);
     DE_TIMED(ctx, "k_msm_accumulate", (double)n * count,
              (k_msm_accumulate<<<(unsigned int)((max_tasks + 127) / 128), 128, 0, st>>>(sorted, offsets, counts, task_off, task_list,
-                                                                                       &scalars_u32[1], CH, d_tables, buckets, partials)));
+                                                                                       scalars_u32, d_tables, buckets, partials)));
     DE_CHECK_LAUNCH(ctx);
     k_msm_merge_small<<<ctx->sm_count * 4, 128, 0, st>>>(multi_small, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
     k_msm_merge_large<<<ctx->sm_count * 2, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    if (sh.c >= 11) {
+    if (sh.c >= 11 && sh.c <= 16 && getenv("DE_MSM_FUSED_REDUCTION")) {
+        // fused two-digit reduction (4c): one launch for every row / column sum, one for the weighted sums and the fold.
+        // Measured at k = 16 (create_proof): single-proof latency 12.5 -> 12.1 ms, but 8-in-flight throughput 137 -> 132
+        // proofs/s (its CTAs occupy whole SMs that the other proofs' bucket fills would use), so it is opt-in.
+        const unsigned int cm1 = sh.c - 1, w0 = (cm1 + 1) / 2, w1 = cm1 - w0;
+        const unsigned int V0 = 1u << w0, V1 = 1u << w1;
+        XYZZ* D0 = red2;
+        XYZZ* D1 = red2 + (size_t)nsets_total * V0;
+        TimedLaunch tl = timing_begin(ctx, "k_msm_digit_sums", (double)n * count);
+        k_bucket_rowcol<<<dim3(V1 + (V0 + 15) / 16, nsets_total), DE_RC_THREADS, 0, st>>>(buckets, sh.NB, w0, w1, D0, D1);
+        DE_CHECK_LAUNCH(ctx);
+        k_bucket_weighted_final<<<nsets_total, 384, 0, st>>>(D0, D1, w0, w1, set_out);
+        DE_CHECK_LAUNCH(ctx);
+        timing_end(ctx, tl);
+    } else if (sh.c >= 11) {
         // two-digit reduction: row / column plain sums by segmented additions, then the short weighted sums
         const unsigned int cm1 = sh.c - 1, w0 = (cm1 + 1) / 2, w1 = cm1 - w0;
         const unsigned long long V0 = 1ull << w0, V1 = 1ull << w1;
@@ -242,7 +254,8 @@ struct de_params {
     uint32_t k;
     size_t n;
     MsmCfg cfg;
-    Affine* tables[2];  // [0] g, [1] g_lagrange; each cfg.ntables tables of n points
+    Affine* tables[2];  // [0] g, [1] g_lagrange; each cfg.ntables tables of n points, carved out of ONE allocation
+    Affine* block;
 };
 
 extern "C" {
@@ -289,13 +302,28 @@ int de_params_upload(de_ctx* ctx, uint32_t k, const de_g1_affine* g, const de_g1
     p->n = n;
     p->cfg = choose_cfg(n, true, max_tables);
     p->tables[0] = p->tables[1] = nullptr;
+    p->block = nullptr;
     const de_g1_affine* src[2] = {g, g_lagrange};
+    {
+        const size_t per_basis = n * p->cfg.ntables;
+        const size_t nb = (g ? 1 : 0) + (g_lagrange ? 1 : 0);
+        if (cudaMalloc((void**)&p->block, sizeof(Affine) * per_basis * nb) != cudaSuccess) {
+            cudaGetLastError();
+            delete p;
+            return fail(ctx, DE_ERR_OOM, "de_params_upload: device allocation failed");
+        }
+        size_t off = 0;
+        for (int b = 0; b < 2; b++)
+            if (src[b]) {
+                p->tables[b] = p->block + off;
+                off += per_basis;
+            }
+    }
     for (int b = 0; b < 2; b++) {
         if (!src[b]) continue;
-        cudaError_t e = cudaMalloc((void**)&p->tables[b], sizeof(Affine) * n * p->cfg.ntables);
-        Affine* staging = nullptr;
-        if (e == cudaSuccess) staging = (Affine*)ctx->ws[WS_IO_B].ensure(sizeof(Affine) * n);
-        if (e != cudaSuccess || !staging) {
+        cudaError_t e = cudaSuccess;
+        Affine* staging = (Affine*)ctx->ws[WS_IO_B].ensure(sizeof(Affine) * n);
+        if (!staging) {
             cudaGetLastError();
             de_params_free(p);
             return fail(ctx, DE_ERR_OOM, "de_params_upload: device allocation failed");
@@ -321,8 +349,7 @@ int de_params_free(de_params* p) {
     if (!p) return DE_OK;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
-    for (int b = 0; b < 2; b++)
-        if (p->tables[b]) cudaFree(p->tables[b]);
+    if (p->block) cudaFree(p->block);
     delete p;
     return DE_OK;
 }
@@ -438,6 +465,17 @@ int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_
 namespace de {
 int commit_canonical_dev(de_params* p, int basis, const Fr* d_scalars, size_t stride, size_t n, size_t count, uint8_t* out_xy) {
     return de_commit_batch_canonical_dev(p, basis, (const de_fr*)d_scalars, stride, n, count, out_xy);
+}
+// `count_lagrange` polynomials committed over g_lagrange followed by `count_coeff` over g, one launch sequence
+int commit_canonical_mixed_dev(de_params* p, const Fr* d_scalars, size_t stride, size_t n, size_t count_lagrange, size_t count_coeff,
+                               uint8_t* out_xy) {
+    de_ctx* ctx = p->ctx;
+    if (!p->tables[0] || !p->tables[1]) return fail(ctx, DE_ERR_ARG, "de_commit: both bases are needed");
+    if (n > p->n) return fail(ctx, DE_ERR_ARG, "de_commit: polynomial longer than the SRS (n > 2^k)");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    // indices are offsets from the start of the shared allocation, so that both bases are reachable with non-negative indices
+    return msm_core(ctx, d_scalars, stride, n, count_lagrange + count_coeff, p->block, p->n, (size_t)(p->tables[1] - p->block), p->cfg, out_xy, 1,
+                    (unsigned int)count_lagrange, (long long)(p->tables[0] - p->tables[1]));
 }
 de_ctx* params_ctx(de_params* p) { return p->ctx; }
 size_t params_n(de_params* p) { return p->n; }

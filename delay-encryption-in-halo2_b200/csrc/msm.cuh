@@ -30,6 +30,8 @@ struct MsmShape {
     unsigned long long n;   // scalars per polynomial
     unsigned long long table_stride;  // elements between consecutive base tables
     unsigned long long base_offset;   // first base of this (sharded) range inside each table
+    unsigned int alt_first;           // polynomials >= alt_first take their bases alt_delta elements further on (the other
+    long long alt_delta;              // basis of the same ParamsKZG): one launch sequence for commitments over both bases
 };
 
 // ---- 1. digits -------------------------------------------------------------------------------------------------
@@ -64,7 +66,9 @@ __global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmSh
         } else {
             const unsigned int key = (b * sh.nsets + set) * sh.NB + (mag - 1);
             keys[e] = key;
-            vals[e] = (unsigned int)(table * sh.table_stride + sh.base_offset + i) | (neg << 31);
+            unsigned long long tb = table * sh.table_stride + sh.base_offset + i;
+            if (b >= sh.alt_first) tb = (unsigned long long)((long long)tb + sh.alt_delta);
+            vals[e] = (unsigned int)tb | (neg << 31);
             atomicAdd(&counts[key], 1u);  // bucket histogram of the counting sort, fused here
         }
     }
@@ -159,10 +163,25 @@ __global__ void k_scan_add(unsigned int* out, unsigned long long n, const unsign
 #define DE_MSM_MAX_CH 128
 
 // pass 1: tasks per bucket, multi-task bucket lists (few partials: one thread merges; many: one warp), length histogram
-__global__ void __launch_bounds__(256) k_msm_task_counts(const unsigned int* counts, unsigned int nbuckets, unsigned int CH, unsigned int* ntasks,
+// task length for this launch, from the ACTUAL number of entries (scal[0], known after the scan): enough tasks to fill the chip
+// several times over, each no longer than CH_max entries.  Witness-like columns produce far fewer entries than the worst case
+// the host can bound, and a task length sized for the worst case would leave most SMs idle.  One thread; writes scal[4].
+__global__ void k_msm_choose_ch(unsigned int* scal, unsigned int nbuckets, unsigned int ch_max, unsigned int target_tasks) {
+    if (blockIdx.x || threadIdx.x) return;
+    const unsigned int entries = scal[0];
+    unsigned int ch = 8;
+    while (ch < ch_max && entries / (ch * 2) >= target_tasks) ch *= 2;
+    const unsigned int avg = (entries + nbuckets - 1) / nbuckets;
+    if (nbuckets >= target_tasks / 2)
+        while (ch < ch_max && ch < 2 * avg) ch *= 2;
+    scal[4] = ch;
+}
+
+__global__ void __launch_bounds__(256) k_msm_task_counts(const unsigned int* counts, unsigned int nbuckets, unsigned int* ntasks,
                                                          unsigned int* multi_small, unsigned int* multi_large, unsigned int* scal,
                                                          unsigned int* len_bins) {
     __shared__ unsigned int sbins[DE_MSM_MAX_CH + 1];
+    const unsigned int CH = scal[4];
     for (unsigned int i = threadIdx.x; i <= CH; i += blockDim.x) sbins[i] = 0;
     __syncthreads();
     unsigned int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,8 +202,9 @@ __global__ void __launch_bounds__(256) k_msm_task_counts(const unsigned int* cou
         if (sbins[i]) atomicAdd(&len_bins[i], sbins[i]);
 }
 // bin start offsets, longest first: start[len] = sum of bins of greater length.  One block.
-__global__ void k_msm_bin_starts(const unsigned int* len_bins, unsigned int CH, unsigned int* bin_cursor) {
+__global__ void k_msm_bin_starts(const unsigned int* len_bins, const unsigned int* scal, unsigned int* bin_cursor) {
     if (threadIdx.x == 0) {
+        const unsigned int CH = scal[4];
         unsigned int run = 0;
         for (int l = (int)CH; l >= 1; l--) {
             bin_cursor[l] = run;
@@ -194,10 +214,11 @@ __global__ void k_msm_bin_starts(const unsigned int* len_bins, unsigned int CH, 
     }
 }
 // pass 2: every bucket writes its tasks (bucket, local index) into the slot range of their length bin
-__global__ void __launch_bounds__(256) k_msm_task_fill(const unsigned int* counts, unsigned int nbuckets, unsigned int CH,
+__global__ void __launch_bounds__(256) k_msm_task_fill(const unsigned int* counts, unsigned int nbuckets, const unsigned int* scal,
                                                        unsigned int* bin_cursor, uint2* task_list) {
     __shared__ unsigned int scount[DE_MSM_MAX_CH + 1];
     __shared__ unsigned int sbase[DE_MSM_MAX_CH + 1];
+    const unsigned int CH = scal[4];
     for (unsigned int i = threadIdx.x; i <= CH; i += blockDim.x) scount[i] = 0;
     __syncthreads();
     unsigned int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,10 +247,11 @@ __device__ __forceinline__ Affine msm_fetch(const Affine* bases, unsigned int v)
 }
 
 __global__ void __launch_bounds__(128) k_msm_accumulate(const unsigned int* sorted, const unsigned int* offsets, const unsigned int* counts,
-                                                        const unsigned int* task_off, const uint2* task_list, const unsigned int* n_tasks,
-                                                        unsigned int CH, const Affine* bases, XYZZ* buckets, XYZZ* partials) {
+                                                        const unsigned int* task_off, const uint2* task_list, const unsigned int* scal,
+                                                        const Affine* bases, XYZZ* buckets, XYZZ* partials) {
     unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= *n_tasks) return;
+    if (t >= scal[1]) return;
+    const unsigned int CH = scal[4];
     const uint2 task = task_list[t];
     const unsigned int b = task.x, local = task.y;
     const unsigned int cnt = counts[b];
@@ -454,6 +476,120 @@ __global__ void __launch_bounds__(128) k_msm_digit_final2(const XYZZ* dsums0, un
         xyzz_add(result, w1);
         XYZZ tot = stotal;
         xyzz_add(result, tot);
+        store_xyzz(&set_out[set], result);
+    }
+}
+
+// ---- 4c. fused two-digit reduction for V0 <= 256, V0 + V1 <= 384 (c <= 16: the proof-sized MSMs) ------------------------
+// The same decomposition as 4b, arranged for latency: ONE launch forms every D1[u] (a CTA per bucket row: 2^w0 contiguous
+// buckets, tree sum in shared memory) and every D0[v] (a CTA per 16 columns: 16 row groups summed serially, then a 4-level
+// tree), and ONE single-CTA-per-set kernel turns D0 / D1 into sum_v v * D0[v], sum_u u * D1[u] by a suffix scan + tree in
+// shared memory (depth 2 * log2 instead of radix-32 digit sums followed by warp-shuffle scans) and folds the result.
+#define DE_RC_THREADS 256
+__device__ __forceinline__ void smem_tree_sum(XYZZ* s, unsigned int tid, unsigned int len) {
+    // s[0] <- sum of s[0 .. len), len a power of two <= blockDim; ends with a barrier
+    for (unsigned int d = len >> 1; d >= 1; d >>= 1) {
+        __syncthreads();
+        if (tid < d) {
+            XYZZ a = load_xyzz(&s[tid]);
+            XYZZ b = load_xyzz(&s[tid + d]);
+            xyzz_add(a, b);
+            store_xyzz(&s[tid], a);
+        }
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(DE_RC_THREADS) k_bucket_rowcol(const XYZZ* buckets, unsigned int NB, unsigned int w0, unsigned int w1, XYZZ* D0,
+                                                                 XYZZ* D1) {
+    __shared__ XYZZ sm[DE_RC_THREADS];
+    const unsigned int V0 = 1u << w0, V1 = 1u << w1;
+    const unsigned int tid = threadIdx.x;
+    const unsigned long long set = blockIdx.y;
+    const XYZZ* B = buckets + set * NB;
+    if (blockIdx.x < V1) {
+        // row sum: D1[u] = sum_v B[u][v], V0 <= 256 contiguous buckets
+        const unsigned int u = blockIdx.x;
+        XYZZ acc = xyzz_identity();
+        if (tid < V0) acc = load_xyzz(&B[(unsigned long long)u * V0 + tid]);
+        store_xyzz(&sm[tid], acc);
+        smem_tree_sum(sm, tid, DE_RC_THREADS);
+        if (tid == 0) store_xyzz(&D1[set * V1 + u], load_xyzz(&sm[0]));
+    } else {
+        // column sums of 16 adjacent columns: thread (g, cv) adds rows g, g + 16, ... of column v0 + cv, then a tree over g
+        const unsigned int v0 = (blockIdx.x - V1) * 16;
+        const unsigned int g = tid >> 4, cv = tid & 15;
+        XYZZ acc = xyzz_identity();
+        if (v0 + cv < V0) {
+            for (unsigned int u = g; u < V1; u += 16) {
+                XYZZ x = load_xyzz(&B[(unsigned long long)u * V0 + v0 + cv]);
+                xyzz_add(acc, x);
+            }
+        }
+        // layout sm[cv * 16 + g] so that each column's 16 partials are contiguous: tree over g inside every 16-element group
+        store_xyzz(&sm[cv * 16 + g], acc);
+        for (unsigned int d = 8; d >= 1; d >>= 1) {
+            __syncthreads();
+            const unsigned int c = tid >> 4, gg = tid & 15;
+            if (gg < d) {
+                XYZZ a = load_xyzz(&sm[c * 16 + gg]);
+                XYZZ b = load_xyzz(&sm[c * 16 + gg + d]);
+                xyzz_add(a, b);
+                store_xyzz(&sm[c * 16 + gg], a);
+            }
+        }
+        __syncthreads();
+        if (tid < 16 && v0 + tid < V0) store_xyzz(&D0[set * V0 + v0 + tid], load_xyzz(&sm[tid * 16]));
+    }
+}
+// one CTA (384 threads) per bucket set: threads [0, 256) own D0, [256, 384) own D1.
+//   suffix scan R_t = sum_{v >= t} D[v]  ->  T = R_0 (array 0 only), W = sum_{t >= 1} R_t = sum_v v * D[v]
+//   result = T + W0 + 2^w0 * W1
+__global__ void __launch_bounds__(384) k_bucket_weighted_final(const XYZZ* D0, const XYZZ* D1, unsigned int w0, unsigned int w1, XYZZ* set_out) {
+    __shared__ XYZZ sm[384];
+    const unsigned int V0 = 1u << w0, V1 = 1u << w1;
+    const unsigned int tid = threadIdx.x;
+    const unsigned long long set = blockIdx.x;
+    const bool arr1 = tid >= 256;
+    const unsigned int t = arr1 ? tid - 256 : tid;
+    const unsigned int len = arr1 ? V1 : V0;
+    XYZZ* s = sm + (arr1 ? 256 : 0);
+    XYZZ mine = xyzz_identity();
+    if (t < len) mine = load_xyzz(arr1 ? &D1[set * V1 + t] : &D0[set * V0 + t]);
+    store_xyzz(&s[t], mine);
+    __syncthreads();
+    // inclusive suffix scan (Hillis-Steele): both arrays run the same number of steps
+    const unsigned int steps_len = V0 > V1 ? V0 : V1;
+    for (unsigned int d = 1; d < steps_len; d <<= 1) {
+        XYZZ o = xyzz_identity();
+        const bool has = t + d < len;
+        if (has) o = load_xyzz(&s[t + d]);
+        __syncthreads();
+        if (has) {
+            xyzz_add(mine, o);
+            store_xyzz(&s[t], mine);
+        }
+        __syncthreads();
+    }
+    const XYZZ total = mine;  // thread 0: R_0 of D0 = sum of all buckets
+    if (t == 0) store_xyzz(&s[0], xyzz_identity());
+    // W = sum_{t >= 1} R_t: tree over each array's own power-of-two length (array 0: 256 slots, array 1: 128 slots)
+    for (unsigned int d = 128; d >= 1; d >>= 1) {
+        __syncthreads();
+        const unsigned int half = arr1 ? (d >> 1) : d;  // array 1 has half as many slots: its tree is one level shorter
+        if (half >= 1 && t < half) {
+            XYZZ a = load_xyzz(&s[t]);
+            XYZZ b = load_xyzz(&s[t + half]);
+            xyzz_add(a, b);
+            store_xyzz(&s[t], a);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        XYZZ w1v = load_xyzz(&sm[256]);
+        for (unsigned int k = 0; k < w0; k++) w1v = xyzz_dbl(w1v);
+        XYZZ result = load_xyzz(&sm[0]);
+        xyzz_add(result, w1v);
+        xyzz_add(result, total);
         store_xyzz(&set_out[set], result);
     }
 }

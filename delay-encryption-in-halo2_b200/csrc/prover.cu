@@ -30,6 +30,7 @@ namespace de {
 
 // msm.cu
 int commit_canonical_dev(de_params* p, int basis, const Fr* d_scalars, size_t stride, size_t n, size_t count, uint8_t* out_xy);
+int commit_canonical_mixed_dev(de_params* p, const Fr* d_scalars, size_t stride, size_t n, size_t count_lagrange, size_t count_coeff, uint8_t* out_xy);
 de_ctx* params_ctx(de_params* p);
 size_t params_n(de_params* p);
 
@@ -439,12 +440,16 @@ struct StreamSwap {  // the NTT / evaluator entry points launch on ctx->stream
 
 namespace {
 
+// column order of the per-proof blocks `lag` / `coef`: [advice | instance | a' | s' | permz | lookup z] (+ one spare column in
+// `lag`); the pk's coset workspace keeps evaluate_h's order [advice | instance | permz | lookup z | a' | s']
 size_t off_advice(const de_prover*) { return 0; }
 size_t off_instance(const de_prover* p) { return p->A; }
-size_t off_permz(const de_prover* p) { return p->A + p->I; }
-size_t off_lookup_z(const de_prover* p) { return p->A + p->I + p->Z; }
-size_t off_lookup_a(const de_prover* p) { return p->A + p->I + p->Z + p->L; }
-size_t off_lookup_s(const de_prover* p) { return p->A + p->I + p->Z + 2 * (size_t)p->L; }
+size_t off_lookup_a(const de_prover* p) { return p->A + p->I; }
+size_t off_lookup_s(const de_prover* p) { return p->A + p->I + p->L; }
+size_t off_permz(const de_prover* p) { return p->A + p->I + 2 * (size_t)p->L; }
+size_t off_lookup_z(const de_prover* p) { return p->A + p->I + 2 * (size_t)p->L + p->Z; }
+size_t work_permz(const de_prover* p) { return p->A + p->I; }
+size_t work_lookup_a(const de_prover* p) { return p->A + p->I + p->Z + p->L; }
 
 HFr to_hfr(const de_fr& v) {
     HFr r;
@@ -563,7 +568,7 @@ int de_prover_create(de_params* params, de_pk* pk, const de_prover_desc* desc, d
     int rc;
 #define DE_PALLOC(field, type, count) \
     if ((rc = dmalloc((void**)&p->field, sizeof(type) * (count))) != DE_OK) return bail(rc)
-    DE_PALLOC(lag, Fr, ncol * n);
+    DE_PALLOC(lag, Fr, (ncol + 1) * n);  // + one column: the random polynomial rides along with the grand products' commit
     DE_PALLOC(coef, Fr, ncol * n);
     DE_PALLOC(fixed_lag, Fr, ((size_t)p->F + p->P) * n + 1);
     DE_PALLOC(comp, Fr, 2 * (size_t)p->L * n + 1);
@@ -747,7 +752,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
 
     // columns [c0, c0 + cnt) are final in lagrange form on `st`: coefficient form and extended coset on the second stream
     // (neither depends on a transcript challenge), overlapping the same columns' commitment
-    auto to_cosets = [&](size_t c0, size_t cnt) -> int {
+    auto to_cosets = [&](size_t c0, size_t cnt, size_t work_c0) -> int {
         if (!cnt) return DE_OK;
         cudaStream_t sb = p->overlap ? p->st_b : st;
         if (p->overlap) {
@@ -757,7 +762,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         StreamSwap sw(ctx, sb);
         DE_CUDA(ctx, cudaMemcpyAsync(p->coef + c0 * n, p->lag + c0 * n, sizeof(Fr) * n * cnt, cudaMemcpyDeviceToDevice, sb));
         DE_TRY(de_lagrange_to_coeff_dev(p->dom, (de_fr*)(p->coef + c0 * n), n, cnt));
-        DE_TRY(de_coeff_to_extended_dev(p->dom, (const de_fr*)(p->coef + c0 * n), n, (de_fr*)(pk->work + c0 * p->ext_n), p->ext_n, cnt));
+        DE_TRY(de_coeff_to_extended_dev(p->dom, (const de_fr*)(p->coef + c0 * n), n, (de_fr*)(pk->work + work_c0 * p->ext_n), p->ext_n, cnt));
         return DE_OK;
     };
 
@@ -765,7 +770,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     for (uint32_t a = 0; a < A; a++) add_tail(p->lag + (off_advice(p) + a) * n + usable, bf + 1);
     rpos += A;  // advice blinds
     DE_TRY(flush_tails());
-    DE_TRY(to_cosets(off_advice(p), (size_t)A + I));
+    DE_TRY(to_cosets(off_advice(p), (size_t)A + I, 0));
     DE_TRY(commit(1, p->lag + off_advice(p) * n, A));
     const HFr theta = tr.squeeze_challenge();
 
@@ -807,7 +812,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         DE_TRY(flush_tails());
         int h_err = 0;
         DE_CUDA(ctx, cudaMemcpyAsync(&h_err, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-        DE_TRY(to_cosets(off_lookup_a(p), 2 * (size_t)L));
+        DE_TRY(to_cosets(off_lookup_a(p), 2 * (size_t)L, work_lookup_a(p)));
         // one launch sequence for the 2L permuted columns (a' block then s' block, adjacent in HBM); the transcript takes
         // them interleaved: a'_0, s'_0, a'_1, s'_1, ...
         std::vector<uint8_t> pas(64 * 2 * (size_t)L);
@@ -877,14 +882,23 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
             rpos += 1;
         }
         DE_TRY(flush_tails());
-        DE_TRY(to_cosets(off_permz(p), zl));
-        DE_TRY(commit(1, p->lag + off_permz(p) * n, zl));
+        DE_TRY(to_cosets(off_permz(p), zl, work_permz(p)));
     }
 
-    // ---- vanishing argument: random polynomial
+    // ---- vanishing argument: the random polynomial.  Its commitment follows the grand products' in the transcript with no
+    // challenge in between, so the two rounds share one launch sequence: zl polynomials over g_lagrange and one over g.
     const Fr* random_poly = p->randoms + rpos;
     rpos += n + 1;  // coefficients + blind
-    DE_TRY(commit(0, random_poly, 1));
+    {
+        // column order in `lag` is [advice | instance | a' | s' | permz | lookup z | spare]: the spare column after the z block
+        // takes the random polynomial, so the batch is contiguous
+        Fr* batch = p->lag + off_permz(p) * n;
+        DE_CUDA(ctx, cudaMemcpyAsync(batch + zl * n, random_poly, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st));
+        if (zl + 1 > 64) return fail(ctx, DE_ERR_UNSUPPORTED, "de_create_proof: more than 64 commitments in one round");
+        DE_TRY(commit_canonical_mixed_dev(p->params, batch, n, n, zl, 1, xy.data()));
+        for (size_t i = 0; i < zl + 1; i++)
+            if (!tr.write_point(xy.data() + 64 * i)) return fail(ctx, DE_ERR_ARG, "de_create_proof: a commitment is the point at infinity");
+    }
     const HFr y = tr.squeeze_challenge();
 
     // ---- quotient: every coset is (being) produced on the second stream
