@@ -36,9 +36,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "delay-encryption-in-halo2_b200"))
 
+# BASELINE.json configs: [2] delay_enc is the headline (the metric's name); [1] pose_enc and [0] mod_pow are selectable with
+# --config for the parity / context runs.  (k, range lookups, used rows, seed, reference bench file:line)
+CONFIGS = {
+    "delay_enc": (16, True, 50400, 0xDE03, "benches/delay_enc.rs:181"),
+    "mod_pow": (17, True, 41766, 0xDE01, "benches/mod_pow.rs:258"),
+    "pose_enc": (11, False, 1450, 0xDE02, "benches/pose_enc.rs:184"),
+}
 K = 16
 USED_ROWS = 50400
 SEED = 0xDE03
+WITH_LOOKUPS = True
+CONFIG_NAME = "delay_enc"
 WORKLOAD = ("delay_enc k=16 create_proof (MainGate + RangeChip shape: 5 advice, 15 fixed, 5 lookups, 6 permutation columns; "
             "satisfied synthetic witness, 50400 used rows): 31 MSM 2^16 (KZG bases resident), 23 iNTT 2^16, 23 coset-NTT 2^18, "
             "evaluate_h over 2^18 rows, 1 iNTT 2^18, 10 lookup sorts, 7 grand products, 58 evaluations, 4 Kate divisions, "
@@ -65,7 +74,7 @@ def _peaks():
 def build_circuit():
     """The satisfied synthetic delay_enc-shaped assignment (canonical integers) and the SRS bases."""
     from de_b200 import circuits, synth
-    asg = circuits.satisfied_assignment(True, K, SEED, USED_ROWS)
+    asg = circuits.satisfied_assignment(WITH_LOOKUPS, K, SEED, USED_ROWS, uniform_values=not WITH_LOOKUPS)
     n = 1 << K
     return asg, synth.gen_bases(n, start=0), synth.gen_bases(n, start=n)
 
@@ -230,7 +239,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=8, help="independent proofs in flight per GPU (one prover + stream each)")
+    ap.add_argument("--config", default="delay_enc", choices=sorted(CONFIGS), help="circuit shape / size (default: the headline delay_enc)")
     args = ap.parse_args()
+    global K, USED_ROWS, SEED, WITH_LOOKUPS, CONFIG_NAME, WORKLOAD, METRIC, CPU_SAMPLE
+    if args.config != "delay_enc":
+        K, WITH_LOOKUPS, USED_ROWS, SEED, where = CONFIGS[args.config]
+        CONFIG_NAME = args.config
+        METRIC = f"{args.config}_create_proof_proofs_per_s"
+        WORKLOAD = (f"{args.config} k={K} create_proof (/root/reference/{where}; MainGate{' + RangeChip' if WITH_LOOKUPS else ''} shape, satisfied "
+                    f"synthetic witness, {USED_ROWS} used rows)")
+        CPU_SAMPLE = CPU_SAMPLE.replace("delay_enc k=16", f"{args.config} k={K}").replace("31 best_multiexp 2^16, 23 + 23 + 1 best_fft, evaluate_h over 2^18 rows",
+                                                                                       "the proof's best_multiexp / best_fft / evaluate_h calls")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -316,7 +335,7 @@ def main():
 
     timed(workers, args.warmup, False)
     first_proof = workers[0].proof
-    assert len(first_proof) == prover0.proof_size == 2848
+    assert len(first_proof) == prover0.proof_size == (2848 if WITH_LOOKUPS else 1792)
     # ---- throughput arm (value): B proofs in flight per GPU, inputs resident in HBM
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -345,8 +364,9 @@ def main():
     ctx.timing_enable(False)
 
     h2d = advice_h.numel() * 8 + prover0.random_count * 32
-    n_points = (len(first_proof) - 32 * 58) // 32
-    d2h = n_points * 64 + 58 * 32
+    n_evals = 58 if WITH_LOOKUPS else 39
+    n_points = (len(first_proof) - 32 * n_evals) // 32
+    d2h = n_points * 64 + n_evals * 32
     peaks, peak_kind = _peaks()
     value = world * args.steps * B / (ms_dev / 1000.0)
     e2e_value = world * args.steps * B / (ms_e2e / 1000.0)
@@ -357,7 +377,7 @@ def main():
         "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proofs_per_step_per_gpu": B, "proof_bytes": len(first_proof),
                    "in_flight": f"{B} independent proofs per GPU, one host thread + CUDA stream each (BASELINE config 5: 64 proofs over "
                                 "8 GPUs = 8 per GPU)",
-                   "l2": f"per-step working set ~{0.8 * B:.1f} GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
+                   "l2": f"per-step working set ~{0.8 * B * 2.0 ** (K - 16):.2f} GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
                    "sharding": "independent proofs across GPUs, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
                 "ms_per_step": ms_e2e / args.steps},

@@ -21,7 +21,8 @@ import numpy as np
 from . import _lib
 from ._lib import DeError
 
-__all__ = ["Context", "EvaluationDomain", "ParamsKZG", "best_multiexp", "best_fft", "DeError", "default_context"]
+__all__ = ["Context", "EvaluationDomain", "ParamsKZG", "best_multiexp", "best_fft", "DeError", "default_context", "read_params_raw",
+           "write_params_raw"]
 
 
 def _np(a, cols=None):
@@ -264,8 +265,47 @@ class EvaluationDomain:
         self.ctx.check(self.ctx.L.de_divide_by_vanishing_dev(self.h, _ptr(d_ext), stride or self.extended_n, batch))
 
 
+def read_params_raw(path):
+    """ParamsKZG::read(reader, SerdeFormat::RawBytes), the format the reference's benches cache their SRS in
+    (/root/reference/benches/delay_enc.rs:43-54): k as u32 LE, g[2^k] and g_lagrange[2^k] as raw
+    64-byte affine points (Montgomery limbs, the in-memory layout the C ABI takes), then g2 and s_g2 (128 bytes each).
+    Returns dict(k, g, g_lagrange, g2, s_g2) with the point arrays memory-mapped (no copy until upload)."""
+    import os
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        k = int.from_bytes(f.read(4), "little")
+    n = 1 << k
+    if k > 28 or size != 4 + 2 * n * 64 + 256:
+        raise ValueError(f"{path}: not a RawBytes ParamsKZG file for k = {k} (size {size})")
+    g = np.memmap(path, dtype=np.uint64, mode="r", offset=4, shape=(n, 8))
+    gl = np.memmap(path, dtype=np.uint64, mode="r", offset=4 + n * 64, shape=(n, 8))
+    tail = np.fromfile(path, dtype=np.uint8, offset=4 + 2 * n * 64)
+    return dict(k=k, g=g, g_lagrange=gl, g2=tail[:128].tobytes(), s_g2=tail[128:].tobytes())
+
+
+def write_params_raw(path, k, g, g_lagrange, g2: bytes, s_g2: bytes):
+    """ParamsKZG::write(writer, SerdeFormat::RawBytes)"""
+    g, gl = _np(g), _np(g_lagrange)
+    if g.size != 8 << k or gl.size != 8 << k or len(g2) != 128 or len(s_g2) != 128:
+        raise ValueError("write_params_raw: wrong sizes")
+    with open(path, "wb") as f:
+        f.write(int(k).to_bytes(4, "little"))
+        f.write(g.tobytes())
+        f.write(gl.tobytes())
+        f.write(g2)
+        f.write(s_g2)
+
+
 class ParamsKZG:
     """poly::kzg::commitment::ParamsKZG: g / g_lagrange staged (with window tables) in HBM once."""
+
+    @classmethod
+    def read(cls, path, ctx: Context | None = None):
+        """ParamsKZG::read(.., SerdeFormat::RawBytes): the file's point arrays are uploaded straight from the mapping"""
+        d = read_params_raw(path)
+        p = cls(d["k"], np.ascontiguousarray(d["g"]), np.ascontiguousarray(d["g_lagrange"]), ctx)
+        p.g2, p.s_g2 = d["g2"], d["s_g2"]
+        return p
 
     def __init__(self, k: int, g=None, g_lagrange=None, ctx: Context | None = None):
         self.ctx = ctx or default_context()

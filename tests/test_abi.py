@@ -45,3 +45,23 @@ def test_oracle_is_not_imported_by_the_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f == "NOTES", f"{f} mentions the oracle: the product path must not use it"
+
+
+def test_params_raw_bytes_file_round_trip(tmp_path):
+    """SerdeFormat::RawBytes params file (SURVEY.md Appendix F): k | g | g_lagrange | g2 | s_g2, Montgomery limbs verbatim"""
+    import numpy as np
+    import de_b200
+    import orc
+    k = 4
+    g, gl = orc.gen_bases(16), orc.gen_bases(16, start=16)
+    g2, s_g2 = bytes(range(128)), bytes(range(128, 256))
+    path = tmp_path / "params_4"
+    de_b200.write_params_raw(path, k, g, gl, g2, s_g2)
+    assert path.stat().st_size == 4 + 2 * 16 * 64 + 256
+    d = de_b200.read_params_raw(path)
+    assert d["k"] == k and (np.asarray(d["g"]) == g).all() and (np.asarray(d["g_lagrange"]) == gl).all()
+    assert d["g2"] == g2 and d["s_g2"] == s_g2
+    with open(path, "ab") as f:
+        f.write(b"x")
+    with pytest.raises(ValueError):
+        de_b200.read_params_raw(path)

@@ -123,6 +123,15 @@ def test_create_proof_delay_enc_shape_k16():
     assert proof2 == proof
 
 
+def test_create_proof_mod_pow_shape_k17():
+    """/root/reference/benches/mod_pow.rs:258: K = 17 although the circuit's 41 766 rows would fit k = 16"""
+    proof, want, ok, proof2 = run_both(True, 17, 41766, 0xDE01)
+    assert len(proof) == 2848
+    assert proof == want, f"first differing 32-byte proof element: #{first_diff(proof, want)}"
+    assert ok
+    assert proof2 == proof
+
+
 def test_unsatisfied_lookup_is_reported():
     k = 6
     asg = circuits.satisfied_assignment(True, k, 0xDE06, 40)
