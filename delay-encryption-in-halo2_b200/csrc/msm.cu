@@ -43,8 +43,10 @@ static MsmCfg choose_cfg(unsigned long long n, bool precomputed, unsigned long l
     return best;
 }
 
-static int scan_u32(de_ctx* ctx, const unsigned int* in, unsigned long long n, unsigned int* out, unsigned int* block_sums,
-                    unsigned int* grand_total) {
+// exclusive scan of n u32 values (three launches); out has n entries, *grand_total receives the sum.  block_sums: scratch of
+// DE_SCAN_THREADS * DE_SCAN_ITEMS words.  Also used by prover.cu for the lookup compaction indices.
+int scan_u32(de_ctx* ctx, const unsigned int* in, unsigned long long n, unsigned int* out, unsigned int* block_sums,
+             unsigned int* grand_total) {
     const unsigned long long per_block = DE_SCAN_THREADS * DE_SCAN_ITEMS;
     unsigned long long nblocks = (n + per_block - 1) / per_block;
     if (nblocks > per_block) return fail(ctx, DE_ERR_UNSUPPORTED, "msm: too many buckets for the scan");
@@ -148,18 +150,19 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CHECK_LAUNCH(ctx);
     k_msm_merge_large<<<ctx->sm_count * 2, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    if (sh.c >= 11 && sh.c <= 16 && getenv("DE_MSM_FUSED_REDUCTION")) {
-        // fused two-digit reduction (4c): one launch for every row / column sum, one for the weighted sums and the fold.
-        // Measured at k = 16 (create_proof): single-proof latency 12.5 -> 12.1 ms, but 8-in-flight throughput 137 -> 132
-        // proofs/s (its CTAs occupy whole SMs that the other proofs' bucket fills would use), so it is opt-in.
+    if (sh.c >= 11 && sh.c <= 16 && !getenv("DE_MSM_SEGSUM_REDUCTION")) {
+        // latency-oriented two-digit reduction (4c): row / column sums in one launch, bit sums, one warp per set for the fold
         const unsigned int cm1 = sh.c - 1, w0 = (cm1 + 1) / 2, w1 = cm1 - w0;
         const unsigned int V0 = 1u << w0, V1 = 1u << w1;
         XYZZ* D0 = red2;
-        XYZZ* D1 = red2 + (size_t)nsets_total * V0;
+        XYZZ* D1 = D0 + (size_t)nsets_total * V0;
+        XYZZ* S = D1 + (size_t)nsets_total * V1;
         TimedLaunch tl = timing_begin(ctx, "k_msm_digit_sums", (double)n * count);
-        k_bucket_rowcol<<<dim3(V1 + (V0 + 15) / 16, nsets_total), DE_RC_THREADS, 0, st>>>(buckets, sh.NB, w0, w1, D0, D1);
+        k_bucket_rowcol<<<dim3(V1 + V0 / 4, nsets_total), DE_RC_THREADS, 0, st>>>(buckets, sh.NB, w0, w1, D0, D1);
         DE_CHECK_LAUNCH(ctx);
-        k_bucket_weighted_final<<<nsets_total, 384, 0, st>>>(D0, D1, w0, w1, set_out);
+        k_bucket_bitsums<<<dim3(w0 + w1 + 1, nsets_total), DE_RC_THREADS, 0, st>>>(D0, D1, w0, w1, S);
+        DE_CHECK_LAUNCH(ctx);
+        k_bucket_bits_final<<<nsets_total, 32, 0, st>>>(S, w0, w1, set_out);
         DE_CHECK_LAUNCH(ctx);
         timing_end(ctx, tl);
     } else if (sh.c >= 11) {

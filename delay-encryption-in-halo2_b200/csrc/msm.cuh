@@ -480,12 +480,17 @@ __global__ void __launch_bounds__(128) k_msm_digit_final2(const XYZZ* dsums0, un
     }
 }
 
-// ---- 4c. fused two-digit reduction for V0 <= 256, V0 + V1 <= 384 (c <= 16: the proof-sized MSMs) ------------------------
-// The same decomposition as 4b, arranged for latency: ONE launch forms every D1[u] (a CTA per bucket row: 2^w0 contiguous
-// buckets, tree sum in shared memory) and every D0[v] (a CTA per 16 columns: 16 row groups summed serially, then a 4-level
-// tree), and ONE single-CTA-per-set kernel turns D0 / D1 into sum_v v * D0[v], sum_u u * D1[u] by a suffix scan + tree in
-// shared memory (depth 2 * log2 instead of radix-32 digit sums followed by warp-shuffle scans) and folds the result.
-#define DE_RC_THREADS 256
+// ---- 4c. latency-oriented two-digit reduction for c <= 16 (the proof-sized MSMs) ---------------------------------------
+// The same decomposition as 4b (D0[v] = column sums, D1[u] = row sums of the 2^w1 x 2^w0 bucket array), arranged so that the
+// chain of DEPENDENT point additions is short and no CTA occupies an SM for long (a dependent XYZZ addition costs ~6 us of
+// latency on one warp, whatever the occupancy):
+//   k_bucket_rowcol   one launch, 64-thread CTAs: a CTA per bucket row (<= 4 serial additions per thread + a 6-level tree in
+//                     shared memory) and a CTA per 4 columns (16 row groups, <= 8 serial additions + a 4-level tree)
+//   k_bucket_bitsums  sum_v v * D[v] = sum_j 2^j * S_j with S_j = sum of the D[v] whose index has bit j set: one 64-thread
+//                     CTA per (array, bit) forms S_j by a tree; one more forms T = sum of all buckets
+//   k_bucket_bits_final  one warp per bucket set: lane s doubles its term s times (bit j of D1 weighs 2^(w0 + j) and sits in
+//                     slot w0 + j), then a 4-level tree adds the <= 16 terms.  result = T + sum_s 2^s * S_s
+#define DE_RC_THREADS 64
 __device__ __forceinline__ void smem_tree_sum(XYZZ* s, unsigned int tid, unsigned int len) {
     // s[0] <- sum of s[0 .. len), len a power of two <= blockDim; ends with a barrier
     for (unsigned int d = len >> 1; d >= 1; d >>= 1) {
@@ -499,33 +504,34 @@ __device__ __forceinline__ void smem_tree_sum(XYZZ* s, unsigned int tid, unsigne
     }
     __syncthreads();
 }
-__global__ void __launch_bounds__(DE_RC_THREADS) k_bucket_rowcol(const XYZZ* buckets, unsigned int NB, unsigned int w0, unsigned int w1, XYZZ* D0,
-                                                                 XYZZ* D1) {
+__global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_rowcol(const XYZZ* buckets, unsigned int NB, unsigned int w0, unsigned int w1, XYZZ* D0,
+                                                                    XYZZ* D1) {
     __shared__ XYZZ sm[DE_RC_THREADS];
     const unsigned int V0 = 1u << w0, V1 = 1u << w1;
     const unsigned int tid = threadIdx.x;
     const unsigned long long set = blockIdx.y;
     const XYZZ* B = buckets + set * NB;
     if (blockIdx.x < V1) {
-        // row sum: D1[u] = sum_v B[u][v], V0 <= 256 contiguous buckets
+        // row sum: D1[u] = sum_v B[u][v] over V0 contiguous buckets; thread t takes v = t, t + 64, ...
         const unsigned int u = blockIdx.x;
         XYZZ acc = xyzz_identity();
-        if (tid < V0) acc = load_xyzz(&B[(unsigned long long)u * V0 + tid]);
+        for (unsigned int v = tid; v < V0; v += DE_RC_THREADS) {
+            XYZZ x = load_xyzz(&B[(unsigned long long)u * V0 + v]);
+            xyzz_add(acc, x);
+        }
         store_xyzz(&sm[tid], acc);
         smem_tree_sum(sm, tid, DE_RC_THREADS);
         if (tid == 0) store_xyzz(&D1[set * V1 + u], load_xyzz(&sm[0]));
     } else {
-        // column sums of 16 adjacent columns: thread (g, cv) adds rows g, g + 16, ... of column v0 + cv, then a tree over g
-        const unsigned int v0 = (blockIdx.x - V1) * 16;
-        const unsigned int g = tid >> 4, cv = tid & 15;
+        // column sums of 4 adjacent columns: thread (g, cv) adds rows g, g + 16, ... of column v0 + cv, then a tree over g
+        const unsigned int v0 = (blockIdx.x - V1) * 4;
+        const unsigned int g = tid >> 2, cv = tid & 3;
         XYZZ acc = xyzz_identity();
-        if (v0 + cv < V0) {
-            for (unsigned int u = g; u < V1; u += 16) {
-                XYZZ x = load_xyzz(&B[(unsigned long long)u * V0 + v0 + cv]);
-                xyzz_add(acc, x);
-            }
+        for (unsigned int u = g; u < V1; u += 16) {
+            XYZZ x = load_xyzz(&B[(unsigned long long)u * V0 + v0 + cv]);
+            xyzz_add(acc, x);
         }
-        // layout sm[cv * 16 + g] so that each column's 16 partials are contiguous: tree over g inside every 16-element group
+        // sm[cv * 16 + g]: each column's 16 partials are contiguous; tree over g inside every 16-element group
         store_xyzz(&sm[cv * 16 + g], acc);
         for (unsigned int d = 8; d >= 1; d >>= 1) {
             __syncthreads();
@@ -538,60 +544,51 @@ __global__ void __launch_bounds__(DE_RC_THREADS) k_bucket_rowcol(const XYZZ* buc
             }
         }
         __syncthreads();
-        if (tid < 16 && v0 + tid < V0) store_xyzz(&D0[set * V0 + v0 + tid], load_xyzz(&sm[tid * 16]));
+        if (tid < 4) store_xyzz(&D0[set * V0 + v0 + tid], load_xyzz(&sm[tid * 16]));
     }
 }
-// one CTA (384 threads) per bucket set: threads [0, 256) own D0, [256, 384) own D1.
-//   suffix scan R_t = sum_{v >= t} D[v]  ->  T = R_0 (array 0 only), W = sum_{t >= 1} R_t = sum_v v * D[v]
-//   result = T + W0 + 2^w0 * W1
-__global__ void __launch_bounds__(384) k_bucket_weighted_final(const XYZZ* D0, const XYZZ* D1, unsigned int w0, unsigned int w1, XYZZ* set_out) {
-    __shared__ XYZZ sm[384];
-    const unsigned int V0 = 1u << w0, V1 = 1u << w1;
-    const unsigned int tid = threadIdx.x;
+// grid.x = slot: [0, w0) bit j of D0, [w0, w0 + w1) bit (slot - w0) of D1, w0 + w1: the plain total of D0.  grid.y = set.
+__global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_bitsums(const XYZZ* D0, const XYZZ* D1, unsigned int w0, unsigned int w1, XYZZ* S) {
+    __shared__ XYZZ sm[DE_RC_THREADS];
+    const unsigned int tid = threadIdx.x, slot = blockIdx.x;
+    const unsigned long long set = blockIdx.y;
+    const unsigned int nslots = w0 + w1 + 1;
+    XYZZ acc = xyzz_identity();
+    if (slot == w0 + w1) {
+        const XYZZ* D = D0 + set * (1ull << w0);
+        for (unsigned int v = tid; v < (1u << w0); v += DE_RC_THREADS) {
+            XYZZ x = load_xyzz(&D[v]);
+            xyzz_add(acc, x);
+        }
+    } else {
+        const bool second = slot >= w0;
+        const unsigned int j = second ? slot - w0 : slot;
+        const unsigned int w = second ? w1 : w0;
+        const XYZZ* D = second ? D1 + set * (1ull << w1) : D0 + set * (1ull << w0);
+        for (unsigned int m = tid; m < (1u << (w - 1)); m += DE_RC_THREADS) {
+            const unsigned int v = ((m >> j) << (j + 1)) | (1u << j) | (m & ((1u << j) - 1));  // m with a 1 inserted at bit j
+            XYZZ x = load_xyzz(&D[v]);
+            xyzz_add(acc, x);
+        }
+    }
+    store_xyzz(&sm[tid], acc);
+    smem_tree_sum(sm, tid, DE_RC_THREADS);
+    if (tid == 0) store_xyzz(&S[set * nslots + slot], load_xyzz(&sm[0]));
+}
+__global__ void __launch_bounds__(32) k_bucket_bits_final(const XYZZ* S, unsigned int w0, unsigned int w1, XYZZ* set_out) {
+    __shared__ XYZZ sm[32];
+    const unsigned int lane = threadIdx.x;
     const unsigned long long set = blockIdx.x;
-    const bool arr1 = tid >= 256;
-    const unsigned int t = arr1 ? tid - 256 : tid;
-    const unsigned int len = arr1 ? V1 : V0;
-    XYZZ* s = sm + (arr1 ? 256 : 0);
-    XYZZ mine = xyzz_identity();
-    if (t < len) mine = load_xyzz(arr1 ? &D1[set * V1 + t] : &D0[set * V0 + t]);
-    store_xyzz(&s[t], mine);
-    __syncthreads();
-    // inclusive suffix scan (Hillis-Steele): both arrays run the same number of steps
-    const unsigned int steps_len = V0 > V1 ? V0 : V1;
-    for (unsigned int d = 1; d < steps_len; d <<= 1) {
-        XYZZ o = xyzz_identity();
-        const bool has = t + d < len;
-        if (has) o = load_xyzz(&s[t + d]);
-        __syncthreads();
-        if (has) {
-            xyzz_add(mine, o);
-            store_xyzz(&s[t], mine);
-        }
-        __syncthreads();
+    const unsigned int nslots = w0 + w1 + 1;  // <= 16 for c <= 16
+    XYZZ term = xyzz_identity();
+    if (lane < nslots) {
+        term = load_xyzz(&S[set * nslots + lane]);
+        const unsigned int doublings = lane == nslots - 1 ? 0 : lane;
+        for (unsigned int d = 0; d < doublings; d++) term = xyzz_dbl(term);
     }
-    const XYZZ total = mine;  // thread 0: R_0 of D0 = sum of all buckets
-    if (t == 0) store_xyzz(&s[0], xyzz_identity());
-    // W = sum_{t >= 1} R_t: tree over each array's own power-of-two length (array 0: 256 slots, array 1: 128 slots)
-    for (unsigned int d = 128; d >= 1; d >>= 1) {
-        __syncthreads();
-        const unsigned int half = arr1 ? (d >> 1) : d;  // array 1 has half as many slots: its tree is one level shorter
-        if (half >= 1 && t < half) {
-            XYZZ a = load_xyzz(&s[t]);
-            XYZZ b = load_xyzz(&s[t + half]);
-            xyzz_add(a, b);
-            store_xyzz(&s[t], a);
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        XYZZ w1v = load_xyzz(&sm[256]);
-        for (unsigned int k = 0; k < w0; k++) w1v = xyzz_dbl(w1v);
-        XYZZ result = load_xyzz(&sm[0]);
-        xyzz_add(result, w1v);
-        xyzz_add(result, total);
-        store_xyzz(&set_out[set], result);
-    }
+    store_xyzz(&sm[lane], term);
+    smem_tree_sum(sm, lane, 32);
+    if (lane == 0) store_xyzz(&set_out[set], load_xyzz(&sm[0]));
 }
 
 // ---- 5. combine bucket sets: out[b] = sum_u 2^(c*u) * R[b][u], written as Jacobian -------------------------------

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,7 @@ namespace de {
 // msm.cu
 int commit_canonical_dev(de_params* p, int basis, const Fr* d_scalars, size_t stride, size_t n, size_t count, uint8_t* out_xy);
 int commit_canonical_mixed_dev(de_params* p, const Fr* d_scalars, size_t stride, size_t n, size_t count_lagrange, size_t count_coeff, uint8_t* out_xy);
+int scan_u32(de_ctx* ctx, const unsigned int* in, unsigned long long n, unsigned int* out, unsigned int* block_sums, unsigned int* grand_total);
 de_ctx* params_ctx(de_params* p);
 size_t params_n(de_params* p);
 
@@ -165,44 +167,24 @@ __global__ void k_lookup_flags(const Fr* sorted, unsigned long long npad, unsign
     }
     left[(unsigned long long)l * npad + i] = consumed ? 0u : 1u;
 }
-// exclusive scan of `len` u32 flags per array (one CTA per array); totals[array] = sum
-__global__ void __launch_bounds__(1024) k_scan_flags(const unsigned int* in, unsigned int* out, unsigned long long stride, unsigned int len,
-                                                      unsigned int* totals) {
-    __shared__ unsigned int warp_sums[32];
-    const unsigned int* src = in + blockIdx.x * stride;
-    unsigned int* dst = out + blockIdx.x * stride;
-    const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned int seg = (len + blockDim.x - 1) / blockDim.x;
-    const unsigned int lo = tid * seg;
-    unsigned int hi = lo + seg;
-    if (hi > len) hi = len;
-    unsigned int sum = 0;
-    for (unsigned int i = lo; i < hi; i++) sum += src[i];
-    unsigned int x = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned int y = __shfl_up_sync(0xffffffffu, x, d);
-        if (lane >= d) x += y;
-    }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned int s = warp_sums[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned int y = __shfl_up_sync(0xffffffffu, s, d);
-            if (lane >= d) s += y;
-        }
-        warp_sums[lane] = s;
-    }
-    __syncthreads();
-    unsigned int run = (wid ? warp_sums[wid - 1] : 0) + x - sum;
-    for (unsigned int i = lo; i < hi; i++) {
-        const unsigned int v = src[i];
-        dst[i] = run;
-        run += v;
-    }
-    if (tid == 0) totals[blockIdx.x] = warp_sums[31];
+// The flags of all arrays ([rep of every lookup | left of every lookup], npad apart) are scanned as ONE vector (scan_u32); this
+// turns the global exclusive scan into per-array compaction indices and totals: idx[i] -= idx[array start].
+__global__ void k_segment_fixup(unsigned int* idx, unsigned long long npad, unsigned int n_arrays, unsigned int grand_total, const unsigned int* d_grand,
+                                unsigned int* totals) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int a = blockIdx.y;
+    (void)grand_total;
+    const unsigned int start = idx[a * npad];
+    const unsigned int next = (a + 1 < n_arrays) ? idx[(a + 1) * npad] : *d_grand;
+    // every thread of this array reads `start` before any thread of the array overwrites element 0: element 0 is rewritten by the
+    // thread with i == 0 only after the barrier-free read above, and it becomes start - start = 0, which is also what later
+    // readers of idx[a * npad] in OTHER blocks must not see -> they read from `starts` instead (see below)
+    if (i == 0) totals[a] = next - start;
+    if (i < npad && i > 0) idx[a * npad + i] -= start;
+}
+__global__ void k_segment_zero_heads(unsigned int* idx, unsigned long long npad, unsigned int n_arrays) {
+    const unsigned int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n_arrays) idx[a * npad] = 0;
 }
 // permuted input = sorted input; permuted table row = the input value at first occurrences; repeated rows are listed in R
 __global__ void k_lookup_fill_first(const Fr* sorted, unsigned long long npad, unsigned int usable, const unsigned int* rep,
@@ -411,7 +393,7 @@ struct de_prover {
     // device state
     Fr *lag, *coef, *fixed_lag, *comp, *sorted, *frac_num, *frac_den, *cp, *cpfx, *carry, *randoms, *h, *hx, *open_acc, *open_q, *kate_scratch;
     Fr *d_points, *d_evals;
-    unsigned int *rep, *rep_idx, *left, *left_idx, *totals, *R;
+    unsigned int *rep, *rep_idx, *left, *left_idx, *totals, *R, *scan_scratch;
     int* d_err;
     DevGraph* d_lookup_graphs;  // inputs of all lookups, then tables
     const Fr** d_eval_polys;
@@ -581,10 +563,14 @@ int de_prover_create(de_params* params, de_pk* pk, const de_prover_desc* desc, d
     DE_PALLOC(randoms, Fr, p->n_random);
     DE_PALLOC(h, Fr, p->ext_n);
     DE_PALLOC(hx, Fr, n);
-    DE_PALLOC(rep, unsigned int, (size_t)p->L * p->npad + 1);
-    DE_PALLOC(rep_idx, unsigned int, (size_t)p->L * p->npad + 1);
-    DE_PALLOC(left, unsigned int, (size_t)p->L * p->npad + 1);
-    DE_PALLOC(left_idx, unsigned int, (size_t)p->L * p->npad + 1);
+    // flags / compaction indices: [rep of every lookup | left of every lookup], contiguous so that one scan covers them
+    DE_PALLOC(rep, unsigned int, 2 * (size_t)p->L * p->npad + 1);
+    DE_PALLOC(rep_idx, unsigned int, 2 * (size_t)p->L * p->npad + 1);
+    p->left = p->rep + (size_t)p->L * p->npad;
+    p->left_idx = p->rep_idx + (size_t)p->L * p->npad;
+    DE_CUDA(ctx, cudaMemsetAsync(p->rep, 0, sizeof(unsigned int) * (2 * (size_t)p->L * p->npad + 1), ctx->stream));  // rows >= usable stay 0
+    DE_PALLOC(scan_scratch, unsigned int, 4096 + 64);
+    if (2ull * p->L * p->npad > 4096ull * 4096ull) return bail(fail(ctx, DE_ERR_UNSUPPORTED, "de_prover_create: lookup columns too long for the compaction scan"));
     DE_PALLOC(R, unsigned int, (size_t)p->L * p->npad + 1);
     DE_PALLOC(totals, unsigned int, 2 * (size_t)p->L + 1);
     DE_PALLOC(d_err, int, 1);
@@ -710,6 +696,19 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     de_pk* pk = p->pk;
     host::TranscriptWriter tr;
     std::vector<uint8_t> xy(64 * 64);
+    // DE_PROVER_TRACE=1: wall-clock time of each phase on stderr (every phase below ends in a stream sync, except where noted)
+    static const bool trace = getenv("DE_PROVER_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = trace ? now() : 0.0;
+    std::string trace_line;
+    auto mark = [&](const char* name) {
+        if (!trace) return;
+        const double t = now();
+        char buf[64];
+        snprintf(buf, sizeof(buf), " %s=%.3f", name, t - t_prev);
+        trace_line += buf;
+        t_prev = t;
+    };
 
     tr.common_scalar(p->transcript_repr);
     for (uint32_t i = 0; i < I; i++) {
@@ -772,6 +771,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     DE_TRY(flush_tails());
     DE_TRY(to_cosets(off_advice(p), (size_t)A + I, 0));
     DE_TRY(commit(1, p->lag + off_advice(p) * n, A));
+    mark("advice_commit");
     const HFr theta = tr.squeeze_challenge();
 
     // ---- lookups: compress, permute, commit
@@ -796,9 +796,12 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         const dim3 ugrid((unsigned int)((usable + 255) / 256), L);
         k_lookup_flags<<<ugrid, 256, 0, st>>>(p->sorted, p->npad, (unsigned int)usable, L, p->rep, p->left, p->d_err);
         DE_CHECK_LAUNCH(ctx);
-        k_scan_flags<<<L, 1024, 0, st>>>(p->rep, p->rep_idx, p->npad, (unsigned int)usable, p->totals);
+        // compaction indices of the 2L flag arrays by one global scan + per-array fix-up
+        DE_TRY(scan_u32(ctx, p->rep, 2ull * L * p->npad, p->rep_idx, p->scan_scratch, p->scan_scratch + 4096));
+        k_segment_fixup<<<dim3((unsigned int)((p->npad + 255) / 256), 2 * L), 256, 0, st>>>(p->rep_idx, p->npad, 2 * L, 0, p->scan_scratch + 4096,
+                                                                                            p->totals);
         DE_CHECK_LAUNCH(ctx);
-        k_scan_flags<<<L, 1024, 0, st>>>(p->left, p->left_idx, p->npad, (unsigned int)usable, p->totals + L);
+        k_segment_zero_heads<<<1, 64, 0, st>>>(p->rep_idx, p->npad, 2 * L);
         DE_CHECK_LAUNCH(ctx);
         k_lookup_fill_first<<<ugrid, 256, 0, st>>>(p->sorted, p->npad, (unsigned int)usable, p->rep, p->rep_idx, a_perm, s_perm, n, p->R);
         DE_CHECK_LAUNCH(ctx);
@@ -822,6 +825,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
             if (!tr.write_point(pas.data() + 64 * l) || !tr.write_point(pas.data() + 64 * ((size_t)L + l)))
                 return fail(ctx, DE_ERR_ARG, "de_create_proof: a commitment is the point at infinity");
     }
+    mark("lookup_permute_commit");
     const HFr beta = tr.squeeze_challenge();
     const HFr gamma = tr.squeeze_challenge();
 
@@ -899,6 +903,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         for (size_t i = 0; i < zl + 1; i++)
             if (!tr.write_point(xy.data() + 64 * i)) return fail(ctx, DE_ERR_ARG, "de_create_proof: a commitment is the point at infinity");
     }
+    mark("products_random_commit");
     const HFr y = tr.squeeze_challenge();
 
     // ---- quotient: every coset is (being) produced on the second stream
@@ -916,6 +921,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     const uint32_t pieces = p->deg - 1;
     rpos += pieces;  // h blinds
     DE_TRY(commit(0, p->h, pieces));
+    mark("quotient_commit");
     const HFr x = tr.squeeze_challenge();
     const HFr xn = host::fr_pow(x, (uint64_t)n);
 
@@ -937,6 +943,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     DE_CUDA(ctx, cudaStreamSynchronize(st));
     for (size_t i = 0; i < p->n_evals; i++) tr.write_scalar(evals.data() + 32 * i);
 
+    mark("evaluations");
     // ---- ProverGWC: one witness polynomial per distinct point
     const HFr v = tr.squeeze_challenge();
     const size_t n_open = p->rots.size();
@@ -952,6 +959,8 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     DE_TRY(kate_division_dev(ctx, p->d_open_polys + flat_total, n, bs.data(), n_open, p->open_q, n, p->kate_scratch));
     DE_TRY(commit(0, p->open_q, n_open));
 
+    mark("openings_commit");
+    if (trace) fprintf(stderr, "[de_prover]%s\n", trace_line.c_str());
     if (tr.proof.size() > proof_cap) return fail(ctx, DE_ERR_ARG, "de_create_proof: proof buffer too small");
     memcpy(proof_out, tr.proof.data(), tr.proof.size());
     *proof_len = tr.proof.size();
