@@ -58,9 +58,9 @@ UNIT = "proofs/s"
 MUL_PEAK_GMULS = 65.9   # measured on this pool's B200 by tools/int_peak (profiles/r01_int_peak.jsonl): Fr Montgomery mul/s
 MULS_PER_POINT = 160    # SURVEY.md 8d convention: 16 windows x (8M + 2S) per point (a uniform scalar)
 MULS_PER_ADD = 10       # XYZZ mixed addition: 8M + 2S
-# (dram__bytes_read.sum + dram__bytes_write.sum) / points of a k_msm_accumulate launch (298.2 MB for 10 x 2^16 points), from the
-# `ncu --set full` capture summarised in profiles/r01_accumulate_ncu.md
-TRAFFIC_BYTES_PER_POINT = 298.2e6 / 655360
+# (dram__bytes_read.sum + dram__bytes_write.sum) / points of a k_msm_accumulate launch (180.7 + 21.2 MB for the 7 x 2^16 points of
+# the grand-product round), from the `ncu --set full` capture summarised in profiles/r01_create_proof_ncu_full.md
+TRAFFIC_BYTES_PER_POINT = 201.9e6 / 458752
 
 
 def _peaks():
@@ -333,6 +333,8 @@ def main():
         barrier()
         return sharding.max_over_ranks(e0.elapsed_time(e1))
 
+    for wk in workers:
+        wk.ctx.set_mode(throughput=B > 1)  # several provers share the GPU in the throughput / e2e arms
     timed(workers, args.warmup, False)
     first_proof = workers[0].proof
     assert len(first_proof) == prover0.proof_size == (2848 if WITH_LOOKUPS else 1792)
@@ -351,6 +353,7 @@ def main():
     for wk in workers:
         assert wk.proof == first_proof, "host-buffer path disagrees with the device-resident path"
     # ---- latency arm: ONE proof in flight; per-kernel CUDA-event timing is taken here (no overlapping streams)
+    ctx.set_mode(throughput=False)
     timed(workers[:1], 2, False)
     ctx.timing_reset()
     ctx.timing_enable(True)
@@ -375,6 +378,7 @@ def main():
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE carry chains)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proofs_per_step_per_gpu": B, "proof_bytes": len(first_proof),
+                   "mode": "DE_MODE_THROUGHPUT" if B > 1 else "DE_MODE_LATENCY",
                    "in_flight": f"{B} independent proofs per GPU, one host thread + CUDA stream each (BASELINE config 5: 64 proofs over "
                                 "8 GPUs = 8 per GPU)",
                    "l2": f"per-step working set ~{0.8 * B * 2.0 ** (K - 16):.2f} GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
@@ -383,7 +387,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "latency": {"create_proof_s": ms_lat / lat_steps / 1000.0, "proofs_in_flight": 1, "steps": lat_steps},
+        "latency": {"create_proof_s": ms_lat / lat_steps / 1000.0, "proofs_in_flight": 1, "steps": lat_steps, "mode": "DE_MODE_LATENCY"},
     }
     ms_ref = ms_lat  # kernel shares are relative to the single-proof latency pass they were measured in
     if acc_n:

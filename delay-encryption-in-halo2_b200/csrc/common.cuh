@@ -91,6 +91,7 @@ struct de_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     int sm_count = 148;
+    int mode = 0;  // DE_MODE_LATENCY / DE_MODE_THROUGHPUT (de_ctx_set_mode)
     std::string err;
     uint64_t launches = 0;
     de::DevBuf ws[de::WS_COUNT];

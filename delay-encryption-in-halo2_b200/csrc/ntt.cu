@@ -398,6 +398,13 @@ int de_ctx_set_stream(de_ctx* ctx, void* s) {
     return DE_OK;
 }
 
+int de_ctx_set_mode(de_ctx* ctx, int mode) {
+    if (!ctx) return DE_ERR_ARG;
+    if (mode != DE_MODE_LATENCY && mode != DE_MODE_THROUGHPUT) return fail(ctx, DE_ERR_ARG, "de_ctx_set_mode: unknown mode");
+    ctx->mode = mode;
+    return DE_OK;
+}
+
 int de_ctx_sync(de_ctx* ctx) {
     if (!ctx) return DE_ERR_ARG;
     DE_CUDA(ctx, cudaSetDevice(ctx->device));

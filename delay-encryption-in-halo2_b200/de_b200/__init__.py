@@ -62,6 +62,10 @@ class Context:
     def sync(self):
         self.check(self.L.de_ctx_sync(self.h))
 
+    def set_mode(self, throughput: bool):
+        """de_ctx_set_mode: latency (default, one proof at a time) or throughput (several contexts share the GPU)"""
+        self.check(self.L.de_ctx_set_mode(self.h, 1 if throughput else 0))
+
     @property
     def launches(self) -> int:
         return int(self.L.de_launch_count(self.h))
