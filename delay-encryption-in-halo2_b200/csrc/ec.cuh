@@ -151,20 +151,4 @@ DE_D void store_xyzz(XYZZ* p, const XYZZ& v) {
     store(&p->x, v.x); store(&p->y, v.y); store(&p->zz, v.zz); store(&p->zzz, v.zzz);
 }
 
-// field inversion by Fermat (p - 2), only used in one-time precomputation
-template <class P>
-DE_D Fp<P> inv(const Fp<P>& a) {
-    Fp<P> acc = Fp<P>::one();
-    // exponent p - 2, scanned MSB first
-    for (int i = 7; i >= 0; i--) {
-        uint32_t w = P::p(i);
-        if (i == 0) w -= 2;  // p is odd and p(0) >= 2 for both fields
-        for (int b = 31; b >= 0; b--) {
-            acc = sqr(acc);
-            if ((w >> b) & 1) acc = mul(acc, a);
-        }
-    }
-    return acc;
-}
-
 }  // namespace de

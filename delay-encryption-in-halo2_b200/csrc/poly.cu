@@ -11,7 +11,7 @@
 
 namespace de {
 
-#define DE_POLY_THREADS 256
+#define DE_POLY_THREADS 512
 #define DE_KATE_CHUNK 32
 #define DE_KATE_SCAN 512
 
@@ -39,7 +39,15 @@ __global__ void __launch_bounds__(DE_POLY_THREADS) k_eval_polynomial(const Fr* c
     if (hi > n) hi = n;
     Fr acc = Fr::zero();
     for (unsigned long long i = hi; i > lo; i--) acc = add(mul(acc, x), load(&p[i - 1]));
-    if (lo < n && lo > 0) acc = mul(acc, pow_u64(x, lo));
+    if (lo < n && lo > 0) {
+        // x^lo, LSB first: stops at the top set bit of the (small) offset
+        Fr pw = Fr::one(), base = x;
+        for (unsigned long long e = lo; e; e >>= 1) {
+            if (e & 1) pw = mul(pw, base);
+            base = sqr(base);
+        }
+        acc = mul(acc, pw);
+    }
     store(&sm[tid], (lo < n) ? acc : Fr::zero());
     block_sum(sm, tid, DE_POLY_THREADS);
     if (tid == 0) {

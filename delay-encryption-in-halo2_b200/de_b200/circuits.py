@@ -61,7 +61,9 @@ def range_table(bit_lens=(8, 4, 1), overflow_bits=(6,)):
 
 
 def satisfied_assignment(with_range_lookups: bool, k: int, seed: int, used_rows: int, uniform_values: bool = False,
-                         copy_fraction: float = 0.25) -> Assignment:
+                         copy_fraction: float = 0.25, n_public: int = 0) -> Assignment:
+    """n_public > 0 exposes that many witness cells as public inputs: instance row i is copy-constrained to an advice cell
+    (the reference's benches pass an empty instance column; MainGate's `expose_public` does exactly this)."""
     shape = plonk.main_gate_shape(with_range_lookups)
     n = 1 << k
     usable = n - (shape.blinding_factors + 1)
@@ -141,14 +143,22 @@ def satisfied_assignment(with_range_lookups: bool, k: int, seed: int, used_rows:
         acc = (a * F[SA][r] + b * F[SB][r] + c * F[SC][r] + d * F[SD][r] + e * F[SE][r] + a * b % FR * F[S_MUL_AB][r]
                + c * d % FR * F[S_MUL_CD][r] + F[SE_NEXT][r] * e_next) % FR
         F[S_CONST][r] = (-acc) % FR
-    return Assignment(shape, k, F, A, [[] for _ in range(shape.n_instance)], copies, used_rows)
+    instances = [[] for _ in range(shape.n_instance)]
+    if n_public:
+        inst_pos = next(i for i, (kind, _) in enumerate(shape.perm_columns) if kind == INSTANCE)
+        for i in range(min(n_public, used_rows)):
+            col, row = rng.randrange(5), rng.randrange(used_rows)
+            instances[0].append(A[col][row])
+            copies.append((inst_pos, i, col, row))
+    return Assignment(shape, k, F, A, instances, copies, used_rows)
 
 
 def check_assignment(asg: Assignment) -> None:
     """MockProver-style check of gates, lookups and copy constraints on the usable rows (raises AssertionError)."""
     shape, n = asg.shape, 1 << asg.k
     usable = n - (shape.blinding_factors + 1)
-    cols = {"fixed": asg.fixed, "advice": asg.advice, "instance": [[0] * n for _ in range(shape.n_instance)]}
+    cols = {"fixed": asg.fixed, "advice": asg.advice,
+            "instance": [list(v) + [0] * (n - len(v)) for v in asg.instances] + [[0] * n for _ in range(shape.n_instance - len(asg.instances))]}
 
     def ev(e, r):
         t = e[0]

@@ -50,3 +50,18 @@ def test_device_field_schedule_on_host(shim, field, p):
 def test_from_mont_on_host(shim):
     a = orc.uniform_fr(13, 1000)
     assert (call(shim, "h_fr_from_mont", a, a) == orc.fr_from_mont(a)).all()
+
+
+@pytest.mark.parametrize("field,p", [("fr", po.FR), ("fq", po.FQ)])
+def test_binary_gcd_inversion_on_host(shim, field, p):
+    """field.cuh inv(): binary extended Euclid on 8 x 32-bit limbs, Montgomery in / out, against modular inverses in Python"""
+    n = 3000
+    a = orc.uniform_fr(14, n)
+    e = edge(p)
+    a[: len(e)] = e
+    got = call(shim, f"h_{field}_inv", a, a)
+    from_m = getattr(orc, field + "_ints_from_mont")
+    to_m = getattr(orc, field + "_mont_from_ints")
+    vals = from_m(a)
+    want = to_m([pow(v, -1, p) if v % p else 0 for v in vals])
+    assert (got == want).all()

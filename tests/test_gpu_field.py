@@ -36,3 +36,23 @@ def test_mont_conversions(ctx):
 def test_empty_vector(ctx):
     z = np.zeros((0, 4), dtype=np.uint64)
     assert ctx.fr_mul(z, z).shape == (0, 4)
+
+
+@pytest.mark.parametrize("field,p", [("fr", po.FR), ("fq", po.FQ)])
+def test_field_inversion(ctx, field, p):
+    """DE_OP_INV: ff::Field::invert on the device (binary extended Euclid), 0 -> 0"""
+    import ctypes as C
+    n = 5000
+    a = orc.uniform_fr(24, n)
+    e = edge(p)
+    a[: len(e)] = e
+    fn = ctx.L.de_fr_vec_op if field == "fr" else ctx.L.de_fq_vec_op
+    out = np.empty_like(a)
+    ctx.check(fn(ctx.h, 5, a.ctypes.data_as(C.c_void_p), None, out.ctypes.data_as(C.c_void_p), n))
+    vals = getattr(orc, field + "_ints_from_mont")(a)
+    want = getattr(orc, field + "_mont_from_ints")([pow(v, -1, p) if v % p else 0 for v in vals])
+    assert (out == want).all()
+    back = getattr(ctx, field + "_mul")(out, a)
+    one = getattr(orc, field + "_mont_from_ints")([1])[0]
+    nz = np.array([v % p != 0 for v in vals])
+    assert (back[nz] == one).all()

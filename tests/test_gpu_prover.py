@@ -61,8 +61,8 @@ def test_commit_canonical_matches_oracle(ctx):
     params.close()
 
 
-def run_both(with_lookups, k, used, seed, check_bytes=True):
-    asg = circuits.satisfied_assignment(with_lookups, k, seed, used)
+def run_both(with_lookups, k, used, seed, check_bytes=True, n_public=0):
+    asg = circuits.satisfied_assignment(with_lookups, k, seed, used, n_public=n_public)
     shape = asg.shape
     n = 1 << k
     oparams = pp.setup(k, 0x5EC2E7 + k)
@@ -113,6 +113,13 @@ def test_create_proof_bytes_match_restated_prover(name, with_lookups, k, used, s
     assert proof == want, f"{name}: first differing 32-byte proof element: #{first_diff(proof, want)}"
     assert ok, "the restated verifier rejects the GPU proof"
     assert proof2 == proof
+
+
+def test_create_proof_with_public_inputs():
+    """non-empty instance column: values hashed into the transcript, instance polynomial in the permutation argument"""
+    proof, want, ok, proof2 = run_both(True, 8, 200, 0xDE18, n_public=5)
+    assert proof == want, f"first differing 32-byte proof element: #{first_diff(proof, want)}"
+    assert ok and proof2 == proof
 
 
 def test_create_proof_delay_enc_shape_k16():

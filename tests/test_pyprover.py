@@ -79,3 +79,19 @@ def test_create_proof_verifies(with_lookups, k, used, size):
     except ValueError:
         return  # a broken lookup input is caught by permute_expression_pair already
     assert not pp.verify_proof(params, pk.vk, asg.instances, proof2)
+
+
+def test_public_inputs_are_bound():
+    """instance column values enter the transcript and the permutation argument: the right inputs verify, others do not"""
+    k = 6
+    asg = circuits.satisfied_assignment(True, k, 0xDE16, 40, n_public=3)
+    circuits.check_assignment(asg)
+    assert len(asg.instances[0]) == 3
+    params = pp.setup(k, 0x1234567)
+    q = pp.Queries(*plonk.collect_queries(asg.shape))
+    pk = pp.keygen(params, asg.shape, q, asg.fixed, asg.copies, 0xABCDEF)
+    proof = pp.create_proof(params, pk, asg.advice, asg.instances, po.Xoshiro(5).uniform_fr)
+    assert pp.verify_proof(params, pk.vk, asg.instances, proof)
+    wrong = [list(asg.instances[0])]
+    wrong[0][1] = (wrong[0][1] + 1) % po.FR
+    assert not pp.verify_proof(params, pk.vk, wrong, proof)
