@@ -160,3 +160,55 @@ def test_unsatisfied_lookup_is_reported():
     with pytest.raises(ValueError):
         pp.create_proof(oparams, opk, asg.advice, asg.instances, po.Xoshiro(1).uniform_fr)
     prover.close(); pk.close(); dom.close(); params.close(); ctx.close()
+
+
+def test_golden_proofs_on_gpu():
+    """the committed golden proofs (tests/golden/golden_proofs_v1.json) are reproduced byte for byte by the CUDA prover"""
+    import importlib.util
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_proofs", os.path.join(gdir, "make_golden_proofs.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = json.load(open(os.path.join(gdir, "golden_proofs_v1.json")))
+    for c in gold["cases"]:
+        asg, oparams, q, opk = mg.build(c)
+        ctx = de_b200.Context(0)
+        params = de_b200.ParamsKZG(c["k"], oparams.g_mont, oparams.g_lagrange_mont, ctx)
+        dom = de_b200.EvaluationDomain(asg.shape.degree(), c["k"], ctx)
+        pk = plonk.ProvingKey(dom, asg.shape, [mont(p) for p in opk.fixed_polys], [mont(p) for p in opk.sigma_polys])
+        prover = plonk.Prover(params, pk, q.advice, q.fixed, c["seed"] + 1)
+        draws = mg.draws_for(c, prover.random_count)
+        proof = prover.create_proof([mont(col) for col in asg.advice], [mont(v) if v else np.zeros((0, 4), dtype=np.uint64) for v in asg.instances],
+                                    mont(draws))
+        assert proof.hex() == c["proof"], c["name"]
+        prover.close(); pk.close(); dom.close(); params.close(); ctx.close()
+
+
+def test_prover_argument_errors():
+    """the asserts / Err results of the Rust API map to DE_ERR_ARG: wrong context pairing, short random stream, oversized public
+    inputs (Error::InstanceTooLarge)"""
+    k = 5
+    asg = circuits.satisfied_assignment(False, k, 0xDE25, 20)
+    oparams = pp.setup(k, 0x5EC2E7)
+    q = pp.Queries(*plonk.collect_queries(asg.shape))
+    opk = pp.keygen(oparams, asg.shape, q, asg.fixed, asg.copies, 1)
+    ctx, ctx2 = de_b200.Context(0), de_b200.Context(0)
+    params = de_b200.ParamsKZG(k, oparams.g_mont, oparams.g_lagrange_mont, ctx)
+    params2 = de_b200.ParamsKZG(k, oparams.g_mont, oparams.g_lagrange_mont, ctx2)
+    dom = de_b200.EvaluationDomain(asg.shape.degree(), k, ctx)
+    pk = plonk.ProvingKey(dom, asg.shape, [mont(p) for p in opk.fixed_polys], [mont(p) for p in opk.sigma_polys])
+    with pytest.raises(de_b200.DeError, match="same context"):
+        plonk.Prover(params2, pk, q.advice, q.fixed, 1)
+    prover = plonk.Prover(params, pk, q.advice, q.fixed, 1)
+    draws = mont([po.Xoshiro(2).uniform_fr() for _ in range(prover.random_count)])
+    adv = [mont(c) for c in asg.advice]
+    with pytest.raises(de_b200.DeError, match="random"):
+        prover.create_proof(adv, [np.zeros((0, 4), dtype=np.uint64)], draws[:-1])
+    with pytest.raises(de_b200.DeError, match="InstanceTooLarge"):
+        prover.create_proof(adv, [np.zeros((1 << k, 4), dtype=np.uint64)], draws)
+    # still usable after the errors
+    proof = prover.create_proof(adv, [np.zeros((0, 4), dtype=np.uint64)], draws)
+    assert len(proof) == 1792 and pp.verify_proof(oparams, opk.vk, asg.instances, proof)
+    prover.close(); pk.close(); dom.close(); params.close(); params2.close(); ctx.close(); ctx2.close()

@@ -95,3 +95,21 @@ def test_public_inputs_are_bound():
     wrong = [list(asg.instances[0])]
     wrong[0][1] = (wrong[0][1] + 1) % po.FR
     assert not pp.verify_proof(params, pk.vk, wrong, proof)
+
+
+def test_golden_proofs_reproduce():
+    """tests/golden/golden_proofs_v1.json (make_golden_proofs.py): the restated prover reproduces the committed proof bytes"""
+    import json
+    import os
+    sys_path = os.path.join(os.path.dirname(__file__), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_proofs", os.path.join(sys_path, "make_golden_proofs.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = json.load(open(os.path.join(sys_path, "golden_proofs_v1.json")))
+    assert [c["name"] for c in gold["cases"]] == [c["name"] for c in mg.CASES]
+    for c in gold["cases"]:
+        asg, params, q, pk = mg.build(c)
+        proof = pp.create_proof(params, pk, asg.advice, asg.instances, mg.draws_for(c))
+        assert proof.hex() == c["proof"], c["name"]
+        assert len(proof) == c["bytes"] == (2848 if c["with_lookups"] else 1792)
