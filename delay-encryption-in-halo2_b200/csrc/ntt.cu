@@ -16,6 +16,7 @@ struct NttPlan {
     int npass = 0;
     int S[3] = {0, 0, 0};
     Fr* wl[3] = {nullptr, nullptr, nullptr};
+    uint4* wl_planes[3] = {nullptr, nullptr, nullptr};  // the same tables in the kernel's shared-memory layout (TMA source)
     Fr* tw_full = nullptr;
     Fr* tw_hi = nullptr;
     Fr* tw_lo = nullptr;
@@ -23,6 +24,8 @@ struct NttPlan {
     ~NttPlan() {
         for (int i = 0; i < 3; i++)
             if (wl[i]) cudaFree(wl[i]);
+        for (int i = 0; i < 3; i++)
+            if (wl_planes[i]) cudaFree(wl_planes[i]);
         if (tw_full) cudaFree(tw_full);
         if (tw_hi) cudaFree(tw_hi);
         if (tw_lo) cudaFree(tw_lo);
@@ -72,6 +75,16 @@ static int get_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, NttPlan** o
     for (int k = 0; k < p->npass && rc == DE_OK; k++) {
         unsigned long long L = 1ull << p->S[k];
         rc = pow_table(ctx, &p->wl[k], L / 2, w, N / L);
+        if (rc == DE_OK && L >= 2) {
+            const unsigned int half = (unsigned int)(L / 2);
+            if (cudaMalloc((void**)&p->wl_planes[k], sizeof(uint4) * 2 * half) != cudaSuccess) {
+                cudaGetLastError();
+                rc = fail(ctx, DE_ERR_OOM, "ntt: twiddle table allocation failed");
+            } else {
+                k_split_planes<<<(half + 255) / 256, 256, 0, ctx->stream>>>(p->wl[k], p->wl_planes[k], half);
+                ctx->launches++;
+            }
+        }
     }
     if (rc == DE_OK && p->npass > 1) {
         if (log_n <= 22) {
@@ -150,7 +163,7 @@ int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, si
         const bool last = (k == P - 1);
         NttPassParams prm;
         memset(&prm, 0, sizeof(prm));
-        prm.wl = plan->wl[k];
+        prm.wl_planes = plan->wl_planes[k];
         // source / destination of this pass
         if (k == 0) {
             prm.in = d_src;

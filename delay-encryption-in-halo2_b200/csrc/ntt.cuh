@@ -21,7 +21,8 @@ struct NttPassParams {
     unsigned int G;                                         // tiles per group
     unsigned long long in_grp, in_blk, in_tt, in_el;        // element strides: group, tile, tile member, sub-transform index
     unsigned long long out_grp, out_blk, out_tt, out_el;
-    const Fr* wl;  // powers of the Lk-th root of unity: wl[i] = w_L^i, i < L/2
+    const uint4* wl_planes;  // powers of the Lk-th root of unity w_L^i, i < L/2, ALREADY in the kernel's shared-memory layout: the
+                             // low 16 bytes of every power, then the high 16 bytes - one TMA bulk copy stages the table
     int tw_mode;   // 0: none, 1: full table tw_full[e] = w_N^e (e < N), 2: two-level tw_hi[e >> lo_bits] * tw_lo[e & mask]
     const Fr* tw_full;
     const Fr* tw_hi;
@@ -45,6 +46,34 @@ __device__ __forceinline__ Fr sm_get(const uint4* lo, const uint4* hi, int slot)
     r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
+}
+
+// ---- TMA (bulk asynchronous copy) of the twiddle table into shared memory, completion tracked by an mbarrier -------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
 }
 
 template <int LT>
@@ -136,9 +165,16 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
     const unsigned long long in_base = grp * p.in_grp + tile * p.in_blk;
     const unsigned long long out_base = grp * p.out_grp + tile * p.out_blk;
 
-    for (int i = tid; i < L / 2; i += nthreads) {
-        Fr w = load(&p.wl[i]);
-        sm_put(wlo, whi, i, w);
+    // the sub-transform's twiddle table arrives by TMA while the threads gather the tile
+    __shared__ __align__(8) unsigned long long tw_bar;
+    if constexpr (L >= 2) {
+        if (tid == 0) mbar_init(&tw_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            constexpr unsigned int bytes = 2u * Sh::WN * sizeof(uint4);
+            mbar_expect_tx(&tw_bar, bytes);
+            tma_bulk_g2s(wlo, p.wl_planes, bytes, &tw_bar);
+        }
     }
     for (int idx = tid; idx < M; idx += nthreads) {
         int tt = idx & (T - 1), t = idx >> LT;
@@ -158,6 +194,7 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
         sm_put(lo, hi, ntt_slot<LT>(t, tt), v);
     }
     __syncthreads();
+    if constexpr (L >= 2) mbar_wait(&tw_bar, 0);
 
     ntt_rounds<S, LT, 0>(lo, hi, wlo, whi, tid, nthreads);
 
@@ -189,6 +226,15 @@ __global__ void k_pow_table(Fr* out, unsigned long long n, Fr base, unsigned lon
         e >>= 1;
     }
     store(&out[i], acc);
+}
+
+// Fr table -> the split-plane layout of NttShape's shared-memory twiddle area: [low 16 B of every entry | high 16 B]
+__global__ void k_split_planes(const Fr* in, uint4* out, unsigned int n) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = load(&in[i]);
+    out[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    out[n + i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
 // element-wise helpers used by the domain operations
