@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+
 #include "common.cuh"
 #include "msm.cuh"
 #include "transcript.hpp"
@@ -416,6 +418,32 @@ int de_commit_range(de_params* p, int basis, const de_fr* scalars, size_t lo, si
     DE_WS(ctx, ds, Fr, WS_IO_A, sizeof(Fr) * n);
     DE_CUDA(ctx, cudaMemcpyAsync(ds, scalars + lo, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
     return msm_core(ctx, ds, n, n, 1, p->tables[basis], p->n, lo, p->cfg, out_partial);
+}
+
+// Base-range sharding inside ONE process (the shape a Rust prover has: one process, several GPUs).  shards[i] is a
+// ParamsKZG staged on its own context / GPU from the base slice [shard_lo[i], shard_lo[i] + shard_len[i]) of the SRS; one
+// host thread per shard commits its slice of `scalars` concurrently, the partial points are summed on shards[0]'s GPU.
+int de_commit_sharded(de_params* const* shards, const size_t* shard_lo, const size_t* shard_len, int n_shards, int basis, const de_fr* scalars,
+                      de_g1* out) {
+    if (!shards || n_shards < 1 || !shards[0]) return DE_ERR_ARG;
+    de_ctx* ctx0 = shards[0]->ctx;
+    if (!shard_lo || !shard_len || !scalars || !out) return fail(ctx0, DE_ERR_ARG, "de_commit_sharded: null pointer");
+    if (n_shards > 64) return fail(ctx0, DE_ERR_ARG, "de_commit_sharded: more than 64 shards");
+    for (int i = 0; i < n_shards; i++) {
+        if (!shards[i]) return fail(ctx0, DE_ERR_ARG, "de_commit_sharded: null shard");
+        if (shard_len[i] > shards[i]->n) return fail(ctx0, DE_ERR_ARG, "de_commit_sharded: slice longer than the shard's bases");
+        for (int j = 0; j < i; j++)
+            if (shards[j]->ctx == shards[i]->ctx) return fail(ctx0, DE_ERR_ARG, "de_commit_sharded: shards must use distinct contexts");
+    }
+    std::vector<de_g1> partial(n_shards);
+    std::vector<int> rc(n_shards, DE_OK);
+    std::vector<std::thread> threads;
+    for (int i = 0; i < n_shards; i++)
+        threads.emplace_back([&, i]() { rc[i] = de_commit(shards[i], basis, scalars + shard_lo[i], shard_len[i], &partial[i]); });
+    for (auto& t : threads) t.join();
+    for (int i = 0; i < n_shards; i++)
+        if (rc[i] != DE_OK) return fail(ctx0, rc[i], std::string("de_commit_sharded: shard ") + std::to_string(i) + ": " + de_last_error(shards[i]->ctx));
+    return de_g1_sum(ctx0, partial.data(), (size_t)n_shards, out);
 }
 
 int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out) {

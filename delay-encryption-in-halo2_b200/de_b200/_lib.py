@@ -21,7 +21,7 @@ SYMBOLS = [
     "de_coeff_to_extended_dev", "de_extended_to_coeff_dev", "de_lagrange_to_coeff_dev", "de_coeff_to_lagrange_dev",
     "de_divide_by_vanishing_dev", "de_pk_upload", "de_pk_free", "de_evaluate_h", "de_evaluate_h_dev", "de_pk_extend_dev", "de_evaluate_h_rows_dev", "de_commit_range", "de_g1_sum", "de_g1_batch_normalize",
     "de_commit_batch_canonical_dev", "de_eval_polynomial", "de_kate_division", "de_prover_create", "de_prover_free",
-    "de_prover_random_count", "de_prover_proof_size", "de_create_proof", "de_create_proof_dev", "de_g1_mul_base_dev", "de_ctx_set_mode",
+    "de_prover_random_count", "de_prover_proof_size", "de_create_proof", "de_create_proof_dev", "de_g1_mul_base_dev", "de_ctx_set_mode", "de_commit_sharded",
 ]
 
 
@@ -99,6 +99,7 @@ def load():
     L.de_prover_proof_size.argtypes = [P]
     L.de_prover_proof_size.restype = SZ
     L.de_create_proof.argtypes = [P, C.POINTER(P), C.POINTER(P), C.POINTER(SZ), P, SZ, P, SZ, C.POINTER(SZ)]
+    L.de_commit_sharded.argtypes = [C.POINTER(P), C.POINTER(SZ), C.POINTER(SZ), I, I, P, P]
     L.de_g1_mul_base_dev.argtypes = [P, P, P, SZ, P]
     L.de_create_proof_dev.argtypes = [P, P, SZ, C.POINTER(P), C.POINTER(SZ), P, SZ, P, SZ, C.POINTER(SZ)]
     for s in SYMBOLS:

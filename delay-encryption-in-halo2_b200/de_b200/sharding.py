@@ -52,3 +52,48 @@ def sharded_commit(params_shard, basis: int, d_scalars_shard, n_shard: int, grou
     partial = params_shard.commit_batch_dev(basis, d_scalars_shard, n_shard, 1)[0]
     parts = gather_partials(partial, group)
     return params_shard.ctx.g1_sum(parts)
+
+
+class ShardedParams:
+    """One process, several GPUs: the SRS basis split into contiguous ranges, one ParamsKZG (bases + window tables) per device.
+    commit() runs de_commit_sharded: one host thread per GPU, partial points summed on the first one."""
+
+    def __init__(self, k: int, bases, devices, basis: int = 1):
+        import numpy as np
+        from . import Context, ParamsKZG
+        bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        n = 1 << k
+        assert bases.shape[0] == n
+        self.basis, self.n = basis, n
+        self.ctxs, self.shards, self.lo, self.len = [], [], [], []
+        for r, dev in enumerate(devices):
+            lo, hi = base_range(n, r, len(devices))
+            m = hi - lo
+            ks = max(1, (m - 1).bit_length())
+            pad = np.zeros((1 << ks, 8), dtype=np.uint64)
+            pad[:m] = bases[lo:hi]
+            ctx = Context(dev)
+            self.ctxs.append(ctx)
+            self.shards.append(ParamsKZG(ks, pad if basis == 0 else None, pad if basis == 1 else None, ctx))
+            self.lo.append(lo)
+            self.len.append(m)
+
+    def commit(self, scalars):
+        import ctypes as C
+        import numpy as np
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+        assert scalars.size == 4 * self.n
+        ns = len(self.shards)
+        arr = (C.c_void_p * ns)(*[s.h for s in self.shards])
+        lo = (C.c_size_t * ns)(*self.lo)
+        ln = (C.c_size_t * ns)(*self.len)
+        out = np.zeros(12, dtype=np.uint64)
+        c0 = self.ctxs[0]
+        c0.check(c0.L.de_commit_sharded(arr, lo, ln, ns, self.basis, scalars.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+        for c in self.ctxs:
+            c.close()

@@ -226,6 +226,12 @@ int de_create_proof_dev(de_prover* p, const de_fr* d_advice, size_t advice_strid
  * the host (or de_g1_sum) adds the n_shards partial points. */
 int de_commit_range(de_params* p, int basis, const de_fr* scalars, size_t lo, size_t hi, de_g1* out_partial);
 int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out);
+/* the same inside ONE process (a Rust prover driving several GPUs): shards[i] = ParamsKZG staged on its own context / GPU
+ * from the base slice [shard_lo[i], shard_lo[i] + shard_len[i]) of the SRS (slice padded to a power of two with identity
+ * points); one host thread per shard commits its slice of `scalars` (host, full length) concurrently and the partial
+ * points are added on shards[0]'s GPU.  Multi-process sharding uses de_commit + an all-gather instead (de_b200/sharding.py). */
+int de_commit_sharded(de_params* const* shards, const size_t* shard_lo, const size_t* shard_len, int n_shards, int basis,
+                      const de_fr* scalars, de_g1* out);
 /* d_out[i] = [d_scalars[i]] base (affine, Montgomery), device-resident: the fixed-base multiplications of
  * ParamsKZG::setup (g[i] = [s^i] G) and the generator of synthetic SRS bases for the size sweeps */
 int de_g1_mul_base_dev(de_ctx* ctx, const de_g1_affine* base, const de_fr* d_scalars, size_t n, de_g1_affine* d_out);

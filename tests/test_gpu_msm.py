@@ -133,3 +133,20 @@ def test_g1_mul_base_matches_oracle(ctx):
     got = d_out.cpu().numpy().view(np.uint64)
     assert (got == orc.g1_mul_many(base, s)).all()
     assert not got[0].any() and (got[1] == base).all()
+
+
+def test_commit_sharded_single_process():
+    """de_commit_sharded: base ranges on several contexts (all the visible GPUs; two contexts on one GPU when only one is
+    visible), one host thread each, partial points summed: equals the oracle's best_multiexp over the whole vector"""
+    import torch
+    from de_b200 import sharding
+    k = 12
+    n = 1 << k
+    bases, s = orc.gen_bases(n), orc.uniform_fr(0x5A4D, n)
+    ndev = torch.cuda.device_count()
+    for devices in ([0, 0], [0, 0, 0], list(range(ndev)) if ndev > 1 else [0]):
+        sp = sharding.ShardedParams(k, bases, devices, basis=1)
+        got = sp.commit(s)
+        want = orc.best_multiexp(s, bases)
+        assert (orc.g1_to_affine(got) == orc.g1_to_affine(want)).all(), devices
+        sp.close()
