@@ -169,16 +169,13 @@ __global__ void k_lookup_flags(const Fr* sorted, unsigned long long npad, unsign
 }
 // The flags of all arrays ([rep of every lookup | left of every lookup], npad apart) are scanned as ONE vector (scan_u32); this
 // turns the global exclusive scan into per-array compaction indices and totals: idx[i] -= idx[array start].
-__global__ void k_segment_fixup(unsigned int* idx, unsigned long long npad, unsigned int n_arrays, unsigned int grand_total, const unsigned int* d_grand,
-                                unsigned int* totals) {
+// The array heads idx[a * npad] are only READ here (every block of array a, and of array a - 1 for its total, needs them);
+// k_segment_zero_heads rewrites them afterwards.
+__global__ void k_segment_fixup(unsigned int* idx, unsigned long long npad, unsigned int n_arrays, const unsigned int* d_grand, unsigned int* totals) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int a = blockIdx.y;
-    (void)grand_total;
     const unsigned int start = idx[a * npad];
     const unsigned int next = (a + 1 < n_arrays) ? idx[(a + 1) * npad] : *d_grand;
-    // every thread of this array reads `start` before any thread of the array overwrites element 0: element 0 is rewritten by the
-    // thread with i == 0 only after the barrier-free read above, and it becomes start - start = 0, which is also what later
-    // readers of idx[a * npad] in OTHER blocks must not see -> they read from `starts` instead (see below)
     if (i == 0) totals[a] = next - start;
     if (i < npad && i > 0) idx[a * npad + i] -= start;
 }
@@ -368,11 +365,6 @@ __global__ void __launch_bounds__(128) k_lincomb(const Fr* const* polys, unsigne
     for (int i = (int)count - 2; i >= 0; i--) acc = add(mul(acc, v), load(&polys[i][j]));
     store(&out[j], acc);
 }
-__global__ void k_from_mont(const Fr* in, Fr* out, unsigned long long n) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) store(&out[i], from_mont(load(&in[i])));
-}
-
 }  // namespace de
 
 using namespace de;
@@ -798,8 +790,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         DE_CHECK_LAUNCH(ctx);
         // compaction indices of the 2L flag arrays by one global scan + per-array fix-up
         DE_TRY(scan_u32(ctx, p->rep, 2ull * L * p->npad, p->rep_idx, p->scan_scratch, p->scan_scratch + 4096));
-        k_segment_fixup<<<dim3((unsigned int)((p->npad + 255) / 256), 2 * L), 256, 0, st>>>(p->rep_idx, p->npad, 2 * L, 0, p->scan_scratch + 4096,
-                                                                                            p->totals);
+        k_segment_fixup<<<dim3((unsigned int)((p->npad + 255) / 256), 2 * L), 256, 0, st>>>(p->rep_idx, p->npad, 2 * L, p->scan_scratch + 4096, p->totals);
         DE_CHECK_LAUNCH(ctx);
         k_segment_zero_heads<<<1, 64, 0, st>>>(p->rep_idx, p->npad, 2 * L);
         DE_CHECK_LAUNCH(ctx);
