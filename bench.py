@@ -240,12 +240,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=8, help="independent proofs in flight per GPU (one prover + stream each)")
     ap.add_argument("--config", default="delay_enc", choices=sorted(CONFIGS), help="circuit shape / size (default: the headline delay_enc)")
+    ap.add_argument("--k", type=int, default=0, help="override the config's k (the reference's README also times k = 15 ... 19)")
     args = ap.parse_args()
     global K, USED_ROWS, SEED, WITH_LOOKUPS, CONFIG_NAME, WORKLOAD, METRIC, CPU_SAMPLE
-    if args.config != "delay_enc":
+    if args.config != "delay_enc" or args.k:
         K, WITH_LOOKUPS, USED_ROWS, SEED, where = CONFIGS[args.config]
+        K = args.k or K
         CONFIG_NAME = args.config
-        METRIC = f"{args.config}_create_proof_proofs_per_s"
+        METRIC = f"{args.config}_create_proof_proofs_per_s" if not args.k else f"{args.config}_k{K}_create_proof_proofs_per_s"
         WORKLOAD = (f"{args.config} k={K} create_proof (/root/reference/{where}; MainGate{' + RangeChip' if WITH_LOOKUPS else ''} shape, satisfied "
                     f"synthetic witness, {USED_ROWS} used rows)")
         CPU_SAMPLE = CPU_SAMPLE.replace("delay_enc k=16", f"{args.config} k={K}").replace("31 best_multiexp 2^16, 23 + 23 + 1 best_fft, evaluate_h over 2^18 rows",
