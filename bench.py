@@ -265,7 +265,7 @@ def main():
     import torch
     import torch.distributed as dist
     import de_b200
-    from de_b200 import keygen, sharding
+    from de_b200 import keygen, plonk, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU path (use --impl reference for the CPU baseline)")
@@ -274,6 +274,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     asg, g, g_lagrange = build_circuit()
     shape = asg.shape
+    plonk_queries = plonk.collect_queries(shape)
     n = 1 << K
     B = max(1, args.inflight)
     main_stream = torch.cuda.current_stream()
@@ -461,6 +462,20 @@ def main():
             same = same and bytes(c) == first_proof[32 * i:32 * i + 32]
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": orc.ncpu(), "kind": "port", "sample": CPU_SAMPLE,
                                 "advice_commitments_match_gpu_proof": bool(same)}
+        # the COMPLETE restated create_proof on the CPU (oracle/pyprover.py: C loops for every vector operation, Python only for
+        # sequencing and the transcript), same circuit, keys, transcript_repr and random draws: its bytes must equal the GPU's
+        import pyprover as pp
+        q_adv, q_fix, q_inst = plonk_queries
+        oparams = pp.Params(K, n, None, None, None, None, np.ascontiguousarray(g), np.ascontiguousarray(g_lagrange))
+        opk = pp.keygen(oparams, shape, pp.Queries(q_adv, q_fix, q_inst), asg.fixed, asg.copies, TRANSCRIPT_REPR)
+        pp._pk_arrays(oparams, opk)  # keygen_pk's cosets: one-time, untimed
+        t0 = time.perf_counter()
+        cpu_proof = pp.create_proof_fast(oparams, opk, list(advice_mont), asg.instances, randoms)
+        dt_full = time.perf_counter() - t0
+        line["cpu_create_proof"] = {"create_proof_s": dt_full, "cores": orc.ncpu(), "proof_bytes_match_gpu": bool(cpu_proof == first_proof),
+                                    "what": "the whole restated create_proof (C inner loops on all cores + Python sequencing / Blake2b "
+                                            "transcript); includes the lookup permutation, grand products, evaluations and openings "
+                                            "that cpu_baseline leaves out"}
     if rank == 0:
         print(json.dumps(line))
     for wk in workers:

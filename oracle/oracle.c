@@ -353,6 +353,127 @@ void orc_g1_mul_many(const u64* base_aff, const u64* scalars_mont, size_t n, u64
     parallel_for(n, threads, mulmany_job, &c);
 }
 
+/* ---------------------------------------------------------------- vector helpers of the prover (halo2_proofs::arithmetic /
+ * poly): used by oracle/pyprover.py's array-based create_proof so that the restated prover runs at the reference's cost
+ * profile (C inner loops, threads) instead of Python integer loops */
+/* ff::BatchInvert over a slice, in place; zeros stay zero.  halo2 calls it per `parallelize` chunk. */
+typedef struct { fe* a; } binv_ctx;
+static void binv_job(void* v, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    fe* a = ((binv_ctx*)v)->a;
+    if (hi <= lo) return;
+    fe* pre = (fe*)malloc(sizeof(fe) * (hi - lo));
+    fe acc = FRF.r;
+    for (size_t i = lo; i < hi; i++) {
+        pre[i - lo] = acc;
+        if (!f_is_zero(&a[i])) f_mul(&FRF, &acc, &acc, &a[i]);
+    }
+    fe inv;
+    f_inv(&FRF, &inv, &acc);
+    for (size_t i = hi; i-- > lo;) {
+        if (f_is_zero(&a[i])) continue;
+        fe t;
+        f_mul(&FRF, &t, &inv, &pre[i - lo]);
+        f_mul(&FRF, &inv, &inv, &a[i]);
+        a[i] = t;
+    }
+    free(pre);
+}
+void orc_fr_batch_invert(u64* a, size_t n, int threads) {
+    binv_ctx c = {(fe*)a};
+    parallel_for(n, threads, binv_job, &c);
+}
+/* z[0] = start; z[i] = z[i-1] * f[i-1] for i < n (the serial running product of permutation::prover / lookup::prover) */
+void orc_fr_running_product(const u64* f, size_t n, const u64* start, u64* z) {
+    const fe* ff = (const fe*)f;
+    fe* zz = (fe*)z;
+    if (n == 0) return;
+    zz[0] = *(const fe*)start;
+    for (size_t i = 1; i < n; i++) f_mul(&FRF, &zz[i], &zz[i - 1], &ff[i - 1]);
+}
+/* arithmetic::eval_polynomial: per-thread Horner over contiguous chunks, each scaled by point^start, then summed */
+typedef struct { const fe* poly; size_t n, chunk; const fe* x; fe* parts; } evp_ctx;
+static void evp_job(void* v, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    evp_ctx* c = (evp_ctx*)v;
+    for (size_t part = lo; part < hi; part++) {
+        size_t s0 = part * c->chunk, s1 = s0 + c->chunk;
+        if (s1 > c->n) s1 = c->n;
+        fe acc;
+        memset(&acc, 0, sizeof(acc));
+        for (size_t i = s1; i-- > s0;) {
+            f_mul(&FRF, &acc, &acc, c->x);
+            f_add(&FRF, &acc, &acc, &c->poly[i]);
+        }
+        u64 e[4] = {(u64)s0, 0, 0, 0};
+        fe pw;
+        f_pow(&FRF, &pw, c->x, e);
+        f_mul(&FRF, &c->parts[part], &acc, &pw);
+    }
+}
+void orc_eval_polynomial(const u64* poly, size_t n, const u64* x, u64* out, int threads) {
+    fe* o = (fe*)out;
+    memset(o, 0, sizeof(fe));
+    if (n == 0) return;
+    if (threads < 1) threads = 1;
+    size_t chunk = (n + (size_t)threads - 1) / (size_t)threads;
+    size_t nparts = (n + chunk - 1) / chunk;
+    fe* parts = (fe*)calloc(nparts, sizeof(fe));
+    evp_ctx c = {(const fe*)poly, n, chunk, (const fe*)x, parts};
+    parallel_for(nparts, threads, evp_job, &c);
+    for (size_t i = 0; i < nparts; i++) f_add(&FRF, o, o, &parts[i]);
+    free(parts);
+}
+/* arithmetic::kate_division: q = a / (X - b), n - 1 coefficients */
+void orc_kate_division(const u64* a, size_t n, const u64* b, u64* q) {
+    const fe* aa = (const fe*)a;
+    fe* qq = (fe*)q;
+    fe tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    for (size_t i = n - 1; i >= 1; i--) {
+        fe t;
+        f_mul(&FRF, &t, &tmp, (const fe*)b);
+        f_add(&FRF, &tmp, &aa[i], &t);
+        qq[i - 1] = tmp;
+    }
+}
+/* acc[i] = acc[i] * s + p[i]  (Polynomial * scalar + &Polynomial, the fold of h pieces / theta compression) */
+typedef struct { fe* acc; const fe* p; const fe* s; } sadd_ctx;
+static void sadd_job(void* v, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    sadd_ctx* c = (sadd_ctx*)v;
+    for (size_t i = lo; i < hi; i++) {
+        f_mul(&FRF, &c->acc[i], &c->acc[i], c->s);
+        f_add(&FRF, &c->acc[i], &c->acc[i], &c->p[i]);
+    }
+}
+void orc_fr_scale_add(u64* acc, const u64* p, const u64* s, size_t n, int threads) {
+    sadd_ctx c = {(fe*)acc, (const fe*)p, (const fe*)s};
+    parallel_for(n, threads, sadd_job, &c);
+}
+/* acc[i] += s * p[i]  (the GWC batch: poly_acc + poly * power_of_v) */
+static void axpy_job(void* v, size_t lo, size_t hi, int tid) {
+    (void)tid;
+    sadd_ctx* c = (sadd_ctx*)v;
+    for (size_t i = lo; i < hi; i++) {
+        fe t;
+        f_mul(&FRF, &t, &c->p[i], c->s);
+        f_add(&FRF, &c->acc[i], &c->acc[i], &t);
+    }
+}
+void orc_fr_axpy(u64* acc, const u64* p, const u64* s, size_t n, int threads) {
+    sadd_ctx c = {(fe*)acc, (const fe*)p, (const fe*)s};
+    parallel_for(n, threads, axpy_job, &c);
+}
+/* out[i] = omega^i * scale for i < n (the delta^j omega^i beta column of the permutation numerator), serial like the reference's
+ * per-chunk running multiplication */
+void orc_fr_geometric(const u64* start, const u64* ratio, size_t n, u64* out) {
+    fe* o = (fe*)out;
+    if (n == 0) return;
+    o[0] = *(const fe*)start;
+    for (size_t i = 1; i < n; i++) f_mul(&FRF, &o[i], &o[i - 1], (const fe*)ratio);
+}
+
 /* ---------------------------------------------------------------- best_multiexp (a3; Appendix B.1) */
 enum { B_NONE = 0, B_AFFINE = 1, B_PROJ = 2 };
 typedef struct { int tag; jac p; } bucket_t; /* Affine keeps x,y in p.x,p.y */

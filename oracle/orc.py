@@ -55,6 +55,13 @@ def lib():
         L.orc_g1_mul.argtypes = [P, P, P]
         L.orc_g1_add.argtypes = [P, P, P]
         L.orc_g1_mul_many.argtypes = [P, P, C.c_size_t, P, C.c_int]
+        L.orc_fr_batch_invert.argtypes = [P, C.c_size_t, C.c_int]
+        L.orc_fr_running_product.argtypes = [P, C.c_size_t, P, P]
+        L.orc_eval_polynomial.argtypes = [P, C.c_size_t, P, P, C.c_int]
+        L.orc_kate_division.argtypes = [P, C.c_size_t, P, P]
+        L.orc_fr_scale_add.argtypes = [P, P, P, C.c_size_t, C.c_int]
+        L.orc_fr_axpy.argtypes = [P, P, P, C.c_size_t, C.c_int]
+        L.orc_fr_geometric.argtypes = [P, P, C.c_size_t, P]
         L.orc_g1_on_curve.argtypes = [P]
         L.orc_g1_on_curve.restype = C.c_int
         L.orc_pk_new.argtypes = [P, P]
@@ -76,16 +83,13 @@ def ncpu() -> int:
 
 # ---- int <-> limb helpers (python big ints, canonical values) -------------------------------------
 def ints_to_limbs(vals) -> np.ndarray:
-    out = np.empty((len(vals), 4), dtype=np.uint64)
-    for i, v in enumerate(vals):
-        for j in range(4):
-            out[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
-    return out
+    raw = b"".join(int(v).to_bytes(32, "little") for v in vals)
+    return np.frombuffer(raw, dtype=np.uint64).reshape(-1, 4).copy()
 
 
 def limbs_to_ints(a: np.ndarray):
-    a = a.reshape(-1, 4)
-    return [int(r[0]) | (int(r[1]) << 64) | (int(r[2]) << 128) | (int(r[3]) << 192) for r in a]
+    raw = np.ascontiguousarray(a, dtype=np.uint64).tobytes()
+    return [int.from_bytes(raw[i:i + 32], "little") for i in range(0, len(raw), 32)]
 
 
 def _un(fn, a):
@@ -272,3 +276,50 @@ class Pk:
 
 def evaluate_h(domain: "Domain", desc_struct, advice, instance, challenges_struct, permz, lookup):
     return Pk(domain, desc_struct).evaluate_h(advice, instance, challenges_struct, permz, lookup)
+
+
+# ---- vector helpers of the restated prover (oracle.c: "vector helpers of the prover") ---------------------------------------
+def fr_batch_invert(a: np.ndarray, threads: int | None = None) -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    lib().orc_fr_batch_invert(_p(out), out.size // 4, threads or ncpu())
+    return out
+
+
+def fr_running_product(f: np.ndarray, start: np.ndarray) -> np.ndarray:
+    f = np.ascontiguousarray(f, dtype=np.uint64)
+    z = np.empty_like(f)
+    lib().orc_fr_running_product(_p(f), f.size // 4, _p(np.ascontiguousarray(start, dtype=np.uint64)), _p(z))
+    return z
+
+
+def eval_polynomial(poly: np.ndarray, x: np.ndarray, threads: int | None = None) -> np.ndarray:
+    poly = np.ascontiguousarray(poly, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_eval_polynomial(_p(poly), poly.size // 4, _p(np.ascontiguousarray(x, dtype=np.uint64)), _p(out), threads or ncpu())
+    return out
+
+
+def kate_division(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    n = a.size // 4
+    q = np.empty((n - 1, 4), dtype=np.uint64)
+    lib().orc_kate_division(_p(a), n, _p(np.ascontiguousarray(b, dtype=np.uint64)), _p(q))
+    return q
+
+
+def fr_scale_add(acc: np.ndarray, p: np.ndarray, s: np.ndarray, threads: int | None = None) -> None:
+    """acc = acc * s + p, in place"""
+    lib().orc_fr_scale_add(_p(acc), _p(np.ascontiguousarray(p, dtype=np.uint64)), _p(np.ascontiguousarray(s, dtype=np.uint64)), acc.size // 4,
+                           threads or ncpu())
+
+
+def fr_axpy(acc: np.ndarray, p: np.ndarray, s: np.ndarray, threads: int | None = None) -> None:
+    """acc += s * p, in place"""
+    lib().orc_fr_axpy(_p(acc), _p(np.ascontiguousarray(p, dtype=np.uint64)), _p(np.ascontiguousarray(s, dtype=np.uint64)), acc.size // 4,
+                      threads or ncpu())
+
+
+def fr_geometric(start: np.ndarray, ratio: np.ndarray, n: int) -> np.ndarray:
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_fr_geometric(_p(np.ascontiguousarray(start, dtype=np.uint64)), _p(np.ascontiguousarray(ratio, dtype=np.uint64)), n, _p(out))
+    return out

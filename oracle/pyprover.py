@@ -647,6 +647,230 @@ def create_proof(params: Params, pk: ProvingKey, advice_values: List[List[int]],
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# create_proof once more, on Montgomery limb arrays with the C oracle's vector loops: the SAME algorithm, step for step, as
+# create_proof() above (tests/test_pyprover.py checks byte equality), but at the reference's cost profile (C inner loops on
+# all cores) instead of Python integer loops.  Used where k >= 16 and as the complete-prover CPU timing of bench.py.
+# ---------------------------------------------------------------------------------------------------------------------
+def _m(v: int) -> np.ndarray:
+    return to_mont([v])[0]
+
+
+def _rows_expr(e, n, fixed, advice, instance, challenges):
+    """plonk::evaluation::evaluate over the n rows; columns are (n, 4) Montgomery arrays"""
+    t = e[0]
+    if t == "const":
+        return np.tile(_m(e[1]), (n, 1))
+    if t in ("fixed", "advice", "instance"):
+        col = {"fixed": fixed, "advice": advice, "instance": instance}[t][e[1]]
+        return np.ascontiguousarray(np.roll(col, -e[2], axis=0)) if e[2] else col
+    if t == "challenge":
+        return np.tile(_m(challenges[e[1]]), (n, 1))
+    if t == "neg":
+        return orc.fr_sub(np.zeros((n, 4), dtype=np.uint64), _rows_expr(e[1], n, fixed, advice, instance, challenges))
+    if t == "sum":
+        return orc.fr_add(_rows_expr(e[1], n, fixed, advice, instance, challenges), _rows_expr(e[2], n, fixed, advice, instance, challenges))
+    if t == "prod":
+        return orc.fr_mul(_rows_expr(e[1], n, fixed, advice, instance, challenges), _rows_expr(e[2], n, fixed, advice, instance, challenges))
+    if t == "scaled":
+        return orc.fr_mul(_rows_expr(e[1], n, fixed, advice, instance, challenges), np.tile(_m(e[2]), (n, 1)))
+    raise ValueError(t)
+
+
+def _pk_arrays(params: Params, pk: ProvingKey):
+    """Montgomery images of the proving key's columns and the evaluator's resident cosets (built once per pk)"""
+    if getattr(pk, "_arrays", None) is None:
+        from de_b200 import plonk
+        shape = pk.vk.shape
+        dom = _cdomain(shape, params.k)
+        fp = [to_mont(p) for p in pk.fixed_polys]
+        sp = [to_mont(p) for p in pk.sigma_polys]
+        desc, keep = plonk.marshal_pk_desc(shape, fp, sp)
+        pk._arrays = dict(dom=dom, fixed_values=[to_mont(c) for c in pk.fixed_values], sigma_values=[to_mont(c) for c in pk.sigma_values],
+                          fixed_polys=fp, sigma_polys=sp, opk=orc.Pk(dom, desc, keep),
+                          omega_pows=orc.fr_geometric(_m(1), dom.omega, params.n))
+    return pk._arrays
+
+
+def create_proof_fast(params: Params, pk: ProvingKey, advice_values, instances, randoms: np.ndarray) -> bytes:
+    """advice_values: (n, 4) Montgomery arrays (or int lists); randoms: (count, 4) Montgomery array of the Fr::random draws."""
+    from de_b200 import plonk
+    vk, shape, q = pk.vk, pk.vk.shape, pk.vk.queries
+    n, k = params.n, params.k
+    A = _pk_arrays(params, pk)
+    dom = A["dom"]
+    pdom = po.EvaluationDomain(shape.degree(), k)
+    omega = pdom.omega
+    bf = shape.blinding_factors
+    usable = n - (bf + 1)
+    tr = Transcript()
+    rpos = [0]
+
+    def draw(count):
+        out = randoms[rpos[0]:rpos[0] + count]
+        assert out.shape[0] == count, "random stream exhausted"
+        rpos[0] += count
+        return out
+
+    def commit_point(basis_mont, scalars):
+        return jac_mont_to_affine(orc.best_multiexp(np.ascontiguousarray(scalars), basis_mont[:scalars.shape[0]]))
+
+    tr.common_scalar(vk.transcript_repr)
+    instance_values = []
+    for vals in instances:
+        assert len(vals) <= usable, "InstanceTooLarge"
+        col = np.zeros((n, 4), dtype=np.uint64)
+        if len(vals):
+            col[:len(vals)] = to_mont(vals)
+        for v in vals:
+            tr.common_scalar(v)
+        instance_values.append(col)
+    instance_polys = [dom.lagrange_to_coeff(c) for c in instance_values]
+    advice = [np.ascontiguousarray(c, dtype=np.uint64).copy() if isinstance(c, np.ndarray) else to_mont(c) for c in advice_values]
+    for col in advice:
+        col[usable:] = draw(bf + 1)
+    draw(len(advice))
+    for col in advice:
+        tr.write_point(commit_point(params.g_lagrange_mont, col))
+    challenges: List[int] = []
+    theta = tr.squeeze_challenge()
+    theta_m = _m(theta)
+    lookups = []
+    for inp, tab in shape.lookups:
+        def compress(exprs):
+            acc = np.zeros((n, 4), dtype=np.uint64)
+            for e in exprs:
+                orc.fr_scale_add(acc, _rows_expr(e, n, A["fixed_values"], advice, instance_values, challenges), theta_m)
+            return acc
+        ci, ct = compress(inp), compress(tab)
+        pi_i, pt_i = permute_expression_pair(from_mont(ci), from_mont(ct), usable)
+        pi = np.concatenate([to_mont(pi_i), draw(bf + 1)])
+        pt = np.concatenate([to_mont(pt_i), draw(bf + 1)])
+        draw(2)
+        tr.write_point(commit_point(params.g_lagrange_mont, pi))
+        tr.write_point(commit_point(params.g_lagrange_mont, pt))
+        lookups.append(dict(ci=ci, ct=ct, pi=pi, pt=pt))
+    beta = tr.squeeze_challenge()
+    gamma = tr.squeeze_challenge()
+    beta_m, gamma_m = np.tile(_m(beta), (n, 1)), np.tile(_m(gamma), (n, 1))
+    cols_any = {ADVICE: advice, FIXED: A["fixed_values"], INSTANCE: instance_values}
+    chunk = shape.chunk_len
+    perm_z = []
+    deltaomega = 1
+    last_z = _m(1)
+    for s0 in range(0, len(shape.perm_columns), chunk):
+        columns = shape.perm_columns[s0:s0 + chunk]
+        modified = np.tile(_m(1), (n, 1))
+        for ci_, (kind, index) in enumerate(columns):
+            t = orc.fr_add(orc.fr_add(orc.fr_mul(beta_m, A["sigma_values"][s0 + ci_]), gamma_m), cols_any[kind][index])
+            modified = orc.fr_mul(modified, t)
+        modified = orc.fr_batch_invert(modified)
+        for (kind, index) in columns:
+            dw = orc.fr_mul(A["omega_pows"], np.tile(_m(deltaomega * beta % FR), (n, 1)))  # delta^j omega^i beta
+            modified = orc.fr_mul(modified, orc.fr_add(orc.fr_add(dw, gamma_m), cols_any[kind][index]))
+            deltaomega = deltaomega * FR_DELTA % FR
+        z = orc.fr_running_product(modified, last_z)
+        z[n - bf:] = draw(bf)
+        last_z = z[n - (bf + 1)].copy()
+        draw(1)
+        tr.write_point(commit_point(params.g_lagrange_mont, z))
+        perm_z.append(z)
+    for L in lookups:
+        den = orc.fr_batch_invert(orc.fr_mul(orc.fr_add(beta_m, L["pi"]), orc.fr_add(gamma_m, L["pt"])))
+        prod = orc.fr_mul(orc.fr_mul(den, orc.fr_add(L["ci"], beta_m)), orc.fr_add(L["ct"], gamma_m))
+        z = orc.fr_running_product(prod, _m(1))
+        z[n - bf:] = draw(bf)
+        draw(1)
+        tr.write_point(commit_point(params.g_lagrange_mont, z))
+        L["z"] = z
+    random_poly = np.ascontiguousarray(draw(n))
+    draw(1)
+    tr.write_point(commit_point(params.g_mont, random_poly))
+    y = tr.squeeze_challenge()
+
+    advice_polys = [dom.lagrange_to_coeff(c) for c in advice]
+    perm_polys = [dom.lagrange_to_coeff(z) for z in perm_z]
+    for L in lookups:
+        L["z_poly"], L["pi_poly"], L["pt_poly"] = dom.lagrange_to_coeff(L["z"]), dom.lagrange_to_coeff(L["pi"]), dom.lagrange_to_coeff(L["pt"])
+    chs, keep2 = plonk.marshal_challenges(y, beta, gamma, theta, challenges)
+    lookup_block = [L["z_poly"] for L in lookups] + [L["pi_poly"] for L in lookups] + [L["pt_poly"] for L in lookups]
+    h_ext = A["opk"].evaluate_h(advice_polys, instance_polys, chs, perm_polys, lookup_block)
+    h_coeff = dom.extended_to_coeff(dom.divide_by_vanishing(h_ext))
+    n_pieces = shape.degree() - 1
+    h_pieces = [np.ascontiguousarray(h_coeff[i * n:(i + 1) * n]) for i in range(n_pieces)]
+    draw(n_pieces)
+    for piece in h_pieces:
+        tr.write_point(commit_point(params.g_mont, piece))
+    x = tr.squeeze_challenge()
+    xn = pow(x, n, FR)
+
+    def point(rot):
+        return _m(rotate_omega(omega, x, rot))
+
+    def ev(poly, rot=0):
+        tr.write_scalar(from_mont(orc.eval_polynomial(poly, point(rot)).reshape(1, 4))[0])
+
+    for col, rot in q.advice:
+        ev(advice_polys[col], rot)
+    for col, rot in q.fixed:
+        ev(A["fixed_polys"][col], rot)
+    h_poly = np.zeros((n, 4), dtype=np.uint64)
+    xn_m = _m(xn)
+    for piece in reversed(h_pieces):
+        orc.fr_scale_add(h_poly, piece, xn_m)
+    ev(random_poly)
+    for sp in A["sigma_polys"]:
+        ev(sp)
+    last_rot = -(bf + 1)
+    for si, zp in enumerate(perm_polys):
+        ev(zp)
+        ev(zp, 1)
+        if si + 1 < len(perm_polys):
+            ev(zp, last_rot)
+    for L in lookups:
+        ev(L["z_poly"])
+        ev(L["z_poly"], 1)
+        ev(L["pi_poly"])
+        ev(L["pi_poly"], -1)
+        ev(L["pt_poly"])
+    queries = [(rot, advice_polys[col]) for col, rot in q.advice]
+    for zp in perm_polys:
+        queries += [(0, zp), (1, zp)]
+    for zp in list(reversed(perm_polys))[1:]:
+        queries.append((last_rot, zp))
+    for L in lookups:
+        queries += [(0, L["z_poly"]), (0, L["pi_poly"]), (0, L["pt_poly"]), (-1, L["pi_poly"]), (1, L["z_poly"])]
+    queries += [(rot, A["fixed_polys"][col]) for col, rot in q.fixed]
+    queries += [(0, sp) for sp in A["sigma_polys"]]
+    queries += [(0, h_poly), (0, random_poly)]
+    v = tr.squeeze_challenge()
+    point_sets: List[Tuple[int, list]] = []
+    for rot, poly in queries:
+        for entry in point_sets:
+            if entry[0] == rot:
+                entry[1].append(poly)
+                break
+        else:
+            point_sets.append((rot, [poly]))
+    for rot, polys in point_sets:
+        acc = np.zeros((n, 4), dtype=np.uint64)
+        pv = 1
+        for poly in polys:
+            orc.fr_axpy(acc, poly, _m(pv))
+            pv = pv * v % FR
+        # kate_division does not read the constant coefficient: subtracting the batched evaluation is a no-op for the quotient
+        w = orc.kate_division(acc, point(rot))
+        tr.write_point(commit_point(params.g_mont, w))
+    assert rpos[0] == random_count(shape, n), "random draw count differs from the int-based prover"
+    return tr.finalize()
+
+
+def random_count(shape, n: int) -> int:
+    """number of Fr::random draws of one create_proof (SURVEY.md Appendix E)"""
+    bf, L = shape.blinding_factors, len(shape.lookups)
+    return shape.n_advice * (bf + 2) + L * (2 * (bf + 1) + 2) + shape.n_perm_sets * (bf + 1) + L * (bf + 1) + n + 1 + (shape.degree() - 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # verify_proof (VerifierGWC, single strategy)
 # ---------------------------------------------------------------------------------------------------------------------
 def l_i_range(omega: int, n: int, x: int, xn: int, rotations: Sequence[int]) -> List[int]:

@@ -113,3 +113,18 @@ def test_golden_proofs_reproduce():
         proof = pp.create_proof(params, pk, asg.advice, asg.instances, mg.draws_for(c))
         assert proof.hex() == c["proof"], c["name"]
         assert len(proof) == c["bytes"] == (2848 if c["with_lookups"] else 1792)
+
+
+@pytest.mark.parametrize("with_lookups,k,used,n_public", [(False, 5, 20, 0), (True, 6, 40, 2), (True, 9, 300, 3)])
+def test_array_based_prover_equals_integer_prover(with_lookups, k, used, n_public):
+    """create_proof_fast (Montgomery arrays, C vector loops) is the same algorithm as create_proof (Python integers)"""
+    asg = circuits.satisfied_assignment(with_lookups, k, 0xFA57 + k, used, n_public=n_public)
+    params = pp.setup(k, 0x1234567)
+    q = pp.Queries(*plonk.collect_queries(asg.shape))
+    pk = pp.keygen(params, asg.shape, q, asg.fixed, asg.copies, 0xABCDEF)
+    rng = po.Xoshiro(99)
+    draws = [rng.uniform_fr() for _ in range(pp.random_count(asg.shape, 1 << k))]
+    it = iter(draws)
+    a = pp.create_proof(params, pk, asg.advice, asg.instances, lambda: next(it))
+    b = pp.create_proof_fast(params, pk, asg.advice, asg.instances, pp.to_mont(draws))
+    assert a == b
