@@ -17,8 +17,9 @@ that exactly this prover's bytes equal the CPU restatement's and pass the restat
   roofline   dominant kernel (k_msm_accumulate): algorithmic bytes per launch / measured launch time, against the measured
              HBM copy bandwidth (MEASURED_PEAKS.json); the kernel is integer-pipe bound, so `int_pipe` gives the fraction of
              the measured Montgomery-multiply peak as well
-  cpu_baseline   the restated reference algorithms (oracle/liboracle.so: best_multiexp / best_fft / evaluate_h as halo2_proofs
-             v2023_04_20 implements them, C + pthreads) on this box's host cores, one proof
+  cpu_baseline   the whole create_proof by the restated reference algorithms (oracle/: best_multiexp / best_fft / evaluate_h /
+             lookup permutation / grand products / openings as halo2_proofs v2023_04_20 implements them, C + pthreads on all
+             host cores, Python sequencing + transcript), one proof, byte-compared with the GPU's
 
 --impl reference times that CPU restatement alone (the Rust prover cannot be built: no cargo/rustc, un-vendored crates).
 N > 1 (torchrun): independent proofs are sharded one stream of proofs per GPU, no collective on the data path (weak scaling).
@@ -198,9 +199,25 @@ def cpu_reference_step(inp, state):
     return np.stack(pts)
 
 
-CPU_SAMPLE = ("one delay_enc k=16 proof's MSM / NTT / evaluate_h work per step: 31 best_multiexp 2^16, 23 + 23 + 1 best_fft, evaluate_h "
-              "over 2^18 rows (restated reference algorithms in C with pthreads, not the Rust binary; the reference's remaining "
-              "host work - lookup sort, grand products, evaluations, Kate division, transcript - is NOT included, which favours the CPU)")
+def cpu_prover_setup(asg, g, g_lagrange):
+    """keys of the restated CPU prover for the same circuit / SRS / transcript_repr (keygen: one-time in the reference too)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import pyprover as pp
+    from de_b200 import plonk
+    n = 1 << K
+    oparams = pp.Params(K, n, None, None, None, None, np.ascontiguousarray(g), np.ascontiguousarray(g_lagrange))
+    opk = pp.keygen(oparams, asg.shape, pp.Queries(*plonk.collect_queries(asg.shape)), asg.fixed, asg.copies, TRANSCRIPT_REPR)
+    pp._pk_arrays(oparams, opk)
+    return pp, oparams, opk
+
+
+CPU_SAMPLE = ("one whole delay_enc k=16 create_proof per step, the same circuit, keys and random draws as the GPU arm: the restated "
+              "reference algorithms (oracle/: best_multiexp, best_fft, evaluate_h, lookup permutation, grand products, eval_polynomial, "
+              "kate_division in C with pthreads on all host cores; Python only sequences the calls and hashes the transcript), not the "
+              "Rust binary; proof bytes equal the GPU's")
+CPU_HOT_SAMPLE = ("the same proof's 31 best_multiexp 2^16, 23 + 23 + 1 best_fft and evaluate_h over 2^18 rows alone (SURVEY.md section 8a "
+                  "rows a3-a9), leaving out the reference's host-side work between them")
 
 
 def run_reference(args, rank, world):
@@ -211,21 +228,23 @@ def run_reference(args, rank, world):
     orc.build()
     asg, g, g_lagrange = build_circuit()
     advice_mont = [orc.fr_mont_from_ints(c) for c in asg.advice]
-    inp = build_cpu_inputs(asg, advice_mont, g, g_lagrange)
-    state = {}
+    pp, oparams, opk = cpu_prover_setup(asg, g, g_lagrange)
+    randoms = random_draws(pp.random_count(asg.shape, 1 << K))
+    proof = None
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_step(inp, state)
+        proof = pp.create_proof_fast(oparams, opk, advice_mont, asg.instances, randoms)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(inp, state)
+        proof = pp.create_proof_fast(oparams, opk, advice_mont, asg.instances, randoms)
     dt = time.perf_counter() - t0
     value = args.steps / dt
     cores = orc.ncpu()
+    import hashlib
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED)},
+        "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proof_bytes": len(proof), "proof_sha256": hashlib.sha256(proof).hexdigest()},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": CPU_SAMPLE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -250,8 +269,7 @@ def main():
         METRIC = f"{args.config}_create_proof_proofs_per_s" if not args.k else f"{args.config}_k{K}_create_proof_proofs_per_s"
         WORKLOAD = (f"{args.config} k={K} create_proof (/root/reference/{where}; MainGate{' + RangeChip' if WITH_LOOKUPS else ''} shape, satisfied "
                     f"synthetic witness, {USED_ROWS} used rows)")
-        CPU_SAMPLE = CPU_SAMPLE.replace("delay_enc k=16", f"{args.config} k={K}").replace("31 best_multiexp 2^16, 23 + 23 + 1 best_fft, evaluate_h over 2^18 rows",
-                                                                                       "the proof's best_multiexp / best_fft / evaluate_h calls")
+        CPU_SAMPLE = CPU_SAMPLE.replace("delay_enc k=16", f"{args.config} k={K}")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -265,7 +283,7 @@ def main():
     import torch
     import torch.distributed as dist
     import de_b200
-    from de_b200 import keygen, plonk, sharding
+    from de_b200 import keygen, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU path (use --impl reference for the CPU baseline)")
@@ -274,7 +292,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     asg, g, g_lagrange = build_circuit()
     shape = asg.shape
-    plonk_queries = plonk.collect_queries(shape)
     n = 1 << K
     B = max(1, args.inflight)
     main_stream = torch.cuda.current_stream()
@@ -460,22 +477,15 @@ def main():
             c = bytearray(xy[i, :4].tobytes())
             c[31] |= (int(xy[i, 4]) & 1) << 7
             same = same and bytes(c) == first_proof[32 * i:32 * i + 32]
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": orc.ncpu(), "kind": "port", "sample": CPU_SAMPLE,
-                                "advice_commitments_match_gpu_proof": bool(same)}
-        # the COMPLETE restated create_proof on the CPU (oracle/pyprover.py: C loops for every vector operation, Python only for
-        # sequencing and the transcript), same circuit, keys, transcript_repr and random draws: its bytes must equal the GPU's
-        import pyprover as pp
-        q_adv, q_fix, q_inst = plonk_queries
-        oparams = pp.Params(K, n, None, None, None, None, np.ascontiguousarray(g), np.ascontiguousarray(g_lagrange))
-        opk = pp.keygen(oparams, shape, pp.Queries(q_adv, q_fix, q_inst), asg.fixed, asg.copies, TRANSCRIPT_REPR)
-        pp._pk_arrays(oparams, opk)  # keygen_pk's cosets: one-time, untimed
+        # the COMPLETE restated create_proof on the CPU, same circuit, keys, transcript_repr and random draws: its bytes must equal
+        # the GPU's; this is the like-for-like CPU baseline of the step
+        pp, oparams, opk = cpu_prover_setup(asg, g, g_lagrange)
         t0 = time.perf_counter()
         cpu_proof = pp.create_proof_fast(oparams, opk, list(advice_mont), asg.instances, randoms)
         dt_full = time.perf_counter() - t0
-        line["cpu_create_proof"] = {"create_proof_s": dt_full, "cores": orc.ncpu(), "proof_bytes_match_gpu": bool(cpu_proof == first_proof),
-                                    "what": "the whole restated create_proof (C inner loops on all cores + Python sequencing / Blake2b "
-                                            "transcript); includes the lookup permutation, grand products, evaluations and openings "
-                                            "that cpu_baseline leaves out"}
+        line["cpu_baseline"] = {"value": 1.0 / dt_full, "unit": UNIT, "cores": orc.ncpu(), "kind": "port", "sample": CPU_SAMPLE,
+                                "create_proof_s": dt_full, "proof_bytes_match_gpu": bool(cpu_proof == first_proof),
+                                "hot_path_only": {"s": dt, "sample": CPU_HOT_SAMPLE, "advice_commitments_match_gpu_proof": bool(same)}}
     if rank == 0:
         print(json.dumps(line))
     for wk in workers:
