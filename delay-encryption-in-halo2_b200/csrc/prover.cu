@@ -958,6 +958,16 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     return DE_OK;
 }
 
+// an early error return may leave transforms queued on the second stream: drain both before the buffers are reused
+static int finish(de_prover* p, int rc) {
+    if (rc != DE_OK) {
+        cudaStreamSynchronize(p->st_b);
+        cudaStreamSynchronize(p->ctx->stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
 static int check_args(de_prover* p, const void* advice, const de_fr* const* instances, const size_t* instance_lens, const void* randoms,
                       size_t n_randoms, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
     de_ctx* ctx = p->ctx;
@@ -979,7 +989,7 @@ int de_create_proof(de_prover* p, const de_fr* const* advice, const de_fr* const
         if (!advice[a]) return fail(ctx, DE_ERR_ARG, "de_create_proof: null advice column");
         DE_CUDA(ctx, cudaMemcpyAsync(p->lag + (off_advice(p) + a) * p->n, advice[a], sizeof(Fr) * p->n, cudaMemcpyHostToDevice, ctx->stream));
     }
-    return prove_core(p, instances, instance_lens, proof_out, proof_cap, proof_len);
+    return finish(p, prove_core(p, instances, instance_lens, proof_out, proof_cap, proof_len));
 }
 
 int de_create_proof_dev(de_prover* p, const de_fr* d_advice, size_t advice_stride, const de_fr* const* instances, const size_t* instance_lens,
@@ -990,7 +1000,7 @@ int de_create_proof_dev(de_prover* p, const de_fr* d_advice, size_t advice_strid
     DE_CUDA(ctx, cudaMemcpyAsync(p->randoms, d_randoms, sizeof(Fr) * p->n_random, cudaMemcpyDeviceToDevice, ctx->stream));
     DE_CUDA(ctx, cudaMemcpy2DAsync(p->lag + off_advice(p) * p->n, sizeof(Fr) * p->n, d_advice, sizeof(Fr) * advice_stride, sizeof(Fr) * p->n, p->A,
                                    cudaMemcpyDeviceToDevice, ctx->stream));
-    return prove_core(p, instances, instance_lens, proof_out, proof_cap, proof_len);
+    return finish(p, prove_core(p, instances, instance_lens, proof_out, proof_cap, proof_len));
 }
 
 }  // extern "C"

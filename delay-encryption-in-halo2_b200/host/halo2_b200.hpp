@@ -1,7 +1,8 @@
 // halo2_b200.hpp — header-only C++ host-side mirror of the halo2_proofs surface served by libde_b200.so.
 // The reference's host language is Rust, which this environment cannot compile; this mirror keeps the reference's names,
 // argument meaning and failure behaviour (the Rust functions panic on violated asserts; these throw std::runtime_error).
-//   halo2_proofs::arithmetic::best_multiexp / best_fft, poly::EvaluationDomain, poly::kzg::commitment::ParamsKZG
+//   halo2_proofs::arithmetic::{best_multiexp, best_fft, eval_polynomial, kate_division}, poly::EvaluationDomain,
+//   poly::kzg::commitment::ParamsKZG, plonk::ProvingKey (device staging), plonk::create_proof (Prover)
 // Element types are the C ABI's (include/de_b200.h): Montgomery limbs, byte-identical to halo2curves.
 #pragma once
 #include <stdexcept>
@@ -115,6 +116,10 @@ public:
     }
 
 private:
+public:
+    de_params* handle() const { return h_; }
+
+private:
     de_g1 commit_basis(int basis, const de_fr* poly, size_t n) const {
         de_g1 out;
         ctx_.check(de_commit(h_, basis, poly, n, &out), "commit");
@@ -124,5 +129,74 @@ private:
     de_params* h_ = nullptr;
     uint32_t k_;
 };
+
+// arithmetic::{eval_polynomial, kate_division}
+inline de_fr eval_polynomial(const Context& ctx, const std::vector<de_fr>& poly, const de_fr& point) {
+    de_fr out;
+    ctx.check(de_eval_polynomial(ctx.handle(), poly.data(), poly.size(), &point, &out), "eval_polynomial");
+    return out;
+}
+inline std::vector<de_fr> kate_division(const Context& ctx, const std::vector<de_fr>& a, const de_fr& b) {
+    if (a.size() < 2) throw std::runtime_error("kate_division: polynomial needs at least 2 coefficients");
+    std::vector<de_fr> q(a.size() - 1);
+    ctx.check(de_kate_division(ctx.handle(), a.data(), a.size(), &b, q.data()), "kate_division");
+    return q;
+}
+
+class ProvingKey {  // the evaluator's / prover's view of plonk::ProvingKey, staged in HBM (de_pk_upload)
+public:
+    ProvingKey(const Context& ctx, const EvaluationDomain& domain, const de_pk_desc& desc) : ctx_(ctx) {
+        ctx.check(de_pk_upload(domain.handle(), &desc, &h_), "ProvingKey");
+    }
+    ~ProvingKey() { de_pk_free(h_); }
+    ProvingKey(const ProvingKey&) = delete;
+    de_pk* handle() const { return h_; }
+
+private:
+    const Context& ctx_;
+    de_pk* h_ = nullptr;
+};
+
+// plonk::create_proof for one circuit (KZG, ProverGWC, Blake2bWrite / Challenge255): every polynomial stays in HBM.
+// `randoms` are the Fr::random(rng) draws in create_proof's order (random_count() of them); returns the proof bytes.
+class Prover {
+public:
+    Prover(const Context& ctx, const ParamsKZG& params, const ProvingKey& pk, const de_prover_desc& desc) : ctx_(ctx) {
+        ctx.check(de_prover_create(params.handle(), pk.handle(), &desc, &h_), "Prover");
+    }
+    ~Prover() { de_prover_free(h_); }
+    Prover(const Prover&) = delete;
+    size_t random_count() const { return de_prover_random_count(h_); }
+    size_t proof_size() const { return de_prover_proof_size(h_); }
+    std::vector<uint8_t> create_proof(const std::vector<const de_fr*>& advice, const std::vector<std::vector<de_fr>>& instances,
+                                      const std::vector<de_fr>& randoms) const {
+        std::vector<const de_fr*> ip;
+        std::vector<size_t> il;
+        for (const auto& v : instances) {
+            ip.push_back(v.data());
+            il.push_back(v.size());
+        }
+        std::vector<uint8_t> proof(proof_size());
+        size_t len = 0;
+        ctx_.check(de_create_proof(h_, advice.data(), ip.data(), il.data(), randoms.data(), randoms.size(), proof.data(), proof.size(), &len),
+                   "create_proof");
+        proof.resize(len);
+        return proof;
+    }
+
+private:
+    const Context& ctx_;
+    de_prover* h_ = nullptr;
+};
+
+// MSM with the bases sharded by contiguous ranges over several GPUs of ONE process (de_commit_sharded)
+inline de_g1 commit_sharded(const std::vector<const ParamsKZG*>& shards, const std::vector<size_t>& lo, const std::vector<size_t>& len, int basis,
+                            const de_fr* scalars, const Context& ctx0) {
+    std::vector<de_params*> h;
+    for (auto* s : shards) h.push_back(s->handle());
+    de_g1 out;
+    ctx0.check(de_commit_sharded(h.data(), lo.data(), len.data(), (int)h.size(), basis, scalars, &out), "commit_sharded");
+    return out;
+}
 
 }  // namespace halo2_b200

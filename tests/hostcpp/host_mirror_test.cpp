@@ -55,6 +55,62 @@ int main(int argc, char** argv) {
         bool threw = false;
         try { bases.pop_back(); halo2_b200::best_multiexp(ctx, scalars, bases); } catch (const std::runtime_error&) { threw = true; }
         if (!threw) { std::cerr << "length mismatch not rejected\n"; fails++; }
+        // arithmetic::eval_polynomial / kate_division
+        {
+            auto point = rd<de_fr>(d + "/point.bin");
+            auto want_eval = rd<de_fr>(d + "/eval.bin");
+            auto want_kate = rd<de_fr>(d + "/kate.bin");
+            std::vector<de_fr> got_eval = {halo2_b200::eval_polynomial(ctx, scalars, point[0])};
+            if (!same(got_eval, want_eval)) { std::cerr << "eval_polynomial mismatch\n"; fails++; }
+            if (!same(halo2_b200::kate_division(ctx, scalars, point[0]), want_kate)) { std::cerr << "kate_division mismatch\n"; fails++; }
+        }
+        // plonk::create_proof through the C++ mirror, from a SERIALISED proving key (the compiled
+        // GraphEvaluator, the permutation columns, the query lists and the polynomials as flat files)
+        {
+            const std::string p = d + "/proof/";
+            auto meta = rd<uint32_t>(p + "meta.bin");  // k, n_fixed, n_advice, n_instance, n_perm, chunk_len, blinding, n_intermediates, degree
+            const uint32_t pk_k = meta[0], n_fixed = meta[1], n_advice = meta[2], n_perm = meta[4];
+            const size_t pn = size_t(1) << pk_k;
+            auto fixed = rd<de_fr>(p + "fixed_coeff.bin"), sigma = rd<de_fr>(p + "sigma_coeff.bin"), advice = rd<de_fr>(p + "advice.bin");
+            auto randoms = rd<de_fr>(p + "randoms.bin"), delta = rd<de_fr>(p + "delta.bin"), trepr = rd<de_fr>(p + "transcript_repr.bin");
+            auto g = rd<de_g1_affine>(p + "g.bin"), gl = rd<de_g1_affine>(p + "g_lagrange.bin");
+            auto perm_kind = rd<uint32_t>(p + "perm_kind.bin"), perm_index = rd<uint32_t>(p + "perm_index.bin");
+            auto consts = rd<de_fr>(p + "g_consts.bin");
+            auto rots = rd<int32_t>(p + "g_rots.bin");
+            auto calcs = rd<de_calculation>(p + "g_calcs.bin");
+            auto parts = rd<de_value_source>(p + "g_parts.bin");
+            auto aq_col = rd<uint32_t>(p + "aq_col.bin"), fq_col = rd<uint32_t>(p + "fq_col.bin");
+            auto aq_rot = rd<int32_t>(p + "aq_rot.bin"), fq_rot = rd<int32_t>(p + "fq_rot.bin");
+            auto want = rd<uint8_t>(p + "want_proof.bin");
+            std::vector<const de_fr*> fptr, sptr, aptr;
+            for (uint32_t i = 0; i < n_fixed; i++) fptr.push_back(fixed.data() + i * pn);
+            for (uint32_t i = 0; i < n_perm; i++) sptr.push_back(sigma.data() + i * pn);
+            for (uint32_t i = 0; i < n_advice; i++) aptr.push_back(advice.data() + i * pn);
+            de_pk_desc desc;
+            std::memset(&desc, 0, sizeof(desc));
+            desc.n_fixed = n_fixed; desc.n_advice = n_advice; desc.n_instance = meta[3];
+            desc.fixed_coeff = fptr.data();
+            desc.n_perm_columns = n_perm; desc.perm_column_kind = perm_kind.data(); desc.perm_column_index = perm_index.data();
+            desc.sigma_coeff = sptr.data();
+            desc.chunk_len = meta[5]; desc.blinding_factors = meta[6]; desc.delta = delta[0];
+            desc.gates.constants = consts.data(); desc.gates.n_constants = (uint32_t)consts.size();
+            desc.gates.rotations = rots.data(); desc.gates.n_rotations = (uint32_t)rots.size();
+            desc.gates.calcs = calcs.data(); desc.gates.n_calcs = (uint32_t)calcs.size();
+            desc.gates.horner_parts = parts.data(); desc.gates.n_horner_parts = (uint32_t)parts.size();
+            desc.gates.n_intermediates = meta[7];
+            halo2_b200::ParamsKZG pparams(ctx, pk_k, g.data(), gl.data());
+            halo2_b200::EvaluationDomain pdom(ctx, meta[8], pk_k);
+            halo2_b200::ProvingKey ppk(ctx, pdom, desc);
+            de_prover_desc pd;
+            std::memset(&pd, 0, sizeof(pd));
+            pd.n_advice_queries = (uint32_t)aq_col.size(); pd.advice_query_column = aq_col.data(); pd.advice_query_rotation = aq_rot.data();
+            pd.n_fixed_queries = (uint32_t)fq_col.size(); pd.fixed_query_column = fq_col.data(); pd.fixed_query_rotation = fq_rot.data();
+            pd.transcript_repr = trepr[0];
+            halo2_b200::Prover prover(ctx, pparams, ppk, pd);
+            if (prover.random_count() != randoms.size()) { std::cerr << "random_count mismatch\n"; fails++; }
+            auto proof = prover.create_proof(aptr, {std::vector<de_fr>()}, randoms);
+            if (!same(proof, want)) { std::cerr << "create_proof bytes mismatch\n"; fails++; }
+        }
         std::cout << (fails ? "FAIL" : "OK") << std::endl;
         return fails ? 1 : 0;
     } catch (const std::exception& e) {

@@ -43,5 +43,49 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     orc.best_fft(s, d.omega, k).tofile(tmp_path / "fft.bin")
     d.coeff_to_extended(s).tofile(tmp_path / "ext.bin")
     orc.g1_to_affine(orc.best_multiexp(s, b)).tofile(tmp_path / "msm_affine.bin")
+    # eval_polynomial / kate_division
+    point = orc.uniform_fr(405, 1)
+    point.tofile(tmp_path / "point.bin")
+    orc.eval_polynomial(s, point[0]).tofile(tmp_path / "eval.bin")
+    orc.kate_division(s, point[0]).tofile(tmp_path / "kate.bin")
+    # a whole proof from a serialised proving key (MainGate-only shape, k = 5), expected bytes from the restated prover
+    import pyprover as pp
+    from de_b200 import circuits, plonk
+    pdir = tmp_path / "proof"
+    pdir.mkdir()
+    kk = 5
+    asg = circuits.satisfied_assignment(False, kk, 0xC9905, 20)
+    shape = asg.shape
+    oparams = pp.setup(kk, 0x5EC2E7)
+    q = pp.Queries(*plonk.collect_queries(shape))
+    trepr = 0xC0FFEE
+    opk = pp.keygen(oparams, shape, q, asg.fixed, asg.copies, trepr)
+    draws = orc.uniform_fr(406, pp.random_count(shape, 1 << kk))
+    want = pp.create_proof_fast(oparams, opk, asg.advice, asg.instances, draws)
+    keep = []
+    graph = plonk._marshal_graph(plonk.compile_gates(shape.gates), keep)
+    consts, rots, calcs, parts = keep
+    np.array([kk, shape.n_fixed, shape.n_advice, shape.n_instance, len(shape.perm_columns), shape.chunk_len, shape.blinding_factors,
+              graph.n_intermediates, shape.degree()], dtype=np.uint32).tofile(pdir / "meta.bin")
+    np.stack([pp.to_mont(p) for p in opk.fixed_polys]).tofile(pdir / "fixed_coeff.bin")
+    np.stack([pp.to_mont(p) for p in opk.sigma_polys]).tofile(pdir / "sigma_coeff.bin")
+    np.stack([pp.to_mont(c) for c in asg.advice]).tofile(pdir / "advice.bin")
+    draws.tofile(pdir / "randoms.bin")
+    np.array(plonk.mont_limbs(plonk.FR_DELTA), dtype=np.uint64).tofile(pdir / "delta.bin")
+    np.array(plonk.mont_limbs(trepr), dtype=np.uint64).tofile(pdir / "transcript_repr.bin")
+    oparams.g_mont.tofile(pdir / "g.bin")
+    oparams.g_lagrange_mont.tofile(pdir / "g_lagrange.bin")
+    np.array([kind for kind, _ in shape.perm_columns], dtype=np.uint32).tofile(pdir / "perm_kind.bin")
+    np.array([i for _, i in shape.perm_columns], dtype=np.uint32).tofile(pdir / "perm_index.bin")
+    consts.tofile(pdir / "g_consts.bin")
+    rots.tofile(pdir / "g_rots.bin")
+    open(pdir / "g_calcs.bin", "wb").write(bytes(calcs)[: 40 * len(plonk.compile_gates(shape.gates).calculations)])
+    n_parts = sum(len(c[3]) for c in plonk.compile_gates(shape.gates).calculations)
+    open(pdir / "g_parts.bin", "wb").write(bytes(parts)[: 12 * n_parts])
+    np.array([c for c, _ in q.advice], dtype=np.uint32).tofile(pdir / "aq_col.bin")
+    np.array([r_ for _, r_ in q.advice], dtype=np.int32).tofile(pdir / "aq_rot.bin")
+    np.array([c for c, _ in q.fixed], dtype=np.uint32).tofile(pdir / "fq_col.bin")
+    np.array([r_ for _, r_ in q.fixed], dtype=np.int32).tofile(pdir / "fq_rot.bin")
+    open(pdir / "want_proof.bin", "wb").write(want)
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
