@@ -65,3 +65,12 @@ def test_params_raw_bytes_file_round_trip(tmp_path):
         f.write(b"x")
     with pytest.raises(ValueError):
         de_b200.read_params_raw(path)
+
+
+def test_rust_sys_crate_declares_every_header_symbol():
+    """integration/de-b200-sys/src/lib.rs (compile-unverified: no Rust toolchain here) stays in sync with include/de_b200.h"""
+    import re
+    from de_b200 import _lib
+    src = open(os.path.join(ROOT, "integration", "de-b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (de_[a-z0-9_]+)\(", src))
+    assert declared == set(_lib.SYMBOLS)
