@@ -187,3 +187,44 @@ def check_assignment(asg: Assignment) -> None:
     for lc, lr, rc, rr in asg.copies:
         (k1, i1), (k2, i2) = shape.perm_columns[lc], shape.perm_columns[rc]
         assert anyc[k1][i1][lr] == anyc[k2][i2][rr], "copy constraint between unequal cells"
+
+
+def mul_table_assignment(k: int, seed: int, used_rows: int) -> Assignment:
+    """A second, differently shaped satisfied circuit for the generic prover paths the MainGate shapes do not reach:
+    3 advice columns, NO instance column, 2 fixed columns, one gate q * (a * b - c) of degree 3, one single-expression lookup
+    a in t (so cs.degree() = 4: three quotient pieces, permutation chunks of 2), and a permutation over the three advice
+    columns AND the fixed table column (a copy constraint may tie an advice cell to a fixed cell)."""
+    from .plonk import Advice, ConstraintSystemShape, Fixed, Neg, Prod, Sum
+    n = 1 << k
+    rng = random.Random(seed)
+    q, t = Fixed(0), Fixed(1)
+    a, b, c = Advice(0), Advice(1), Advice(2)
+    shape = ConstraintSystemShape(n_fixed=2, n_advice=3, n_instance=0, gates=[Prod(q, Sum(Prod(a, b), Neg(c)))], lookups=[([a], [t])],
+                                  perm_columns=[(ADVICE, 0), (ADVICE, 1), (ADVICE, 2), (FIXED, 1)])
+    usable = n - (shape.blinding_factors + 1)
+    used_rows = min(used_rows, usable)
+    assert usable >= 16
+    F = [[0] * n for _ in range(2)]
+    A = [[0] * n for _ in range(3)]
+    for r in range(16):
+        F[1][r] = r  # table: 0 .. 15 (then zeros)
+    copies = []
+    for r in range(used_rows):
+        F[0][r] = 1
+        A[0][r], A[1][r] = rng.randrange(4), rng.randrange(4)
+        A[2][r] = A[0][r] * A[1][r]
+    for _ in range(used_rows // 3):
+        i, j = rng.randrange(used_rows), rng.randrange(used_rows)
+        if A[2][i] >= 16:
+            continue  # the copied value becomes a lookup input: it must stay inside the table
+        # a[j] := c[i]; row j's product is recomputed
+        A[0][j] = A[2][i]
+        A[2][j] = A[0][j] * A[1][j] % FR
+        copies.append((2, i, 0, j))
+    # copies recorded before a later overwrite of their source would be stale: keep only those that still hold
+    copies = [cp for cp in copies if A[cp[0]][cp[1]] == A[cp[2]][cp[3]]]
+    for _ in range(used_rows // 4):
+        i = rng.randrange(used_rows)
+        if A[0][i] < 16:
+            copies.append((0, i, 3, A[0][i]))  # advice cell = fixed table cell holding the same value
+    return Assignment(shape, k, F, A, [], copies, used_rows)

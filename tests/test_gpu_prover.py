@@ -61,8 +61,8 @@ def test_commit_canonical_matches_oracle(ctx):
     params.close()
 
 
-def run_both(with_lookups, k, used, seed, check_bytes=True, n_public=0):
-    asg = circuits.satisfied_assignment(with_lookups, k, seed, used, n_public=n_public)
+def run_both(with_lookups, k, used, seed, check_bytes=True, n_public=0, asg=None):
+    asg = asg or circuits.satisfied_assignment(with_lookups, k, seed, used, n_public=n_public)
     shape = asg.shape
     n = 1 << k
     oparams = pp.setup(k, 0x5EC2E7 + k)
@@ -122,6 +122,16 @@ def test_create_proof_bytes_match_restated_prover(name, with_lookups, k, used, s
 def test_create_proof_with_public_inputs():
     """non-empty instance column: values hashed into the transcript, instance polynomial in the permutation argument"""
     proof, want, ok, proof2 = run_both(True, 8, 200, 0xDE18, n_public=5)
+    assert proof == want, f"first differing 32-byte proof element: #{first_diff(proof, want)}"
+    assert ok and proof2 == proof
+
+
+@pytest.mark.parametrize("k,used", [(6, 40), (10, 800)])
+def test_create_proof_second_shape(k, used):
+    """circuits.mul_table_assignment: no instance column, cs.degree() = 4 (three h pieces, chunks of 2), one lookup with single
+    expressions, a fixed column inside the permutation"""
+    asg = circuits.mul_table_assignment(k, 0xB200 + k, used)
+    proof, want, ok, proof2 = run_both(None, k, used, 0xB200 + k, asg=asg)
     assert proof == want, f"first differing 32-byte proof element: #{first_diff(proof, want)}"
     assert ok and proof2 == proof
 

@@ -128,3 +128,23 @@ def test_array_based_prover_equals_integer_prover(with_lookups, k, used, n_publi
     a = pp.create_proof(params, pk, asg.advice, asg.instances, lambda: next(it))
     b = pp.create_proof_fast(params, pk, asg.advice, asg.instances, pp.to_mont(draws))
     assert a == b
+
+
+def test_second_shape_degree4_fixed_in_permutation():
+    """no instance column, one degree-3 gate, one single-expression lookup (cs.degree() = 4), a fixed column in the permutation"""
+    k = 6
+    asg = circuits.mul_table_assignment(k, 0xB2, 40)
+    circuits.check_assignment(asg)
+    assert asg.shape.degree() == 4 and asg.shape.n_perm_sets == 2 and asg.copies
+    params = pp.setup(k, 0x1234567)
+    q = pp.Queries(*plonk.collect_queries(asg.shape))
+    pk = pp.keygen(params, asg.shape, q, asg.fixed, asg.copies, 7)
+    draws = [po.Xoshiro(3).uniform_fr() for _ in range(pp.random_count(asg.shape, 1 << k))]
+    it = iter(draws)
+    proof = pp.create_proof(params, pk, asg.advice, asg.instances, lambda: next(it))
+    assert proof == pp.create_proof_fast(params, pk, asg.advice, asg.instances, pp.to_mont(draws))
+    # points: 3 advice + 2 lookup + 2 perm z + 1 lookup z + 1 random + 3 h + openings; evals: see Appendix C's formula
+    assert pp.verify_proof(params, pk.vk, asg.instances, proof)
+    bad = bytearray(proof)
+    bad[100] ^= 4
+    assert not pp.verify_proof(params, pk.vk, asg.instances, bytes(bad))
