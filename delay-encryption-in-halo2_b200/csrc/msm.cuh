@@ -491,22 +491,48 @@ __global__ void __launch_bounds__(128) k_msm_digit_final2(const XYZZ* dsums0, un
 //   k_bucket_bits_final  one warp per bucket set: lane s doubles its term s times (bit j of D1 weighs 2^(w0 + j) and sits in
 //                     slot w0 + j), then a 4-level tree adds the <= 16 terms.  result = T + sum_s 2^s * S_s
 #define DE_RC_THREADS 64
-__device__ __forceinline__ void smem_tree_sum(XYZZ* s, unsigned int tid, unsigned int len) {
-    // s[0] <- sum of s[0 .. len), len a power of two <= blockDim; ends with a barrier
+// XYZZ points in shared memory as 8 planes of 16-byte words (plane p, slot i at planes[p * N + i]): consecutive threads touch
+// consecutive 16-byte words, where an array of 128-byte structures would put every thread of a quarter-warp on the same banks
+template <int N>
+struct SmemPoints {
+    uint4 w[8 * N];
+    __device__ __forceinline__ void put(unsigned int i, const XYZZ& v) {
+        const Fq* f = &v.x;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            w[(2 * q) * N + i] = make_uint4(f[q].l[0], f[q].l[1], f[q].l[2], f[q].l[3]);
+            w[(2 * q + 1) * N + i] = make_uint4(f[q].l[4], f[q].l[5], f[q].l[6], f[q].l[7]);
+        }
+    }
+    __device__ __forceinline__ XYZZ get(unsigned int i) const {
+        XYZZ v;
+        Fq* f = &v.x;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 a = w[(2 * q) * N + i], b = w[(2 * q + 1) * N + i];
+            f[q].l[0] = a.x; f[q].l[1] = a.y; f[q].l[2] = a.z; f[q].l[3] = a.w;
+            f[q].l[4] = b.x; f[q].l[5] = b.y; f[q].l[6] = b.z; f[q].l[7] = b.w;
+        }
+        return v;
+    }
+};
+template <int N>
+__device__ __forceinline__ void smem_tree_sum(SmemPoints<N>& s, unsigned int tid, unsigned int len) {
+    // slot 0 <- sum of slots [0, len), len a power of two <= blockDim; ends with a barrier
     for (unsigned int d = len >> 1; d >= 1; d >>= 1) {
         __syncthreads();
         if (tid < d) {
-            XYZZ a = load_xyzz(&s[tid]);
-            XYZZ b = load_xyzz(&s[tid + d]);
+            XYZZ a = s.get(tid);
+            XYZZ b = s.get(tid + d);
             xyzz_add(a, b);
-            store_xyzz(&s[tid], a);
+            s.put(tid, a);
         }
     }
     __syncthreads();
 }
 __global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_rowcol(const XYZZ* buckets, unsigned int NB, unsigned int w0, unsigned int w1, XYZZ* D0,
                                                                     XYZZ* D1) {
-    __shared__ XYZZ sm[DE_RC_THREADS];
+    __shared__ SmemPoints<DE_RC_THREADS> sm;
     const unsigned int V0 = 1u << w0, V1 = 1u << w1;
     const unsigned int tid = threadIdx.x;
     const unsigned long long set = blockIdx.y;
@@ -519,9 +545,9 @@ __global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_rowcol(const XYZZ* 
             XYZZ x = load_xyzz(&B[(unsigned long long)u * V0 + v]);
             xyzz_add(acc, x);
         }
-        store_xyzz(&sm[tid], acc);
+        sm.put(tid, acc);
         smem_tree_sum(sm, tid, DE_RC_THREADS);
-        if (tid == 0) store_xyzz(&D1[set * V1 + u], load_xyzz(&sm[0]));
+        if (tid == 0) store_xyzz(&D1[set * V1 + u], sm.get(0));
     } else {
         // column sums of 4 adjacent columns: thread (g, cv) adds rows g, g + 16, ... of column v0 + cv, then a tree over g
         const unsigned int v0 = (blockIdx.x - V1) * 4;
@@ -532,24 +558,24 @@ __global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_rowcol(const XYZZ* 
             xyzz_add(acc, x);
         }
         // sm[cv * 16 + g]: each column's 16 partials are contiguous; tree over g inside every 16-element group
-        store_xyzz(&sm[cv * 16 + g], acc);
+        sm.put(cv * 16 + g, acc);
         for (unsigned int d = 8; d >= 1; d >>= 1) {
             __syncthreads();
             const unsigned int c = tid >> 4, gg = tid & 15;
             if (gg < d) {
-                XYZZ a = load_xyzz(&sm[c * 16 + gg]);
-                XYZZ b = load_xyzz(&sm[c * 16 + gg + d]);
+                XYZZ a = sm.get(c * 16 + gg);
+                XYZZ b = sm.get(c * 16 + gg + d);
                 xyzz_add(a, b);
-                store_xyzz(&sm[c * 16 + gg], a);
+                sm.put(c * 16 + gg, a);
             }
         }
         __syncthreads();
-        if (tid < 4) store_xyzz(&D0[set * V0 + v0 + tid], load_xyzz(&sm[tid * 16]));
+        if (tid < 4) store_xyzz(&D0[set * V0 + v0 + tid], sm.get(tid * 16));
     }
 }
 // grid.x = slot: [0, w0) bit j of D0, [w0, w0 + w1) bit (slot - w0) of D1, w0 + w1: the plain total of D0.  grid.y = set.
 __global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_bitsums(const XYZZ* D0, const XYZZ* D1, unsigned int w0, unsigned int w1, XYZZ* S) {
-    __shared__ XYZZ sm[DE_RC_THREADS];
+    __shared__ SmemPoints<DE_RC_THREADS> sm;
     const unsigned int tid = threadIdx.x, slot = blockIdx.x;
     const unsigned long long set = blockIdx.y;
     const unsigned int nslots = w0 + w1 + 1;
@@ -571,12 +597,12 @@ __global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_bitsums(const XYZZ*
             xyzz_add(acc, x);
         }
     }
-    store_xyzz(&sm[tid], acc);
+    sm.put(tid, acc);
     smem_tree_sum(sm, tid, DE_RC_THREADS);
-    if (tid == 0) store_xyzz(&S[set * nslots + slot], load_xyzz(&sm[0]));
+    if (tid == 0) store_xyzz(&S[set * nslots + slot], sm.get(0));
 }
 __global__ void __launch_bounds__(32) k_bucket_bits_final(const XYZZ* S, unsigned int w0, unsigned int w1, XYZZ* set_out) {
-    __shared__ XYZZ sm[32];
+    __shared__ SmemPoints<32> sm;
     const unsigned int lane = threadIdx.x;
     const unsigned long long set = blockIdx.x;
     const unsigned int nslots = w0 + w1 + 1;  // <= 16 for c <= 16
@@ -586,9 +612,9 @@ __global__ void __launch_bounds__(32) k_bucket_bits_final(const XYZZ* S, unsigne
         const unsigned int doublings = lane == nslots - 1 ? 0 : lane;
         for (unsigned int d = 0; d < doublings; d++) term = xyzz_dbl(term);
     }
-    store_xyzz(&sm[lane], term);
+    sm.put(lane, term);
     smem_tree_sum(sm, lane, 32);
-    if (lane == 0) store_xyzz(&set_out[set], load_xyzz(&sm[0]));
+    if (lane == 0) store_xyzz(&set_out[set], sm.get(0));
 }
 
 // ---- 5. combine bucket sets: out[b] = sum_u 2^(c*u) * R[b][u], written as Jacobian -------------------------------
