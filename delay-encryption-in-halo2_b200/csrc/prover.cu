@@ -250,13 +250,18 @@ __global__ void __launch_bounds__(128) k_lookup_fractions(const Fr* comp, const 
     store(&num[(unsigned long long)l * n + i], mul(add(ci, beta), add(ct, gamma)));
     store(&den[(unsigned long long)l * n + i], mul(add(beta, a), add(gamma, s)));
 }
-// num[i] <- num[i] / den[i] (zero denominators give zero, as ff::BatchInvert leaves them): Montgomery's trick per thread over
-// DE_INV_CHUNK elements, one Fermat inversion each
-__global__ void __launch_bounds__(128) k_frac_finish(Fr* num, const Fr* den, unsigned long long total) {
-    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long lo = t * DE_INV_CHUNK;
-    if (lo >= total) return;
-    const unsigned int cnt = (unsigned int)((total - lo) < DE_INV_CHUNK ? (total - lo) : DE_INV_CHUNK);
+// num[i] <- num[i] / den[i] (zero denominators give zero, as ff::BatchInvert leaves them).  Montgomery's trick at CTA scope:
+// every thread multiplies up DE_INV_CHUNK denominators, a prefix and a suffix product scan over the 256 thread totals run in the
+// same loop, ONE thread inverts the CTA's total (a single active lane: no divergence in the Euclidean loop), and each thread
+// gets the inverse of its own total as total^-1 * (product of the totals before it) * (product of those after it).
+#define DE_INV_THREADS 256
+__global__ void __launch_bounds__(DE_INV_THREADS) k_frac_finish(Fr* num, const Fr* den, unsigned long long total) {
+    __shared__ Fr s_pre[DE_INV_THREADS];
+    __shared__ Fr s_suf[DE_INV_THREADS];
+    __shared__ Fr s_inv;
+    const unsigned int tid = threadIdx.x;
+    const unsigned long long lo = ((unsigned long long)blockIdx.x * DE_INV_THREADS + tid) * DE_INV_CHUNK;
+    const unsigned int cnt = lo >= total ? 0u : (unsigned int)((total - lo) < DE_INV_CHUNK ? (total - lo) : DE_INV_CHUNK);
     Fr pre[DE_INV_CHUNK];
     Fr acc = Fr::one();
     for (unsigned int k = 0; k < cnt; k++) {
@@ -264,7 +269,27 @@ __global__ void __launch_bounds__(128) k_frac_finish(Fr* num, const Fr* den, uns
         const Fr d = load(&den[lo + k]);
         if (!d.is_zero()) acc = mul(acc, d);
     }
-    Fr ai = inv(acc);
+    store(&s_pre[tid], acc);
+    store(&s_suf[tid], acc);
+    __syncthreads();
+    // inclusive prefix products in s_pre, inclusive suffix products in s_suf
+    for (unsigned int d = 1; d < DE_INV_THREADS; d <<= 1) {
+        Fr a = Fr::one(), b = Fr::one();
+        const bool hp = tid >= d, hs = tid + d < DE_INV_THREADS;
+        if (hp) a = load(&s_pre[tid - d]);
+        if (hs) b = load(&s_suf[tid + d]);
+        __syncthreads();
+        if (hp) store(&s_pre[tid], mul(load(&s_pre[tid]), a));
+        if (hs) store(&s_suf[tid], mul(load(&s_suf[tid]), b));
+        __syncthreads();
+    }
+    if (tid == 0) store(&s_inv, inv(load(&s_pre[DE_INV_THREADS - 1])));
+    __syncthreads();
+    if (cnt == 0) return;
+    Fr ai = load(&s_inv);
+    if (tid > 0) ai = mul(ai, load(&s_pre[tid - 1]));
+    if (tid + 1 < DE_INV_THREADS) ai = mul(ai, load(&s_suf[tid + 1]));
+    // ai = 1 / (this thread's product of non-zero denominators)
     for (int k = (int)cnt - 1; k >= 0; k--) {
         const Fr d = load(&den[lo + k]);
         Fr r = Fr::zero();
@@ -853,7 +878,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         }
         const size_t total = zl * n;
         const size_t inv_threads = (total + DE_INV_CHUNK - 1) / DE_INV_CHUNK;
-        k_frac_finish<<<(unsigned int)((inv_threads + 127) / 128), 128, 0, st>>>(p->frac_num, p->frac_den, total);
+        k_frac_finish<<<(unsigned int)((inv_threads + DE_INV_THREADS - 1) / DE_INV_THREADS), DE_INV_THREADS, 0, st>>>(p->frac_num, p->frac_den, total);
         DE_CHECK_LAUNCH(ctx);
         const dim3 cgrid((unsigned int)((nchunks + 127) / 128), (unsigned int)zl);
         k_pp_chunks<<<cgrid, 128, 0, st>>>(p->frac_num, n, nchunks, p->cp);
