@@ -226,3 +226,22 @@ def test_prover_argument_errors():
     proof = prover.create_proof(adv, [np.zeros((0, 4), dtype=np.uint64)], draws)
     assert len(proof) == 1792 and pp.verify_proof(oparams, opk.vk, asg.instances, proof)
     prover.close(); pk.close(); dom.close(); params.close(); params2.close(); ctx.close(); ctx2.close()
+
+
+@pytest.mark.parametrize("seed", range(0x5EED00, 0x5EED0C))
+def test_create_proof_many_seeds(seed):
+    """different witnesses, copy-constraint graphs, table hit patterns and random streams: shapes alternate between MainGate,
+    MainGate + RangeChip (with public inputs) and the degree-4 shape; k and the number of used rows vary with the seed"""
+    import random
+    rng = random.Random(seed)
+    kind = seed % 3
+    k = rng.choice([6, 7, 8, 9])
+    used = rng.randrange(20, (1 << k) - 6)
+    if kind == 2:
+        asg = circuits.mul_table_assignment(k, seed, used)
+    else:
+        asg = circuits.satisfied_assignment(kind == 1, k, seed, used, uniform_values=bool(seed & 4), n_public=rng.randrange(0, 4))
+    circuits.check_assignment(asg)
+    proof, want, ok, proof2 = run_both(None, k, used, seed, asg=asg)
+    assert proof == want, f"first differing 32-byte proof element: #{first_diff(proof, want)}"
+    assert ok and proof2 == proof
