@@ -65,3 +65,4 @@ def test_binary_gcd_inversion_on_host(shim, field, p):
     vals = from_m(a)
     want = to_m([pow(v, -1, p) if v % p else 0 for v in vals])
     assert (got == want).all()
+
