@@ -76,7 +76,7 @@ __global__ void k_mixed(double* out, double a, double b, unsigned int ua, int it
 #pragma unroll
             for (int i = 0; i < ILP; i++) {
                 asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(a), "d"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(wacc[i]) : "r"(ua + i), "r"(ua));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(wacc[i]) : "r"((unsigned int)wacc[i]), "r"(ua));  // operand changes: not hoistable
             }
     }
     double s = 0;
@@ -84,16 +84,25 @@ __global__ void k_mixed(double* out, double a, double b, unsigned int ua, int it
     for (int i = 0; i < ILP; i++) s += acc[i] + (double)wacc[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// IMAD.WIDE.U32 with a 64-bit accumulator and NO carry flag; one multiplicand changes every step (by an ALU add, on the other
+// pipe) so that the product cannot be hoisted out of the loop
 template <int ILP>
 __global__ void k_imad_wide_clean(unsigned long long* out, unsigned int a, int iters) {
     unsigned long long acc[ILP];
+    unsigned int x[ILP];
 #pragma unroll
-    for (int i = 0; i < ILP; i++) acc[i] = threadIdx.x + i;
+    for (int i = 0; i < ILP; i++) {
+        acc[i] = threadIdx.x + i;
+        x[i] = a + 3 * i + threadIdx.x;
+    }
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < 8; r++)
 #pragma unroll
-            for (int i = 0; i < ILP; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a + i), "r"(a));
+            for (int i = 0; i < ILP; i++) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(x[i]), "r"(a));
+                x[i] += 0x9e3779b9u;
+            }
     }
     unsigned long long s = 0;
 #pragma unroll

@@ -1,8 +1,9 @@
 // mul29_experiment.cuh — EXPERIMENT, not part of libde_b200.so: a carry-less Montgomery multiplication on 9 x 29-bit limbs
 // (64-bit column accumulators, 81 + 81 IMAD.WIDE without carry flags), measured by tools/int_peak against the product's
 // word-serial carry-chain multiplier (field.cuh mul).  Result on B200 (profiles/r01_int_peak_v2.jsonl): 38-39 Gmul/s against
-// 65.9: ptxas splits every `mad.wide` with a 64-bit addend into IMAD.WIDE (addend RZ) + a 3-input IADD3 / IADD3.X pair, so the
-// ALU pipe carries ~290 instructions per multiplication and becomes the limiter.  Kept for the record of what was tried.
+// 65.9: a 32x32->64 multiply-add is half-rate in every form (so 162 of them lose to 136), and ptxas splits every `mad.wide`
+// with a 64-bit addend into IMAD.WIDE (addend RZ) + a 3-input IADD3 / IADD3.X pair, which loads the ALU pipe with ~290
+// instructions per multiplication.  Kept for the record of what was tried.
 #pragma once
 #include "field.cuh"
 
