@@ -300,8 +300,112 @@ def write_params_raw(path, k, g, g_lagrange, g2: bytes, s_g2: bytes):
         f.write(s_g2)
 
 
+_FR = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+_FQ = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+# halo2curves::bn256::G2Affine::generator(): (x.c0, x.c1), (y.c0, y.c1)
+_G2_GEN = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+            11559732032986387107991004021392285783925812861821192530917403151452391805634),
+           (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+            4082367875863433681332203403145435568316851327593401208105741076214120093531))
+
+
+def _g2_mul(point, k: int):
+    """[k] point on the twist y^2 = x^3 + 3 / (9 + u) over Fq2 = Fq[u] / (u^2 + 1): ONE scalar multiplication per setup
+    (s_g2 = [s] G2), done in Python integers; the product has no other G2 arithmetic."""
+    q = _FQ
+
+    def mul2(a, b):
+        return ((a[0] * b[0] - a[1] * b[1]) % q, (a[0] * b[1] + a[1] * b[0]) % q)
+
+    def inv2(a):
+        d = pow(a[0] * a[0] + a[1] * a[1], -1, q)
+        return (a[0] * d % q, -a[1] * d % q)
+
+    def sub2(a, b):
+        return ((a[0] - b[0]) % q, (a[1] - b[1]) % q)
+
+    def add_pts(P, Q):
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        if P[0] == Q[0]:
+            if P[1] != Q[1] or P[1] == (0, 0):
+                return None
+            lam = mul2(mul2((3, 0), mul2(P[0], P[0])), inv2(mul2((2, 0), P[1])))
+        else:
+            lam = mul2(sub2(Q[1], P[1]), inv2(sub2(Q[0], P[0])))
+        x3 = sub2(sub2(mul2(lam, lam), P[0]), Q[0])
+        return (x3, sub2(mul2(lam, sub2(P[0], x3)), P[1]))
+
+    acc = None
+    for bit in bin(k % _FR)[2:] if k % _FR else "":
+        acc = add_pts(acc, acc)
+        if bit == "1":
+            acc = add_pts(acc, point)
+    return acc
+
+
+def _g2_raw_bytes(pt) -> bytes:
+    """SerdeFormat::RawBytes of a G2Affine: x.c0, x.c1, y.c0, y.c1 as Montgomery limbs (identity: zeros)"""
+    if pt is None:
+        return bytes(128)
+    out = b""
+    for coord in pt:
+        for c in coord:
+            out += (c * (1 << 256) % _FQ).to_bytes(32, "little")
+    return out
+
+
 class ParamsKZG:
     """poly::kzg::commitment::ParamsKZG: g / g_lagrange staged (with window tables) in HBM once."""
+
+    @classmethod
+    def setup(cls, k: int, s: int, ctx: Context | None = None, keep_host: bool = True):
+        """ParamsKZG::setup with a caller-supplied secret s (the reference draws it from OsRng, benches/delay_enc.rs:43):
+        g[i] = [s^i] G, g_lagrange[i] = [l_i(s)] G with l_i(s) = omega^i (s^n - 1) / (n (s - omega^i)), g2 = G2, s_g2 = [s] G2.
+        The 2 * 2^k fixed-base multiplications run on the device (de_g1_mul_base_dev); the scalars (powers of s, one batched
+        inversion) are one-time host integers."""
+        import torch
+        ctx = ctx or default_context()
+        n = 1 << k
+        s %= _FR
+        root = pow(7, (_FR - 1) >> 28, _FR)
+        omega = pow(root, 1 << (28 - k), _FR)
+        pows, w = [1] * n, [1] * n
+        for i in range(1, n):
+            pows[i] = pows[i - 1] * s % _FR
+            w[i] = w[i - 1] * omega % _FR
+        den = [(s - w[i]) * n % _FR for i in range(n)]
+        pre, acc = [], 1
+        for d in den:
+            pre.append(acc)
+            acc = acc * d % _FR
+        inv = pow(acc, -1, _FR)  # s is not an n-th root of unity (probability n / r)
+        sn1 = (pow(s, n, _FR) - 1) % _FR
+        lag = [0] * n
+        for i in range(n - 1, -1, -1):
+            lag[i] = w[i] * sn1 % _FR * (inv * pre[i] % _FR) % _FR
+            inv = inv * den[i] % _FR
+        gen = np.array([(1 << 256) % _FQ >> (64 * j) & 0xFFFFFFFFFFFFFFFF for j in range(4)] +
+                       [2 * (1 << 256) % _FQ >> (64 * j) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+        outs = []
+        for scal in (pows, lag):
+            raw = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in scal), dtype=np.uint64).reshape(n, 4)
+            d_s = torch.from_numpy(ctx.fr_to_mont(raw).view(np.int64)).cuda(ctx.device)
+            d_o = torch.empty((n, 8), dtype=torch.int64, device=d_s.device)
+            ctx.g1_mul_base_dev(gen, d_s, n, d_o)
+            ctx.sync()
+            outs.append(d_o.cpu().numpy().view(np.uint64))
+        p = cls(k, outs[0], outs[1], ctx)
+        p.g2, p.s_g2 = _g2_raw_bytes(_G2_GEN), _g2_raw_bytes(_g2_mul(_G2_GEN, s))
+        if keep_host:
+            p.g_host, p.g_lagrange_host = outs
+        return p
+
+    def write(self, path):
+        """ParamsKZG::write(.., SerdeFormat::RawBytes); needs the host copies kept by setup() / read()"""
+        write_params_raw(path, self.k, self.g_host, self.g_lagrange_host, self.g2, self.s_g2)
 
     @classmethod
     def read(cls, path, ctx: Context | None = None):
@@ -309,6 +413,7 @@ class ParamsKZG:
         d = read_params_raw(path)
         p = cls(d["k"], np.ascontiguousarray(d["g"]), np.ascontiguousarray(d["g_lagrange"]), ctx)
         p.g2, p.s_g2 = d["g2"], d["s_g2"]
+        p.g_host, p.g_lagrange_host = d["g"], d["g_lagrange"]
         return p
 
     def __init__(self, k: int, g=None, g_lagrange=None, ctx: Context | None = None):

@@ -150,3 +150,24 @@ def test_commit_sharded_single_process():
         want = orc.best_multiexp(s, bases)
         assert (orc.g1_to_affine(got) == orc.g1_to_affine(want)).all(), devices
         sp.close()
+
+
+def test_params_setup_matches_restated_setup(ctx, tmp_path):
+    """ParamsKZG::setup on the device (fixed-base multiplications) equals the restated setup: g, g_lagrange, s_g2; and the
+    RawBytes file written from it reads back to the same commitments"""
+    import pairing
+    import pyprover as pp
+    k, s = 7, 0x5EC2E7123456789
+    want = pp.setup(k, s)
+    params = de_b200.ParamsKZG.setup(k, s, ctx)
+    assert (params.g_host == want.g_mont).all() and (params.g_lagrange_host == want.g_lagrange_mont).all()
+    raw = params.s_g2
+    coords = [int.from_bytes(raw[32 * i:32 * i + 32], "little") * pow(1 << 256, -1, po.FQ) % po.FQ for i in range(4)]
+    assert ((coords[0], coords[1]), (coords[2], coords[3])) == pairing.g2_mul(pairing.G2_GEN, s)
+    path = tmp_path / "params_7"
+    params.write(path)
+    again = de_b200.ParamsKZG.read(path, ctx)
+    poly = orc.uniform_fr(77, 1 << k)
+    assert (orc.g1_to_affine(again.commit_lagrange(poly)) == orc.g1_to_affine(orc.best_multiexp(poly, want.g_lagrange_mont))).all()
+    assert (orc.g1_to_affine(params.commit(poly)) == orc.g1_to_affine(orc.best_multiexp(poly, want.g_mont))).all()
+    params.close(); again.close()
