@@ -259,6 +259,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=8, help="independent proofs in flight per GPU (one prover + stream each)")
     ap.add_argument("--config", default="delay_enc", choices=sorted(CONFIGS), help="circuit shape / size (default: the headline delay_enc)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "latency", "throughput"],
+                    help="de_ctx_set_mode of the in-flight arms (auto: throughput when more than one proof is in flight)")
     ap.add_argument("--k", type=int, default=0, help="override the config's k (the reference's README also times k = 15 ... 19)")
     args = ap.parse_args()
     global K, USED_ROWS, SEED, WITH_LOOKUPS, CONFIG_NAME, WORKLOAD, METRIC, CPU_SAMPLE
@@ -354,7 +356,7 @@ def main():
         return sharding.max_over_ranks(e0.elapsed_time(e1))
 
     for wk in workers:
-        wk.ctx.set_mode(throughput=B > 1)  # several provers share the GPU in the throughput / e2e arms
+        wk.ctx.set_mode(throughput=(B > 1) if args.mode == "auto" else args.mode == "throughput")  # several provers share the GPU
     timed(workers, args.warmup, False)
     first_proof = workers[0].proof
     assert len(first_proof) == prover0.proof_size == (2848 if WITH_LOOKUPS else 1792)
@@ -398,7 +400,7 @@ def main():
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE carry chains)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proofs_per_step_per_gpu": B, "proof_bytes": len(first_proof),
-                   "mode": "DE_MODE_THROUGHPUT" if B > 1 else "DE_MODE_LATENCY",
+                   "mode": "DE_MODE_THROUGHPUT" if ((B > 1) if args.mode == "auto" else args.mode == "throughput") else "DE_MODE_LATENCY",
                    "in_flight": f"{B} independent proofs per GPU, one host thread + CUDA stream each (BASELINE config 5: 64 proofs over "
                                 "8 GPUs = 8 per GPU)",
                    "l2": f"per-step working set ~{0.8 * B * 2.0 ** (K - 16):.2f} GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",

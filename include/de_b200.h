@@ -54,8 +54,8 @@ int de_ctx_sync(de_ctx* ctx);
 /* Scheduling hint.  DE_MODE_LATENCY (default): one proof / one MSM at a time owns the GPU, so latency-bound tails are given
  * short dependency chains even at the price of idle lanes (tree-shaped bucket reduction).  DE_MODE_THROUGHPUT: several
  * contexts run concurrently on the same GPU (batches of proofs), so kernels keep every lane busy and leave the overlap to the
- * other streams (serial segmented sums).  Results are identical; measured at k = 16: 10.3 ms vs 11.7 ms per proof alone,
- * 135 vs 138 proofs/s with 8 proofs in flight. */
+ * other streams (serial segmented sums).  Results are identical; measured at k = 16: 10.0 ms vs 11.5 ms per proof alone,
+ * 139 vs 145 proofs/s with 8 proofs in flight. */
 enum de_mode { DE_MODE_LATENCY = 0, DE_MODE_THROUGHPUT = 1 };
 int de_ctx_set_mode(de_ctx* ctx, int mode);
 const char* de_last_error(de_ctx* ctx); /* ctx may be NULL: returns the last error of a failed de_ctx_create */
