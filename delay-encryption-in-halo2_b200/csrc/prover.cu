@@ -909,6 +909,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     // challenge in between, so the two rounds share one launch sequence: zl polynomials over g_lagrange and one over g.
     const Fr* random_poly = p->randoms + rpos;
     rpos += n + 1;  // coefficients + blind
+    if (rpos + (p->deg - 1) != p->n_random) return fail(ctx, DE_ERR_ARG, "de_create_proof: internal error: random-draw layout out of step");
     {
         // column order in `lag` is [advice | instance | a' | s' | permz | lookup z | spare]: the spare column after the z block
         // takes the random polynomial, so the batch is contiguous
