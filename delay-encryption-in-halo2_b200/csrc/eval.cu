@@ -58,9 +58,9 @@ __global__ void __launch_bounds__(128) k_eval_h(const __grid_constant__ EvalPara
     for (uint32_t n = 0; n < p.n_lookups; n++) {
         c.prev = Fr::zero();
         const Fr table_value = run_graph(c, p.lookups[n]);
-        const Fr* zc = p.lookup + (unsigned long long)n * p.ext_n;  // block order: all z | all a' | all s'
-        const Fr* ac = zc + (unsigned long long)p.n_lookups * p.ext_n;
-        const Fr* sc = ac + (unsigned long long)p.n_lookups * p.ext_n;
+        const Fr* zc = p.lookup_z + (unsigned long long)n * p.ext_n;
+        const Fr* ac = p.lookup_a + (unsigned long long)n * p.ext_n;
+        const Fr* sc = p.lookup_s + (unsigned long long)n * p.ext_n;
         const Fr z = load(&zc[idx]), a = load(&ac[idx]), s = load(&sc[idx]);
         const Fr a_minus_s = sub(a, s);
         value = add(mul(value, y), mul(sub(one, z), l0));
@@ -217,14 +217,20 @@ int de_pk_extend_dev(de_pk* pk, const de_fr* d_advice, const de_fr* d_instance, 
         return fail(ctx, DE_ERR_ARG, "de_pk_extend_dev: missing polynomial block");
     DE_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t ext_n = pk->ext_n;
+    const size_t L = pk->n_lookups;
     Fr* w_adv = pk->work;
     Fr* w_inst = w_adv + (size_t)pk->n_advice * ext_n;
-    Fr* w_permz = w_inst + (size_t)pk->n_instance * ext_n;
-    Fr* w_lookup = w_permz + (size_t)pk->n_sets * ext_n;
+    Fr* w_la = w_inst + (size_t)pk->n_instance * ext_n;  // a' block, then s' block
+    Fr* w_permz = w_la + 2 * L * ext_n;
+    Fr* w_lz = w_permz + (size_t)pk->n_sets * ext_n;
     if (pk->n_advice) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_advice, stride, (de_fr*)w_adv, ext_n, pk->n_advice));
     if (pk->n_instance) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_instance, stride, (de_fr*)w_inst, ext_n, pk->n_instance));
     if (pk->n_sets) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_permz, stride, (de_fr*)w_permz, ext_n, pk->n_sets));
-    if (pk->n_lookups) DE_TRY(de_coeff_to_extended_dev(pk->dom, d_lookup, stride, (de_fr*)w_lookup, ext_n, 3 * (size_t)pk->n_lookups));
+    if (L) {
+        // the API's lookup block is [all z | all a' | all s']
+        DE_TRY(de_coeff_to_extended_dev(pk->dom, d_lookup, stride, (de_fr*)w_lz, ext_n, L));
+        DE_TRY(de_coeff_to_extended_dev(pk->dom, d_lookup + L * stride, stride, (de_fr*)w_la, ext_n, 2 * L));
+    }
     return DE_OK;
 }
 
@@ -236,8 +242,10 @@ int de_evaluate_h_rows_dev(de_pk* pk, const de_challenges* ch, de_fr* d_h_ext) {
     const size_t ext_n = pk->ext_n;
     Fr* w_adv = pk->work;
     Fr* w_inst = w_adv + (size_t)pk->n_advice * ext_n;
-    Fr* w_permz = w_inst + (size_t)pk->n_instance * ext_n;
-    Fr* w_lookup = w_permz + (size_t)pk->n_sets * ext_n;
+    Fr* w_la = w_inst + (size_t)pk->n_instance * ext_n;
+    Fr* w_ls = w_la + (size_t)pk->n_lookups * ext_n;
+    Fr* w_permz = w_ls + (size_t)pk->n_lookups * ext_n;
+    Fr* w_lz = w_permz + (size_t)pk->n_sets * ext_n;
     if (ch->n_challenges > pk->challenges_cap) {
         Fr* d = nullptr;
         DE_CUDA(ctx, cudaMalloc((void**)&d, sizeof(Fr) * ch->n_challenges));
@@ -258,7 +266,7 @@ int de_evaluate_h_rows_dev(de_pk* pk, const de_challenges* ch, de_fr* d_h_ext) {
     p.l_last = p.l0 + ext_n;
     p.l_active = p.l_last + ext_n;
     p.omega_pows = p.l_active + ext_n;
-    p.advice = w_adv; p.instance = w_inst; p.permz = w_permz; p.lookup = w_lookup;
+    p.advice = w_adv; p.instance = w_inst; p.permz = w_permz; p.lookup_z = w_lz; p.lookup_a = w_la; p.lookup_s = w_ls;
     p.challenges = pk->d_challenges;
     p.y = fr_from_host(ch->y); p.beta = fr_from_host(ch->beta); p.gamma = fr_from_host(ch->gamma); p.theta = fr_from_host(ch->theta);
     p.delta = pk->delta;

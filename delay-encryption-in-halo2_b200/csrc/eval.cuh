@@ -35,7 +35,7 @@ struct EvalParams {
     // resident pk cosets (column-major, ext_n apart)
     const Fr* fixed; const Fr* sigma; const Fr* l0; const Fr* l_last; const Fr* l_active; const Fr* omega_pows;
     // per-proof cosets
-    const Fr* advice; const Fr* instance; const Fr* permz; const Fr* lookup;
+    const Fr* advice; const Fr* instance; const Fr* permz; const Fr* lookup_z; const Fr* lookup_a; const Fr* lookup_s;
     const Fr* challenges;
     Fr y, beta, gamma, theta, delta, delta_start;  // delta_start holds ZETA (Montgomery)
     DevGraph gates;
@@ -124,7 +124,7 @@ struct de_pk {
     uint32_t k, ek;
     Fr* resident;  // fixed | sigma | l0 | l_last | l_active | omega_pows, ext_n apart
     Fr* coeff;     // fixed | sigma polynomials in coefficient form, n apart (the prover opens and evaluates them)
-    Fr* work;      // advice | instance | permz | lookup (3 per lookup) cosets, ext_n apart
+    Fr* work;      // per-proof cosets, ext_n apart, in the prover's column order: advice | instance | a' | s' | permz | lookup z
     Fr* d_challenges;
     uint32_t challenges_cap;
     uint32_t *d_perm_kind, *d_perm_index;
