@@ -14,6 +14,9 @@
 namespace de {
 
 struct NttPlan;
+struct NttDistPlan;
+template <bool DIST>
+struct NttDistArgs;
 
 struct DevBuf {
     void* p = nullptr;
@@ -65,7 +68,7 @@ struct PinnedBuf {
 };
 
 enum { WS_IO_A = 0, WS_IO_B, WS_NTT_SCRATCH, WS_MSM_KEYS, WS_MSM_VALS, WS_MSM_SORTED, WS_MSM_COUNTS, WS_MSM_BUCKETS,
-       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_RED, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_COUNT };
+       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_RED, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_NTT_DIST, WS_COUNT };
 
 }  // namespace de
 
@@ -97,6 +100,8 @@ struct de_ctx {
     de::DevBuf ws[de::WS_COUNT];
     de::PinnedBuf pinned;
     std::vector<de::NttPlan*> plans;
+    std::vector<de::NttDistPlan*> dist_plans;           // multi-GPU transform tables (ntt.cu)
+    cudaEvent_t dist_ev[2] = {nullptr, nullptr};        // stage-1 / stage-2 completion of de_ntt_sharded_dev on this context
 };
 
 namespace de {
@@ -188,7 +193,8 @@ inline de_fr fr_to_host(const Fr& v) {
 
 // ntt.cu
 int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, size_t src_stride, Fr* d_dst, size_t dst_stride,
-            size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3);
+            size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3,
+            const NttDistArgs<true>* dist = nullptr);
 void ntt_free_plans(de_ctx* ctx);
 // device-side Fr helpers running single-thread kernels, used for domain constants (ntt.cu)
 int fr_host_pow(de_ctx* ctx, const de_fr& base, uint64_t e, de_fr* out);

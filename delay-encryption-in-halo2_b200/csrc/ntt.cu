@@ -32,9 +32,31 @@ struct NttPlan {
     }
 };
 
+// Tables of the multi-GPU transform (de_ntt_dist_*): w_N^e two-level for the inter-stage twiddle w_N^(rank * j2), the root of
+// the local N/W-point transform and the W/2 powers of the cross-rank root.
+struct NttDistPlan {
+    uint32_t log_n = 0, log_w = 0;
+    de_fr omega, omega_local;
+    Fr* tw_hi = nullptr;
+    Fr* tw_lo = nullptr;
+    uint32_t tw_lo_bits = 0;
+    Fr wcross[4];
+    ~NttDistPlan() {
+        if (tw_hi) cudaFree(tw_hi);
+        if (tw_lo) cudaFree(tw_lo);
+    }
+};
+
 void ntt_free_plans(de_ctx* ctx) {
     for (auto* p : ctx->plans) delete p;
     ctx->plans.clear();
+    for (auto* p : ctx->dist_plans) delete p;
+    ctx->dist_plans.clear();
+    for (auto& e : ctx->dist_ev)
+        if (e) {
+            cudaEventDestroy(e);
+            e = nullptr;
+        }
 }
 
 static int pow_table(de_ctx* ctx, Fr** out, unsigned long long n, const Fr& base, unsigned long long step) {
@@ -104,17 +126,18 @@ static int get_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, NttPlan** o
     return DE_OK;
 }
 
-template <int S, int LT>
-static int launch_pass_t(de_ctx* ctx, const NttPassParams& prm, unsigned int blocks, unsigned int batch) {
+template <int S, int LT, bool DIST>
+static int launch_pass_t(de_ctx* ctx, const NttPassParams& prm, const NttDistArgs<DIST>& dx, unsigned int blocks, unsigned int batch) {
     using Sh = NttShape<S, LT>;
     static bool configured[16] = {false};
     int dev = ctx->device & 15;
     if (!configured[dev]) {
-        DE_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<S, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::SMEM));
+        DE_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<S, LT, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::SMEM));
         configured[dev] = true;
     }
     dim3 grid(blocks, batch);
-    DE_TIMED(ctx, "k_ntt_pass", (double)blocks * batch * Sh::M, (k_ntt_pass<S, LT><<<grid, Sh::NTHREADS, Sh::SMEM, ctx->stream>>>(prm)));
+    DE_TIMED(ctx, DIST ? "k_ntt_pass_dist" : "k_ntt_pass", (double)blocks * batch * Sh::M,
+             (k_ntt_pass<S, LT, DIST><<<grid, Sh::NTHREADS, Sh::SMEM, ctx->stream>>>(prm, dx)));
     DE_CHECK_LAUNCH(ctx);
     return DE_OK;
 }
@@ -128,17 +151,28 @@ static int tile_log(int S) {
 }
 
 static int launch_pass(de_ctx* ctx, int S, int LT, const NttPassParams& prm, unsigned int blocks, unsigned int batch) {
+    const NttDistArgs<false> none{};
 #define CASE(s, lt) \
-    if (S == s && LT == lt) return launch_pass_t<s, lt>(ctx, prm, blocks, batch);
+    if (S == s && LT == lt) return launch_pass_t<s, lt, false>(ctx, prm, none, blocks, batch);
     CASE(1, 0) CASE(2, 0) CASE(3, 0) CASE(4, 0) CASE(5, 0) CASE(6, 0) CASE(7, 0) CASE(8, 0) CASE(9, 0) CASE(10, 0)
     CASE(1, 3) CASE(2, 3) CASE(3, 3) CASE(4, 3) CASE(5, 3) CASE(6, 3) CASE(7, 3) CASE(8, 3) CASE(9, 2) CASE(10, 1)
 #undef CASE
     return fail(ctx, DE_ERR_UNSUPPORTED, "ntt: no kernel for this pass shape");
 }
 
+// last pass of the local transform of the multi-GPU NTT (peer-store epilogue); local sizes 2^11 .. 2^25 end in one of these
+static int launch_pass_dist(de_ctx* ctx, int S, int LT, const NttPassParams& prm, const NttDistArgs<true>& dx, unsigned int blocks) {
+#define CASE(s, lt) \
+    if (S == s && LT == lt) return launch_pass_t<s, lt, true>(ctx, prm, dx, blocks, 1);
+    CASE(5, 3) CASE(6, 3) CASE(7, 3) CASE(8, 3) CASE(9, 2) CASE(10, 1)
+#undef CASE
+    return fail(ctx, DE_ERR_UNSUPPORTED, "ntt (multi-GPU): no peer-store kernel for this pass shape");
+}
+
 int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, size_t src_stride, Fr* d_dst, size_t dst_stride,
-            size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3) {
+            size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3, const NttDistArgs<true>* dist) {
     if (batch == 0) return DE_OK;
+    if (dist && (batch != 1 || log_n < 11)) return fail(ctx, DE_ERR_ARG, "ntt (multi-GPU): local transform must be one vector of >= 2^11");
     if (batch > 65535) return fail(ctx, DE_ERR_ARG, "ntt: batch too large");
     if (log_n == 0) {
         if (in_mode != 0 || out_mode != 0) return fail(ctx, DE_ERR_ARG, "ntt: fused scaling needs log_n >= 1");
@@ -233,7 +267,8 @@ int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, si
             prm.out_el = N / L;
             blocks = N / (T * L);
         }
-        DE_TRY(launch_pass(ctx, S, LT, prm, (unsigned int)blocks, (unsigned int)batch));
+        if (last && dist) DE_TRY(launch_pass_dist(ctx, S, LT, prm, *dist, (unsigned int)blocks));
+        else DE_TRY(launch_pass(ctx, S, LT, prm, (unsigned int)blocks, (unsigned int)batch));
         Lprod *= L;
     }
     return DE_OK;
@@ -250,6 +285,18 @@ __global__ void k_fr_pow(Fr base, unsigned long long e, Fr* out) {
         e >>= 1;
     }
     store(out, acc);
+}
+
+// base^e on the device, result read back (plan constants; synchronises the context's stream)
+int fr_host_pow(de_ctx* ctx, const de_fr& base, uint64_t e, de_fr* out) {
+    DE_WS(ctx, d, Fr, WS_IO_B, sizeof(Fr));
+    k_fr_pow<<<1, 1, 0, ctx->stream>>>(fr_from_host(base), e, d);
+    DE_CHECK_LAUNCH(ctx);
+    Fr h;
+    DE_CUDA(ctx, cudaMemcpyAsync(&h, d, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = fr_to_host(h);
+    return DE_OK;
 }
 
 template <class P>
@@ -504,6 +551,220 @@ int de_ntt(de_ctx* ctx, de_fr* a, const de_fr* omega, uint32_t log_n) {
     DE_TRY(ntt_run(ctx, *omega, log_n, d, n, d, n, 1, 0, 0, nullptr, 0, nullptr));
     DE_CUDA(ctx, cudaMemcpyAsync(a, d, sizeof(Fr) * n, cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
+}  // extern "C"
+
+// ---- multi-GPU best_fft (SURVEY.md section 8e, row "NTT: single huge vector") --------------------------------
+// N = W * M (W ranks).  Rank r holds x_r[t] = a[r + W t] (cyclic).  With i = i1 + W i2 and j = j2 + M j1:
+//   A[j2 + M j1] = sum_i1 w_W^(i1 j1) * [ w_N^(i1 j2) * sum_i2 a[i1 + W i2] w_M^(i2 j2) ]
+// stage 1 (rank i1): local M-point transform, twiddle, peer-store of column j2 into row i1 of the exchange buffer of rank
+// j2 / C (C = M / W);  stage 2 (rank q): W-point transform down every column of its exchange buffer, peer-store of output j1
+// into rank j1's block at q C + c.  Result: rank j1 holds A[j1 M .. (j1 + 1) M) - natural order, contiguous blocks.
+static int get_dist_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, uint32_t world, NttDistPlan** out) {
+    uint32_t lw = 0;
+    while ((1u << lw) < world) lw++;
+    if ((1u << lw) != world || world > 8) return fail(ctx, DE_ERR_ARG, "ntt (multi-GPU): world must be 1, 2, 4 or 8");
+    if (log_n > 28 || log_n < 11 + lw) return fail(ctx, DE_ERR_ARG, "ntt (multi-GPU): need 11 + log2(world) <= log_n <= 28");
+    for (auto* p : ctx->dist_plans)
+        if (p->log_n == log_n && p->log_w == lw && memcmp(&p->omega, &omega, sizeof(de_fr)) == 0) {
+            *out = p;
+            return DE_OK;
+        }
+    NttDistPlan* p = new NttDistPlan();
+    p->log_n = log_n;
+    p->log_w = lw;
+    p->omega = omega;
+    const unsigned long long N = 1ull << log_n;
+    Fr w = fr_from_host(omega);
+    p->tw_lo_bits = 12;
+    int rc = pow_table(ctx, &p->tw_lo, 1ull << p->tw_lo_bits, w, 1);
+    if (rc == DE_OK) rc = pow_table(ctx, &p->tw_hi, N >> p->tw_lo_bits, w, 1ull << p->tw_lo_bits);
+    if (rc == DE_OK) rc = fr_host_pow(ctx, omega, world, &p->omega_local);
+    for (uint32_t i = 0; rc == DE_OK && i < 4; i++) {
+        // w_W^i = w_N^(i * N / W); entries beyond W/2 are unused
+        de_fr t;
+        rc = fr_host_pow(ctx, omega, (uint64_t)i * (N >> lw), &t);
+        p->wcross[i] = fr_from_host(t);
+    }
+    if (rc != DE_OK) {
+        delete p;
+        return rc;
+    }
+    ctx->dist_plans.push_back(p);
+    *out = p;
+    return DE_OK;
+}
+
+template <int LW>
+static int launch_cross(de_ctx* ctx, const NttDistPlan* plan, const Fr* d_z, de_fr* const* d_out_peers, uint32_t rank) {
+    NttCrossArgs<LW> a;
+    memset(&a, 0, sizeof(a));
+    const unsigned long long M = 1ull << (plan->log_n - LW);
+    a.z = d_z;
+    a.C = M >> LW;
+    a.out_off = (unsigned long long)rank * a.C;
+    for (int i = 0; i < (1 << LW); i++) a.peer_out[i] = (Fr*)d_out_peers[i];
+    for (int i = 0; i < ((1 << LW) / 2 < 1 ? 1 : (1 << LW) / 2); i++) a.w[i] = plan->wcross[i];
+    const unsigned int threads = 128;
+    DE_TIMED(ctx, "k_ntt_cross", (double)M, (k_ntt_cross<LW><<<(unsigned int)((a.C + threads - 1) / threads), threads, 0, ctx->stream>>>(a)));
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
+static int dist_args_ok(de_ctx* ctx, const void* a, const de_fr* omega, const void* const* peers, uint32_t world, uint32_t rank) {
+    if (!a || !omega || !peers) return fail(ctx, DE_ERR_ARG, "ntt (multi-GPU): null pointer");
+    if (world == 0 || world > 8 || rank >= world) return fail(ctx, DE_ERR_ARG, "ntt (multi-GPU): need rank < world <= 8");
+    for (uint32_t i = 0; i < world; i++)
+        if (!peers[i]) return fail(ctx, DE_ERR_ARG, "ntt (multi-GPU): null peer pointer");
+    return DE_OK;
+}
+
+extern "C" {
+
+int de_ntt_dist_stage1(de_ctx* ctx, const de_fr* d_x, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank,
+                       de_fr* const* d_z_peers) {
+    if (!ctx) return DE_ERR_ARG;
+    DE_TRY(dist_args_ok(ctx, d_x, omega, (const void* const*)d_z_peers, world, rank));
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    NttDistPlan* plan = nullptr;
+    DE_TRY(get_dist_plan(ctx, *omega, log_n, world, &plan));
+    const uint32_t m = log_n - plan->log_w;
+    NttDistArgs<true> dx;
+    memset(&dx, 0, sizeof(dx));
+    for (uint32_t i = 0; i < world; i++) dx.peer[i] = (Fr*)d_z_peers[i];
+    dx.col_bits = m - plan->log_w;
+    dx.row_off = (unsigned long long)rank << dx.col_bits;
+    dx.rank = rank;
+    dx.tw_hi = plan->tw_hi;
+    dx.tw_lo = plan->tw_lo;
+    dx.tw_lo_bits = plan->tw_lo_bits;
+    const size_t M = (size_t)1 << m;
+    return ntt_run(ctx, plan->omega_local, m, (const Fr*)d_x, M, nullptr, M, 1, 0, 0, nullptr, 0, nullptr, &dx);
+}
+
+int de_ntt_dist_stage2(de_ctx* ctx, const de_fr* d_z, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank,
+                       de_fr* const* d_out_peers) {
+    if (!ctx) return DE_ERR_ARG;
+    DE_TRY(dist_args_ok(ctx, d_z, omega, (const void* const*)d_out_peers, world, rank));
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    NttDistPlan* plan = nullptr;
+    DE_TRY(get_dist_plan(ctx, *omega, log_n, world, &plan));
+    switch (plan->log_w) {
+        case 0: return launch_cross<0>(ctx, plan, (const Fr*)d_z, d_out_peers, rank);
+        case 1: return launch_cross<1>(ctx, plan, (const Fr*)d_z, d_out_peers, rank);
+        case 2: return launch_cross<2>(ctx, plan, (const Fr*)d_z, d_out_peers, rank);
+        default: return launch_cross<3>(ctx, plan, (const Fr*)d_z, d_out_peers, rank);
+    }
+}
+
+int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x, de_fr* const* d_out, const de_fr* omega, uint32_t log_n) {
+    if (!ctxs || n_gpus < 1 || !ctxs[0]) return DE_ERR_ARG;
+    de_ctx* c0 = ctxs[0];
+    if (n_gpus > 8 || (n_gpus & (n_gpus - 1))) return fail(c0, DE_ERR_ARG, "de_ntt_sharded_dev: n_gpus must be 1, 2, 4 or 8");
+    if (!d_x || !d_out || !omega) return fail(c0, DE_ERR_ARG, "de_ntt_sharded_dev: null pointer");
+    uint32_t lw = 0;
+    while ((1 << lw) < n_gpus) lw++;
+    if (log_n > 28 || log_n < 11 + lw) return fail(c0, DE_ERR_ARG, "de_ntt_sharded_dev: need 11 + log2(n_gpus) <= log_n <= 28");
+    const size_t M = (size_t)1 << (log_n - lw);
+    de_fr* z[8];
+    for (int r = 0; r < n_gpus; r++) {
+        de_ctx* c = ctxs[r];
+        if (!c || !d_x[r] || !d_out[r]) return fail(c0, DE_ERR_ARG, "de_ntt_sharded_dev: null context or buffer");
+        DE_CUDA(c0, cudaSetDevice(c->device));
+        for (int q = 0; q < n_gpus; q++) {
+            // every rank stores into every other rank's buffers
+            const int peer = ctxs[q] ? ctxs[q]->device : c->device;
+            if (peer == c->device) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                return fail(c0, DE_ERR_CUDA, std::string("de_ntt_sharded_dev: no peer access between the GPUs: ") + cudaGetErrorString(e));
+            }
+            cudaGetLastError();
+        }
+        z[r] = (de_fr*)c->ws[WS_NTT_DIST].ensure(sizeof(Fr) * M);
+        if (!z[r]) return fail(c0, DE_ERR_OOM, "de_ntt_sharded_dev: exchange buffer allocation failed");
+        for (auto& e : c->dist_ev)
+            if (!e) DE_CUDA(c0, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // stage 1 everywhere; stage 2 of a rank starts when every rank's stage-1 stores have landed; the call is complete on a
+    // rank's stream when every rank's stage-2 stores have landed (which also orders the next call's stage 1 behind them)
+    for (int r = 0; r < n_gpus; r++) {
+        de_ctx* c = ctxs[r];
+        int rc = de_ntt_dist_stage1(c, d_x[r], omega, log_n, (uint32_t)n_gpus, (uint32_t)r, z);
+        if (rc != DE_OK) return fail(c0, rc, std::string(c->err));
+        DE_CUDA(c0, cudaEventRecord(c->dist_ev[0], c->stream));
+    }
+    for (int q = 0; q < n_gpus; q++) {
+        de_ctx* c = ctxs[q];
+        DE_CUDA(c0, cudaSetDevice(c->device));
+        for (int r = 0; r < n_gpus; r++)
+            if (r != q) DE_CUDA(c0, cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[0], 0));
+        int rc = de_ntt_dist_stage2(c, z[q], omega, log_n, (uint32_t)n_gpus, (uint32_t)q, d_out);
+        if (rc != DE_OK) return fail(c0, rc, std::string(c->err));
+        DE_CUDA(c0, cudaEventRecord(c->dist_ev[1], c->stream));
+    }
+    for (int q = 0; q < n_gpus; q++) {
+        de_ctx* c = ctxs[q];
+        DE_CUDA(c0, cudaSetDevice(c->device));
+        for (int r = 0; r < n_gpus; r++)
+            if (r != q) DE_CUDA(c0, cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[1], 0));
+    }
+    return DE_OK;
+}
+
+// ---- device buffers that can be mapped into another process (one process per GPU: the ranks exchange these handles once,
+// e.g. with torch.distributed.all_gather_object, and pass the mapped pointers to de_ntt_dist_stage1 / 2) -------------------------
+int de_dev_alloc(de_ctx* ctx, size_t bytes, void** d_ptr) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!d_ptr || bytes == 0) return fail(ctx, DE_ERR_ARG, "de_dev_alloc: bad argument");
+    *d_ptr = nullptr;
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DE_CUDA(ctx, cudaMalloc(d_ptr, bytes));
+    return DE_OK;
+}
+int de_dev_free(de_ctx* ctx, void* d_ptr) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!d_ptr) return DE_OK;
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DE_CUDA(ctx, cudaFree(d_ptr));
+    return DE_OK;
+}
+int de_dev_copy(de_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+    if (!ctx) return DE_ERR_ARG;
+    if (bytes == 0) return DE_OK;
+    if (!d_dst || !d_src) return fail(ctx, DE_ERR_ARG, "de_dev_copy: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DE_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DE_OK;
+}
+int de_ipc_export(de_ctx* ctx, void* d_ptr, uint8_t handle[64]) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!d_ptr || !handle) return fail(ctx, DE_ERR_ARG, "de_ipc_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    DE_CUDA(ctx, cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return DE_OK;
+}
+int de_ipc_import(de_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!d_ptr || !handle) return fail(ctx, DE_ERR_ARG, "de_ipc_import: null pointer");
+    *d_ptr = nullptr;
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    DE_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DE_OK;
+}
+int de_ipc_release(de_ctx* ctx, void* d_ptr) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!d_ptr) return DE_OK;
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DE_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
     return DE_OK;
 }
 

@@ -36,6 +36,22 @@ struct NttPassParams {
     Fr oscale[3];
 };
 
+// Extra arguments of the multi-GPU transform's first stage (DIST = true): the last pass of the local N/G-point transform
+// multiplies output j by w_N^(rank*j) and stores it straight into the exchange buffer of the rank that owns column j - a
+// peer-memory store over NVLink, so the all-to-all of the four-step transform costs no pass of its own.
+template <bool DIST>
+struct NttDistArgs {};
+template <>
+struct NttDistArgs<true> {
+    Fr* peer[8];                   // exchange buffers of the ranks (peer-mapped device pointers), world <= 8
+    unsigned int col_bits;         // log2 C, C = N / world^2 columns per destination rank
+    unsigned long long row_off;    // rank * C: this rank's row inside every exchange buffer
+    unsigned long long rank;       // twiddle exponent = rank * j
+    const Fr* tw_hi;               // w_N^(e >> lo_bits << lo_bits), w_N^(e & mask)
+    const Fr* tw_lo;
+    unsigned int tw_lo_bits;
+};
+
 __device__ __forceinline__ void sm_put(uint4* lo, uint4* hi, int slot, const Fr& v) {
     lo[slot] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     hi[slot] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
@@ -149,8 +165,9 @@ __device__ __forceinline__ Fr ntt_twiddle(const NttPassParams& p, unsigned long 
     return mul(h, l);
 }
 
-template <int S, int LT>
-__global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MINBLOCKS) k_ntt_pass(const __grid_constant__ NttPassParams p) {
+template <int S, int LT, bool DIST = false>
+__global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MINBLOCKS)
+    k_ntt_pass(const __grid_constant__ NttPassParams p, const __grid_constant__ NttDistArgs<DIST> dx) {
     using Sh = NttShape<S, LT>;
     constexpr int T = Sh::T, M = Sh::M, L = Sh::L;
     extern __shared__ uint4 smem[];
@@ -208,8 +225,63 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
             if (e != 0) v = mul(v, ntt_twiddle(p, e));
         }
         unsigned long long go = out_base + tt * p.out_tt + (unsigned long long)j * p.out_el;
-        if (p.out_mode == 1) v = mul(v, p.oscale[(unsigned int)(go % 3ull)]);
-        store(&out[go], v);
+        if constexpr (DIST) {
+            // go = column j2 of the local transform: twiddle w_N^(rank * j2), then row `rank` of the owner's exchange buffer
+            unsigned long long e = dx.rank * go;
+            if (e != 0) {
+                Fr h = load(&dx.tw_hi[e >> dx.tw_lo_bits]);
+                Fr l = load(&dx.tw_lo[e & ((1ull << dx.tw_lo_bits) - 1)]);
+                v = mul(v, mul(h, l));
+            }
+            Fr* dst = dx.peer[go >> dx.col_bits];
+            store(&dst[dx.row_off + (go & ((1ull << dx.col_bits) - 1))], v);
+        } else {
+            if (p.out_mode == 1) v = mul(v, p.oscale[(unsigned int)(go % 3ull)]);
+            store(&out[go], v);
+        }
+    }
+}
+
+// Second stage of the multi-GPU transform: a W-point transform ACROSS the ranks for every column of this rank's exchange
+// buffer z[W][C] (row i1 came from rank i1), root w_W = w_N^(N/W).  Output j1 of column c is element
+// A[j1 * (N/W) + rank * C + c] of the result and is stored into rank j1's output block - the second exchange, again as
+// peer stores (one thread per column: a warp writes 1 KiB contiguous per destination).
+template <int LW>
+struct NttCrossArgs {
+    const Fr* z;
+    Fr* peer_out[1 << LW];
+    unsigned long long C;
+    unsigned long long out_off;  // rank * C
+    Fr w[(1 << LW) / 2 < 1 ? 1 : (1 << LW) / 2];  // w_W^i, i < W/2
+};
+template <int LW>
+__global__ void __launch_bounds__(128) k_ntt_cross(const __grid_constant__ NttCrossArgs<LW> a) {
+    constexpr int W = 1 << LW;
+    unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    Fr x[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) x[i] = load(&a.z[(unsigned long long)i * a.C + c]);
+    // decimation in frequency; position p ends up holding output bit-reverse(p)
+#pragma unroll
+    for (int u = 0; u < LW; u++) {
+        const int half = W >> (u + 1);
+#pragma unroll
+        for (int e = 0; e < W; e++) {
+            if (e & half) continue;
+            Fr s = add(x[e], x[e + half]);
+            Fr d = sub(x[e], x[e + half]);
+            const int ex = (e & (half - 1)) << u;
+            x[e] = s;
+            x[e + half] = ex == 0 ? d : mul(d, a.w[ex]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < W; p++) {
+        int j1 = 0;
+#pragma unroll
+        for (int b = 0; b < LW; b++) j1 |= ((p >> b) & 1) << (LW - 1 - b);
+        store(&a.peer_out[j1][a.out_off + c], x[p]);
     }
 }
 

@@ -3,7 +3,10 @@
   * batch of independent proofs: proof i runs on rank i mod world_size; the only cross-rank traffic is the timing
     barrier / max reduction;
   * MSM base ranges: rank r commits scalars[lo:hi] against its slice of the resident base tables (de_commit_range) and the
-    world_size partial points (96 bytes each) are added (de_g1_sum).
+    world_size partial points (96 bytes each) are added (de_g1_sum);
+  * one NTT vector over W = 2, 4 or 8 GPUs (the one row of section 8e with a real exchange): four-step transform, cyclic input
+    slices, contiguous natural-order output blocks, both transposes done as peer-memory stores from inside the kernels
+    (de_ntt_dist_stage1 / 2) - ShardedNtt inside one process, DistNtt with one process per GPU (CUDA IPC + a stream barrier).
 """
 from __future__ import annotations
 
@@ -97,3 +100,155 @@ class ShardedParams:
             s.close()
         for c in self.ctxs:
             c.close()
+
+
+# ---- one NTT vector over several GPUs -----------------------------------------------------------------------------------
+def ntt_layout(log_n: int, world: int):
+    """(M, C): elements per rank and columns per (source rank, destination rank) pair of the exchange"""
+    lw = world.bit_length() - 1
+    if world < 1 or (1 << lw) != world or world > 8:
+        raise ValueError("world must be 1, 2, 4 or 8")
+    if log_n < 11 + lw or log_n > 28:
+        raise ValueError("need 11 + log2(world) <= log_n <= 28")
+    m = (1 << log_n) >> lw
+    return m, m >> lw
+
+
+def ntt_input_slice(a, rank: int, world: int):
+    """rank's input of the multi-GPU transform: a[rank], a[rank + W], a[rank + 2 W], ...  (a: (N, 4) u64)"""
+    return a[rank::world]
+
+
+def ntt_output_range(log_n: int, rank: int, world: int):
+    """rank's output block [lo, hi) of best_fft(a)"""
+    m, _ = ntt_layout(log_n, world)
+    return rank * m, (rank + 1) * m
+
+
+def ntt_exchange_slot(log_n: int, world: int, src_rank: int, column: int):
+    """where stage 1 on `src_rank` stores column j2 of its local transform: (destination rank, index in its exchange buffer)"""
+    _, c = ntt_layout(log_n, world)
+    return column // c, src_rank * c + column % c
+
+
+class ShardedNtt:
+    """best_fft of one vector over several GPUs driven by ONE process (de_ntt_sharded_dev): one Context per entry of `devices`
+    (the same device may appear several times - used by the single-GPU parity tests)."""
+
+    def __init__(self, devices):
+        from . import Context
+        self.ctxs = [Context(d) for d in devices]
+        self.world = len(devices)
+
+    def best_fft_dev(self, d_x, d_out, omega, log_n: int):
+        """d_x[r] / d_out[r]: torch int64 tensors on rank r's device holding the cyclic input slice / receiving the output block.
+        Asynchronous on the contexts' streams; sync() waits."""
+        import ctypes as C
+        import numpy as np
+        w = len(self.ctxs)
+        ntt_layout(log_n, w)
+        om = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
+        ctxs = (C.c_void_p * w)(*[c.h for c in self.ctxs])
+        xs = (C.c_void_p * w)(*[t.data_ptr() for t in d_x])
+        outs = (C.c_void_p * w)(*[t.data_ptr() for t in d_out])
+        c0 = self.ctxs[0]
+        c0.check(c0.L.de_ntt_sharded_dev(ctxs, w, xs, outs, om.ctypes.data_as(C.c_void_p), log_n))
+
+    def sync(self):
+        for c in self.ctxs:
+            c.sync()
+
+    def best_fft(self, a, omega, log_n: int):
+        """host vector in natural order in and out (scatter to the cyclic slices, transform, gather the blocks)"""
+        import numpy as np
+        import torch
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        if a.shape[0] != 1 << log_n:
+            raise ValueError("best_fft: a.len() != 1 << log_n")
+        w = self.world
+        xs = [torch.from_numpy(np.ascontiguousarray(ntt_input_slice(a, r, w)).view(np.int64)).to(f"cuda:{c.device}")
+              for r, c in enumerate(self.ctxs)]
+        outs = [torch.empty_like(x) for x in xs]
+        for c in self.ctxs:
+            torch.cuda.synchronize(c.device)
+        self.best_fft_dev(xs, outs, omega, log_n)
+        self.sync()
+        return np.concatenate([o.cpu().numpy().view(np.uint64) for o in outs], axis=0)
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+
+class DistNtt:
+    """The same transform with one process per GPU (torch.distributed, NCCL): every rank allocates its exchange and output buffers
+    with de_dev_alloc, the 64-byte CUDA IPC handles are all-gathered once, and each call is
+        stage 1 (peer stores into the owners' exchange buffers) -> barrier -> stage 2 (peer stores into the owners' output blocks)
+        -> barrier,
+    the barriers being 1-element all-reduces enqueued on the context's stream.  No bulk data goes through a library collective."""
+
+    def __init__(self, ctx, log_n: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.log_n, self.group = ctx, log_n, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.m, self.c = ntt_layout(log_n, self.world)
+        self.stream = torch.cuda.Stream(device=ctx.device)
+        ctx.set_stream(self.stream.cuda_stream)
+        self.token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{ctx.device}")
+        L = ctx.L
+        self.own, self.mapped = [], []
+        peers = []
+        for _ in range(3):  # input, exchange, output
+            p = C.c_void_p()
+            ctx.check(L.de_dev_alloc(ctx.h, 32 * self.m, C.byref(p)))
+            self.own.append(p.value)
+            h = (C.c_uint8 * 64)()
+            ctx.check(L.de_ipc_export(ctx.h, C.c_void_p(p.value), h))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(h), group=group)
+            ptrs = []
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(p.value)
+                    continue
+                q = C.c_void_p()
+                ctx.check(L.de_ipc_import(ctx.h, (C.c_uint8 * 64).from_buffer_copy(hb), C.byref(q)))
+                self.mapped.append(q.value)
+                ptrs.append(q.value)
+            peers.append(ptrs)
+        self.d_x, self.d_z, self.d_out = self.own
+        self.z_peers = (C.c_void_p * self.world)(*peers[1])
+        self.out_peers = (C.c_void_p * self.world)(*peers[2])
+
+    def _barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.token, group=self.group)
+
+    def run(self, omega):
+        """transforms d_x (this rank's cyclic slice) into d_out (this rank's block); asynchronous on self.stream"""
+        import ctypes as C
+        import numpy as np
+        import torch
+        om = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
+        ctx, L = self.ctx, self.ctx.L
+        with torch.cuda.stream(self.stream):
+            ctx.check(L.de_ntt_dist_stage1(ctx.h, C.c_void_p(self.d_x), om.ctypes.data_as(C.c_void_p), self.log_n, self.world, self.rank,
+                                           self.z_peers))
+            self._barrier()
+            ctx.check(L.de_ntt_dist_stage2(ctx.h, C.c_void_p(self.d_z), om.ctypes.data_as(C.c_void_p), self.log_n, self.world, self.rank,
+                                           self.out_peers))
+            self._barrier()
+
+    def close(self):
+        import ctypes as C
+        import torch.distributed as dist
+        self.stream.synchronize()
+        dist.barrier(group=self.group)
+        for q in self.mapped:
+            self.ctx.L.de_ipc_release(self.ctx.h, C.c_void_p(q))
+        dist.barrier(group=self.group)
+        for p in self.own:
+            self.ctx.L.de_dev_free(self.ctx.h, C.c_void_p(p))
+        self.ctx.set_stream(None)

@@ -232,6 +232,35 @@ int de_g1_sum(de_ctx* ctx, const de_g1* points, size_t count, de_g1* out);
  * points are added on shards[0]'s GPU.  Multi-process sharding uses de_commit + an all-gather instead (de_b200/sharding.py). */
 int de_commit_sharded(de_params* const* shards, const size_t* shard_lo, const size_t* shard_len, int n_shards, int basis,
                       const de_fr* scalars, de_g1* out);
+/* ---- multi-GPU: best_fft of ONE vector spread over W = 1, 2, 4 or 8 GPUs (NTT row) ----------- */
+/* Four-step transform N = W * M with both exchanges done as peer-memory stores (NVLink) from inside the kernels, no copy pass
+ * and no library collective:
+ *   input  (cyclic):  rank r holds x_r[t] = a[r + W t], t < M;
+ *   output (blocks):  rank q holds A[q M .. (q + 1) M), natural order -  A = best_fft(a, omega, log_n).
+ * stage 1 on rank r: local M-point transform whose last pass multiplies column j by omega^(r j) and stores it into row r of the
+ * exchange buffer z (M elements) of rank j / (M / W);  stage 2 on rank q: W-point transform down the columns of its z, output j1
+ * stored into rank j1's output block.  d_z_peers / d_out_peers hold the W ranks' buffers as pointers valid on THIS device
+ * (peer access inside one process, de_ipc_import across processes).  The caller orders the stages: every rank's stage 1 must
+ * have completed before any stage 2 starts, and every stage 2 before the outputs are read or the next stage 1 begins (stream
+ * events inside one process - de_ntt_sharded_dev does it -, a barrier on the stream across processes).  11 + log2 W <= log_n <= 28. */
+int de_ntt_dist_stage1(de_ctx* ctx, const de_fr* d_x, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank,
+                       de_fr* const* d_z_peers);
+int de_ntt_dist_stage2(de_ctx* ctx, const de_fr* d_z, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank,
+                       de_fr* const* d_out_peers);
+/* The same inside ONE process: ctxs[r] is rank r (normally one context per GPU; several contexts on one GPU also work), d_x[r] /
+ * d_out[r] its input / output block (d_out[r] may equal d_x[r]).  Asynchronous: the result is complete in stream order on every
+ * context's stream; exchange buffers live in the contexts' workspaces. */
+int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x, de_fr* const* d_out, const de_fr* omega,
+                       uint32_t log_n);
+/* plain device allocations that another process can map (cudaMalloc + CUDA IPC; 64-byte handles) */
+int de_dev_alloc(de_ctx* ctx, size_t bytes, void** d_ptr);
+int de_dev_free(de_ctx* ctx, void* d_ptr);
+/* device-to-device copy on the context's stream (fills / reads de_dev_alloc buffers from other device memory) */
+int de_dev_copy(de_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+int de_ipc_export(de_ctx* ctx, void* d_ptr, uint8_t handle[64]);
+int de_ipc_import(de_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+int de_ipc_release(de_ctx* ctx, void* d_ptr);
+
 /* d_out[i] = [d_scalars[i]] base (affine, Montgomery), device-resident: the fixed-base multiplications of
  * ParamsKZG::setup (g[i] = [s^i] G) and the generator of synthetic SRS bases for the size sweeps */
 int de_g1_mul_base_dev(de_ctx* ctx, const de_g1_affine* base, const de_fr* d_scalars, size_t n, de_g1_affine* d_out);

@@ -89,6 +89,15 @@ extern "C" {
     pub fn de_commit_range(p: *mut de_params, basis: c_int, scalars: *const de_fr, lo: usize, hi: usize, out_partial: *mut de_g1) -> c_int;
     pub fn de_g1_sum(ctx: *mut de_ctx, points: *const de_g1, count: usize, out: *mut de_g1) -> c_int;
     pub fn de_commit_sharded(shards: *mut *mut de_params, shard_lo: *const usize, shard_len: *const usize, n_shards: c_int, basis: c_int, scalars: *const de_fr, out: *mut de_g1) -> c_int;
+    pub fn de_ntt_dist_stage1(ctx: *mut de_ctx, d_x: *const de_fr, omega: *const de_fr, log_n: u32, world: u32, rank: u32, d_z_peers: *const *mut de_fr) -> c_int;
+    pub fn de_ntt_dist_stage2(ctx: *mut de_ctx, d_z: *const de_fr, omega: *const de_fr, log_n: u32, world: u32, rank: u32, d_out_peers: *const *mut de_fr) -> c_int;
+    pub fn de_ntt_sharded_dev(ctxs: *const *mut de_ctx, n_gpus: c_int, d_x: *const *const de_fr, d_out: *const *mut de_fr, omega: *const de_fr, log_n: u32) -> c_int;
+    pub fn de_dev_alloc(ctx: *mut de_ctx, bytes: usize, d_ptr: *mut *mut c_void) -> c_int;
+    pub fn de_dev_free(ctx: *mut de_ctx, d_ptr: *mut c_void) -> c_int;
+    pub fn de_dev_copy(ctx: *mut de_ctx, d_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
+    pub fn de_ipc_export(ctx: *mut de_ctx, d_ptr: *mut c_void, handle: *mut u8) -> c_int;
+    pub fn de_ipc_import(ctx: *mut de_ctx, handle: *const u8, d_ptr: *mut *mut c_void) -> c_int;
+    pub fn de_ipc_release(ctx: *mut de_ctx, d_ptr: *mut c_void) -> c_int;
     pub fn de_g1_mul_base_dev(ctx: *mut de_ctx, base: *const de_g1_affine, d_scalars: *const de_fr, n: usize, d_out: *mut de_g1_affine) -> c_int;
     pub fn de_g1_batch_normalize(ctx: *mut de_ctx, points: *const de_g1, count: usize, out: *mut de_g1_affine) -> c_int;
 }
