@@ -257,6 +257,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ntt-multi-gpu", action="store_true", help="skip the one-vector-over-all-ranks NTT line of a multi-GPU run")
     ap.add_argument("--inflight", type=int, default=8, help="independent proofs in flight per GPU (one prover + stream each)")
     ap.add_argument("--config", default="delay_enc", choices=sorted(CONFIGS), help="circuit shape / size (default: the headline delay_enc)")
     ap.add_argument("--mode", default="auto", choices=["auto", "latency", "throughput"],
@@ -459,6 +460,19 @@ def main():
                        "frac_hbm": gbs / peaks["hbm_gbs"], "gmul_s": n_cols * ext_n / 2 * ek / (ms_ntt * 1e-3) / 1e9,
                        "frac_int_pipe": n_cols * ext_n / 2 * ek / (ms_ntt * 1e-3) / 1e9 / MUL_PEAK_GMULS}
         del src, dst
+    if world > 1 and not args.no_ntt_multi_gpu:
+        # BASELINE's "NTT GB/s at 1/2/4/8 B200": ONE 2^24 vector over all ranks (four-step transform, both exchanges as peer-memory
+        # stores from inside the kernels), checked on rank 0 against the single-GPU transform of the same vector
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ntt_dist_sweep
+        nctx = de_b200.Context(local_rank)
+        try:
+            res = ntt_dist_sweep.measure_dist(nctx, 24, 5, emit=False)
+        except RuntimeError as e:  # raised on every rank together (DistNtt's setup is collective)
+            res = {"error": str(e)}
+        nctx.close()
+        if rank == 0:
+            line["ntt_multi_gpu"] = res
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import orc

@@ -68,7 +68,7 @@ struct PinnedBuf {
 };
 
 enum { WS_IO_A = 0, WS_IO_B, WS_NTT_SCRATCH, WS_MSM_KEYS, WS_MSM_VALS, WS_MSM_SORTED, WS_MSM_COUNTS, WS_MSM_BUCKETS,
-       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_RED, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_NTT_DIST, WS_COUNT };
+       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_RED, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_NTT_DIST, WS_NTT_DIST_X, WS_COUNT };
 
 }  // namespace de
 
@@ -101,7 +101,7 @@ struct de_ctx {
     de::PinnedBuf pinned;
     std::vector<de::NttPlan*> plans;
     std::vector<de::NttDistPlan*> dist_plans;           // multi-GPU transform tables (ntt.cu)
-    cudaEvent_t dist_ev[2] = {nullptr, nullptr};        // stage-1 / stage-2 completion of de_ntt_sharded_dev on this context
+    cudaEvent_t dist_ev[3] = {nullptr, nullptr, nullptr};  // stage-1 / stage-2 / deal completion of de_ntt_sharded* on this context
 };
 
 namespace de {

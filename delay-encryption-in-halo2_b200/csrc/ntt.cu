@@ -3,6 +3,8 @@
 // Reference semantics: halo2_proofs::arithmetic::best_fft and poly::EvaluationDomain.
 #include <string.h>
 
+#include <thread>
+
 #include "common.cuh"
 #include "ntt.cuh"
 
@@ -713,6 +715,83 @@ int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x,
             if (r != q) DE_CUDA(c0, cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[1], 0));
     }
     return DE_OK;
+}
+
+// best_fft(a, omega, log_n) on a HOST vector in natural order, spread over the GPUs of `ctxs`: block r goes up GPU r's own PCIe
+// link (one host thread per GPU, as in de_commit_sharded), is dealt round-robin to the ranks' cyclic slices by peer stores,
+// transformed by de_ntt_sharded_dev, and block r of the result comes back down the same link.
+int de_ntt_sharded(de_ctx* const* ctxs, int n_gpus, de_fr* a, const de_fr* omega, uint32_t log_n) {
+    if (!ctxs || n_gpus < 1 || !ctxs[0]) return DE_ERR_ARG;
+    de_ctx* c0 = ctxs[0];
+    if (n_gpus > 8 || (n_gpus & (n_gpus - 1))) return fail(c0, DE_ERR_ARG, "de_ntt_sharded: n_gpus must be 1, 2, 4 or 8");
+    if (!a || !omega) return fail(c0, DE_ERR_ARG, "de_ntt_sharded: null pointer");
+    uint32_t lw = 0;
+    while ((1 << lw) < n_gpus) lw++;
+    if (log_n > 28 || log_n < 11 + lw) return fail(c0, DE_ERR_ARG, "de_ntt_sharded: need 11 + log2(n_gpus) <= log_n <= 28");
+    for (int r = 0; r < n_gpus; r++) {
+        if (!ctxs[r]) return fail(c0, DE_ERR_ARG, "de_ntt_sharded: null context");
+        for (int q = 0; q < r; q++)
+            if (ctxs[q] == ctxs[r]) return fail(c0, DE_ERR_ARG, "de_ntt_sharded: contexts must be distinct");
+    }
+    const size_t M = (size_t)1 << (log_n - lw), C = M >> lw;
+    Fr* stage[8];
+    Fr* x[8];
+    for (int r = 0; r < n_gpus; r++) {
+        de_ctx* c = ctxs[r];
+        DE_CUDA(c0, cudaSetDevice(c->device));
+        for (int q = 0; q < n_gpus; q++) {
+            if (ctxs[q]->device == c->device) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                return fail(c0, DE_ERR_CUDA, std::string("de_ntt_sharded: no peer access between the GPUs: ") + cudaGetErrorString(e));
+            }
+            cudaGetLastError();
+        }
+        stage[r] = (Fr*)c->ws[WS_IO_A].ensure(sizeof(Fr) * M);
+        x[r] = (Fr*)c->ws[WS_NTT_DIST_X].ensure(sizeof(Fr) * M);
+        if (!stage[r] || !x[r]) return fail(c0, DE_ERR_OOM, "de_ntt_sharded: staging allocation failed");
+        if (!c->dist_ev[2]) DE_CUDA(c0, cudaEventCreateWithFlags(&c->dist_ev[2], cudaEventDisableTiming));
+    }
+    std::vector<int> rc(n_gpus, DE_OK);
+    auto each_gpu = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int r = 0; r < n_gpus; r++) th.emplace_back([&, r]() { rc[r] = fn(r); });
+        for (auto& t : th) t.join();
+        for (int r = 0; r < n_gpus; r++)
+            if (rc[r] != DE_OK) return fail(c0, rc[r], std::string("de_ntt_sharded: GPU ") + std::to_string(r) + ": " + std::string(ctxs[r]->err));
+        return (int)DE_OK;
+    };
+    DE_TRY(each_gpu([&](int r) -> int {
+        de_ctx* c = ctxs[r];
+        DE_CUDA(c, cudaSetDevice(c->device));
+        DE_CUDA(c, cudaMemcpyAsync(stage[r], a + (size_t)r * M, sizeof(Fr) * M, cudaMemcpyHostToDevice, c->stream));
+        NttDealArgs d;
+        memset(&d, 0, sizeof(d));
+        d.stage = stage[r];
+        for (int q = 0; q < n_gpus; q++) d.peer_x[q] = x[q];
+        d.log_w = lw;
+        d.C = C;
+        d.M = M;
+        d.row_off = (unsigned long long)r * C;
+        k_ntt_deal<<<(unsigned int)((M + 255) / 256), 256, 0, c->stream>>>(d);
+        DE_CHECK_LAUNCH(c);
+        DE_CUDA(c, cudaEventRecord(c->dist_ev[2], c->stream));
+        return DE_OK;
+    }));
+    for (int q = 0; q < n_gpus; q++) {
+        DE_CUDA(c0, cudaSetDevice(ctxs[q]->device));
+        for (int r = 0; r < n_gpus; r++)
+            if (r != q) DE_CUDA(c0, cudaStreamWaitEvent(ctxs[q]->stream, ctxs[r]->dist_ev[2], 0));
+    }
+    DE_TRY(de_ntt_sharded_dev(ctxs, n_gpus, (const de_fr* const*)x, (de_fr* const*)stage, omega, log_n));
+    return each_gpu([&](int r) -> int {
+        de_ctx* c = ctxs[r];
+        DE_CUDA(c, cudaSetDevice(c->device));
+        DE_CUDA(c, cudaMemcpyAsync(a + (size_t)r * M, stage[r], sizeof(Fr) * M, cudaMemcpyDeviceToHost, c->stream));
+        DE_CUDA(c, cudaStreamSynchronize(c->stream));
+        return DE_OK;
+    });
 }
 
 // ---- device buffers that can be mapped into another process (one process per GPU: the ranks exchange these handles once,

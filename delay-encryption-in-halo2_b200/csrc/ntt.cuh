@@ -285,6 +285,22 @@ __global__ void __launch_bounds__(128) k_ntt_cross(const __grid_constant__ NttCr
     }
 }
 
+// Deal a contiguous block of the natural-order vector round-robin to the ranks (host entry point de_ntt_sharded: every GPU
+// receives the block a[rank M, (rank + 1) M) over its own PCIe link and forwards element rank M + u to rank u mod W, slot
+// rank C + u / W of its cyclic input slice): thread (q, v) reads stage[v W + q], stores peer_x[q][rank C + v] (coalesced stores).
+struct NttDealArgs {
+    const Fr* stage;
+    Fr* peer_x[8];
+    unsigned int log_w;
+    unsigned long long C, M, row_off;
+};
+__global__ void __launch_bounds__(256) k_ntt_deal(const __grid_constant__ NttDealArgs a) {
+    unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= a.M) return;
+    unsigned long long q = id / a.C, v = id - q * a.C;
+    store(&a.peer_x[q][a.row_off + v], load(&a.stage[(v << a.log_w) + q]));
+}
+
 // out[i] = base^(i * step) for i < n  (twiddle tables; one-time per plan)
 __global__ void k_pow_table(Fr* out, unsigned long long n, Fr base, unsigned long long step) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -22,7 +22,7 @@ SYMBOLS = [
     "de_divide_by_vanishing_dev", "de_pk_upload", "de_pk_free", "de_evaluate_h", "de_evaluate_h_dev", "de_pk_extend_dev", "de_evaluate_h_rows_dev", "de_commit_range", "de_g1_sum", "de_g1_batch_normalize",
     "de_commit_batch_canonical_dev", "de_eval_polynomial", "de_kate_division", "de_prover_create", "de_prover_free",
     "de_prover_random_count", "de_prover_proof_size", "de_create_proof", "de_create_proof_dev", "de_g1_mul_base_dev", "de_ctx_set_mode", "de_commit_sharded",
-    "de_ntt_dist_stage1", "de_ntt_dist_stage2", "de_ntt_sharded_dev", "de_dev_alloc", "de_dev_free", "de_dev_copy", "de_ipc_export", "de_ipc_import",
+    "de_ntt_dist_stage1", "de_ntt_dist_stage2", "de_ntt_sharded_dev", "de_ntt_sharded", "de_dev_alloc", "de_dev_free", "de_dev_copy", "de_ipc_export", "de_ipc_import",
     "de_ipc_release",
 ]
 
@@ -107,6 +107,7 @@ def load():
     L.de_ntt_dist_stage1.argtypes = [P, P, P, U32, U32, U32, C.POINTER(P)]
     L.de_ntt_dist_stage2.argtypes = [P, P, P, U32, U32, U32, C.POINTER(P)]
     L.de_ntt_sharded_dev.argtypes = [C.POINTER(P), I, C.POINTER(P), C.POINTER(P), P, U32]
+    L.de_ntt_sharded.argtypes = [C.POINTER(P), I, P, P, U32]
     L.de_dev_alloc.argtypes = [P, SZ, C.POINTER(P)]
     L.de_dev_free.argtypes = [P, P]
     L.de_dev_copy.argtypes = [P, P, P, SZ]

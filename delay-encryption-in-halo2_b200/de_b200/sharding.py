@@ -158,8 +158,24 @@ class ShardedNtt:
         for c in self.ctxs:
             c.sync()
 
+    def best_fft_host(self, a, omega, log_n: int):
+        """arithmetic::best_fft on a host vector, natural order in and out, through de_ntt_sharded (the library deals the blocks to
+        the cyclic slices on the devices; needs one context per rank, which this class always has)"""
+        import ctypes as C
+        import numpy as np
+        a = np.array(a, dtype=np.uint64, order="C").reshape(-1, 4)
+        if a.shape[0] != 1 << log_n:
+            raise ValueError("best_fft: a.len() != 1 << log_n")
+        w = len(self.ctxs)
+        ntt_layout(log_n, w)
+        om = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
+        ctxs = (C.c_void_p * w)(*[c.h for c in self.ctxs])
+        c0 = self.ctxs[0]
+        c0.check(c0.L.de_ntt_sharded(ctxs, w, a.ctypes.data_as(C.c_void_p), om.ctypes.data_as(C.c_void_p), log_n))
+        return a
+
     def best_fft(self, a, omega, log_n: int):
-        """host vector in natural order in and out (scatter to the cyclic slices, transform, gather the blocks)"""
+        """host vector in natural order in and out, dealing the cyclic slices on the host (exercises de_ntt_sharded_dev)"""
         import numpy as np
         import torch
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
@@ -199,13 +215,16 @@ class DistNtt:
         self.token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{ctx.device}")
         L = ctx.L
         self.own, self.mapped = [], []
-        peers = []
+        peers, err = [], None
         for _ in range(3):  # input, exchange, output
             p = C.c_void_p()
-            ctx.check(L.de_dev_alloc(ctx.h, 32 * self.m, C.byref(p)))
-            self.own.append(p.value)
             h = (C.c_uint8 * 64)()
-            ctx.check(L.de_ipc_export(ctx.h, C.c_void_p(p.value), h))
+            try:
+                ctx.check(L.de_dev_alloc(ctx.h, 32 * self.m, C.byref(p)))
+                self.own.append(p.value)
+                ctx.check(L.de_ipc_export(ctx.h, C.c_void_p(p.value), h))
+            except Exception as e:  # keep the collectives below matched on every rank, fail together afterwards
+                err = err or e
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(h), group=group)
             ptrs = []
@@ -214,10 +233,19 @@ class DistNtt:
                     ptrs.append(p.value)
                     continue
                 q = C.c_void_p()
-                ctx.check(L.de_ipc_import(ctx.h, (C.c_uint8 * 64).from_buffer_copy(hb), C.byref(q)))
-                self.mapped.append(q.value)
+                try:
+                    if err is None:
+                        ctx.check(L.de_ipc_import(ctx.h, (C.c_uint8 * 64).from_buffer_copy(hb), C.byref(q)))
+                        self.mapped.append(q.value)
+                except Exception as e:
+                    err = err or e
                 ptrs.append(q.value)
             peers.append(ptrs)
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=f"cuda:{ctx.device}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self._release(lambda: dist.barrier(group=group))
+            raise RuntimeError(f"DistNtt: mapping the ranks' buffers failed on at least one rank ({err or 'another rank'})")
         self.d_x, self.d_z, self.d_out = self.own
         self.z_peers = (C.c_void_p * self.world)(*peers[1])
         self.out_peers = (C.c_void_p * self.world)(*peers[2])
@@ -241,14 +269,20 @@ class DistNtt:
                                            self.out_peers))
             self._barrier()
 
-    def close(self):
+    def _release(self, group_barrier=None):
         import ctypes as C
-        import torch.distributed as dist
-        self.stream.synchronize()
-        dist.barrier(group=self.group)
         for q in self.mapped:
             self.ctx.L.de_ipc_release(self.ctx.h, C.c_void_p(q))
-        dist.barrier(group=self.group)
+        self.mapped = []
+        if group_barrier:
+            group_barrier()  # an exporter frees only after every importer has unmapped
         for p in self.own:
             self.ctx.L.de_dev_free(self.ctx.h, C.c_void_p(p))
+        self.own = []
         self.ctx.set_stream(None)
+
+    def close(self):
+        import torch.distributed as dist
+        self.stream.synchronize()
+        dist.barrier(group=self.group)  # nobody unmaps or frees while a peer may still be storing into these buffers
+        self._release(lambda: dist.barrier(group=self.group))

@@ -199,4 +199,13 @@ inline de_g1 commit_sharded(const std::vector<const ParamsKZG*>& shards, const s
     return out;
 }
 
+// arithmetic::best_fft for a vector spread over several GPUs of ONE process (de_ntt_sharded): natural order in and out
+inline void best_fft_sharded(const std::vector<const Context*>& ctxs, std::vector<de_fr>& a, const de_fr& omega, uint32_t log_n) {
+    if (ctxs.empty()) throw std::runtime_error("best_fft_sharded: no contexts");
+    if (a.size() != (size_t(1) << log_n)) throw std::runtime_error("best_fft: a.len() != 1 << log_n");
+    std::vector<de_ctx*> h;
+    for (auto* c : ctxs) h.push_back(c->handle());
+    ctxs[0]->check(de_ntt_sharded(h.data(), (int)h.size(), a.data(), &omega, log_n), "best_fft_sharded");
+}
+
 }  // namespace halo2_b200

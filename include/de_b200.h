@@ -252,6 +252,10 @@ int de_ntt_dist_stage2(de_ctx* ctx, const de_fr* d_z, const de_fr* omega, uint32
  * context's stream; exchange buffers live in the contexts' workspaces. */
 int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x, de_fr* const* d_out, const de_fr* omega,
                        uint32_t log_n);
+/* best_fft(a, omega, log_n) for a HOST vector, natural order in and out, over the GPUs of ctxs (distinct contexts): block r
+ * travels over GPU r's own PCIe link (one host thread per GPU), is dealt to the cyclic slices by peer stores, transformed as
+ * above and read back.  Synchronous. */
+int de_ntt_sharded(de_ctx* const* ctxs, int n_gpus, de_fr* a, const de_fr* omega, uint32_t log_n);
 /* plain device allocations that another process can map (cudaMalloc + CUDA IPC; 64-byte handles) */
 int de_dev_alloc(de_ctx* ctx, size_t bytes, void** d_ptr);
 int de_dev_free(de_ctx* ctx, void* d_ptr);

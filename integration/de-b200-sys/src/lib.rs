@@ -92,6 +92,7 @@ extern "C" {
     pub fn de_ntt_dist_stage1(ctx: *mut de_ctx, d_x: *const de_fr, omega: *const de_fr, log_n: u32, world: u32, rank: u32, d_z_peers: *const *mut de_fr) -> c_int;
     pub fn de_ntt_dist_stage2(ctx: *mut de_ctx, d_z: *const de_fr, omega: *const de_fr, log_n: u32, world: u32, rank: u32, d_out_peers: *const *mut de_fr) -> c_int;
     pub fn de_ntt_sharded_dev(ctxs: *const *mut de_ctx, n_gpus: c_int, d_x: *const *const de_fr, d_out: *const *mut de_fr, omega: *const de_fr, log_n: u32) -> c_int;
+    pub fn de_ntt_sharded(ctxs: *const *mut de_ctx, n_gpus: c_int, a: *mut de_fr, omega: *const de_fr, log_n: u32) -> c_int;
     pub fn de_dev_alloc(ctx: *mut de_ctx, bytes: usize, d_ptr: *mut *mut c_void) -> c_int;
     pub fn de_dev_free(ctx: *mut de_ctx, d_ptr: *mut c_void) -> c_int;
     pub fn de_dev_copy(ctx: *mut de_ctx, d_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;

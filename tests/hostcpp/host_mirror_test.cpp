@@ -45,6 +45,17 @@ int main(int argc, char** argv) {
         auto a = scalars;
         halo2_b200::best_fft(ctx, a, omega[0], k);
         if (!same(a, want_fft)) { std::cerr << "best_fft mismatch\n"; fails++; }
+        // best_fft over two contexts (ranks of the multi-GPU transform; both on device 0 here)
+        {
+            halo2_b200::Context ctx1(0);
+            auto v = rd<de_fr>(d + "/sharded_in.bin");
+            auto w13 = rd<de_fr>(d + "/sharded_omega.bin");
+            halo2_b200::best_fft_sharded({&ctx, &ctx1}, v, w13[0], 13);
+            if (!same(v, rd<de_fr>(d + "/sharded_fft.bin"))) { std::cerr << "best_fft_sharded mismatch\n"; fails++; }
+            bool threw2 = false;
+            try { v.pop_back(); halo2_b200::best_fft_sharded({&ctx, &ctx1}, v, w13[0], 13); } catch (const std::runtime_error&) { threw2 = true; }
+            if (!threw2) { std::cerr << "best_fft_sharded length mismatch not rejected\n"; fails++; }
+        }
         // EvaluationDomain
         halo2_b200::EvaluationDomain dom(ctx, 5, k);
         if (!same(dom.coeff_to_extended(scalars), want_ext)) { std::cerr << "coeff_to_extended mismatch\n"; fails++; }

@@ -36,6 +36,20 @@ def test_sharded_best_fft_matches_oracle(world, log_n):
         s.close()
 
 
+@pytest.mark.parametrize("world,log_n", [(1, 12), (2, 13), (4, 16), (8, 18), (8, 22)])
+def test_host_vector_entry_point(world, log_n):
+    """de_ntt_sharded: natural-order host vector in and out (block upload, deal kernel, transform, block download)"""
+    s = sharding.ShardedNtt(devices(world))
+    try:
+        a = orc.uniform_fr(0xD200 + world + log_n, 1 << log_n)
+        w = omega_for(log_n)
+        want = orc.best_fft(a, w, log_n)
+        assert (s.best_fft_host(a, w, log_n) == want).all()
+        assert (s.best_fft_host(a, w, log_n) == want).all()   # second call reuses every buffer
+    finally:
+        s.close()
+
+
 def test_all_on_one_device_and_spread_agree():
     import torch
     if torch.cuda.device_count() < 2:

@@ -43,6 +43,12 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     orc.best_fft(s, d.omega, k).tofile(tmp_path / "fft.bin")
     d.coeff_to_extended(s).tofile(tmp_path / "ext.bin")
     orc.g1_to_affine(orc.best_multiexp(s, b)).tofile(tmp_path / "msm_affine.bin")
+    # best_fft_sharded (two contexts): a 2^13 vector
+    d13 = orc.Domain(2, 13)
+    s13 = orc.uniform_fr(407, 1 << 13)
+    s13.tofile(tmp_path / "sharded_in.bin")
+    d13.omega.tofile(tmp_path / "sharded_omega.bin")
+    orc.best_fft(s13, d13.omega, 13).tofile(tmp_path / "sharded_fft.bin")
     # eval_polynomial / kate_division
     point = orc.uniform_fr(405, 1)
     point.tofile(tmp_path / "point.bin")

@@ -50,7 +50,7 @@ def uniform_fr_dev(n, seed, device):
     return t
 
 
-def line(mode, world, log_n, ms, ok, single_ms=None, **extra):
+def line(mode, world, log_n, ms, ok, single_ms=None, emit=True, **extra):
     n = 1 << log_n
     d = {"op": "ntt_multi_gpu", "mode": mode, "n_gpus": world, "log_n": log_n, "ms": ms, "gb_s": 64 * n / ms / 1e6,
          "frac_hbm_aggregate": 64 * n / ms / 1e6 / (HBM * world), "gmul_s": n / 2 * log_n / ms / 1e6,
@@ -60,24 +60,26 @@ def line(mode, world, log_n, ms, ok, single_ms=None, **extra):
         d["single_gpu_ms"] = single_ms
         d["speedup_vs_single_gpu"] = single_ms / ms
     d.update(extra)
-    print(json.dumps(d), flush=True)
+    if emit:
+        print(json.dumps(d), flush=True)
+    return d
 
 
-def single_gpu_reference(ctx0, slices, log_n, omega, reps):
-    """re-assemble a from the cyclic slices on device 0, transform with de_ntt_dev; returns (result tensor, best ms)"""
+def single_gpu_reference(ctx0, slices, log_n, omega, reps, dev="cuda:0"):
+    """re-assemble a from the cyclic slices on `dev`, transform with de_ntt_dev; returns (result tensor, best ms)"""
     world = len(slices)
     n = 1 << log_n
-    full = torch.empty((n, 4), dtype=torch.int64, device="cuda:0")
+    full = torch.empty((n, 4), dtype=torch.int64, device=dev)
     for r, s in enumerate(slices):
-        full[r::world] = s.to("cuda:0")
-    torch.cuda.synchronize(0)
-    st = torch.cuda.Stream(device=0)
+        full[r::world] = s.to(dev)
+    torch.cuda.synchronize(dev)
+    st = torch.cuda.Stream(device=dev)
     ctx0.set_stream(st.cuda_stream)
     best = 1e30
     src = full.clone()
     for i in range(reps + 1):
         full.copy_(src)
-        torch.cuda.synchronize(0)
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(st):
             e0.record(st)
@@ -137,54 +139,63 @@ def run_sharded(args):
     ref_ctx.close()
 
 
+def measure_dist(ctx, log_n, reps, emit=True):
+    """one process per GPU (torch.distributed already initialised, NCCL): transform one 2^log_n vector over all ranks with DistNtt,
+    check it on rank 0 against the single-GPU transform, return the result line there (None elsewhere).  bench.py calls this too."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = f"cuda:{ctx.device}"
+    omega = omega_for(log_n)
+    d = sharding.DistNtt(ctx, log_n)
+    m = d.m
+    x = uniform_fr_dev(m, 0xDE06 + 97 * rank + log_n, dev)
+    torch.cuda.synchronize()
+    dtod(ctx, d.d_x, x.data_ptr(), 32 * m)  # d_x is a de_dev_alloc buffer
+    ctx.sync()
+    dist.barrier()
+    best = 1e30
+    for i in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(d.stream):
+            d._barrier()
+            e0.record(d.stream)
+            d.run(omega)
+            e1.record(d.stream)
+        e1.synchronize()
+        t = sharding.max_over_ranks(e0.elapsed_time(e1))
+        if i >= 2:
+            best = min(best, t)
+    out = torch.empty((m, 4), dtype=torch.int64, device=dev)
+    dtod(ctx, out.data_ptr(), d.d_out, 32 * m)
+    ctx.sync()
+    xs = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
+    os_ = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
+    dist.gather(x, xs, dst=0)
+    dist.gather(out, os_, dst=0)
+    res = None
+    if rank == 0:
+        ref_ctx = de_b200.Context(ctx.device)
+        want, single_ms = single_gpu_reference(ref_ctx, xs, log_n, omega, reps, dev)
+        ok = all(torch.equal(o, want[r * m:(r + 1) * m]) for r, o in enumerate(os_))
+        res = line("one process per GPU (CUDA IPC peer buffers, NCCL 1-element barriers)", world, log_n, best, ok, single_ms, emit=emit,
+                   peer_bytes_per_gpu=2 * 32 * m * (world - 1) // world)
+        ref_ctx.close()
+        del want
+    del xs, os_, x, out
+    d.close()
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_dist(args):
     import torch.distributed as dist
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     ctx = de_b200.Context(local)
     for log_n in args.log_n:
-        omega = omega_for(log_n)
-        d = sharding.DistNtt(ctx, log_n)
-        m = d.m
-        x = uniform_fr_dev(m, 0xDE06 + 97 * rank + log_n, f"cuda:{local}")
-        # d_x is a de_dev_alloc buffer: fill it from the torch tensor with a device-to-device copy
-        torch.cuda.synchronize()
-        dtod(ctx, d.d_x, x.data_ptr(), 32 * m)
-        ctx.sync()
-        dist.barrier()
-        best = 1e30
-        for i in range(args.reps + 2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(d.stream):
-                d._barrier()
-                e0.record(d.stream)
-                d.run(omega)
-                e1.record(d.stream)
-            e1.synchronize()
-            t = sharding.max_over_ranks(e0.elapsed_time(e1))
-            if i >= 2:
-                best = min(best, t)
-        # check on rank 0: gather the slices and the blocks, compare with the single-GPU transform
-        out = torch.empty((m, 4), dtype=torch.int64, device=f"cuda:{local}")
-        dtod(ctx, out.data_ptr(), d.d_out, 32 * m)
-        ctx.sync()
-        xs = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
-        os_ = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
-        dist.gather(x, xs, dst=0)
-        dist.gather(out, os_, dst=0)
-        if rank == 0:
-            ref_ctx = de_b200.Context(local)
-            want, single_ms = single_gpu_reference(ref_ctx, xs, log_n, omega, args.reps)
-            ok = all(torch.equal(o, want[r * m:(r + 1) * m]) for r, o in enumerate(os_))
-            line("one process per GPU (CUDA IPC peer buffers, NCCL 1-element barriers)", world, log_n, best, ok, single_ms,
-                 peer_bytes_per_gpu=2 * 32 * m * (world - 1) // world)
-            ref_ctx.close()
-            del want
-        del xs, os_, x, out
-        d.close()
-        torch.cuda.empty_cache()
+        measure_dist(ctx, log_n, args.reps)
     ctx.close()
     dist.destroy_process_group()
 
