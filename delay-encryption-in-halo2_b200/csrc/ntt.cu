@@ -42,10 +42,13 @@ struct NttDistPlan {
     Fr* tw_hi = nullptr;
     Fr* tw_lo = nullptr;
     uint32_t tw_lo_bits = 0;
+    Fr* tw_rank = nullptr;   // w_N^(rank * j), j < N / W, for the rank this context last ran stage 1 as
+    uint32_t tw_rank_of = 0;
     Fr wcross[4];
     ~NttDistPlan() {
         if (tw_hi) cudaFree(tw_hi);
         if (tw_lo) cudaFree(tw_lo);
+        if (tw_rank) cudaFree(tw_rank);
     }
 };
 
@@ -580,7 +583,7 @@ static int get_dist_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, uint32
     p->omega = omega;
     const unsigned long long N = 1ull << log_n;
     Fr w = fr_from_host(omega);
-    p->tw_lo_bits = 12;
+    p->tw_lo_bits = log_n < 12 ? log_n : 12;
     int rc = pow_table(ctx, &p->tw_lo, 1ull << p->tw_lo_bits, w, 1);
     if (rc == DE_OK) rc = pow_table(ctx, &p->tw_hi, N >> p->tw_lo_bits, w, 1ull << p->tw_lo_bits);
     if (rc == DE_OK) rc = fr_host_pow(ctx, omega, world, &p->omega_local);
@@ -638,11 +641,18 @@ int de_ntt_dist_stage1(de_ctx* ctx, const de_fr* d_x, const de_fr* omega, uint32
     for (uint32_t i = 0; i < world; i++) dx.peer[i] = (Fr*)d_z_peers[i];
     dx.col_bits = m - plan->log_w;
     dx.row_off = (unsigned long long)rank << dx.col_bits;
-    dx.rank = rank;
-    dx.tw_hi = plan->tw_hi;
-    dx.tw_lo = plan->tw_lo;
-    dx.tw_lo_bits = plan->tw_lo_bits;
     const size_t M = (size_t)1 << m;
+    if (rank != 0 && (!plan->tw_rank || plan->tw_rank_of != rank)) {
+        if (!plan->tw_rank && cudaMalloc((void**)&plan->tw_rank, sizeof(Fr) * M) != cudaSuccess) {
+            cudaGetLastError();
+            plan->tw_rank = nullptr;
+            return fail(ctx, DE_ERR_OOM, "ntt (multi-GPU): twiddle table allocation failed");
+        }
+        k_dist_twiddles<<<(unsigned int)((M + 255) / 256), 256, 0, ctx->stream>>>(plan->tw_rank, M, rank, plan->tw_hi, plan->tw_lo, plan->tw_lo_bits);
+        DE_CHECK_LAUNCH(ctx);
+        plan->tw_rank_of = rank;
+    }
+    dx.tw = rank != 0 ? plan->tw_rank : nullptr;
     return ntt_run(ctx, plan->omega_local, m, (const Fr*)d_x, M, nullptr, M, 1, 0, 0, nullptr, 0, nullptr, &dx);
 }
 

@@ -46,10 +46,8 @@ struct NttDistArgs<true> {
     Fr* peer[8];                   // exchange buffers of the ranks (peer-mapped device pointers), world <= 8
     unsigned int col_bits;         // log2 C, C = N / world^2 columns per destination rank
     unsigned long long row_off;    // rank * C: this rank's row inside every exchange buffer
-    unsigned long long rank;       // twiddle exponent = rank * j
-    const Fr* tw_hi;               // w_N^(e >> lo_bits << lo_bits), w_N^(e & mask)
-    const Fr* tw_lo;
-    unsigned int tw_lo_bits;
+    const Fr* tw;                  // tw[j] = w_N^(rank * j), j < M (resident per plan: one multiplication per element, the table is
+                                   // read at HBM speed, which this path does not come near); NULL on rank 0 (all ones)
 };
 
 __device__ __forceinline__ void sm_put(uint4* lo, uint4* hi, int slot, const Fr& v) {
@@ -227,12 +225,7 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
         unsigned long long go = out_base + tt * p.out_tt + (unsigned long long)j * p.out_el;
         if constexpr (DIST) {
             // go = column j2 of the local transform: twiddle w_N^(rank * j2), then row `rank` of the owner's exchange buffer
-            unsigned long long e = dx.rank * go;
-            if (e != 0) {
-                Fr h = load(&dx.tw_hi[e >> dx.tw_lo_bits]);
-                Fr l = load(&dx.tw_lo[e & ((1ull << dx.tw_lo_bits) - 1)]);
-                v = mul(v, mul(h, l));
-            }
+            if (dx.tw != nullptr && go != 0) v = mul(v, load(&dx.tw[go]));
             Fr* dst = dx.peer[go >> dx.col_bits];
             store(&dst[dx.row_off + (go & ((1ull << dx.col_bits) - 1))], v);
         } else {
@@ -240,6 +233,14 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
             store(&out[go], v);
         }
     }
+}
+
+// out[j] = w^(rank * j) for j < n from the two-level tables hi[e >> bits] * lo[e & mask] (one-time per plan and rank)
+__global__ void k_dist_twiddles(Fr* out, unsigned long long n, unsigned long long rank, const Fr* hi, const Fr* lo, unsigned int bits) {
+    unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    unsigned long long e = rank * j;
+    store(&out[j], mul(load(&hi[e >> bits]), load(&lo[e & ((1ull << bits) - 1)])));
 }
 
 // Second stage of the multi-GPU transform: a W-point transform ACROSS the ranks for every column of this rank's exchange

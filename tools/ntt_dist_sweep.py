@@ -130,7 +130,15 @@ def run_sharded(args):
                 best = min(best, t)
         want, single_ms = single_gpu_reference(ref_ctx, xs, log_n, omega, args.reps)
         ok = all(torch.equal(o.to("cuda:0"), want[r * m:(r + 1) * m]) for r, o in enumerate(outs))
-        stage = {}
+        # per-kernel CUDA-event times of one more call (max over the ranks): local passes, exchange pass, cross-rank stage
+        for c in s.ctxs:
+            c.timing_reset()
+            c.timing_enable(True)
+        s.best_fft_dev(xs, outs, omega, log_n)
+        s.sync()
+        stage = {"kernel_ms": {k: max(c.timing_get(k)[0] for c in s.ctxs) for k in ("k_ntt_pass", "k_ntt_pass_dist", "k_ntt_cross")}}
+        for c in s.ctxs:
+            c.timing_enable(False)
         line("one process, W contexts (de_ntt_sharded_dev)", world, log_n, best, ok, single_ms,
              devices=sorted(set(devs)), peer_bytes_per_gpu=2 * 32 * m * (world - 1) // world, **stage)
         del xs, outs, want
