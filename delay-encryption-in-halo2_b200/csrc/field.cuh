@@ -403,6 +403,26 @@ DE_D void store(Fp<P>* p, const Fp<P>& v) {
 #endif
 }
 
+#if defined(__CUDACC__)
+// One 256-bit access per element (LDG/STG.E.256, sm_100+): a warp touches 1 KiB of whole 128-byte lines per instruction.  Used
+// where stores cross NVLink (the multi-GPU transform's exchanges): two 16-byte stores per thread leave every line half written
+// per instruction, and a peer cannot merge the halves the way the local L2 does.
+template <class P>
+__device__ __forceinline__ Fp<P> load256(const Fp<P>* p) {
+    Fp<P> r;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+                 : "l"(p));
+    return r;
+}
+template <class P>
+__device__ __forceinline__ void store256(Fp<P>* p, const Fp<P>& v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.l[0]), "r"(v.l[1]), "r"(v.l[2]), "r"(v.l[3]),
+                 "r"(v.l[4]), "r"(v.l[5]), "r"(v.l[6]), "r"(v.l[7])
+                 : "memory");
+}
+#endif
+
 typedef Fp<FrParams> Fr;
 typedef Fp<FqParams> Fq;
 

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
             // go = column j2 of the local transform: twiddle w_N^(rank * j2), then row `rank` of the owner's exchange buffer
             if (dx.tw != nullptr && go != 0) v = mul(v, load(&dx.tw[go]));
             Fr* dst = dx.peer[go >> dx.col_bits];
-            store(&dst[dx.row_off + (go & ((1ull << dx.col_bits) - 1))], v);
+            store256(&dst[dx.row_off + (go & ((1ull << dx.col_bits) - 1))], v);
         } else {
             if (p.out_mode == 1) v = mul(v, p.oscale[(unsigned int)(go % 3ull)]);
             store(&out[go], v);
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128) k_ntt_cross(const __grid_constant__ NttCr
     if (c >= a.C) return;
     Fr x[W];
 #pragma unroll
-    for (int i = 0; i < W; i++) x[i] = load(&a.z[(unsigned long long)i * a.C + c]);
+    for (int i = 0; i < W; i++) x[i] = load256(&a.z[(unsigned long long)i * a.C + c]);
     // decimation in frequency; position p ends up holding output bit-reverse(p)
 #pragma unroll
     for (int u = 0; u < LW; u++) {
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(128) k_ntt_cross(const __grid_constant__ NttCr
         int j1 = 0;
 #pragma unroll
         for (int b = 0; b < LW; b++) j1 |= ((p >> b) & 1) << (LW - 1 - b);
-        store(&a.peer_out[j1][a.out_off + c], x[p]);
+        store256(&a.peer_out[j1][a.out_off + c], x[p]);
     }
 }
 
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) k_ntt_deal(const __grid_constant__ NttDea
     unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= a.M) return;
     unsigned long long q = id / a.C, v = id - q * a.C;
-    store(&a.peer_x[q][a.row_off + v], load(&a.stage[(v << a.log_w) + q]));
+    store256(&a.peer_x[q][a.row_off + v], load256(&a.stage[(v << a.log_w) + q]));
 }
 
 // out[i] = base^(i * step) for i < n  (twiddle tables; one-time per plan)

@@ -82,6 +82,7 @@ def ev_time(stream, fn, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--msm-to", type=int, default=24)
+    ap.add_argument("--msm-from", type=int, default=16, help="2^26 on one GPU wants DE_MSM_TABLE_MB=80000 (64 GiB of window tables)")
     ap.add_argument("--ntt-to", type=int, default=27)
     args = ap.parse_args()
     stream = torch.cuda.Stream()
@@ -111,6 +112,8 @@ def main():
         for log_n in [16, 17, 18, 20, 22, 24, 26]:
             if log_n > args.msm_to:
                 break
+            if log_n < args.msm_from:
+                continue
             n = 1 << log_n
             idx = np.zeros((n, 4), dtype=np.uint64)
             idx[:, 0] = np.arange(1, n + 1, dtype=np.uint64)
