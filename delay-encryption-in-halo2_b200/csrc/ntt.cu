@@ -34,15 +34,15 @@ struct NttPlan {
     }
 };
 
-// Tables of the multi-GPU transform (de_ntt_dist_*): w_N^e two-level for the inter-stage twiddle w_N^(rank * j2), the root of
-// the local N/W-point transform and the W/2 powers of the cross-rank root.
+// Tables of the multi-GPU transform (de_ntt_dist_*): w_N^e two-level, from which the resident inter-stage twiddles of a rank are
+// built, the root of the local N/W-point transform and the W/2 powers of the cross-rank root.
 struct NttDistPlan {
     uint32_t log_n = 0, log_w = 0;
     de_fr omega, omega_local;
     Fr* tw_hi = nullptr;
     Fr* tw_lo = nullptr;
     uint32_t tw_lo_bits = 0;
-    Fr* tw_rank = nullptr;   // w_N^(rank * j), j < N / W, for the rank this context last ran stage 1 as
+    Fr* tw_rank = nullptr;   // inter-stage twiddles (k_dist_twiddles) of the rank this context last ran stage 2 as
     uint32_t tw_rank_of = 0;
     Fr wcross[4];
     ~NttDistPlan() {
@@ -564,8 +564,8 @@ int de_ntt(de_ctx* ctx, de_fr* a, const de_fr* omega, uint32_t log_n) {
 // ---- multi-GPU best_fft (SURVEY.md section 8e, row "NTT: single huge vector") --------------------------------
 // N = W * M (W ranks).  Rank r holds x_r[t] = a[r + W t] (cyclic).  With i = i1 + W i2 and j = j2 + M j1:
 //   A[j2 + M j1] = sum_i1 w_W^(i1 j1) * [ w_N^(i1 j2) * sum_i2 a[i1 + W i2] w_M^(i2 j2) ]
-// stage 1 (rank i1): local M-point transform, twiddle, peer-store of column j2 into row i1 of the exchange buffer of rank
-// j2 / C (C = M / W);  stage 2 (rank q): W-point transform down every column of its exchange buffer, peer-store of output j1
+// stage 1 (rank i1): local M-point transform, peer-store of column j2 into row i1 of the exchange buffer of rank j2 / C
+// (C = M / W);  stage 2 (rank q): twiddle, W-point transform down every column of its exchange buffer, peer-store of output j1
 // into rank j1's block at q C + c.  Result: rank j1 holds A[j1 M .. (j1 + 1) M) - natural order, contiguous blocks.
 static int get_dist_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, uint32_t world, NttDistPlan** out) {
     uint32_t lw = 0;
@@ -603,12 +603,25 @@ static int get_dist_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, uint32
 }
 
 template <int LW>
-static int launch_cross(de_ctx* ctx, const NttDistPlan* plan, const Fr* d_z, de_fr* const* d_out_peers, uint32_t rank) {
+static int launch_cross(de_ctx* ctx, NttDistPlan* plan, const Fr* d_z, de_fr* const* d_out_peers, uint32_t rank) {
     NttCrossArgs<LW> a;
     memset(&a, 0, sizeof(a));
     const unsigned long long M = 1ull << (plan->log_n - LW);
     a.z = d_z;
     a.C = M >> LW;
+    if (LW > 0 && (!plan->tw_rank || plan->tw_rank_of != rank)) {
+        const unsigned long long cnt = a.C * ((1u << LW) - 1);
+        if (!plan->tw_rank && cudaMalloc((void**)&plan->tw_rank, sizeof(Fr) * cnt) != cudaSuccess) {
+            cudaGetLastError();
+            plan->tw_rank = nullptr;
+            return fail(ctx, DE_ERR_OOM, "ntt (multi-GPU): twiddle table allocation failed");
+        }
+        k_dist_twiddles<<<(unsigned int)((cnt + 255) / 256), 256, 0, ctx->stream>>>(plan->tw_rank, a.C, (1u << LW) - 1, (unsigned long long)rank * a.C,
+                                                                             plan->tw_hi, plan->tw_lo, plan->tw_lo_bits);
+        DE_CHECK_LAUNCH(ctx);
+        plan->tw_rank_of = rank;
+    }
+    a.tw = plan->tw_rank;
     a.out_off = (unsigned long long)rank * a.C;
     for (int i = 0; i < (1 << LW); i++) a.peer_out[i] = (Fr*)d_out_peers[i];
     for (int i = 0; i < ((1 << LW) / 2 < 1 ? 1 : (1 << LW) / 2); i++) a.w[i] = plan->wcross[i];
@@ -642,17 +655,6 @@ int de_ntt_dist_stage1(de_ctx* ctx, const de_fr* d_x, const de_fr* omega, uint32
     dx.col_bits = m - plan->log_w;
     dx.row_off = (unsigned long long)rank << dx.col_bits;
     const size_t M = (size_t)1 << m;
-    if (rank != 0 && (!plan->tw_rank || plan->tw_rank_of != rank)) {
-        if (!plan->tw_rank && cudaMalloc((void**)&plan->tw_rank, sizeof(Fr) * M) != cudaSuccess) {
-            cudaGetLastError();
-            plan->tw_rank = nullptr;
-            return fail(ctx, DE_ERR_OOM, "ntt (multi-GPU): twiddle table allocation failed");
-        }
-        k_dist_twiddles<<<(unsigned int)((M + 255) / 256), 256, 0, ctx->stream>>>(plan->tw_rank, M, rank, plan->tw_hi, plan->tw_lo, plan->tw_lo_bits);
-        DE_CHECK_LAUNCH(ctx);
-        plan->tw_rank_of = rank;
-    }
-    dx.tw = rank != 0 ? plan->tw_rank : nullptr;
     return ntt_run(ctx, plan->omega_local, m, (const Fr*)d_x, M, nullptr, M, 1, 0, 0, nullptr, 0, nullptr, &dx);
 }
 

@@ -36,9 +36,10 @@ struct NttPassParams {
     Fr oscale[3];
 };
 
-// Extra arguments of the multi-GPU transform's first stage (DIST = true): the last pass of the local N/G-point transform
-// multiplies output j by w_N^(rank*j) and stores it straight into the exchange buffer of the rank that owns column j - a
-// peer-memory store over NVLink, so the all-to-all of the four-step transform costs no pass of its own.
+// Extra arguments of the multi-GPU transform's first stage (DIST = true): the last pass of the local N/W-point transform stores
+// column j straight into the exchange buffer of the rank that owns it - a peer-memory store over NVLink, so the all-to-all of the
+// four-step transform costs no pass of its own.  (The inter-stage twiddle w_N^(rank * j) is applied by the receiving side in
+// k_ntt_cross, whose integer pipe is idle while it waits for NVLink.)
 template <bool DIST>
 struct NttDistArgs {};
 template <>
@@ -46,8 +47,6 @@ struct NttDistArgs<true> {
     Fr* peer[8];                   // exchange buffers of the ranks (peer-mapped device pointers), world <= 8
     unsigned int col_bits;         // log2 C, C = N / world^2 columns per destination rank
     unsigned long long row_off;    // rank * C: this rank's row inside every exchange buffer
-    const Fr* tw;                  // tw[j] = w_N^(rank * j), j < M (resident per plan: one multiplication per element, the table is
-                                   // read at HBM speed, which this path does not come near); NULL on rank 0 (all ones)
 };
 
 __device__ __forceinline__ void sm_put(uint4* lo, uint4* hi, int slot, const Fr& v) {
@@ -224,8 +223,7 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
         }
         unsigned long long go = out_base + tt * p.out_tt + (unsigned long long)j * p.out_el;
         if constexpr (DIST) {
-            // go = column j2 of the local transform: twiddle w_N^(rank * j2), then row `rank` of the owner's exchange buffer
-            if (dx.tw != nullptr && go != 0) v = mul(v, load(&dx.tw[go]));
+            // go = column j2 of the local transform -> row `rank` of its owner's exchange buffer
             Fr* dst = dx.peer[go >> dx.col_bits];
             store256(&dst[dx.row_off + (go & ((1ull << dx.col_bits) - 1))], v);
         } else {
@@ -235,21 +233,26 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
     }
 }
 
-// out[j] = w^(rank * j) for j < n from the two-level tables hi[e >> bits] * lo[e & mask] (one-time per plan and rank)
-__global__ void k_dist_twiddles(Fr* out, unsigned long long n, unsigned long long rank, const Fr* hi, const Fr* lo, unsigned int bits) {
-    unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    unsigned long long e = rank * j;
-    store(&out[j], mul(load(&hi[e >> bits]), load(&lo[e & ((1ull << bits) - 1)])));
+// Inter-stage twiddles of rank q, resident per plan: out[(i1 - 1) C + c] = w_N^(i1 (q C + c)) for 1 <= i1 < W, c < C, from the
+// two-level tables hi[e >> bits] * lo[e & mask] (one-time per plan and rank)
+__global__ void k_dist_twiddles(Fr* out, unsigned long long C, unsigned int rows, unsigned long long col0, const Fr* hi, const Fr* lo,
+                                unsigned int bits) {
+    unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= C * rows) return;
+    unsigned long long i1 = id / C + 1, c = id % C;
+    unsigned long long e = i1 * (col0 + c);
+    store(&out[id], mul(load(&hi[e >> bits]), load(&lo[e & ((1ull << bits) - 1)])));
 }
 
 // Second stage of the multi-GPU transform: a W-point transform ACROSS the ranks for every column of this rank's exchange
-// buffer z[W][C] (row i1 came from rank i1), root w_W = w_N^(N/W).  Output j1 of column c is element
+// buffer z[W][C] (row i1 came from rank i1, still to be multiplied by w_N^(i1 j2), j2 = rank C + c: table tw), root
+// w_W = w_N^(N/W).  Output j1 of column c is element
 // A[j1 * (N/W) + rank * C + c] of the result and is stored into rank j1's output block - the second exchange, again as
 // peer stores (one thread per column: a warp writes 1 KiB contiguous per destination).
 template <int LW>
 struct NttCrossArgs {
     const Fr* z;
+    const Fr* tw;  // (W - 1) x C inter-stage twiddles (k_dist_twiddles)
     Fr* peer_out[1 << LW];
     unsigned long long C;
     unsigned long long out_off;  // rank * C
@@ -263,6 +266,8 @@ __global__ void __launch_bounds__(128) k_ntt_cross(const __grid_constant__ NttCr
     Fr x[W];
 #pragma unroll
     for (int i = 0; i < W; i++) x[i] = load256(&a.z[(unsigned long long)i * a.C + c]);
+#pragma unroll
+    for (int i = 1; i < W; i++) x[i] = mul(x[i], load256(&a.tw[(unsigned long long)(i - 1) * a.C + c]));
     // decimation in frequency; position p ends up holding output bit-reverse(p)
 #pragma unroll
     for (int u = 0; u < LW; u++) {

@@ -237,9 +237,9 @@ int de_commit_sharded(de_params* const* shards, const size_t* shard_lo, const si
  * and no library collective:
  *   input  (cyclic):  rank r holds x_r[t] = a[r + W t], t < M;
  *   output (blocks):  rank q holds A[q M .. (q + 1) M), natural order -  A = best_fft(a, omega, log_n).
- * stage 1 on rank r: local M-point transform whose last pass multiplies column j by omega^(r j) and stores it into row r of the
- * exchange buffer z (M elements) of rank j / (M / W);  stage 2 on rank q: W-point transform down the columns of its z, output j1
- * stored into rank j1's output block.  d_z_peers / d_out_peers hold the W ranks' buffers as pointers valid on THIS device
+ * stage 1 on rank r: local M-point transform whose last pass stores column j into row r of the exchange buffer z (M elements) of
+ * rank j / (M / W);  stage 2 on rank q: row i1 of its z times omega^(i1 j), W-point transform down the columns, output j1 stored
+ * into rank j1's output block.  d_z_peers / d_out_peers hold the W ranks' buffers as pointers valid on THIS device
  * (peer access inside one process, de_ipc_import across processes).  The caller orders the stages: every rank's stage 1 must
  * have completed before any stage 2 starts, and every stage 2 before the outputs are read or the next stage 1 begins (stream
  * events inside one process - de_ntt_sharded_dev does it -, a barrier on the stream across processes).  11 + log2 W <= log_n <= 28. */
