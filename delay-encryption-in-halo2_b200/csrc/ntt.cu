@@ -686,6 +686,8 @@ int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x,
     for (int r = 0; r < n_gpus; r++) {
         de_ctx* c = ctxs[r];
         if (!c || !d_x[r] || !d_out[r]) return fail(c0, DE_ERR_ARG, "de_ntt_sharded_dev: null context or buffer");
+        for (int q = 0; q < r; q++)
+            if (ctxs[q] == c) return fail(c0, DE_ERR_ARG, "de_ntt_sharded_dev: contexts must be distinct (one per rank)");
         DE_CUDA(c0, cudaSetDevice(c->device));
         for (int q = 0; q < n_gpus; q++) {
             // every rank stores into every other rank's buffers

@@ -136,6 +136,8 @@ def test_rejects_bad_arguments():
         assert rc == -1 and b"1, 2, 4 or 8" in c0.L.de_last_error(c0.h)
         rc = c0.L.de_ntt_sharded_dev(ctxs, 2, ptrs, ptrs, w.ctypes.data_as(C.c_void_p), 11)
         assert rc == -1
+        rc = c0.L.de_ntt_sharded_dev(ctxs, 2, ptrs, ptrs, w.ctypes.data_as(C.c_void_p), 16)   # the same context twice
+        assert rc == -1 and b"distinct" in c0.L.de_last_error(c0.h)
         peers = (C.c_void_p * 2)(t[0].data_ptr(), None)
         rc = c0.L.de_ntt_dist_stage1(c0.h, C.c_void_p(t[0].data_ptr()), w.ctypes.data_as(C.c_void_p), 12, 2, 0, peers)
         assert rc == -1
