@@ -23,7 +23,10 @@ struct NttPlan {
     Fr* tw_hi = nullptr;
     Fr* tw_lo = nullptr;
     uint32_t tw_lo_bits = 0;
+    Fr* tw_pass[2] = {nullptr, nullptr};  // log_n > 22: pass-ordered twiddles of the strided-column passes (N entries each)
     ~NttPlan() {
+        for (int i = 0; i < 2; i++)
+            if (tw_pass[i]) cudaFree(tw_pass[i]);
         for (int i = 0; i < 3; i++)
             if (wl[i]) cudaFree(wl[i]);
         for (int i = 0; i < 3; i++)
@@ -120,6 +123,30 @@ static int get_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, NttPlan** o
             p->tw_lo_bits = 12;
             rc = pow_table(ctx, &p->tw_lo, 1ull << p->tw_lo_bits, w, 1);
             if (rc == DE_OK) rc = pow_table(ctx, &p->tw_hi, N >> p->tw_lo_bits, w, 1ull << p->tw_lo_bits);
+            // 180 GB of HBM: keep every inter-pass twiddle resident in the order its pass reads it (2 x 32 N bytes per plan) instead of
+            // rebuilding it from the two-level tables with a second multiplication per element.  Budget per plan: DE_NTT_TABLE_MB
+            // (default 16 GiB, i.e. up to N = 2^28); beyond it, or if the allocation fails, the two-level path stays.
+            size_t budget = (size_t)16 << 30;
+            if (const char* e = getenv("DE_NTT_TABLE_MB")) budget = (size_t)atoll(e) << 20;
+            if (rc == DE_OK && sizeof(Fr) * N * (p->npass - 1) <= budget) {
+                unsigned long long lprod = 1;
+                for (int k = 0; k + 1 < p->npass; k++) {
+                    const unsigned long long L = 1ull << p->S[k];
+                    const unsigned long long M = N / (lprod * L);
+                    if (cudaMalloc((void**)&p->tw_pass[k], sizeof(Fr) * N) != cudaSuccess) {
+                        cudaGetLastError();
+                        for (int i = 0; i < 2; i++) {
+                            if (p->tw_pass[i]) cudaFree(p->tw_pass[i]);
+                            p->tw_pass[i] = nullptr;
+                        }
+                        break;
+                    }
+                    k_pass_twiddles<<<(unsigned int)((N + 255) / 256), 256, 0, ctx->stream>>>(p->tw_pass[k], N, M, L * M, lprod, p->tw_hi, p->tw_lo,
+                                                                                          p->tw_lo_bits);
+                    ctx->launches++;
+                    lprod *= L;
+                }
+            }
         }
     }
     if (rc != DE_OK) {
@@ -243,6 +270,9 @@ int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, si
             if (plan->tw_full) {
                 prm.tw_mode = 1;
                 prm.tw_full = plan->tw_full;
+            } else if (plan->tw_pass[k]) {
+                prm.tw_mode = 3;
+                prm.tw_pass = plan->tw_pass[k];
             } else {
                 prm.tw_mode = 2;
                 prm.tw_hi = plan->tw_hi;

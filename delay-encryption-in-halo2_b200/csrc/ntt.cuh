@@ -23,7 +23,10 @@ struct NttPassParams {
     unsigned long long out_grp, out_blk, out_tt, out_el;
     const uint4* wl_planes;  // powers of the Lk-th root of unity w_L^i, i < L/2, ALREADY in the kernel's shared-memory layout: the
                              // low 16 bytes of every power, then the high 16 bytes - one TMA bulk copy stages the table
-    int tw_mode;   // 0: none, 1: full table tw_full[e] = w_N^e (e < N), 2: two-level tw_hi[e >> lo_bits] * tw_lo[e & mask]
+    int tw_mode;   // 0: none, 1: full table tw_full[e] = w_N^e (e < N), 2: two-level tw_hi[e >> lo_bits] * tw_lo[e & mask],
+                   // 3: tw_pass[o] = the twiddle of output position o of THIS pass (resident per plan and pass; read with the
+                   //    same coalesced pattern as the store, one multiplication per element at any N)
+    const Fr* tw_pass;
     const Fr* tw_full;
     const Fr* tw_hi;
     const Fr* tw_lo;
@@ -216,12 +219,14 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
         int tt = idx & (T - 1), j = idx >> LT;
         int pos = (S == 0) ? 0 : (int)(__brev((unsigned)j) >> (32 - (S == 0 ? 1 : S)));
         Fr v = sm_get(lo, hi, ntt_slot<LT>(pos, tt));
-        if (p.tw_mode != 0) {
+        unsigned long long go = out_base + tt * p.out_tt + (unsigned long long)j * p.out_el;
+        if (p.tw_mode == 3) {
+            v = mul(v, load(&p.tw_pass[go]));
+        } else if (p.tw_mode != 0) {
             unsigned long long c = (unsigned long long)tile * T + tt;
             unsigned long long e = c * (unsigned long long)j * p.tw_mul;
             if (e != 0) v = mul(v, ntt_twiddle(p, e));
         }
-        unsigned long long go = out_base + tt * p.out_tt + (unsigned long long)j * p.out_el;
         if constexpr (DIST) {
             // go = column j2 of the local transform -> row `rank` of its owner's exchange buffer
             Fr* dst = dx.peer[go >> dx.col_bits];
@@ -231,6 +236,17 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
             store(&out[go], v);
         }
     }
+}
+
+// Pass-ordered twiddles (tw_mode 3) of a strided-column pass over groups of L*M elements: output position o = g L M + j M + c
+// gets w_N^(c j Lprod).  One-time per plan and pass.
+__global__ void k_pass_twiddles(Fr* out, unsigned long long n, unsigned long long M, unsigned long long LM, unsigned long long lprod,
+                                const Fr* hi, const Fr* lo, unsigned int bits) {
+    unsigned long long o = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    unsigned long long gi = o % LM;
+    unsigned long long e = (gi % M) * (gi / M) * lprod;
+    store(&out[o], e == 0 ? Fr::one() : mul(load(&hi[e >> bits]), load(&lo[e & ((1ull << bits) - 1)])));
 }
 
 // Inter-stage twiddles of rank q, resident per plan: out[(i1 - 1) C + c] = w_N^(i1 (q C + c)) for 1 <= i1 < W, c < C, from the
