@@ -468,7 +468,7 @@ def main():
         nctx = de_b200.Context(local_rank)
         try:
             res = ntt_dist_sweep.measure_dist(nctx, 24, 5, emit=False)
-        except RuntimeError as e:  # raised on every rank together (DistNtt's setup is collective)
+        except (RuntimeError, ValueError) as e:  # raised on every rank together (layout check; DistNtt's collective setup)
             res = {"error": str(e)}
         nctx.close()
         if rank == 0:
