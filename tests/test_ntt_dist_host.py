@@ -82,6 +82,29 @@ def test_schedule_simulated_ranks(world):
         assert (out[r] == want[lo:hi]).all()
 
 
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_layouts_are_partitions(world):
+    """the cyclic input slices cover every index once, the exchange slots of all (source rank, column) pairs fill every rank's buffer
+    exactly once, and the output blocks tile [0, N)"""
+    from de_b200 import sharding
+    log_n = 11 + world.bit_length() - 1
+    n = 1 << log_n
+    m, c = sharding.ntt_layout(log_n, world)
+    assert m * world == n and c * world == m
+    idx = np.arange(n)
+    seen = np.concatenate([sharding.ntt_input_slice(idx, r, world) for r in range(world)])
+    assert sorted(seen.tolist()) == list(range(n))
+    filled = np.zeros((world, m), dtype=np.int64)
+    for src in range(world):
+        for col in range(m):
+            q, pos = sharding.ntt_exchange_slot(log_n, world, src, col)
+            assert 0 <= q < world and pos // c == src      # row `src` of rank q's buffer
+            filled[q, pos] += 1
+    assert (filled == 1).all()
+    blocks = [sharding.ntt_output_range(log_n, r, world) for r in range(world)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == n and all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+
+
 def test_layout_rejects_bad_arguments():
     from de_b200 import sharding
     for log_n, world in [(11, 2), (29, 2), (16, 3), (16, 16), (16, 0)]:
