@@ -8,6 +8,14 @@ use std::ffi::CStr;
 
 thread_local! { static CTX: *mut de_ctx = unsafe { let mut c = std::ptr::null_mut(); ok(de_ctx_create(0, &mut c), std::ptr::null_mut()); c }; }
 fn ctx() -> *mut de_ctx { CTX.with(|c| *c) }
+// one context per visible GPU, largest power of two of them (DE_B200_GPUS caps it); element 0 is ctx()
+thread_local! { static ALL: Vec<*mut de_ctx> = unsafe {
+    let want: usize = std::env::var("DE_B200_GPUS").ok().and_then(|v| v.parse().ok()).unwrap_or(8);
+    let mut v = vec![ctx()];
+    for dev in 1..want { let mut c = std::ptr::null_mut(); if de_ctx_create(dev as i32, &mut c) != 0 { break; } v.push(c); }
+    let mut n = 1; while n * 2 <= v.len() { n *= 2; } v.truncate(n); v
+}; }
+fn all_ctxs() -> Vec<*mut de_ctx> { ALL.with(|v| v.clone()) }
 fn ok(rc: i32, c: *mut de_ctx) { if rc != 0 { panic!("de_b200: {}", unsafe { CStr::from_ptr(de_last_error(c)) }.to_string_lossy()); } }
 
 // ---- src/arithmetic.rs -------------------------------------------------------------------------------------------------
@@ -18,7 +26,14 @@ pub fn best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1 {
 }
 pub fn best_fft(a: &mut [Fr], omega: Fr, log_n: u32) {
     assert_eq!(a.len(), 1 << log_n);
-    unsafe { ok(de_ntt(ctx(), a.as_mut_ptr() as _, &omega as *const Fr as _, log_n), ctx()) }
+    // long vectors go over every GPU of the box (all_ctxs(): one de_ctx per visible device, a power of two of them): block r travels
+    // over GPU r's PCIe link and the two transposes of the four-step transform are NVLink peer stores inside the kernels
+    let gpus = all_ctxs();
+    if gpus.len() > 1 && log_n >= 22 {
+        unsafe { ok(de_ntt_sharded(gpus.as_ptr(), gpus.len() as i32, a.as_mut_ptr() as _, &omega as *const Fr as _, log_n), ctx()) }
+    } else {
+        unsafe { ok(de_ntt(ctx(), a.as_mut_ptr() as _, &omega as *const Fr as _, log_n), ctx()) }
+    }
 }
 pub fn eval_polynomial(poly: &[Fr], point: Fr) -> Fr {
     let mut out = Fr::zero();
