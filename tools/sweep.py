@@ -84,13 +84,14 @@ def main():
     ap.add_argument("--msm-to", type=int, default=24)
     ap.add_argument("--msm-from", type=int, default=16, help="2^26 on one GPU wants DE_MSM_TABLE_MB=80000 (64 GiB of window tables)")
     ap.add_argument("--ntt-to", type=int, default=27)
+    ap.add_argument("--ntt-from", type=int, default=16)
     args = ap.parse_args()
     stream = torch.cuda.Stream()
     ctx = de_b200.Context(0)
     ctx.set_stream(stream.cuda_stream)
     with torch.cuda.stream(stream):
         # ---------------- NTT
-        for log_n in range(16, args.ntt_to + 1):
+        for log_n in range(args.ntt_from, args.ntt_to + 1):
             n = 1 << log_n
             dom = de_b200.EvaluationDomain(2, log_n, ctx)  # j = 2: extended_k = k, omega = ROOT_OF_UNITY^(2^(28 - k))
             a = uniform_fr_dev(n, 0xDE06 + log_n)
