@@ -14,9 +14,13 @@ that exactly this prover's bytes equal the CPU restatement's and pass the restat
   value      proofs/s with the advice columns and the random draws already resident in HBM (device-timed, CUDA events)
   e2e        the same through the host-buffer entry point: pinned host advice columns + random draws are copied to the
              device inside the timed region; commitments / evaluations are read back as the transcript needs them
-  roofline   dominant kernel (k_msm_accumulate): algorithmic bytes per launch / measured launch time, against the measured
-             HBM copy bandwidth (MEASURED_PEAKS.json); the kernel is integer-pipe bound, so `int_pipe` gives the fraction of
-             the measured Montgomery-multiply peak as well
+  roofline   dominant kernel (k_msm_accumulate), integer-pipe bound: field multiplications actually executed (10 per bucket
+             addition, additions counted on the device) / measured launch time, against the Montgomery-multiply peak measured
+             IN THIS RUN (de_int_peak); `hbm` inside it keeps the algorithmic-bytes fraction of the measured HBM copy bandwidth
+  msm        whole commitments (not one kernel) at 2^16 (alone / batch of 8), 2^20, 2^24 with the CPU restatement's
+             best_multiexp on the same inputs beside them; msm_multi_gpu (N > 1): one commitment with the base range sharded
+             over the ranks, partial points exchanged over NCCL, against the same commitment on one GPU
+  other_configs  short runs of the other two bench circuits (pose_enc k = 11, mod_pow k = 17)
   cpu_baseline   the whole create_proof by the restated reference algorithms (oracle/: best_multiexp / best_fft / evaluate_h /
              lookup permutation / grand products / openings as halo2_proofs v2023_04_20 implements them, C + pthreads on all
              host cores, Python sequencing + transcript), one proof, byte-compared with the GPU's
@@ -49,19 +53,18 @@ USED_ROWS = 50400
 SEED = 0xDE03
 WITH_LOOKUPS = True
 CONFIG_NAME = "delay_enc"
-WORKLOAD = ("delay_enc k=16 create_proof (MainGate + RangeChip shape: 5 advice, 15 fixed, 5 lookups, 6 permutation columns; "
+DEFAULT_WORKLOAD = WORKLOAD = ("delay_enc k=16 create_proof (MainGate + RangeChip shape: 5 advice, 15 fixed, 5 lookups, 6 permutation columns; "
             "satisfied synthetic witness, 50400 used rows): 31 MSM 2^16 (KZG bases resident), 23 iNTT 2^16, 23 coset-NTT 2^18, "
             "evaluate_h over 2^18 rows, 1 iNTT 2^18, 10 lookup sorts, 7 grand products, 58 evaluations, 4 Kate divisions, "
             "Blake2b transcript -> 2848-byte proof")
-METRIC = "delay_enc_create_proof_proofs_per_s"
+DEFAULT_METRIC = METRIC = "delay_enc_create_proof_proofs_per_s"
 TRANSCRIPT_REPR = 0xDE1A7E9C0DE
 UNIT = "proofs/s"
-MUL_PEAK_GMULS = 65.9   # measured on this pool's B200 by tools/int_peak (profiles/r01_int_peak.jsonl): Fr Montgomery mul/s
-MULS_PER_POINT = 160    # SURVEY.md 8d convention: 16 windows x (8M + 2S) per point (a uniform scalar)
-MULS_PER_ADD = 10       # XYZZ mixed addition: 8M + 2S
-# (dram__bytes_read.sum + dram__bytes_write.sum) / points of a k_msm_accumulate launch (180.7 + 21.2 MB for the 7 x 2^16 points of
-# the grand-product round), from the `ncu --set full` capture summarised in profiles/r01_create_proof_ncu_full.md
-TRAFFIC_BYTES_PER_POINT = 201.9e6 / 458752
+MUL_PEAK_FALLBACK_GMULS = 65.9  # only if de_int_peak fails: this pool's B200 by tools/int_peak (profiles/r01_int_peak.jsonl)
+MULS_PER_ADD = 10       # XYZZ mixed addition: 8M + 2S (field.cuh has no cheaper squaring)
+# DRAM bytes of a k_msm_accumulate launch per executed bucket addition, from ONE `ncu --set full` capture (dram__bytes_read.sum +
+# dram__bytes_write.sum of the launch / its bucket additions); the file names the capture it came from.  Absent -> traffic: null.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "msm_accumulate_traffic.json")
 
 
 def _peaks():
@@ -212,7 +215,7 @@ def cpu_prover_setup(asg, g, g_lagrange):
     return pp, oparams, opk
 
 
-CPU_SAMPLE = ("one whole delay_enc k=16 create_proof per step, the same circuit, keys and random draws as the GPU arm: the restated "
+DEFAULT_CPU_SAMPLE = CPU_SAMPLE = ("one whole delay_enc k=16 create_proof per step, the same circuit, keys and random draws as the GPU arm: the restated "
               "reference algorithms (oracle/: best_multiexp, best_fft, evaluate_h, lookup permutation, grand products, eval_polynomial, "
               "kate_division in C with pthreads on all host cores; Python only sequences the calls and hashes the transcript), not the "
               "Rust binary; proof bytes equal the GPU's")
@@ -250,53 +253,27 @@ def run_reference(args, rank, world):
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ntt-multi-gpu", action="store_true", help="skip the one-vector-over-all-ranks NTT line of a multi-GPU run")
-    ap.add_argument("--inflight", type=int, default=8, help="independent proofs in flight per GPU (one prover + stream each)")
-    ap.add_argument("--config", default="delay_enc", choices=sorted(CONFIGS), help="circuit shape / size (default: the headline delay_enc)")
-    ap.add_argument("--mode", default="auto", choices=["auto", "latency", "throughput"],
-                    help="de_ctx_set_mode of the in-flight arms (auto: throughput when more than one proof is in flight)")
-    ap.add_argument("--k", type=int, default=0, help="override the config's k (the reference's README also times k = 15 ... 19)")
-    args = ap.parse_args()
-    global K, USED_ROWS, SEED, WITH_LOOKUPS, CONFIG_NAME, WORKLOAD, METRIC, CPU_SAMPLE
-    if args.config != "delay_enc" or args.k:
-        K, WITH_LOOKUPS, USED_ROWS, SEED, where = CONFIGS[args.config]
-        K = args.k or K
-        CONFIG_NAME = args.config
-        METRIC = f"{args.config}_create_proof_proofs_per_s" if not args.k else f"{args.config}_k{K}_create_proof_proofs_per_s"
-        WORKLOAD = (f"{args.config} k={K} create_proof (/root/reference/{where}; MainGate{' + RangeChip' if WITH_LOOKUPS else ''} shape, satisfied "
-                    f"synthetic witness, {USED_ROWS} used rows)")
-        CPU_SAMPLE = CPU_SAMPLE.replace("delay_enc k=16", f"{args.config} k={K}")
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if args.warmup < 3:
-        args.warmup = 3  # timing hygiene: at least three untimed steps
+def measure_int_peak(ctx):
+    """Fr Montgomery multiplications / s of this GPU, measured now (de_int_peak): the denominator of every int-pipe fraction"""
+    try:
+        return ctx.int_peak(), "measured_in_run (de_int_peak: dependent Fr Montgomery product chains, 16 warps/SM x 2 chains, best of 4)"
+    except Exception as e:  # noqa: BLE001 - the line must still be printed
+        return MUL_PEAK_FALLBACK_GMULS, f"fallback (de_int_peak failed: {e}); tools/int_peak on this pool's B200, profiles/r01_int_peak.jsonl"
 
+
+def proof_bench(args, local_rank, world, steps, warmup, B, detail):
+    """The proof arms for the CURRENT configuration globals (K, WITH_LOOKUPS, ...): throughput (value), end-to-end (host buffers),
+    latency (one proof in flight; with `detail` also the per-kernel CUDA-event timings).  Returns (line dict, artefacts dict)."""
+    import hashlib
     import numpy as np
     import torch
-    import torch.distributed as dist
     import de_b200
     from de_b200 import keygen, sharding
+    import torch.distributed as dist
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU path (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     asg, g, g_lagrange = build_circuit()
     shape = asg.shape
     n = 1 << K
-    B = max(1, args.inflight)
     main_stream = torch.cuda.current_stream()
     as_i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
 
@@ -314,9 +291,9 @@ def main():
                     self.keys = first.keys.clone_on(self.ctx)
             self.proof = None
 
-        def run(self, steps, host):
+        def run(self, nsteps, host):
             with torch.cuda.stream(self.stream):
-                for _ in range(steps):
+                for _ in range(nsteps):
                     if host:
                         self.proof = self.keys.prover.create_proof([advice_h[i] for i in range(shape.n_advice)], [], randoms_h)
                     else:
@@ -337,15 +314,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(active, steps, host):
-        """K steps on every active worker concurrently; device time between two events on the main stream that fence all
+    def timed(active, nsteps, host):
+        """nsteps on every active worker concurrently; device time between two events on the main stream that fence all
         worker streams; max over ranks"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(main_stream)
         for wk in active:
             wk.stream.wait_event(e0)
-        threads = [threading.Thread(target=wk.run, args=(steps, host)) for wk in active]
+        threads = [threading.Thread(target=wk.run, args=(nsteps, host)) for wk in active]
         for t in threads:
             t.start()
         for t in threads:
@@ -356,79 +333,105 @@ def main():
         barrier()
         return sharding.max_over_ranks(e0.elapsed_time(e1))
 
+    throughput_mode = (B > 1) if args.mode == "auto" else args.mode == "throughput"
     for wk in workers:
-        wk.ctx.set_mode(throughput=(B > 1) if args.mode == "auto" else args.mode == "throughput")  # several provers share the GPU
-    timed(workers, args.warmup, False)
+        wk.ctx.set_mode(throughput=throughput_mode)  # several provers share the GPU
+    timed(workers, warmup, False)
     first_proof = workers[0].proof
     assert len(first_proof) == prover0.proof_size == (2848 if WITH_LOOKUPS else 1792)
     # ---- throughput arm (value): B proofs in flight per GPU, inputs resident in HBM
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = sum(wk.ctx.launches for wk in workers)
-    ms_dev = timed(workers, args.steps, False)
+    ms_dev = timed(workers, steps, False)
     launches = sum(wk.ctx.launches for wk in workers) - launches0
     clocks = sampler.stop()
     for wk in workers:
         assert wk.proof == first_proof, "proof bytes differ between workers / steps"
     # ---- end-to-end arm: pinned host advice + random draws in, proof bytes out, every proof
     timed(workers, 2, True)
-    ms_e2e = timed(workers, args.steps, True)
+    ms_e2e = timed(workers, steps, True)
     for wk in workers:
         assert wk.proof == first_proof, "host-buffer path disagrees with the device-resident path"
     # ---- latency arm: ONE proof in flight; per-kernel CUDA-event timing is taken here (no overlapping streams)
     ctx.set_mode(throughput=False)
     timed(workers[:1], 2, False)
-    ctx.timing_reset()
-    ctx.timing_enable(True)
-    lat_steps = max(5, min(args.steps, 20))
+    if detail:
+        ctx.timing_reset()
+        ctx.timing_enable(True)
+    lat_steps = max(5, min(steps, 20))
     ms_lat = timed(workers[:1], lat_steps, False)
+    assert workers[0].proof == first_proof, "latency-mode proof differs"
+
+    h2d = advice_h.numel() * 8 + prover0.random_count * 32
+    n_evals = 58 if WITH_LOOKUPS else 39
+    n_points = (len(first_proof) - 32 * n_evals) // 32
+    d2h = n_points * 64 + n_evals * 32
+    value = world * steps * B / (ms_dev / 1000.0)
+    e2e_value = world * steps * B / (ms_e2e / 1000.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE carry chains)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proofs_per_step_per_gpu": B, "proof_bytes": len(first_proof),
+                   "proof_sha256": hashlib.sha256(first_proof).hexdigest(),
+                   "mode": "DE_MODE_THROUGHPUT" if throughput_mode else "DE_MODE_LATENCY",
+                   "in_flight": f"{B} independent proofs per GPU, one host thread + CUDA stream each (BASELINE config 5: 64 proofs over "
+                                "8 GPUs = 8 per GPU)",
+                   "l2": f"per-step working set ~{0.8 * B * 2.0 ** (K - 16):.2f} GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
+                   "sharding": "independent proofs across GPUs, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
+                "ms_per_step": ms_e2e / steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "latency": {"create_proof_s": ms_lat / lat_steps / 1000.0, "proofs_in_flight": 1, "steps": lat_steps, "mode": "DE_MODE_LATENCY"},
+    }
+    art = dict(asg=asg, g=g, g_lagrange=g_lagrange, advice_mont=advice_mont, randoms=randoms, first_proof=first_proof, workers=workers,
+               ctx=ctx, advice_d=advice_d, ms_lat=ms_lat, lat_steps=lat_steps, shape=shape)
+    return line, art
+
+
+def add_rooflines(line, art, rank):
+    """roofline (dominant kernel k_msm_accumulate, integer-pipe bound: executed field multiplications against the multiply peak
+    measured in this run), kernel shares, and the NTT GB/s block"""
+    import torch
+    ctx, ms_ref, lat_steps, shape = art["ctx"], art["ms_lat"], art["lat_steps"], art["shape"]
     acc_ms, acc_pts, acc_n = ctx.timing_get("k_msm_accumulate")
     ntt_ms, ntt_el, ntt_n = ctx.timing_get("k_ntt_pass")
     ev_ms, ev_rows, ev_n = ctx.timing_get("k_eval_h")
     red_ms, _, red_n = ctx.timing_get("k_msm_digit_sums")
     _, bucket_adds, _ = ctx.timing_get("msm_bucket_adds")
     ctx.timing_enable(False)
-
-    h2d = advice_h.numel() * 8 + prover0.random_count * 32
-    n_evals = 58 if WITH_LOOKUPS else 39
-    n_points = (len(first_proof) - 32 * n_evals) // 32
-    d2h = n_points * 64 + n_evals * 32
     peaks, peak_kind = _peaks()
-    value = world * args.steps * B / (ms_dev / 1000.0)
-    e2e_value = world * args.steps * B / (ms_e2e / 1000.0)
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE carry chains)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proofs_per_step_per_gpu": B, "proof_bytes": len(first_proof),
-                   "mode": "DE_MODE_THROUGHPUT" if ((B > 1) if args.mode == "auto" else args.mode == "throughput") else "DE_MODE_LATENCY",
-                   "in_flight": f"{B} independent proofs per GPU, one host thread + CUDA stream each (BASELINE config 5: 64 proofs over "
-                                "8 GPUs = 8 per GPU)",
-                   "l2": f"per-step working set ~{0.8 * B * 2.0 ** (K - 16):.2f} GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
-                   "sharding": "independent proofs across GPUs, no data-path collective"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "latency": {"create_proof_s": ms_lat / lat_steps / 1000.0, "proofs_in_flight": 1, "steps": lat_steps, "mode": "DE_MODE_LATENCY"},
-    }
-    ms_ref = ms_lat  # kernel shares are relative to the single-proof latency pass they were measured in
+    mul_peak, mul_peak_src = measure_int_peak(ctx)
+    line["int_peak_gmul_s"] = mul_peak
     if acc_n:
         pts_per_launch = acc_pts / acc_n
+        adds_per_launch = bucket_adds / acc_n
         avg_ms = acc_ms / acc_n
-        achieved = 96.0 * pts_per_launch / (avg_ms * 1e-3) / 1e9
-        line["roofline"] = {"kernel": "k_msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": TRAFFIC_BYTES_PER_POINT * pts_per_launch, "peak_source": peak_kind,
-                            "measured_in": "latency arm (one proof in flight, CUDA events around every launch on its stream)",
-                            "share_of_step": acc_ms / ms_ref, "launches": acc_n, "avg_launch_ms": avg_ms,
-                            "int_pipe": {"achieved_gmuls": MULS_PER_ADD * bucket_adds / (acc_ms * 1e-3) / 1e9,
-                                         "peak_gmuls": MUL_PEAK_GMULS,
-                                         "frac": MULS_PER_ADD * bucket_adds / (acc_ms * 1e-3) / 1e9 / MUL_PEAK_GMULS,
-                                         "bucket_adds_per_step": bucket_adds / lat_steps,
-                                         "note": "field muls actually executed by the bucket fill (10 per mixed add, zero digits of "
-                                                 "witness-like columns skipped) / time in k_msm_accumulate; peak = measured Fr "
-                                                 "Montgomery mul/s of this chip (tools/int_peak, 99% of the IMAD.WIDE issue limit)"}}
-        line["msm_gpts_s"] = acc_pts / (acc_ms * 1e-3) / 1e9
+        gmuls = MULS_PER_ADD * bucket_adds / (acc_ms * 1e-3) / 1e9
+        hbm_gbs = 96.0 * pts_per_launch / (avg_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, "no ncu capture on file"
+        try:
+            with open(TRAFFIC_FILE) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_bucket_add"] * adds_per_launch
+            traffic_src = tj["source"]
+        except Exception:
+            pass
+        line["roofline"] = {
+            "kernel": "k_msm_accumulate", "bound": "int_pipe", "achieved": gmuls, "peak": mul_peak, "unit": "Gmul/s (Fr/Fq Montgomery multiplications)",
+            "frac": gmuls / mul_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": mul_peak_src,
+            "work": {"bucket_adds_per_launch": adds_per_launch, "muls_per_bucket_add": MULS_PER_ADD, "points_per_launch": pts_per_launch,
+                     "bucket_adds_per_proof": bucket_adds / lat_steps,
+                     "note": "achieved = 10 x bucket additions actually executed (counted on the device: non-zero signed 16-bit digits) / "
+                             "kernel time; SURVEY.md 8d's fixed 160 mul/point convention would also count the zero digits of the "
+                             "witness columns, which are legitimately skipped"},
+            "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"], "peak_source": peak_kind,
+                    "note": "algorithmic 96 B/point (32 B scalar + 64 B base) / kernel time: the kernel is nowhere near the memory roof"},
+            "measured_in": "latency arm (one proof in flight, CUDA events around every launch on its stream)",
+            "share_of_step": acc_ms / ms_ref, "launches": acc_n, "avg_launch_ms": avg_ms}
+        line["msm_fill_gpts_s"] = acc_pts / (acc_ms * 1e-3) / 1e9
     if ntt_n:
         line["kernel_share"] = {"k_msm_accumulate": acc_ms / ms_ref, "k_msm_digit_sums": red_ms / ms_ref,
                                 "k_ntt_pass": ntt_ms / ms_ref, "k_eval_h": ev_ms / ms_ref,
@@ -437,20 +440,22 @@ def main():
     # NTT GB/s on its own (inside the prover the transforms overlap the commitments): the proof's batch of coset transforms,
     # coeff_to_extended of all per-proof columns, 64 B of algorithmic traffic per output element
     if rank == 0:
-        kz = workers[0].keys
+        wk0 = art["workers"][0]
+        kz = wk0.keys
+        n = 1 << K
         n_cols = shape.n_advice + shape.n_instance + shape.n_perm_sets + 3 * len(shape.lookups)
         ext_n = kz.domain.extended_n
-        with torch.cuda.stream(workers[0].stream):
+        with torch.cuda.stream(wk0.stream):
             src = torch.zeros((n_cols, n, 4), dtype=torch.int64, device="cuda")
-            src[:shape.n_advice] = advice_d
+            src[:shape.n_advice] = art["advice_d"]
             dst = torch.empty((n_cols, ext_n, 4), dtype=torch.int64, device="cuda")
             for _ in range(3):
                 kz.domain.coeff_to_extended_dev(src, dst, batch=n_cols)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(workers[0].stream)
+            e0.record(wk0.stream)
             for _ in range(10):
                 kz.domain.coeff_to_extended_dev(src, dst, batch=n_cols)
-            e1.record(workers[0].stream)
+            e1.record(wk0.stream)
             e1.synchronize()
             ms_ntt = e0.elapsed_time(e1) / 10
         gbs = 64.0 * ext_n * n_cols / (ms_ntt * 1e-3) / 1e9
@@ -458,12 +463,83 @@ def main():
         line["ntt_gb_s"] = gbs
         line["ntt"] = {"what": f"coeff_to_extended of {n_cols} columns 2^{K} -> 2^{ek} alone on the GPU", "ms": ms_ntt, "gb_s": gbs,
                        "frac_hbm": gbs / peaks["hbm_gbs"], "gmul_s": n_cols * ext_n / 2 * ek / (ms_ntt * 1e-3) / 1e9,
-                       "frac_int_pipe": n_cols * ext_n / 2 * ek / (ms_ntt * 1e-3) / 1e9 / MUL_PEAK_GMULS}
+                       "frac_int_pipe": n_cols * ext_n / 2 * ek / (ms_ntt * 1e-3) / 1e9 / mul_peak,
+                       "int_pipe_peak_gmul_s": mul_peak}
         del src, dst
+    return mul_peak
+
+
+def close_workers(art):
+    for wk in art["workers"]:
+        wk.keys.close()
+        wk.ctx.close()
+    art["workers"] = []
+
+
+def set_config(name, k=0):
+    global K, USED_ROWS, SEED, WITH_LOOKUPS, CONFIG_NAME, WORKLOAD, METRIC, CPU_SAMPLE
+    K, WITH_LOOKUPS, USED_ROWS, SEED, where = CONFIGS[name]
+    K = k or K
+    CONFIG_NAME = name
+    if name == "delay_enc" and not k:
+        WORKLOAD, METRIC, CPU_SAMPLE = DEFAULT_WORKLOAD, DEFAULT_METRIC, DEFAULT_CPU_SAMPLE
+        return
+    METRIC = f"{name}_create_proof_proofs_per_s" if not k else f"{name}_k{K}_create_proof_proofs_per_s"
+    WORKLOAD = (f"{name} k={K} create_proof (/root/reference/{where}; MainGate{' + RangeChip' if WITH_LOOKUPS else ''} shape, satisfied "
+                f"synthetic witness, {USED_ROWS} used rows)")
+    CPU_SAMPLE = DEFAULT_CPU_SAMPLE.replace("delay_enc k=16", f"{name} k={K}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ntt-multi-gpu", action="store_true", help="skip the one-vector-over-all-ranks NTT line of a multi-GPU run")
+    ap.add_argument("--no-msm", action="store_true", help="skip the whole-commitment MSM block (1 GPU) / msm_multi_gpu (N GPUs)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short pose_enc / mod_pow runs of the 1-GPU line")
+    ap.add_argument("--inflight", type=int, default=8, help="independent proofs in flight per GPU (one prover + stream each)")
+    ap.add_argument("--config", default="delay_enc", choices=sorted(CONFIGS), help="circuit shape / size (default: the headline delay_enc)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "latency", "throughput"],
+                    help="de_ctx_set_mode of the in-flight arms (auto: throughput when more than one proof is in flight)")
+    ap.add_argument("--k", type=int, default=0, help="override the config's k (the reference's README also times k = 15 ... 19)")
+    args = ap.parse_args()
+    headline = args.config == "delay_enc" and not args.k
+    set_config(args.config, args.k)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3  # timing hygiene: at least three untimed steps
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import de_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = max(1, args.inflight)
+    line, art = proof_bench(args, local_rank, world, args.steps, args.warmup, B, detail=True)
+    mul_peak = add_rooflines(line, art, rank)
+    asg, g, g_lagrange, advice_mont, randoms = art["asg"], art["g"], art["g_lagrange"], art["advice_mont"], art["randoms"]
+    first_proof, shape = art["first_proof"], art["shape"]
+    close_workers(art)
+    del art
+    torch.cuda.empty_cache()
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+
     if world > 1 and not args.no_ntt_multi_gpu:
         # BASELINE's "NTT GB/s at 1/2/4/8 B200": ONE 2^24 vector over all ranks (four-step transform, both exchanges as peer-memory
         # stores from inside the kernels), checked on rank 0 against the single-GPU transform of the same vector
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
         import ntt_dist_sweep
         nctx = de_b200.Context(local_rank)
         try:
@@ -473,9 +549,34 @@ def main():
         nctx.close()
         if rank == 0:
             line["ntt_multi_gpu"] = res
+    msm_single = None
+    if not args.no_msm and headline:
+        import msm_bench
+        mstream = torch.cuda.Stream()
+        mctx = de_b200.Context(local_rank)
+        mctx.set_stream(mstream.cuda_stream)
+        if world > 1:
+            # north_star's first split: "MSM base ranges are sharded per commitment ... combined over NVLink" 
+            res = []
+            for log_n in [24] + ([26] if world >= 4 else []):
+                try:
+                    r = msm_bench.measure_sharded(mctx, mstream, rank, world, log_n, reps=5)
+                except (RuntimeError, ValueError) as e:
+                    r = {"op": "msm_multi_gpu", "log_n": log_n, "error": str(e)}
+                res.append(r)
+            if rank == 0:
+                line["msm_multi_gpu"] = res
+        else:
+            try:
+                msm_single = msm_bench.measure_single(mctx, mstream, (16, 20, 24), keep_host=() if args.no_cpu_baseline else (16, 20))
+            except (RuntimeError, ValueError) as e:
+                msm_single = [{"error": str(e)}]
+        mctx.close()
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import orc
+        n = 1 << K
         inp = build_cpu_inputs(asg, list(advice_mont), g, g_lagrange)
         # the prover's blinding rows, so that the CPU's advice commitments can be compared with the proof's
         usable = n - (shape.blinding_factors + 1)
@@ -502,11 +603,48 @@ def main():
         line["cpu_baseline"] = {"value": 1.0 / dt_full, "unit": UNIT, "cores": orc.ncpu(), "kind": "port", "sample": CPU_SAMPLE,
                                 "create_proof_s": dt_full, "proof_bytes_match_gpu": bool(cpu_proof == first_proof),
                                 "hot_path_only": {"s": dt, "sample": CPU_HOT_SAMPLE, "advice_commitments_match_gpu_proof": bool(same)}}
+        if msm_single:
+            # the reference's best_multiexp (restated, all host cores) on the very inputs the GPU committed, results compared
+            for rec in msm_single:
+                host = rec.pop("_host", None)
+                if host is None:
+                    continue
+                scal, bases, got = host
+                t0 = time.perf_counter()
+                want = orc.best_multiexp(scal, bases)
+                rec["cpu_best_multiexp_s"] = time.perf_counter() - t0
+                rec["cpu_gpts_s"] = scal.shape[0] / rec["cpu_best_multiexp_s"] / 1e9
+                rec["cpu_cores"] = orc.ncpu()
+                rec["equals_cpu_best_multiexp"] = bool((orc.g1_to_affine(got.reshape(1, 12)) == orc.g1_to_affine(want.reshape(1, 12))).all())
+    if msm_single is not None and rank == 0:
+        for rec in msm_single:
+            rec.pop("_host", None)
+        line["msm"] = {"what": "WHOLE ParamsKZG::commit_lagrange calls (digits, sort, bucket fill, reduction, readback), bases + window tables "
+                               "resident, scalars resident, one GPU, CUDA events, best of 3; Gpts/s = polynomials x 2^log_n / time",
+                       "runs": msm_single}
+        u = {(r.get("log_n"), r.get("polys_per_call")): r.get("gpts_s") for r in msm_single if r.get("scalars") == "U"}
+        line["msm_gpts_s"] = u.get((24, 1))
+    if rank == 0 and world == 1 and headline and not args.no_other_configs:
+        # BASELINE configs[0] / [1] under the driver's eyes: short runs of the other two bench circuits (their byte parity with the
+        # CPU restatement is in tests/test_gpu_prover.py)
+        others = {}
+        for name in ("pose_enc", "mod_pow"):
+            try:
+                set_config(name)
+                l2, a2 = proof_bench(args, local_rank, world, 5, 3, B, detail=False)
+                others[name] = {"metric": l2["metric"], "value": l2["value"], "unit": UNIT, "k": K, "proofs_per_step_per_gpu": B, "steps": 5,
+                                "ms_per_step": l2["ms_per_step"], "e2e": l2["e2e"]["value"], "latency_create_proof_s": l2["latency"]["create_proof_s"],
+                                "proof_bytes": l2["config"]["proof_bytes"], "proof_sha256": l2["config"]["proof_sha256"],
+                                "workload": l2["config"]["workload"]}
+                close_workers(a2)
+                del a2
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001 - the headline line must still be printed
+                others[name] = {"error": f"{type(e).__name__}: {e}"}
+        set_config(args.config, args.k)
+        line["other_configs"] = others
     if rank == 0:
         print(json.dumps(line))
-    for wk in workers:
-        wk.keys.close()
-        wk.ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

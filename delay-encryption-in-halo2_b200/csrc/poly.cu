@@ -188,11 +188,68 @@ int kate_division_dev(de_ctx* ctx, const Fr* const* d_as, size_t n, const de_fr*
     return DE_OK;
 }
 
+// ---- roofline denominator measured in the run (bench.py `roofline.peak`): dependent chains of Fr Montgomery products, the
+// instruction mix every hot kernel of this library is made of (136 IMAD.WIDE.U32(.X) per product).  ILP independent chains
+// per thread; the result is stored so that nothing is eliminated.
+template <int ILP>
+__global__ void __launch_bounds__(128) k_int_peak(Fr* out, const Fr* in, int iters) {
+    Fr x[ILP];
+    const Fr y = load(&in[threadIdx.x & 31]);
+#pragma unroll
+    for (int i = 0; i < ILP; i++) x[i] = load(&in[(threadIdx.x + i) & 63]);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) x[i] = mul(x[i], y);
+    }
+    Fr s = x[0];
+#pragma unroll
+    for (int i = 1; i < ILP; i++) s = add(s, x[i]);
+    store(&out[(size_t)blockIdx.x * blockDim.x + threadIdx.x], s);
+}
+
 }  // namespace de
 
 using namespace de;
 
 extern "C" {
+
+int de_int_peak(de_ctx* ctx, double* gmul_per_s) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!gmul_per_s) return fail(ctx, DE_ERR_ARG, "de_int_peak: null pointer");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int tpb = 128, warps_per_sm = 16, iters = 512, ILP = 2;
+    const int blocks = ctx->sm_count * warps_per_sm * 32 / tpb;
+    const size_t nthreads = (size_t)blocks * tpb;
+    DE_WS(ctx, buf, Fr, WS_IO_A, sizeof(Fr) * (nthreads + 64));
+    Fr* in = buf + nthreads;
+    Fr h[64];
+    for (int i = 0; i < 64; i++)
+        for (int k = 0; k < 8; k++) h[i].l[k] = (k == 7) ? (0x0fffffffu - i) : (0x9e3779b9u * (i * 8 + k + 1));
+    DE_CUDA(ctx, cudaMemcpyAsync(in, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t e0, e1;
+    DE_CUDA(ctx, cudaEventCreate(&e0));
+    DE_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {  // the first two launches warm the clocks up
+        cudaEventRecord(e0, ctx->stream);
+        k_int_peak<ILP><<<blocks, tpb, 0, ctx->stream>>>(buf, in, iters);
+        ctx->launches++;
+        cudaEventRecord(e1, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return fail(ctx, DE_ERR_CUDA, std::string("de_int_peak: ") + cudaGetErrorString(e));
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gmul_per_s = (double)nthreads * iters * ILP / (best * 1e-3) / 1e9;
+    return DE_OK;
+}
 
 int de_eval_polynomial(de_ctx* ctx, const de_fr* poly, size_t n, const de_fr* point, de_fr* out) {
     if (!ctx) return DE_ERR_ARG;

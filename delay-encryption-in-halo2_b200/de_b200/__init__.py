@@ -82,6 +82,12 @@ class Context:
         self.check(self.L.de_timing_get(self.h, kernel.encode(), C.byref(ms), C.byref(units), C.byref(n)))
         return ms.value, units.value, int(n.value)
 
+    def int_peak(self) -> float:
+        """de_int_peak: Fr Montgomery multiplications per second (in G/s) this device sustains, measured now"""
+        v = C.c_double()
+        self.check(self.L.de_int_peak(self.h, C.byref(v)))
+        return v.value
+
     def close(self):
         if getattr(self, "h", None):
             self.L.de_ctx_destroy(self.h)

@@ -23,7 +23,7 @@ SYMBOLS = [
     "de_commit_batch_canonical_dev", "de_eval_polynomial", "de_kate_division", "de_prover_create", "de_prover_free",
     "de_prover_random_count", "de_prover_proof_size", "de_create_proof", "de_create_proof_dev", "de_g1_mul_base_dev", "de_ctx_set_mode", "de_commit_sharded",
     "de_ntt_dist_stage1", "de_ntt_dist_stage2", "de_ntt_sharded_dev", "de_ntt_sharded", "de_dev_alloc", "de_dev_free", "de_dev_copy", "de_ipc_export", "de_ipc_import",
-    "de_ipc_release",
+    "de_ipc_release", "de_int_peak",
 ]
 
 
@@ -114,6 +114,7 @@ def load():
     L.de_ipc_export.argtypes = [P, P, P]
     L.de_ipc_import.argtypes = [P, P, C.POINTER(P)]
     L.de_ipc_release.argtypes = [P, P]
+    L.de_int_peak.argtypes = [P, C.POINTER(C.c_double)]
     for s in SYMBOLS:
         fn = getattr(L, s)
         if s not in ("de_last_error", "de_version", "de_launch_count", "de_prover_random_count", "de_prover_proof_size"):

@@ -62,6 +62,11 @@ const char* de_last_error(de_ctx* ctx); /* ctx may be NULL: returns the last err
 const char* de_version(void);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
 uint64_t de_launch_count(de_ctx* ctx);
+/* Roofline denominator, measured on the device the context is bound to ("the build must measure it on
+ * the box"): Fr Montgomery multiplications per second of dependent-product chains at full occupancy (16 warps per SM, two
+ * independent chains per thread) - the 136 IMAD.WIDE.U32 carry-chain multiplier every hot kernel here is made of.  Best of four
+ * timed launches after two warm-up launches, ~10 ms in total; synchronises the context's stream. */
+int de_int_peak(de_ctx* ctx, double* gmul_per_s);
 
 /* per-kernel device timing: CUDA events recorded around the named kernels on the context's stream.
  * Known names: "k_msm_accumulate", "k_msm_digit_sums", "k_ntt_pass", "k_eval_h".  units = points / elements / rows. */
