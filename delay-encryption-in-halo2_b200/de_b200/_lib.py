@@ -24,6 +24,9 @@ SYMBOLS = [
     "de_prover_random_count", "de_prover_proof_size", "de_create_proof", "de_create_proof_dev", "de_g1_mul_base_dev", "de_ctx_set_mode", "de_commit_sharded",
     "de_ntt_dist_stage1", "de_ntt_dist_stage2", "de_ntt_sharded_dev", "de_ntt_sharded", "de_dev_alloc", "de_dev_free", "de_dev_copy", "de_ipc_export", "de_ipc_import",
     "de_ipc_release", "de_int_peak",
+    "de_circuit_synthesize", "de_circuit_witness", "de_assignment_free", "de_assignment_info", "de_assignment_fixed", "de_assignment_advice",
+    "de_assignment_copies", "de_assignment_outputs", "de_assignment_sigma", "de_frontend_last_error", "de_poseidon_permute",
+    "de_poseidon_cipher",
 ]
 
 
@@ -115,9 +118,23 @@ def load():
     L.de_ipc_import.argtypes = [P, P, C.POINTER(P)]
     L.de_ipc_release.argtypes = [P, P]
     L.de_int_peak.argtypes = [P, C.POINTER(C.c_double)]
+    L.de_circuit_synthesize.argtypes = [P, C.POINTER(P)]
+    L.de_circuit_witness.argtypes = [P, P, P]
+    L.de_assignment_free.argtypes = [P]
+    L.de_assignment_free.restype = None
+    L.de_assignment_info.argtypes = [P, P]
+    L.de_assignment_fixed.argtypes = [P, U32, P]
+    L.de_assignment_advice.argtypes = [P, U32, P]
+    L.de_assignment_copies.argtypes = [P, P]
+    L.de_assignment_outputs.argtypes = [P, P]
+    L.de_assignment_sigma.argtypes = [P, P, P, U32, P]
+    L.de_frontend_last_error.restype = C.c_char_p
+    L.de_poseidon_permute.argtypes = [U32, U32, U32, P]
+    L.de_poseidon_cipher.argtypes = [I, P, P, U32, P]
     for s in SYMBOLS:
         fn = getattr(L, s)
-        if s not in ("de_last_error", "de_version", "de_launch_count", "de_prover_random_count", "de_prover_proof_size"):
+        if s not in ("de_last_error", "de_version", "de_launch_count", "de_prover_random_count", "de_prover_proof_size",
+                     "de_assignment_free", "de_frontend_last_error"):
             fn.restype = C.c_int
     _lib = L
     return L

@@ -94,9 +94,7 @@ class Keys:
 def keygen(ctx, shape: ConstraintSystemShape, k: int, g, g_lagrange, fixed_values: Sequence[Sequence[int]],
            copies: Sequence[Tuple[int, int, int, int]], transcript_repr: int, queries=None) -> Keys:
     """keygen_vk + keygen_pk + the prover object.  fixed_values: canonical integers per fixed column (n each)."""
-    import torch
     n = 1 << k
-    params = ParamsKZG(k, g, g_lagrange, ctx)
     domain = EvaluationDomain(shape.degree(), k, ctx)
     omega = int.from_bytes(ctx.fr_from_mont(domain.omega.reshape(1, 4)).tobytes(), "little")
     asm = PermutationAssembly(len(shape.perm_columns), n)
@@ -105,17 +103,36 @@ def keygen(ctx, shape: ConstraintSystemShape, k: int, g, g_lagrange, fixed_value
     sigma_values = asm.sigma_values(omega)
     cols = [ctx.fr_to_mont(canonical_limbs(c)) for c in list(fixed_values) + sigma_values]
     block = np.stack(cols) if cols else np.zeros((0, n, 4), dtype=np.uint64)
-    d = torch.from_numpy(block.view(np.int64)).cuda(ctx.device)
-    commitments = params.commit_batch_canonical_dev(1, d, n, len(cols)) if cols else np.zeros((0, 64), dtype=np.uint8)
-    if cols:
-        domain.lagrange_to_coeff_dev(d, batch=len(cols))
+    return _keygen_from_columns(ctx, shape, k, g, g_lagrange, domain, block, transcript_repr, queries)
+
+
+def keygen_from_synthesized(ctx, syn, g, g_lagrange, transcript_repr: int, queries=None) -> Keys:
+    """keygen_vk + keygen_pk for a circuit the front-end synthesised (de_b200.frontend: fixed columns and copy constraints of
+    one Circuit::synthesize pass, /root/reference/benches/delay_enc.rs:86,103).  The sigma columns come from the library's
+    permutation assembly (de_assignment_sigma); everything is already in Montgomery form."""
+    domain = EvaluationDomain(syn.shape.degree(), syn.k, ctx)
+    block = np.concatenate([syn.fixed, syn.sigma(domain.omega)], axis=0)
+    return _keygen_from_columns(ctx, syn.shape, syn.k, g, g_lagrange, domain, block, transcript_repr, queries)
+
+
+def _keygen_from_columns(ctx, shape, k, g, g_lagrange, domain, block, transcript_repr, queries) -> Keys:
+    """block: (n_fixed + n_perm_columns, n, 4) Montgomery lagrange values, fixed columns first"""
+    import torch
+    n = 1 << k
+    params = ParamsKZG(k, g, g_lagrange, ctx)
+    ncols = block.shape[0]
+    d = torch.from_numpy(np.ascontiguousarray(block).view(np.int64)).cuda(ctx.device)
+    commitments = params.commit_batch_canonical_dev(1, d, n, ncols) if ncols else np.zeros((0, 64), dtype=np.uint8)
+    if ncols:
+        domain.lagrange_to_coeff_dev(d, batch=ncols)
     ctx.sync()
     polys = d.cpu().numpy().view(np.uint64)
     nf = shape.n_fixed
-    pk = ProvingKey(domain, shape, [polys[i] for i in range(nf)], [polys[nf + i] for i in range(len(sigma_values))])
+    nsig = ncols - nf
+    pk = ProvingKey(domain, shape, [polys[i] for i in range(nf)], [polys[nf + i] for i in range(nsig)])
     aq, fq, _ = queries if queries is not None else collect_queries(shape)
     prover = Prover(params, pk, aq, fq, transcript_repr)
     host = dict(k=k, g=g, g_lagrange=g_lagrange, shape=shape, fixed_polys=[polys[i] for i in range(nf)],
-                sigma_polys=[polys[nf + i] for i in range(len(sigma_values))], advice_queries=aq, fixed_queries=fq,
+                sigma_polys=[polys[nf + i] for i in range(nsig)], advice_queries=aq, fixed_queries=fq,
                 transcript_repr=transcript_repr)
     return Keys(params, domain, pk, prover, commitments[:nf], commitments[nf:], host)

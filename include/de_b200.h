@@ -277,6 +277,58 @@ int de_g1_mul_base_dev(de_ctx* ctx, const de_g1_affine* base, const de_fr* d_sca
  * depends on the (atomic) accumulation order; the affine point does not. */
 int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_affine* out);
 
+/* ---- section 8f row 3: circuit front-end (witness generation) ---------------------------------------------------- */
+/* The reference's chips (/root/reference/src/big_integer, src/rsa, src/poseidon/chip.rs, src/hash, src/encryption) and its
+ * three bench circuits as HOST witness generators for the MainGate + RangeChip constraint-system shape this library proves
+ * (de_b200/plonk.py: main_gate_shape): Circuit::synthesize of
+ *   DE_CIRCUIT_MOD_POW    benches/mod_pow.rs:36-140        RSACircuit (x^e mod n, variable exp_bits-bit e)
+ *   DE_CIRCUIT_POSE_ENC   src/encryption/chip.rs:114-198   PoseidonEncCircuit (key[2], message)
+ *   DE_CIRCUIT_DELAY_ENC  src/lib.rs:103-318               DelayEncryptCircuit (n, e, x, message)
+ *   DE_CIRCUIT_RSA_PKCS1  src/rsa/chip.rs:119-212          verify_pkcs1v15_signature (n, e fixed, x = signature, message =
+ *                                                          SHA-256 digest as four 64-bit limbs); output = the accept bit
+ * One pass yields the fixed columns, the advice columns and the copy constraints; keygen uses fixed + copies, create_proof
+ * the advice columns.  No context and no GPU: these run wherever the library loads.  Errors: de_frontend_last_error(). */
+enum de_circuit_kind { DE_CIRCUIT_MOD_POW = 0, DE_CIRCUIT_POSE_ENC = 1, DE_CIRCUIT_DELAY_ENC = 2, DE_CIRCUIT_RSA_PKCS1 = 3 };
+typedef struct {
+    uint32_t kind;       /* de_circuit_kind */
+    uint32_t k;          /* 2^k rows */
+    uint32_t bits_len;   /* BITS_LEN (2048) */
+    uint32_t exp_bits;   /* EXP_LIMB_BITS (5) */
+    const uint8_t* n; size_t n_len;   /* little-endian bytes */
+    const uint8_t* e; size_t e_len;
+    const uint8_t* x; size_t x_len;
+    const de_fr* message; uint32_t message_len;   /* Montgomery field elements */
+    de_fr key[2];                                  /* DE_CIRCUIT_POSE_ENC only */
+    uint32_t witness_only;  /* 1: the pass create_proof makes - advice columns only, no fixed columns / copy constraints */
+} de_circuit_desc;
+typedef struct {
+    uint32_t k, n_fixed, n_advice, n_outputs;
+    uint64_t used_rows, n_copies;
+    double synthesis_ms;
+} de_assignment_info_t;
+typedef struct de_assignment de_assignment;
+int de_circuit_synthesize(const de_circuit_desc* desc, de_assignment** out);
+/* the pass create_proof makes, straight into the caller's buffer: advice_out receives the 5 advice columns, 2^k Montgomery
+ * elements each, column after column (e.g. the pinned staging buffer de_create_proof uploads from); info may be NULL */
+int de_circuit_witness(const de_circuit_desc* desc, de_fr* advice_out, de_assignment_info_t* info);
+void de_assignment_free(de_assignment* a);
+int de_assignment_info(const de_assignment* a, de_assignment_info_t* info);
+/* column `column` as 2^k Montgomery field elements */
+int de_assignment_fixed(const de_assignment* a, uint32_t column, de_fr* out);
+int de_assignment_advice(const de_assignment* a, uint32_t column, de_fr* out);
+/* n_copies x (left column, left row, right column, right row); columns are positions in the permutation: 0-4 advice, 5 instance */
+int de_assignment_copies(const de_assignment* a, uint32_t* out);
+/* the circuit's results: mod_pow / delay_enc: the limbs of x^e mod n (delay_enc: then the two key words and the three
+ * ciphertext words); pose_enc: the ciphertext; rsa_pkcs1: the accept bit */
+int de_assignment_outputs(const de_assignment* a, de_fr* out);
+/* permutation::keygen::Assembly::build_pk's sigma columns from the copy constraints: n_columns x 2^k values, lagrange form */
+int de_assignment_sigma(const de_assignment* a, const de_fr* omega, const de_fr* delta, uint32_t n_columns, de_fr* out);
+const char* de_frontend_last_error(void);
+/* native Poseidon (src/poseidon/permutation.rs Spec::permute with Spec::new(r_f, r_p), width t) and the duplex cipher
+ * (src/encryption/poseidon_enc.rs PoseidonCipher::{encrypt, decrypt}; decrypt returns DE_ERR_UNSUPPORTED on a bad tag) */
+int de_poseidon_permute(uint32_t t, uint32_t r_f, uint32_t r_p, de_fr* state);
+int de_poseidon_cipher(int decrypt, const de_fr key[2], const de_fr* in, uint32_t n_in, de_fr* out);
+
 #ifdef __cplusplus
 }
 #endif

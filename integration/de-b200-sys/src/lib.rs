@@ -27,6 +27,17 @@ pub enum de_ctx {} pub enum de_params {} pub enum de_domain {} pub enum de_pk {}
                                        pub lookup_input_graphs: *const de_graph, pub lookup_table_graphs: *const de_graph,
                                        pub transcript_repr: de_fr }
 
+#[repr(C)] pub struct de_circuit_desc { pub kind: u32, pub k: u32, pub bits_len: u32, pub exp_bits: u32,
+                                        pub n: *const u8, pub n_len: usize, pub e: *const u8, pub e_len: usize, pub x: *const u8, pub x_len: usize,
+                                        pub message: *const de_fr, pub message_len: u32, pub key: [de_fr; 2], pub witness_only: u32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct de_assignment_info_t { pub k: u32, pub n_fixed: u32, pub n_advice: u32, pub n_outputs: u32,
+                                                                    pub used_rows: u64, pub n_copies: u64, pub synthesis_ms: f64 }
+pub enum de_assignment {}
+pub const DE_CIRCUIT_MOD_POW: u32 = 0;
+pub const DE_CIRCUIT_POSE_ENC: u32 = 1;
+pub const DE_CIRCUIT_DELAY_ENC: u32 = 2;
+pub const DE_CIRCUIT_RSA_PKCS1: u32 = 3;
+
 pub const DE_OK: c_int = 0;
 pub const DE_ERR_ARG: c_int = -1;
 pub const DE_ERR_CUDA: c_int = -2;
@@ -101,4 +112,18 @@ extern "C" {
     pub fn de_ipc_release(ctx: *mut de_ctx, d_ptr: *mut c_void) -> c_int;
     pub fn de_g1_mul_base_dev(ctx: *mut de_ctx, base: *const de_g1_affine, d_scalars: *const de_fr, n: usize, d_out: *mut de_g1_affine) -> c_int;
     pub fn de_g1_batch_normalize(ctx: *mut de_ctx, points: *const de_g1, count: usize, out: *mut de_g1_affine) -> c_int;
+    pub fn de_int_peak(ctx: *mut de_ctx, gmul_per_s: *mut f64) -> c_int;
+    // circuit front-end (host only)
+    pub fn de_circuit_synthesize(desc: *const de_circuit_desc, out: *mut *mut de_assignment) -> c_int;
+    pub fn de_circuit_witness(desc: *const de_circuit_desc, advice_out: *mut de_fr, info: *mut de_assignment_info_t) -> c_int;
+    pub fn de_assignment_free(a: *mut de_assignment);
+    pub fn de_assignment_info(a: *const de_assignment, info: *mut de_assignment_info_t) -> c_int;
+    pub fn de_assignment_fixed(a: *const de_assignment, column: u32, out: *mut de_fr) -> c_int;
+    pub fn de_assignment_advice(a: *const de_assignment, column: u32, out: *mut de_fr) -> c_int;
+    pub fn de_assignment_copies(a: *const de_assignment, out: *mut u32) -> c_int;
+    pub fn de_assignment_outputs(a: *const de_assignment, out: *mut de_fr) -> c_int;
+    pub fn de_assignment_sigma(a: *const de_assignment, omega: *const de_fr, delta: *const de_fr, n_columns: u32, out: *mut de_fr) -> c_int;
+    pub fn de_frontend_last_error() -> *const c_char;
+    pub fn de_poseidon_permute(t: u32, r_f: u32, r_p: u32, state: *mut de_fr) -> c_int;
+    pub fn de_poseidon_cipher(decrypt: c_int, key: *const de_fr, input: *const de_fr, n_in: u32, out: *mut de_fr) -> c_int;
 }

@@ -1,0 +1,163 @@
+"""Circuit front-end (C++ in delay-encryption-in-halo2_b200/frontend/, C ABI de_circuit_*): the
+reference's chips and bench circuits as witness generators.  CPU tests (the front-end needs no GPU):
+
+  * the reference's own known-answer vectors: Poseidon permutations (src/poseidon/permutation.rs:154-158,190-196), the
+    PKCS#1 v1.5 RSA triples (src/rsa/chip.rs:706-716 valid, :796-806 corrupted), encrypt -> decrypt (poseidon_enc.rs:167-177);
+  * every synthesised circuit satisfies its constraint system (oracle/mockprover.py, the MockProver check the reference's
+    tests run: src/lib.rs:353, src/encryption/chip.rs:237, src/rsa/chip.rs:341);
+  * used rows against the reference README's row counts; the witness-only pass equals the full pass; the library's permutation
+    assembly equals the Python one.
+"""
+import numpy as np
+import pytest
+
+import mockprover
+import orc
+import pyoracle as po
+from de_b200 import frontend as fe
+from de_b200 import keygen, plonk
+
+
+def ints(cols):
+    return [orc.fr_ints_from_mont(np.ascontiguousarray(c)) for c in cols]
+
+
+def mock_check(syn):
+    mockprover.check(syn.shape, syn.k, ints(syn.fixed), ints(syn.advice), syn.instances, [tuple(int(v) for v in c) for c in syn.copies])
+
+
+# the reference's PKCS#1 v1.5 known-answer triples (n, signature, SHA-256 digest as an integer):
+# /root/reference/src/rsa/chip.rs:706-716 and :751-761 verify, :796-806 (one digit of the second signature changed) does not
+RSA_N1 = int("27333278531038650284292446400685983964543820405055158402397263907659995327446166369388984969315774410223081038389734916442552953312548988147687296936649645550823280957757266695625382122565413076484125874545818286099364801140117875853249691189224238587206753225612046406534868213180954324992542640955526040556053150097561640564120642863954208763490114707326811013163227280580130702236406906684353048490731840275232065153721031968704703853746667518350717957685569289022049487955447803273805415754478723962939325870164033644600353029240991739641247820015852898600430315191986948597672794286676575642204004244219381500407")
+RSA_SIG1 = int("27166015521685750287064830171899789431519297967327068200526003963687696216659347317736779094212876326032375924944649760206771585778103092909024744594654706678288864890801000499430246054971129440518072676833029702477408973737931913964693831642228421821166326489172152903376352031367604507095742732994611253344812562891520292463788291973539285729019102238815435155266782647328690908245946607690372534644849495733662205697837732960032720813567898672483741410294744324300408404611458008868294953357660121510817012895745326996024006347446775298357303082471522757091056219893320485806442481065207020262668955919408138704593")
+RSA_N2 = int("24226501697440012621102249466312043787685293040734225606346036389705515508545746221669035424138747582133889500686654172873671086178893587422987328751464627501601101326475761646014534358699943642495332701081302954020983110372109611581202820849485662540890985814355975252780310958088652613376767040069489530039075302709233494829280591680666351811024913107949144932224439129715181798714328219977771472462901856297952813239115577652450722815852332547886777292613005505949100406231716599634852632308325816916535875123863510650526931916871614411907700873376659841257216885666098127478325534982891697988739616416855214839339")
+RSA_SIG2 = int("18928545496959757512579438348223103860103247450097569223971486743312798156950374943336714741350742176674694049986481729075548718599712271054643150030165230392897481507710187505775911256946250999396358633095137650326818007610162375520522758780751710735664264200260854016867498935206556916247099180950775474524799944404833222133011134000549939512938205188018503377612813102061504146765520561811620128786062447005833886367575841545493555268747671930923697279690399480501746857825917608323993022396398648205737336204493624060285359455268389160802763426461171262704764369336704988874821898000892148693988241020931055723252")
+RSA_SIG2_BAD = int("18928545496959756512579438348223103860103247450097569223971486743312798156950374943336714741350742176674694049986481729075548718599712271054643150030165230392897481507710187505775911256946250999396358633095137650326818007610162375520522758780751710735664264200260854016867498935206556916247099180950775474524799944404833222133011134000549939512938205188018503377612813102061504146765520561811620128786062447005833886367575841545493555268747671930923697279690399480501746857825917608323993022396398648205737336204493624060285359455268389160802763426461171262704764369336704988874821898000892148693988241020931055723252")
+RSA_DIGEST = int("83814198383102558219731078260892729932246618004265700685467928187377105751529")
+
+
+def test_poseidon_permutation_known_answers():
+    want3 = [7853200120776062878684798364095072458815029376092732009249414926327459813530,
+             7142104613055408817911962100316808866448378443474503659992478482890339429929,
+             6549537674122432311777789598043107870002137484850126429160507761192163713804]
+    assert fe.poseidon_permute([0, 1, 2], 3, 8, 57) == want3
+    want5 = [18821383157269793795438455681495246036402687001665670618754263018637548127333,
+             7817711165059374331357136443537800893307845083525445872661165200086166013245,
+             16733335996448830230979566039396561240864200624113062088822991822580465420551,
+             6644334865470350789317807668685953492649391266180911382577082600917830417726,
+             3372108894677221197912083238087960099443657816445944159266857514496320565191]
+    assert fe.poseidon_permute([0, 1, 2, 3, 4], 5, 8, 60) == want5
+    # the optimised parameter set agrees with the plain round function of the checker's own restatement
+    assert fe.poseidon_permute([5, 6, 7, 8, 9], 5, 8, 57) == po.poseidon_permute_ref([5, 6, 7, 8, 9], 5, 8, 57)
+
+
+def test_encrypt_decrypt_round_trip():
+    for key in ((0, 0), (0x1234, po.FR - 5)):
+        c = fe.poseidon_encrypt(key, [0, 0])   # the message of the reference's test and benches
+        assert len(c) == 3 and fe.poseidon_decrypt(key, c) == [0, 0]
+        bad = list(c)
+        bad[2] = (bad[2] + 1) % po.FR
+        assert fe.poseidon_decrypt(key, bad) is None
+        assert fe.poseidon_decrypt((key[0] + 1, key[1]), c) is None
+    # ciphertext words are state + message; the tag is state[1] after the second permutation
+    s = fe.poseidon_permute([0, 0, 7, 9, 1], 5, 8, 57)
+    c = fe.poseidon_encrypt((7, 9), [0, 0])
+    assert c[0] == s[1] and c[1] == s[2] and c[2] == fe.poseidon_permute(s, 5, 8, 57)[1]
+
+
+def test_pose_enc_circuit_satisfied_and_row_count():
+    key = (0x5EED1, 0x5EED2)
+    syn = fe.pose_enc(key, [0, 0], k=11)
+    assert syn.outputs == fe.poseidon_encrypt(key, [0, 0])
+    assert abs(syn.used_rows - 1450) <= 5          # /root/reference/benches/README.md:90 "1450" used rows
+    assert syn.fixed.shape == (9, 2048, 4) and syn.advice.shape == (5, 2048, 4)
+    mock_check(syn)
+    wit = fe.synthesize(fe.POSE_ENC, 11, message=[0, 0], key=key, witness_only=True)
+    assert (wit.advice == syn.advice).all() and wit.fixed.shape[0] == 0 and len(wit.copies) == 0
+
+
+def test_pose_enc_nonzero_message_is_rejected_like_the_reference():
+    # the circuit adds the message twice (encryption/chip.rs:93-103 then chip.rs:237-249), the native cipher never absorbs a
+    # short message (poseidon_enc.rs:107-124): they agree on the all-zero message only, and assert_equal fails otherwise
+    with pytest.raises(fe.DeError):
+        fe.pose_enc((1, 2), [3, 4], k=11)
+
+
+def test_tampered_witness_is_caught_by_the_checker():
+    syn = fe.pose_enc((11, 22), [0, 0], k=11)
+    fixed, copies = ints(syn.fixed), [tuple(int(v) for v in c) for c in syn.copies]
+    # a cell the gate reads (s_mul_ab = 1 on that row): the gate fails; a cell only a copy constraint reads: the copy fails
+    row = next(r for r in range(syn.used_rows) if fixed[6][r] == 1)
+    adv = ints(syn.advice)
+    adv[0][row] = (adv[0][row] + 1) % po.FR
+    with pytest.raises(AssertionError, match="gate|copy"):
+        mockprover.check(syn.shape, syn.k, fixed, adv, syn.instances, copies)
+    adv = ints(syn.advice)
+    lc, lr, rc, rr = copies[len(copies) // 2]
+    adv[rc][rr] = (adv[rc][rr] + 1) % po.FR
+    with pytest.raises(AssertionError):
+        mockprover.check(syn.shape, syn.k, fixed, adv, syn.instances, copies)
+
+
+def test_sigma_columns_match_python_assembly():
+    syn = fe.pose_enc((3, 4), [0, 0], k=11)
+    n = 1 << syn.k
+    omega = pow(po.FR_ROOT_OF_UNITY, 1 << (po.FR_S - syn.k), po.FR)
+    got = ints(syn.sigma(orc.fr_mont_from_ints([omega])[0]))
+    asm = keygen.PermutationAssembly(len(syn.shape.perm_columns), n)
+    for lc, lr, rc, rr in syn.copies:
+        asm.copy(int(lc), int(lr), int(rc), int(rr))
+    assert got == asm.sigma_values(omega)
+
+
+def test_mod_pow_circuit():
+    n, e, x = fe.sample_rsa_inputs(0xDE01)
+    syn = fe.mod_pow(n, e, x, k=16)    # 41 766 rows fit k = 16 (the bench uses K = 17)
+    assert sum(l << (64 * i) for i, l in enumerate(syn.outputs)) == pow(x, e, n)
+    assert abs(syn.used_rows - 41766) / 41766 < 0.05    # /root/reference/benches/README.md:73
+    assert syn.fixed.shape[0] == 15
+    mock_check(syn)
+
+
+def test_delay_enc_circuit():
+    n, e, x = fe.sample_rsa_inputs(0xDE03)
+    syn = fe.delay_enc(n, e, x, [0, 0], k=16)
+    limbs, key, cipher = syn.outputs[:32], syn.outputs[32:34], syn.outputs[34:]
+    assert sum(l << (64 * i) for i, l in enumerate(limbs)) == pow(x, e, n)
+    # hash input: three 64-bit limbs per element, the last from limbs 30 and 31 (src/lib.rs:229-255); key = words 1, 2
+    packed = [limbs[3 * i] + (limbs[3 * i + 1] << 64) + (limbs[3 * i + 2] << 128) for i in range(10)] + [limbs[30] + (limbs[31] << 64)]
+    state = [1 << 64, 0, 0, 0, 0]
+    for off in (0, 4, 8):
+        chunk = packed[off:off + 4]
+        for i, v in enumerate(chunk):
+            state[1 + i] = (state[1 + i] + v) % po.FR
+        if len(chunk) < 4:
+            state[1 + len(chunk)] = (state[1 + len(chunk)] + 1) % po.FR
+        state = fe.poseidon_permute(state, 5, 8, 57)
+    assert key == state[1:3]
+    assert cipher == fe.poseidon_encrypt(key, [0, 0]) and fe.poseidon_decrypt(key, cipher) == [0, 0]
+    mock_check(syn)
+    wit = fe.synthesize(fe.DELAY_ENC, 16, n, e, x, [0, 0], witness_only=True)
+    assert (wit.advice == syn.advice).all()
+    # rows per exponent bit: README 7 981 ((58 417 - 34 473) / 3, benches/README.md:57-58)
+    rows = {b: fe.synthesize(fe.DELAY_ENC, 17, n, 1, x, [0, 0], exp_bits=b, witness_only=True).used_rows for b in (3, 6)}
+    assert abs((rows[6] - rows[3]) / 3 - 7981) / 7981 < 0.03
+
+
+def test_rsa_pkcs1_known_answers():
+    digest = [(RSA_DIGEST >> (64 * i)) & (2 ** 64 - 1) for i in range(4)]
+    ok = fe.rsa_pkcs1(RSA_N1, 65537, RSA_SIG1, digest, k=17)
+    assert ok.outputs == [1]
+    mock_check(ok)
+    assert fe.rsa_pkcs1(RSA_N2, 65537, RSA_SIG2, digest, k=17).outputs == [1]
+    assert fe.rsa_pkcs1(RSA_N2, 65537, RSA_SIG2_BAD, digest, k=17).outputs == [0]
+
+
+def test_errors():
+    n, e, x = fe.sample_rsa_inputs(1)
+    with pytest.raises(fe.DeError):
+        fe.delay_enc(n, e, x, [0, 0], k=12)       # not enough rows
+    with pytest.raises(fe.DeError):
+        fe.mod_pow(n, 1 << 6, x, k=17)            # e wider than EXP_LIMB_BITS
+    with pytest.raises(fe.DeError):
+        fe.mod_pow(n, e, n + 5, k=17)             # x >= n: assert_in_field
