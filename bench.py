@@ -53,8 +53,9 @@ USED_ROWS = 50400
 SEED = 0xDE03
 WITH_LOOKUPS = True
 CONFIG_NAME = "delay_enc"
-DEFAULT_WORKLOAD = WORKLOAD = ("delay_enc k=16 create_proof (MainGate + RangeChip shape: 5 advice, 15 fixed, 5 lookups, 6 permutation columns; "
-            "satisfied synthetic witness, 50400 used rows): 31 MSM 2^16 (KZG bases resident), 23 iNTT 2^16, 23 coset-NTT 2^18, "
+DEFAULT_WORKLOAD = WORKLOAD = ("delay_enc k=16 create_proof of the reference's DelayEncryptCircuit (RSA-2048 x^e mod n with a 5-bit e -> Poseidon hash -> "
+            "Poseidon encryption of the 2-word zero message; witness by the C++ front-end, 44658 used rows; MainGate + RangeChip shape: 5 "
+            "advice, 15 fixed, 5 lookups, 6 permutation columns): 31 MSM 2^16 (KZG bases resident), 23 iNTT 2^16, 23 coset-NTT 2^18, "
             "evaluate_h over 2^18 rows, 1 iNTT 2^18, 10 lookup sorts, 7 grand products, 58 evaluations, 4 Kate divisions, "
             "Blake2b transcript -> 2848-byte proof")
 DEFAULT_METRIC = METRIC = "delay_enc_create_proof_proofs_per_s"
@@ -75,12 +76,81 @@ def _peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+WITNESS = "real"   # --witness: "real" = the reference's circuit through the C++ front-end; "synthetic" = round 1's stand-in
+
+
+class Circuit:
+    """The proved circuit of the current configuration.  "real": Circuit::synthesize of the reference's bench circuit by the C++
+    front-end (de_b200.frontend; DelayEncryptCircuit src/lib.rs:103-318, RSACircuit benches/mod_pow.rs:36-140, PoseidonEncCircuit
+    src/encryption/chip.rs:114-198) on inputs drawn as the benches draw them, from a seeded generator.  "synthetic": a satisfied
+    random assignment of the same constraint-system shape (de_b200/circuits.py)."""
+
+    def __init__(self):
+        from de_b200 import circuits, frontend as fe
+        self.kind = WITNESS
+        if WITNESS == "synthetic":
+            self.asg = circuits.satisfied_assignment(WITH_LOOKUPS, K, SEED, USED_ROWS, uniform_values=not WITH_LOOKUPS)
+            self.shape, self.instances, self.used_rows, self.syn = self.asg.shape, self.asg.instances, self.asg.used_rows, None
+            return
+        kind = {"delay_enc": fe.DELAY_ENC, "mod_pow": fe.MOD_POW, "pose_enc": fe.POSE_ENC}[CONFIG_NAME]
+        n, e, x = fe.sample_rsa_inputs(SEED) if kind != fe.POSE_ENC else (0, 0, 0)
+        self.inputs = dict(kind=kind, k=K, n=n, e=e, x=x, message=() if kind == fe.MOD_POW else (0,) * fe.MESSAGE_CAPACITY,
+                           key=(SEED * 0x9E3779B97F4A7C15 % fe.plonk.FR, (SEED + 1) * 0xC2B2AE3D27D4EB4F % fe.plonk.FR))
+        self.syn = fe.synthesize(**self.inputs)
+        self.shape, self.instances, self.used_rows = self.syn.shape, self.syn.instances, self.syn.used_rows
+
+    def keygen(self, ctx, g, g_lagrange):
+        from de_b200 import keygen
+        if self.syn is None:
+            return keygen.keygen(ctx, self.shape, K, g, g_lagrange, self.asg.fixed, self.asg.copies, TRANSCRIPT_REPR)
+        return keygen.keygen_from_synthesized(ctx, self.syn, g, g_lagrange, TRANSCRIPT_REPR)
+
+    def advice_mont(self, ctx):
+        import numpy as np
+        from de_b200 import keygen
+        if self.syn is None:
+            return np.stack([ctx.fr_to_mont(keygen.canonical_limbs(c)) for c in self.asg.advice])
+        return self.syn.advice
+
+    def witness_pass(self):
+        """a fresh de_circuit_witness runner (None for the synthetic stand-in, which has no front-end)"""
+        from de_b200 import frontend as fe
+        return fe.WitnessPass(**self.inputs) if self.syn is not None else None
+
+    def cpu_view(self):
+        """(fixed columns as integer lists, copy constraints as tuples, advice columns in Montgomery form) for the CPU arm's own
+        keygen; conversions use the checker library: only the CPU legs call this"""
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import numpy as np
+        import orc
+        if self.syn is None:
+            return self.asg.fixed, self.asg.copies, [orc.fr_mont_from_ints(c) for c in self.asg.advice]
+        fixed = [orc.fr_ints_from_mont(np.ascontiguousarray(c)) for c in self.syn.fixed]
+        return fixed, [tuple(int(v) for v in c) for c in self.syn.copies], [np.ascontiguousarray(c) for c in self.syn.advice]
+
+    def witness_stats(self, ctx):
+        """value distribution of the advice cells of the used rows (SURVEY.md 8d guessed 45 % < 2^8, 35 % < 2^64, 10 % < 2^134,
+        10 % wider): what the MSM's zero-digit skipping sees"""
+        import numpy as np
+        adv = self.advice_mont(ctx)[:, :self.used_rows]
+        can = np.stack([ctx.fr_from_mont(np.ascontiguousarray(c)) for c in adv]).reshape(-1, 4)
+        hi3, hi2, hi1 = can[:, 3] != 0, can[:, 2] != 0, can[:, 1] != 0
+        zero = ~(hi3 | hi2 | hi1) & (can[:, 0] == 0)
+        lt8 = ~(hi3 | hi2 | hi1) & (can[:, 0] < 256) & ~zero
+        lt64 = ~(hi3 | hi2 | hi1) & ~lt8 & ~zero
+        lt134 = ~hi3 & (can[:, 2] < 64) & (hi2 | hi1)
+        wide = ~(zero | lt8 | lt64 | lt134)
+        t = float(can.shape[0])
+        return {"cells": int(t), "zero": float(zero.sum() / t), "lt_2^8": float(lt8.sum() / t), "lt_2^64": float(lt64.sum() / t),
+                "lt_2^134": float(lt134.sum() / t), "wider": float(wide.sum() / t),
+                "survey_guess": {"lt_2^8": 0.45, "lt_2^64": 0.35, "lt_2^134": 0.10, "wider": 0.10}}
+
+
 def build_circuit():
-    """The satisfied synthetic delay_enc-shaped assignment (canonical integers) and the SRS bases."""
-    from de_b200 import circuits, synth
-    asg = circuits.satisfied_assignment(WITH_LOOKUPS, K, SEED, USED_ROWS, uniform_values=not WITH_LOOKUPS)
+    """The circuit of the current configuration and the SRS bases."""
+    from de_b200 import synth
     n = 1 << K
-    return asg, synth.gen_bases(n, start=0), synth.gen_bases(n, start=n)
+    return Circuit(), synth.gen_bases(n, start=0), synth.gen_bases(n, start=n)
 
 
 def random_draws(count):
@@ -88,13 +158,13 @@ def random_draws(count):
     return synth.uniform_fr(SEED + 777, count)
 
 
-def build_cpu_inputs(asg, advice_mont, g, g_lagrange):
+def build_cpu_inputs(circ, advice_mont, g, g_lagrange):
     """Columns for the CPU arm's hot-path schedule: the assignment's advice columns; every other column (permuted lookup
     columns, grand products, random / opening polynomials, fixed and sigma polynomials) is a uniform column of the same
     size — the reference algorithms' cost does not depend on their values."""
     import numpy as np
     from de_b200 import prover, synth
-    shape = asg.shape
+    shape = circ.shape
     w = prover.Workload(shape, K)
     n, o = w.n, w.offsets()
     cols = np.empty((w.n_cols, n, 4), dtype=np.uint64)
@@ -202,7 +272,7 @@ def cpu_reference_step(inp, state):
     return np.stack(pts)
 
 
-def cpu_prover_setup(asg, g, g_lagrange):
+def cpu_prover_setup(circ, g, g_lagrange):
     """keys of the restated CPU prover for the same circuit / SRS / transcript_repr (keygen: one-time in the reference too)"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
@@ -210,12 +280,14 @@ def cpu_prover_setup(asg, g, g_lagrange):
     from de_b200 import plonk
     n = 1 << K
     oparams = pp.Params(K, n, None, None, None, None, np.ascontiguousarray(g), np.ascontiguousarray(g_lagrange))
-    opk = pp.keygen(oparams, asg.shape, pp.Queries(*plonk.collect_queries(asg.shape)), asg.fixed, asg.copies, TRANSCRIPT_REPR)
+    fixed, copies, _ = circ.cpu_view()
+    opk = pp.keygen(oparams, circ.shape, pp.Queries(*plonk.collect_queries(circ.shape)), fixed, copies, TRANSCRIPT_REPR)
     pp._pk_arrays(oparams, opk)
     return pp, oparams, opk
 
 
-DEFAULT_CPU_SAMPLE = CPU_SAMPLE = ("one whole delay_enc k=16 create_proof per step, the same circuit, keys and random draws as the GPU arm: the restated "
+DEFAULT_CPU_SAMPLE = CPU_SAMPLE = ("one whole delay_enc k=16 create_proof per step (Circuit::synthesize by this repository's C++ front-end, then the prover), the same "
+              "circuit, keys and random draws as the GPU arm: the restated "
               "reference algorithms (oracle/: best_multiexp, best_fft, evaluate_h, lookup permutation, grand products, eval_polynomial, "
               "kate_division in C with pthreads on all host cores; Python only sequences the calls and hashes the transcript), not the "
               "Rust binary; proof bytes equal the GPU's")
@@ -227,18 +299,33 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
     import orc
     orc.build()
-    asg, g, g_lagrange = build_circuit()
-    advice_mont = [orc.fr_mont_from_ints(c) for c in asg.advice]
-    pp, oparams, opk = cpu_prover_setup(asg, g, g_lagrange)
-    randoms = random_draws(pp.random_count(asg.shape, 1 << K))
+    circ, g, g_lagrange = build_circuit()
+    _, _, advice_mont = circ.cpu_view()
+    pp, oparams, opk = cpu_prover_setup(circ, g, g_lagrange)
+    randoms = random_draws(pp.random_count(circ.shape, 1 << K))
+    wp = circ.witness_pass()
+    buf = np.empty((circ.shape.n_advice, 1 << K, 4), dtype=np.uint64)
     proof = None
+    synth_ms = []
+
+    def step():
+        # the reference's create_proof starts with Circuit::synthesize (benches/delay_enc.rs:123-131): the witness pass is part of
+        # the step.  The Rust synthesize cannot run here; this repository's C++ front-end stands in for it on BOTH arms.
+        cols = advice_mont
+        if wp is not None:
+            synth_ms.append(wp.run(buf))
+            cols = [buf[i] for i in range(buf.shape[0])]
+        return pp.create_proof_fast(oparams, opk, cols, circ.instances, randoms)
+
     for _ in range(max(args.warmup, 0)):
-        proof = pp.create_proof_fast(oparams, opk, advice_mont, asg.instances, randoms)
+        proof = step()
+    del synth_ms[:]
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        proof = pp.create_proof_fast(oparams, opk, advice_mont, asg.instances, randoms)
+        proof = step()
     dt = time.perf_counter() - t0
     value = args.steps / dt
     cores = orc.ncpu()
@@ -249,6 +336,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery limbs)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "k": K, "seed": hex(SEED), "proof_bytes": len(proof), "proof_sha256": hashlib.sha256(proof).hexdigest()},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": CPU_SAMPLE},
+        "synthesis_ms": (sum(synth_ms) / len(synth_ms)) if synth_ms else None,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -271,8 +359,8 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
     from de_b200 import keygen, sharding
     import torch.distributed as dist
 
-    asg, g, g_lagrange = build_circuit()
-    shape = asg.shape
+    circ, g, g_lagrange = build_circuit()
+    shape = circ.shape
     n = 1 << K
     main_stream = torch.cuda.current_stream()
     as_i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
@@ -286,15 +374,23 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
             self.ctx.set_stream(self.stream.cuda_stream)
             with torch.cuda.stream(self.stream):
                 if first is None:
-                    self.keys = keygen.keygen(self.ctx, shape, K, g, g_lagrange, asg.fixed, asg.copies, TRANSCRIPT_REPR)
+                    self.keys = circ.keygen(self.ctx, g, g_lagrange)
                 else:
                     self.keys = first.keys.clone_on(self.ctx)
             self.proof = None
+            # end-to-end arm: this worker's own witness pass and pinned staging buffer for the advice columns
+            self.wp = circ.witness_pass()
+            self.stage = torch.empty((shape.n_advice, n, 4), dtype=torch.int64).pin_memory() if self.wp is not None else None
+            self.synth_ms = []
 
         def run(self, nsteps, host):
             with torch.cuda.stream(self.stream):
                 for _ in range(nsteps):
-                    if host:
+                    if host and self.wp is not None:
+                        # Circuit::synthesize (witness pass, host) -> advice columns in pinned memory -> de_create_proof (H2D inside)
+                        self.synth_ms.append(self.wp.run(self.stage))
+                        self.proof = self.keys.prover.create_proof([self.stage[i] for i in range(shape.n_advice)], [], randoms_h)
+                    elif host:
                         self.proof = self.keys.prover.create_proof([advice_h[i] for i in range(shape.n_advice)], [], randoms_h)
                     else:
                         self.proof = self.keys.prover.create_proof_dev(advice_d, randoms_d)
@@ -302,7 +398,7 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
     workers = [Worker()]
     ctx = workers[0].ctx
     prover0 = workers[0].keys.prover
-    advice_mont = np.stack([ctx.fr_to_mont(keygen.canonical_limbs(c)) for c in asg.advice])
+    advice_mont = np.ascontiguousarray(circ.advice_mont(ctx))
     randoms = random_draws(prover0.random_count)
     advice_h, randoms_h = as_i64(advice_mont).pin_memory(), as_i64(randoms).pin_memory()
     advice_d, randoms_d = advice_h.cuda(), randoms_h.cuda()
@@ -350,9 +446,12 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
         assert wk.proof == first_proof, "proof bytes differ between workers / steps"
     # ---- end-to-end arm: pinned host advice + random draws in, proof bytes out, every proof
     timed(workers, 2, True)
+    for wk in workers:
+        del wk.synth_ms[:]
     ms_e2e = timed(workers, steps, True)
     for wk in workers:
         assert wk.proof == first_proof, "host-buffer path disagrees with the device-resident path"
+    synth_all = [v for wk in workers for v in wk.synth_ms]
     # ---- latency arm: ONE proof in flight; per-kernel CUDA-event timing is taken here (no overlapping streams)
     ctx.set_mode(throughput=False)
     timed(workers[:1], 2, False)
@@ -381,12 +480,21 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
                    "l2": f"per-step working set ~{0.8 * B * 2.0 ** (K - 16):.2f} GB (columns, cosets, pk cosets, base tables) > 126 MB L2; no explicit flush",
                    "sharding": "independent proofs across GPUs, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
-                "ms_per_step": ms_e2e / steps},
+                "ms_per_step": ms_e2e / steps,
+                "includes": ("Circuit::synthesize (witness pass of the C++ front-end, one host thread per in-flight proof) + H2D of the advice "
+                             "columns and random draws + create_proof + D2H of commitments / evaluations") if synth_all else
+                            "H2D of the advice columns and random draws + create_proof + D2H of commitments / evaluations",
+                "synthesis_ms": (sum(synth_all) / len(synth_all)) if synth_all else None},
+        "synthesis_ms": (sum(synth_all) / len(synth_all)) if synth_all else None,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "latency": {"create_proof_s": ms_lat / lat_steps / 1000.0, "proofs_in_flight": 1, "steps": lat_steps, "mode": "DE_MODE_LATENCY"},
     }
-    art = dict(asg=asg, g=g, g_lagrange=g_lagrange, advice_mont=advice_mont, randoms=randoms, first_proof=first_proof, workers=workers,
+    line["config"]["witness"] = circ.kind
+    line["config"]["used_rows"] = int(circ.used_rows)
+    if detail:
+        line["witness_stats"] = circ.witness_stats(ctx)
+    art = dict(circ=circ, g=g, g_lagrange=g_lagrange, advice_mont=advice_mont, randoms=randoms, first_proof=first_proof, workers=workers,
                ctx=ctx, advice_d=advice_d, ms_lat=ms_lat, lat_steps=lat_steps, shape=shape)
     return line, art
 
@@ -481,12 +589,12 @@ def set_config(name, k=0):
     K, WITH_LOOKUPS, USED_ROWS, SEED, where = CONFIGS[name]
     K = k or K
     CONFIG_NAME = name
-    if name == "delay_enc" and not k:
+    if name == "delay_enc" and not k and WITNESS == "real":
         WORKLOAD, METRIC, CPU_SAMPLE = DEFAULT_WORKLOAD, DEFAULT_METRIC, DEFAULT_CPU_SAMPLE
         return
     METRIC = f"{name}_create_proof_proofs_per_s" if not k else f"{name}_k{K}_create_proof_proofs_per_s"
-    WORKLOAD = (f"{name} k={K} create_proof (/root/reference/{where}; MainGate{' + RangeChip' if WITH_LOOKUPS else ''} shape, satisfied "
-                f"synthetic witness, {USED_ROWS} used rows)")
+    WORKLOAD = (f"{name} k={K} create_proof (/root/reference/{where}; MainGate{' + RangeChip' if WITH_LOOKUPS else ''} shape, "
+                + ("witness of the reference's circuit by the C++ front-end)" if WITNESS == "real" else f"satisfied synthetic witness, {USED_ROWS} used rows)"))
     CPU_SAMPLE = DEFAULT_CPU_SAMPLE.replace("delay_enc k=16", f"{name} k={K}")
 
 
@@ -505,7 +613,11 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "latency", "throughput"],
                     help="de_ctx_set_mode of the in-flight arms (auto: throughput when more than one proof is in flight)")
     ap.add_argument("--k", type=int, default=0, help="override the config's k (the reference's README also times k = 15 ... 19)")
+    ap.add_argument("--witness", default="real", choices=["real", "synthetic"],
+                    help="real: the reference's circuit synthesised by the C++ front-end (default); synthetic: round 1's satisfied random assignment")
     args = ap.parse_args()
+    global WITNESS
+    WITNESS = args.witness
     headline = args.config == "delay_enc" and not args.k
     set_config(args.config, args.k)
     rank = int(os.environ.get("RANK", "0"))
@@ -530,7 +642,7 @@ def main():
     B = max(1, args.inflight)
     line, art = proof_bench(args, local_rank, world, args.steps, args.warmup, B, detail=True)
     mul_peak = add_rooflines(line, art, rank)
-    asg, g, g_lagrange, advice_mont, randoms = art["asg"], art["g"], art["g_lagrange"], art["advice_mont"], art["randoms"]
+    circ, g, g_lagrange, advice_mont, randoms = art["circ"], art["g"], art["g_lagrange"], art["advice_mont"], art["randoms"]
     first_proof, shape = art["first_proof"], art["shape"]
     close_workers(art)
     del art
@@ -577,7 +689,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import orc
         n = 1 << K
-        inp = build_cpu_inputs(asg, list(advice_mont), g, g_lagrange)
+        inp = build_cpu_inputs(circ, list(advice_mont), g, g_lagrange)
         # the prover's blinding rows, so that the CPU's advice commitments can be compared with the proof's
         usable = n - (shape.blinding_factors + 1)
         for i in range(shape.n_advice):
@@ -596,12 +708,19 @@ def main():
             same = same and bytes(c) == first_proof[32 * i:32 * i + 32]
         # the COMPLETE restated create_proof on the CPU, same circuit, keys, transcript_repr and random draws: its bytes must equal
         # the GPU's; this is the like-for-like CPU baseline of the step
-        pp, oparams, opk = cpu_prover_setup(asg, g, g_lagrange)
+        pp, oparams, opk = cpu_prover_setup(circ, g, g_lagrange)
+        wp = circ.witness_pass()
         t0 = time.perf_counter()
-        cpu_proof = pp.create_proof_fast(oparams, opk, list(advice_mont), asg.instances, randoms)
+        cols = list(advice_mont)
+        if wp is not None:  # Circuit::synthesize is the first thing the reference's create_proof does
+            buf = np.empty_like(advice_mont)
+            wp.run(buf)
+            cols = [buf[i] for i in range(buf.shape[0])]
+        cpu_proof = pp.create_proof_fast(oparams, opk, cols, circ.instances, randoms)
         dt_full = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 1.0 / dt_full, "unit": UNIT, "cores": orc.ncpu(), "kind": "port", "sample": CPU_SAMPLE,
                                 "create_proof_s": dt_full, "proof_bytes_match_gpu": bool(cpu_proof == first_proof),
+                                "synthesis_ms": wp.info.synthesis_ms if wp is not None else None,
                                 "hot_path_only": {"s": dt, "sample": CPU_HOT_SAMPLE, "advice_commitments_match_gpu_proof": bool(same)}}
         if msm_single:
             # the reference's best_multiexp (restated, all host cores) on the very inputs the GPU committed, results compared

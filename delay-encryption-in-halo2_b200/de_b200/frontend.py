@@ -129,6 +129,38 @@ def synthesize(kind: int, k: int, n: int = 0, e: int = 0, x: int = 0, message=()
                               [[] for _ in range(shape.n_instance)], handle)
 
 
+class WitnessPass:
+    """The synthesis pass create_proof makes (advice columns only) for fixed circuit inputs, written into a caller's buffer
+    of 5 * 2^k field elements (numpy array or pinned torch tensor): de_circuit_witness.  Thread-safe across instances; the call
+    releases the GIL."""
+
+    def __init__(self, kind: int, k: int, n: int = 0, e: int = 0, x: int = 0, message=(), key=(0, 0), bits_len: int = BITS_LEN,
+                 exp_bits: int = EXP_LIMB_BITS):
+        self.L = _lib.load()
+        d = _Desc()
+        d.kind, d.k, d.bits_len, d.exp_bits = kind, k, bits_len, exp_bits
+        nb = max(1, bits_len // 8)
+        self._bufs = [np.frombuffer(int(v).to_bytes(nb, "little"), dtype=np.uint8).copy() for v in (n, e, x)]
+        d.n, d.e, d.x = (b.ctypes.data for b in self._bufs)
+        d.n_len = d.e_len = d.x_len = nb
+        self._msg = _mont(message)
+        d.message, d.message_len = (self._msg.ctypes.data if len(message) else None), len(message)
+        kk = _mont(key)
+        for i in range(2):
+            for j in range(4):
+                d.key[i].l[j] = int(kk[i, j])
+        self.desc, self.k = d, k
+        self.info = _Info()
+
+    def run(self, out) -> float:
+        """fills `out` (5 * 2^k * 4 uint64); returns the synthesis time in ms"""
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        rc = self.L.de_circuit_witness(C.byref(self.desc), C.c_void_p(ptr), C.byref(self.info))
+        if rc != 0:
+            raise DeError(rc, self.L.de_frontend_last_error().decode())
+        return float(self.info.synthesis_ms)
+
+
 def delay_enc(n: int, e: int, x: int, message=(0,) * MESSAGE_CAPACITY, k: int = 16) -> SynthesizedCircuit:
     return synthesize(DELAY_ENC, k, n, e, x, message)
 
