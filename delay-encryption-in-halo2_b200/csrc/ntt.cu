@@ -1,6 +1,7 @@
 // ntt.cu — host side of the NTT / EvaluationDomain entry points: transform plans (pass geometry + twiddle tables
 // resident in HBM), kernel dispatch, and the C ABI functions de_ntt*, de_domain_*, de_coeff_to_extended*, ...
 // Reference semantics: halo2_proofs::arithmetic::best_fft and poly::EvaluationDomain.
+#include <atomic>
 #include <string.h>
 
 #include <thread>
@@ -161,11 +162,13 @@ static int get_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, NttPlan** o
 template <int S, int LT, bool DIST>
 static int launch_pass_t(de_ctx* ctx, const NttPassParams& prm, const NttDistArgs<DIST>& dx, unsigned int blocks, unsigned int batch) {
     using Sh = NttShape<S, LT>;
-    static bool configured[16] = {false};
-    int dev = ctx->device & 15;
-    if (!configured[dev]) {
+    // the attribute is per (kernel, device); several host threads (one per in-flight proof) may get here at once: setting it
+    // twice is harmless, so a relaxed atomic flag per device is enough.  Devices beyond the table set it on every launch.
+    static std::atomic<bool> configured[64];
+    const bool tracked = ctx->device >= 0 && ctx->device < 64;
+    if (!tracked || !configured[ctx->device].load(std::memory_order_acquire)) {
         DE_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<S, LT, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::SMEM));
-        configured[dev] = true;
+        if (tracked) configured[ctx->device].store(true, std::memory_order_release);
     }
     dim3 grid(blocks, batch);
     DE_TIMED(ctx, DIST ? "k_ntt_pass_dist" : "k_ntt_pass", (double)blocks * batch * Sh::M,
@@ -736,28 +739,44 @@ int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x,
             if (!e) DE_CUDA(c0, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     // stage 1 everywhere; stage 2 of a rank starts when every rank's stage-1 stores have landed; the call is complete on a
-    // rank's stream when every rank's stage-2 stores have landed (which also orders the next call's stage 1 behind them)
+    // rank's stream when every rank's stage-2 stores have landed (which also orders the next call's stage 1 behind them).
+    // Once the first kernel is queued an error must not return while peers may still be storing into buffers the caller is
+    // about to reuse or free: drain() waits for every participating stream first.
+    auto drain = [&](int rc, const std::string& msg) -> int {
+        for (int r = 0; r < n_gpus; r++) {
+            cudaSetDevice(ctxs[r]->device);
+            cudaStreamSynchronize(ctxs[r]->stream);
+        }
+        cudaGetLastError();
+        return fail(c0, rc, msg);
+    };
+#define DE_DIST_CUDA(expr)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) return drain(DE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
     for (int r = 0; r < n_gpus; r++) {
         de_ctx* c = ctxs[r];
         int rc = de_ntt_dist_stage1(c, d_x[r], omega, log_n, (uint32_t)n_gpus, (uint32_t)r, z);
-        if (rc != DE_OK) return fail(c0, rc, std::string(c->err));
-        DE_CUDA(c0, cudaEventRecord(c->dist_ev[0], c->stream));
+        if (rc != DE_OK) return drain(rc, std::string(c->err));
+        DE_DIST_CUDA(cudaEventRecord(c->dist_ev[0], c->stream));
     }
     for (int q = 0; q < n_gpus; q++) {
         de_ctx* c = ctxs[q];
-        DE_CUDA(c0, cudaSetDevice(c->device));
+        DE_DIST_CUDA(cudaSetDevice(c->device));
         for (int r = 0; r < n_gpus; r++)
-            if (r != q) DE_CUDA(c0, cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[0], 0));
+            if (r != q) DE_DIST_CUDA(cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[0], 0));
         int rc = de_ntt_dist_stage2(c, z[q], omega, log_n, (uint32_t)n_gpus, (uint32_t)q, d_out);
-        if (rc != DE_OK) return fail(c0, rc, std::string(c->err));
-        DE_CUDA(c0, cudaEventRecord(c->dist_ev[1], c->stream));
+        if (rc != DE_OK) return drain(rc, std::string(c->err));
+        DE_DIST_CUDA(cudaEventRecord(c->dist_ev[1], c->stream));
     }
     for (int q = 0; q < n_gpus; q++) {
         de_ctx* c = ctxs[q];
-        DE_CUDA(c0, cudaSetDevice(c->device));
+        DE_DIST_CUDA(cudaSetDevice(c->device));
         for (int r = 0; r < n_gpus; r++)
-            if (r != q) DE_CUDA(c0, cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[1], 0));
+            if (r != q) DE_DIST_CUDA(cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[1], 0));
     }
+#undef DE_DIST_CUDA
     return DE_OK;
 }
 

@@ -740,7 +740,9 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     size_t rpos = 0;
     TailDescs tails;
     unsigned int n_tails = 0;
+    int* tail_rc_p = nullptr;
     auto flush_tails = [&]() -> int {
+        if (tail_rc_p && *tail_rc_p != DE_OK) return *tail_rc_p;  // an earlier launch of this round failed
         if (n_tails) {
             k_write_tails<<<n_tails, 32, 0, st>>>(tails);
             DE_CHECK_LAUNCH(ctx);
@@ -748,8 +750,13 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
         n_tails = 0;
         return DE_OK;
     };
+    int tail_rc = DE_OK;  // a failed intermediate flush is reported by the flush that ends the round (DE_TRY(flush_tails()))
+    tail_rc_p = &tail_rc;
     auto add_tail = [&](Fr* dst, size_t count) {
-        if (n_tails == DE_MAX_TAILS) flush_tails();
+        if (n_tails == DE_MAX_TAILS) {
+            const int rc = flush_tails();
+            if (rc != DE_OK && tail_rc == DE_OK) tail_rc = rc;
+        }
         tails.dst[n_tails] = dst;
         tails.src[n_tails] = p->randoms + rpos;
         tails.count[n_tails] = (unsigned int)count;

@@ -112,6 +112,8 @@ class Context:
     def fr_sub(self, a, b): return self._vec(self.L.de_fr_vec_op, _lib.OP_SUB, a, b)
     def fr_from_mont(self, a): return self._vec(self.L.de_fr_vec_op, _lib.OP_FROM_MONT, a, None)
     def fr_to_mont(self, a): return self._vec(self.L.de_fr_vec_op, _lib.OP_TO_MONT, a, None)
+    def fq_from_mont(self, a): return self._vec(self.L.de_fq_vec_op, _lib.OP_FROM_MONT, a, None)
+    def fq_to_mont(self, a): return self._vec(self.L.de_fq_vec_op, _lib.OP_TO_MONT, a, None)
     def fq_mul(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_MUL, a, b)
     def fq_add(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_ADD, a, b)
     def fq_sub(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_SUB, a, b)

@@ -254,7 +254,10 @@ int de_ntt_dist_stage2(de_ctx* ctx, const de_fr* d_z, const de_fr* omega, uint32
                        de_fr* const* d_out_peers);
 /* The same inside ONE process: ctxs[r] is rank r (normally one context per GPU; several contexts on one GPU also work), d_x[r] /
  * d_out[r] its input / output block (d_out[r] may equal d_x[r]).  Asynchronous: the result is complete in stream order on every
- * context's stream; exchange buffers live in the contexts' workspaces. */
+ * context's stream; exchange buffers live in the contexts' workspaces.  Two exceptions to "asynchronous": the FIRST call for a
+ * given (context, log_n, omega) builds the plan's twiddle tables (device allocations and one stream synchronisation); and when
+ * a launch fails part-way the call waits for every participating stream before it returns the error, so that no peer is still
+ * storing into a buffer the caller may now free. */
 int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x, de_fr* const* d_out, const de_fr* omega,
                        uint32_t log_n);
 /* best_fft(a, omega, log_n) for a HOST vector, natural order in and out, over the GPUs of ctxs (distinct contexts): block r

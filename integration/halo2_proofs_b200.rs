@@ -18,6 +18,29 @@ thread_local! { static ALL: Vec<*mut de_ctx> = unsafe {
 fn all_ctxs() -> Vec<*mut de_ctx> { ALL.with(|v| v.clone()) }
 fn ok(rc: i32, c: *mut de_ctx) { if rc != 0 { panic!("de_b200: {}", unsafe { CStr::from_ptr(de_last_error(c)) }.to_string_lossy()); } }
 
+// A de_ctx (its stream and workspaces) is NOT thread-safe, and a de_params / de_domain / de_prover handle stays bound to the
+// context it was created on.  halo2's ParamsKZG, EvaluationDomain and ProvingKey are Sync and routinely shared between rayon or
+// prover threads, so every device-side object carries ITS OWN context behind a Mutex: whichever thread calls takes the lock,
+// and errors are read from the object's context, not from the calling thread's.  (The free functions above and below use the
+// calling thread's private context and need no lock.)  One context per object costs a stream and grow-only workspaces; a
+// prover that wants N proofs in flight clones N (ParamsKZG, ProvingKey) pairs, as bench.py's workers do.
+pub struct Dev<T> { inner: std::sync::Mutex<(*mut de_ctx, *mut T)> }
+unsafe impl<T> Send for Dev<T> {}
+unsafe impl<T> Sync for Dev<T> {}
+impl<T> Dev<T> {
+    /// `make` receives a fresh context on `device` and returns the handle created on it
+    pub fn new(device: i32, make: impl FnOnce(*mut de_ctx) -> *mut T) -> Self {
+        let mut c = std::ptr::null_mut();
+        unsafe { ok(de_ctx_create(device, &mut c), std::ptr::null_mut()) };
+        Dev { inner: std::sync::Mutex::new((c, make(c))) }
+    }
+    /// runs `f(handle)` under the lock and panics with the OBJECT's error string on a non-zero status
+    pub fn call(&self, f: impl FnOnce(*mut T) -> i32) {
+        let g = self.inner.lock().unwrap();
+        ok(f(g.1), g.0);
+    }
+}
+
 // ---- src/arithmetic.rs -------------------------------------------------------------------------------------------------
 pub fn best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1 {
     assert_eq!(coeffs.len(), bases.len());
@@ -46,55 +69,61 @@ pub fn kate_division(a: &[Fr], b: Fr) -> Vec<Fr> {
     q
 }
 
-// ---- src/poly/domain.rs: EvaluationDomain gains `dev: *mut de_domain` (de_domain_create in new(), de_domain_free in Drop) ----
+// ---- src/poly/domain.rs: EvaluationDomain gains `dev: Dev<de_domain>` (Dev::new(0, |c| de_domain_create(c, j, k, ..)) in new();
+//      de_domain_free + de_ctx_destroy in Drop) ----
 impl EvaluationDomain<Fr> {
     pub fn coeff_to_extended(&self, p: Polynomial<Fr, Coeff>) -> Polynomial<Fr, ExtendedLagrangeCoeff> {
         let mut out = vec![Fr::zero(); self.extended_len()];
-        unsafe { ok(de_coeff_to_extended(self.dev, p.values.as_ptr() as _, out.as_mut_ptr() as _), ctx()) };
+        self.dev.call(|d| unsafe { de_coeff_to_extended(d, p.values.as_ptr() as _, out.as_mut_ptr() as _) });
         Polynomial { values: out, _marker: PhantomData }
     }
     pub fn extended_to_coeff(&self, mut p: Polynomial<Fr, ExtendedLagrangeCoeff>) -> Vec<Fr> {
         let mut len = 0usize;
-        unsafe { ok(de_extended_to_coeff(self.dev, p.values.as_mut_ptr() as _, &mut len), ctx()) };
+        self.dev.call(|d| unsafe { de_extended_to_coeff(d, p.values.as_mut_ptr() as _, &mut len) });
         p.values.truncate(len);
         p.values
     }
     pub fn lagrange_to_coeff(&self, mut p: Polynomial<Fr, LagrangeCoeff>) -> Polynomial<Fr, Coeff> {
-        unsafe { ok(de_lagrange_to_coeff(self.dev, p.values.as_mut_ptr() as _), ctx()) };
+        self.dev.call(|d| unsafe { de_lagrange_to_coeff(d, p.values.as_mut_ptr() as _) });
         Polynomial { values: p.values, _marker: PhantomData }
     }
     pub fn coeff_to_lagrange(&self, mut p: Polynomial<Fr, Coeff>) -> Polynomial<Fr, LagrangeCoeff> {
-        unsafe { ok(de_coeff_to_lagrange(self.dev, p.values.as_mut_ptr() as _), ctx()) };
+        self.dev.call(|d| unsafe { de_coeff_to_lagrange(d, p.values.as_mut_ptr() as _) });
         Polynomial { values: p.values, _marker: PhantomData }
     }
     pub fn divide_by_vanishing_poly(&self, mut p: Polynomial<Fr, ExtendedLagrangeCoeff>) -> Polynomial<Fr, ExtendedLagrangeCoeff> {
-        unsafe { ok(de_divide_by_vanishing(self.dev, p.values.as_mut_ptr() as _), ctx()) };
+        self.dev.call(|d| unsafe { de_divide_by_vanishing(d, p.values.as_mut_ptr() as _) });
         p
     }
 }
 
-// ---- src/poly/kzg/commitment.rs: ParamsKZG gains `dev: *mut de_params` (de_params_upload once in setup() / read()) ----------
+// ---- src/poly/kzg/commitment.rs: ParamsKZG gains `dev: Dev<de_params>` (de_params_upload once in setup() / read()) ----------
 impl ParamsKZG<Bn256> {
     pub fn commit(&self, poly: &Polynomial<Fr, Coeff>, _: Blind<Fr>) -> G1 { self.commit_basis(0, &poly.values) }
     pub fn commit_lagrange(&self, poly: &Polynomial<Fr, LagrangeCoeff>, _: Blind<Fr>) -> G1 { self.commit_basis(1, &poly.values) }
     fn commit_basis(&self, basis: i32, v: &[Fr]) -> G1 {
         let mut out = std::mem::MaybeUninit::<de_g1>::uninit();
-        unsafe { ok(de_commit(self.dev, basis, v.as_ptr() as _, v.len(), out.as_mut_ptr()), ctx()); std::mem::transmute(out.assume_init()) }
+        self.dev.call(|p| unsafe { de_commit(p, basis, v.as_ptr() as _, v.len(), out.as_mut_ptr()) });
+        unsafe { std::mem::transmute(out.assume_init()) }
     }
 }
 
 // ---- src/plonk/prover.rs: create_proof for KZGCommitmentScheme<Bn256>, ProverGWC, Blake2bWrite<_, _, Challenge255<_>> ---------
-// pk.dev_prover is built once in keygen_pk: de_pk_upload (serialised pk.ev + fixed / sigma polynomials)
+// pk.dev_prover: Dev<de_prover> is built once in keygen_pk on ONE context (params, domain, pk and prover of a proving key share
+// it: de_prover_create refuses handles of different contexts): de_pk_upload (serialised pk.ev + fixed / sigma polynomials)
 // and de_prover_create (cs.advice_queries, cs.fixed_queries, theta-compression graphs per lookup, vk.transcript_repr).
 pub fn create_proof_b200<R: RngCore>(pk: &ProvingKey<G1Affine>, advice: &[Polynomial<Fr, LagrangeCoeff>], instances: &[&[Fr]], mut rng: R,
                                      transcript: &mut Blake2bWrite<Vec<u8>, G1Affine, Challenge255<G1Affine>>) {
-    let need = unsafe { de_prover_random_count(pk.dev_prover) };
+    let (mut need, mut size) = (0usize, 0usize);
+    pk.dev_prover.call(|p| unsafe { need = de_prover_random_count(p); size = de_prover_proof_size(p); 0 });
     let randoms: Vec<Fr> = (0..need).map(|_| Fr::random(&mut rng)).collect();   // drawn in create_proof's order
     let adv: Vec<*const de_fr> = advice.iter().map(|p| p.values.as_ptr() as *const de_fr).collect();
     let ins: Vec<*const de_fr> = instances.iter().map(|v| v.as_ptr() as *const de_fr).collect();
     let lens: Vec<usize> = instances.iter().map(|v| v.len()).collect();
-    let mut proof = vec![0u8; unsafe { de_prover_proof_size(pk.dev_prover) }];
+    let mut proof = vec![0u8; size];
     let mut len = 0usize;
-    unsafe { ok(de_create_proof(pk.dev_prover, adv.as_ptr(), ins.as_ptr(), lens.as_ptr(), randoms.as_ptr() as _, need, proof.as_mut_ptr(), proof.len(), &mut len), ctx()) };
+    // the lock is held for the whole proof: two threads proving with the same ProvingKey serialise (clone the key per thread for
+    // concurrency); the error string comes from the prover's own context
+    pk.dev_prover.call(|p| unsafe { de_create_proof(p, adv.as_ptr(), ins.as_ptr(), lens.as_ptr(), randoms.as_ptr() as _, need, proof.as_mut_ptr(), proof.len(), &mut len) });
     transcript.extend_proof_bytes(&proof[..len]);   // appends to the writer's inner Vec<u8>
 }
