@@ -127,14 +127,15 @@ def read_vk(path_or_bytes, shape) -> VerifyingKeyRaw:
     return vk
 
 
-def read_pk(path_or_bytes, shape) -> ProvingKeyRaw:
-    """ProvingKey::read(reader, SerdeFormat::RawBytes).  Accepts a path (memory-mapped: a k = 16 key is 276 MiB) or bytes."""
+def read_pk(path_or_bytes, shape, n_selectors: int | None = None) -> ProvingKeyRaw:
+    """ProvingKey::read(reader, SerdeFormat::RawBytes).  Accepts a path (memory-mapped: a k = 16 key is 276 MiB) or bytes.
+    n_selectors: selector vectors in the embedded vk (default: what this repository's shapes have)"""
     if isinstance(path_or_bytes, (bytes, bytearray, memoryview)):
         data = path_or_bytes
     else:
         data = np.memmap(path_or_bytes, dtype=np.uint8, mode="r")
     r = _Reader(data, _detect_order(bytes(data[:4])))
-    vk = _read_vk(r, len(shape.perm_columns), n_selectors_of(shape))
+    vk = _read_vk(r, len(shape.perm_columns), n_selectors_of(shape) if n_selectors is None else n_selectors)
     l0, l_last, l_active = r.polynomial(), r.polynomial(), r.polynomial()
     fixed_values, fixed_polys, fixed_cosets = r.slice(), r.slice(), r.slice()
     permutations, polys, cosets = r.slice(), r.slice(), r.slice()
