@@ -9,9 +9,16 @@
 //   -> permutation argument constraints -> every lookup's five constraints
 // folding with y exactly in the reference's order, so the output equals evaluate_h's bit for bit.
 #include "eval.cuh"
+#include "transcript.hpp"
 
 namespace de {
 
+// The reference folds every constraint into one value by Horner's rule in y (value = value * y + constraint), each constraint
+// already multiplied by its l0 / l_last / l_active factor: two multiplications per constraint.  The field is exact, so any
+// arrangement of the same polynomial identity gives the same element: here constraint j (of T, in the reference's order) is
+// multiplied by the precomputed power y^(T-1-j) and added to the running sum of ITS indicator column, and the three sums meet
+// their indicator once at the end:
+//   value = gates * y^T + l0 * S0 + l_last * SL + l_active * SA          (one multiplication per constraint + 4)
 __global__ void __launch_bounds__(128) k_eval_h(const __grid_constant__ EvalParams p) {
     const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.ext_n) return;
@@ -19,24 +26,30 @@ __global__ void __launch_bounds__(128) k_eval_h(const __grid_constant__ EvalPara
     c.p = &p;
     c.idx = idx;
     const Fr one = Fr::one();
-    const Fr y = p.y;
-    // ---- custom gates: value = Horner(previous = 0, gate polynomials, y) inside the compiled program
+    // ---- custom gates: Horner(previous = 0, gate polynomials, y) inside the compiled program
     c.prev = Fr::zero();
-    Fr value = run_graph(c, p.gates);
-    const Fr l0 = load(&p.l0[idx]), l_last = load(&p.l_last[idx]), l_active = load(&p.l_active[idx]);
+    const Fr gates = run_graph(c, p.gates);
     const unsigned int r_next = rot_index(idx, 1, p.rot_scale, p.ext_mask);
     const unsigned int r_prev = rot_index(idx, -1, p.rot_scale, p.ext_mask);
+    const Fr* yp = p.ypows + p.n_terms;  // yp[-1 - j] = y^(T-1-j): the power constraint j carries
+    Fr s0 = Fr::zero(), sl = Fr::zero(), sa = Fr::zero();
+    int j = 0;
+#define DE_TERM(acc, expr)                               \
+    do {                                                 \
+        acc = add(acc, mul((expr), load(&yp[-1 - j])));  \
+        j++;                                             \
+    } while (0)
     // ---- permutation argument
     if (p.n_sets > 0) {
         const unsigned int r_last = rot_index(idx, p.last_rotation, p.rot_scale, p.ext_mask);
         const Fr z_first = load(&p.permz[idx]);
-        value = add(mul(value, y), mul(sub(one, z_first), l0));
+        DE_TERM(s0, sub(one, z_first));
         const Fr z_lastset = load(&p.permz[(unsigned long long)(p.n_sets - 1) * p.ext_n + idx]);
-        value = add(mul(value, y), mul(sub(sqr(z_lastset), z_lastset), l_last));
+        DE_TERM(sl, sub(sqr(z_lastset), z_lastset));
         for (uint32_t s = 1; s < p.n_sets; s++) {
             Fr zi = load(&p.permz[(unsigned long long)s * p.ext_n + idx]);
             Fr zp = load(&p.permz[(unsigned long long)(s - 1) * p.ext_n + r_last]);
-            value = add(mul(value, y), mul(sub(zi, zp), l0));
+            DE_TERM(s0, sub(zi, zp));
         }
         Fr current_delta = mul(mul(p.beta, p.delta_start), load(&p.omega_pows[idx]));  // beta * ZETA * extended_omega^idx
         for (uint32_t s = 0; s < p.n_sets; s++) {
@@ -51,7 +64,7 @@ __global__ void __launch_bounds__(128) k_eval_h(const __grid_constant__ EvalPara
                 right = mul(right, add(add(v, current_delta), p.gamma));
                 current_delta = mul(current_delta, p.delta);
             }
-            value = add(mul(value, y), mul(sub(left, right), l_active));
+            DE_TERM(sa, sub(left, right));
         }
     }
     // ---- lookups
@@ -63,13 +76,17 @@ __global__ void __launch_bounds__(128) k_eval_h(const __grid_constant__ EvalPara
         const Fr* sc = p.lookup_s + (unsigned long long)n * p.ext_n;
         const Fr z = load(&zc[idx]), a = load(&ac[idx]), s = load(&sc[idx]);
         const Fr a_minus_s = sub(a, s);
-        value = add(mul(value, y), mul(sub(one, z), l0));
-        value = add(mul(value, y), mul(sub(sqr(z), z), l_last));
-        Fr t = sub(mul(mul(load(&zc[r_next]), add(a, p.beta)), add(s, p.gamma)), mul(z, table_value));
-        value = add(mul(value, y), mul(t, l_active));
-        value = add(mul(value, y), mul(a_minus_s, l0));
-        value = add(mul(value, y), mul(mul(a_minus_s, sub(a, load(&ac[r_prev]))), l_active));
+        DE_TERM(s0, sub(one, z));
+        DE_TERM(sl, sub(sqr(z), z));
+        DE_TERM(sa, sub(mul(mul(load(&zc[r_next]), add(a, p.beta)), add(s, p.gamma)), mul(z, table_value)));
+        DE_TERM(s0, a_minus_s);
+        DE_TERM(sa, mul(a_minus_s, sub(a, load(&ac[r_prev]))));
     }
+#undef DE_TERM
+    Fr value = mul(gates, load(&p.ypows[p.n_terms]));
+    value = add(value, mul(s0, load(&p.l0[idx])));
+    value = add(value, mul(sl, load(&p.l_last[idx])));
+    value = add(value, mul(sa, load(&p.l_active[idx])));
     store(&p.out[idx], value);
 }
 
@@ -139,6 +156,7 @@ int de_pk_upload(de_domain* dom, const de_pk_desc* desc, de_pk** out) {
     pk->n = dv->n; pk->ext_n = dv->ext_n; pk->k = dv->k; pk->ek = dv->ek;
     pk->delta = fr_from_host(desc->delta);
     pk->d_challenges = nullptr; pk->challenges_cap = 0;
+    pk->d_ypows = nullptr; pk->ypows_cap = 0;
     const size_t n = dv->n, ext_n = dv->ext_n;
     const size_t n_res = (size_t)desc->n_fixed + desc->n_perm_columns + 4;  // + l0, l_last, l_active, omega_pows
     const size_t n_work = (size_t)desc->n_advice + desc->n_instance + pk->n_sets + 3 * (size_t)desc->n_lookups;
@@ -254,8 +272,28 @@ int de_evaluate_h_rows_dev(de_pk* pk, const de_challenges* ch, de_fr* d_h_ext) {
         pk->challenges_cap = ch->n_challenges;
     }
     if (ch->n_challenges) DE_CUDA(ctx, cudaMemcpyAsync(pk->d_challenges, ch->challenges, sizeof(Fr) * ch->n_challenges, cudaMemcpyHostToDevice, ctx->stream));
+    // powers of y for the constraints behind the custom gates (k_eval_h): y^0 .. y^T, T = permutation + lookup constraints
+    const uint32_t n_terms = (pk->n_sets ? 2 + (pk->n_sets - 1) + pk->n_sets : 0) + 5 * pk->n_lookups;
+    {
+        std::vector<host::HFr> yp(n_terms + 1);
+        host::HFr yv;
+        memcpy(yv.l, ch->y.l, 32);
+        yp[0] = host::fr_one();
+        for (uint32_t i = 1; i <= n_terms; i++) yp[i] = host::fr_mul(yp[i - 1], yv);
+        if (!pk->d_ypows || pk->ypows_cap < n_terms + 1) {
+            Fr* d = nullptr;
+            DE_CUDA(ctx, cudaMalloc((void**)&d, sizeof(Fr) * (n_terms + 1)));
+            pk->allocs.push_back(d);
+            pk->d_ypows = d;
+            pk->ypows_cap = n_terms + 1;
+        }
+        // pageable source: the runtime stages it before cudaMemcpyAsync returns, so the vector may go out of scope
+        DE_CUDA(ctx, cudaMemcpyAsync(pk->d_ypows, yp.data(), sizeof(Fr) * (n_terms + 1), cudaMemcpyHostToDevice, ctx->stream));
+    }
     EvalParams p;
     memset(&p, 0, sizeof(p));
+    p.ypows = pk->d_ypows;
+    p.n_terms = n_terms;
     p.ext_mask = (uint32_t)(ext_n - 1);
     p.rot_scale = 1u << (pk->ek - pk->k);
     p.ext_n = ext_n;

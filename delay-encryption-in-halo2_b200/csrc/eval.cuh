@@ -16,6 +16,7 @@ struct de_domain_view {  // layout prefix of de_domain (ntt.cu) that this unit r
 
 namespace de {
 
+#define DE_CALC_HORNER_FROM_ZERO 8  // internal: DE_CALC_HORNER with a zero start value (set by upload_graph)
 #define DE_MAX_INTER 24   // live intermediates per row AFTER slot allocation (upload_graph); local memory per thread
 #define DE_MAX_ROT 16
 
@@ -37,6 +38,8 @@ struct EvalParams {
     // per-proof cosets
     const Fr* advice; const Fr* instance; const Fr* permz; const Fr* lookup_z; const Fr* lookup_a; const Fr* lookup_s;
     const Fr* challenges;
+    const Fr* ypows;   // y^0 .. y^n_terms (device); n_terms = constraints folded after the custom gates
+    uint32_t n_terms;
     Fr y, beta, gamma, theta, delta, delta_start;  // delta_start holds ZETA (Montgomery)
     DevGraph gates;
     const DevGraph* lookups;
@@ -98,6 +101,12 @@ __device__ inline Fr run_graph(RowCtx& c, const DevGraph& g) {
                 for (uint32_t k = 0; k < cc.hlen; k++) r = add(mul(r, f), fetch(c, g, g.hparts[cc.hfirst + k]));
                 break;
             }
+            case DE_CALC_HORNER_FROM_ZERO: {  // Horner whose start value is zero: 0 * f + part_0 = part_0, one multiplication less
+                Fr f = fetch(c, g, cc.b);
+                r = fetch(c, g, g.hparts[cc.hfirst]);
+                for (uint32_t k = 1; k < cc.hlen; k++) r = add(mul(r, f), fetch(c, g, g.hparts[cc.hfirst + k]));
+                break;
+            }
             default: r = a; break;  // DE_CALC_STORE
         }
         c.inter[cc.target] = r;
@@ -127,6 +136,8 @@ struct de_pk {
     Fr* work;      // per-proof cosets, ext_n apart, in the prover's column order: advice | instance | a' | s' | permz | lookup z
     Fr* d_challenges;
     uint32_t challenges_cap;
+    Fr* d_ypows;
+    uint32_t ypows_cap;
     uint32_t *d_perm_kind, *d_perm_index;
     DevGraph gates;
     DevGraph* d_lookups;
@@ -173,6 +184,18 @@ inline int upload_graph(de_ctx* ctx, const de_graph& g, DevGraph* out, std::vect
             if (!(calcs[i].op == DE_CALC_STORE && i + 1 != calcs.size())) kept.push_back(calcs[i]);
         calcs.swap(kept);
     }
+    // 1b. Horner(start, f, parts) with start = the constant 0 (the theta-compressions of the lookup arguments) or PreviousValue
+    //     (zero in every kernel that runs these programs: the gates' fold starts from nothing): 0 * f + part_0 is part_0
+    {
+        auto is_zero_const = [&](const DevSrc& s) {
+            if (s.kind == DE_VAL_PREVIOUS) return true;
+            if (s.kind != DE_VAL_CONSTANT || s.index >= g.n_constants) return false;
+            const de_fr& v = g.constants[s.index];
+            return (v.l[0] | v.l[1] | v.l[2] | v.l[3]) == 0;
+        };
+        for (auto& c : calcs)
+            if (c.op == DE_CALC_HORNER && c.hlen >= 1 && is_zero_const(c.a)) c.op = DE_CALC_HORNER_FROM_ZERO;
+    }
     // 2. slot allocation by liveness: an intermediate's slot is reused after its last consumer
     {
         const uint32_t nc = (uint32_t)calcs.size();
@@ -183,7 +206,7 @@ inline int upload_graph(de_ctx* ctx, const de_graph& g, DevGraph* out, std::vect
         for (uint32_t i = 0; i < nc; i++) {
             use(calcs[i].a, (int)i);
             use(calcs[i].b, (int)i);
-            if (calcs[i].op == DE_CALC_HORNER)
+            if (calcs[i].op == DE_CALC_HORNER || calcs[i].op == DE_CALC_HORNER_FROM_ZERO)
                 for (uint32_t k = 0; k < calcs[i].hlen; k++) use(parts[calcs[i].hfirst + k], (int)i);
         }
         std::vector<int> slot_of(g.n_intermediates, -1);
@@ -195,7 +218,7 @@ inline int upload_graph(de_ctx* ctx, const de_graph& g, DevGraph* out, std::vect
         for (uint32_t i = 0; i < nc; i++) {
             remap(calcs[i].a);
             remap(calcs[i].b);
-            if (calcs[i].op == DE_CALC_HORNER)
+            if (calcs[i].op == DE_CALC_HORNER || calcs[i].op == DE_CALC_HORNER_FROM_ZERO)
                 for (uint32_t k = 0; k < calcs[i].hlen; k++)
                     if (!part_done[calcs[i].hfirst + k]) {
                         remap(parts[calcs[i].hfirst + k]);
