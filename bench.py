@@ -378,19 +378,33 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
                 else:
                     self.keys = first.keys.clone_on(self.ctx)
             self.proof = None
-            # end-to-end arm: this worker's own witness pass and pinned staging buffer for the advice columns
+            # end-to-end arm: this worker's own witness pass and TWO pinned staging buffers for the advice columns, so that
+            # Circuit::synthesize of the next proof (a host thread; the C call releases the GIL) runs while the GPU proves the
+            # current one - what a prover service with a queue of statements does
             self.wp = circ.witness_pass()
-            self.stage = torch.empty((shape.n_advice, n, 4), dtype=torch.int64).pin_memory() if self.wp is not None else None
+            self.stage = [torch.empty((shape.n_advice, n, 4), dtype=torch.int64).pin_memory() for _ in range(2)] if self.wp is not None else None
             self.synth_ms = []
+
+        def _synth(self, slot):
+            self.synth_ms.append(self.wp.run(self.stage[slot]))
 
         def run(self, nsteps, host):
             with torch.cuda.stream(self.stream):
+                if host and self.wp is not None:
+                    # every proof gets its own witness pass: step i's runs during step i - 1's create_proof (the first one up front)
+                    self._synth(0)
+                    for i in range(nsteps):
+                        nxt = None
+                        if i + 1 < nsteps:
+                            nxt = threading.Thread(target=self._synth, args=((i + 1) & 1,))
+                            nxt.start()
+                        buf = self.stage[i & 1]
+                        self.proof = self.keys.prover.create_proof([buf[c] for c in range(shape.n_advice)], [], randoms_h)
+                        if nxt is not None:
+                            nxt.join()
+                    return
                 for _ in range(nsteps):
-                    if host and self.wp is not None:
-                        # Circuit::synthesize (witness pass, host) -> advice columns in pinned memory -> de_create_proof (H2D inside)
-                        self.synth_ms.append(self.wp.run(self.stage))
-                        self.proof = self.keys.prover.create_proof([self.stage[i] for i in range(shape.n_advice)], [], randoms_h)
-                    elif host:
+                    if host:
                         self.proof = self.keys.prover.create_proof([advice_h[i] for i in range(shape.n_advice)], [], randoms_h)
                     else:
                         self.proof = self.keys.prover.create_proof_dev(advice_d, randoms_d)
@@ -481,8 +495,9 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
                    "sharding": "independent proofs across GPUs, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
                 "ms_per_step": ms_e2e / steps,
-                "includes": ("Circuit::synthesize (witness pass of the C++ front-end, one host thread per in-flight proof) + H2D of the advice "
-                             "columns and random draws + create_proof + D2H of commitments / evaluations") if synth_all else
+                "includes": ("Circuit::synthesize for EVERY proof (witness pass of the C++ front-end on a host thread per in-flight prover, "
+                             "double-buffered: proof i + 1 is synthesised while proof i is on the GPU) + H2D of the advice columns and random "
+                             "draws + create_proof + D2H of commitments / evaluations") if synth_all else
                             "H2D of the advice columns and random draws + create_proof + D2H of commitments / evaluations",
                 "synthesis_ms": (sum(synth_all) / len(synth_all)) if synth_all else None},
         "synthesis_ms": (sum(synth_all) / len(synth_all)) if synth_all else None,
