@@ -17,6 +17,7 @@ struct NttPlan;
 struct NttDistPlan;
 template <bool DIST>
 struct NttDistArgs;
+struct NttDistChunks;
 
 struct DevBuf {
     void* p = nullptr;
@@ -101,7 +102,11 @@ struct de_ctx {
     de::PinnedBuf pinned;
     std::vector<de::NttPlan*> plans;
     std::vector<de::NttDistPlan*> dist_plans;           // multi-GPU transform tables (ntt.cu)
-    cudaEvent_t dist_ev[3] = {nullptr, nullptr, nullptr};  // stage-1 / stage-2 / deal completion of de_ntt_sharded* on this context
+    // multi-GPU transform (ntt.cu): events [0 .. 7] = exchange-pass chunk k complete, [8] = cross stage complete, [9] = deal
+    // complete, [10] = scratch; a second, high-priority stream for the cross stage; the error word of the flag waits
+    cudaEvent_t dist_ev[11] = {};
+    cudaStream_t dist_stream = nullptr;
+    unsigned int* dist_error = nullptr;
 };
 
 namespace de {
@@ -194,7 +199,7 @@ inline de_fr fr_to_host(const Fr& v) {
 // ntt.cu
 int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, size_t src_stride, Fr* d_dst, size_t dst_stride,
             size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3,
-            const NttDistArgs<true>* dist = nullptr);
+            const NttDistArgs<true>* dist = nullptr, NttDistChunks* chunks = nullptr);
 void ntt_free_plans(de_ctx* ctx);
 // device-side Fr helpers running single-thread kernels, used for domain constants (ntt.cu)
 int fr_host_pow(de_ctx* ctx, const de_fr& base, uint64_t e, de_fr* out);

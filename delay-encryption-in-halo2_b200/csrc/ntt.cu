@@ -2,6 +2,7 @@
 // resident in HBM), kernel dispatch, and the C ABI functions de_ntt*, de_domain_*, de_coeff_to_extended*, ...
 // Reference semantics: halo2_proofs::arithmetic::best_fft and poly::EvaluationDomain.
 #include <atomic>
+#include <functional>
 #include <string.h>
 
 #include <thread>
@@ -61,6 +62,14 @@ void ntt_free_plans(de_ctx* ctx) {
     ctx->plans.clear();
     for (auto* p : ctx->dist_plans) delete p;
     ctx->dist_plans.clear();
+    if (ctx->dist_stream) {
+        cudaStreamDestroy(ctx->dist_stream);
+        ctx->dist_stream = nullptr;
+    }
+    if (ctx->dist_error) {
+        cudaFree(ctx->dist_error);
+        ctx->dist_error = nullptr;
+    }
     for (auto& e : ctx->dist_ev)
         if (e) {
             cudaEventDestroy(e);
@@ -204,8 +213,18 @@ static int launch_pass_dist(de_ctx* ctx, int S, int LT, const NttPassParams& prm
     return fail(ctx, DE_ERR_UNSUPPORTED, "ntt (multi-GPU): no peer-store kernel for this pass shape");
 }
 
+// Pipelined exchange of the multi-GPU transform: the peer-store pass is launched as `chunks` contiguous ranges of CTAs and
+// after_chunk(k) runs on the host after range k has been enqueued (it records an event or enqueues a flag signal).  On return
+// `period` = the number of columns one sub-row of the pass spans (M / L) and `chunks` the count actually used.
+struct NttDistChunks {
+    int chunks = 1;
+    std::function<int(int)> after_chunk;
+    unsigned long long period = 0;
+};
+
 int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, size_t src_stride, Fr* d_dst, size_t dst_stride,
-            size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3, const NttDistArgs<true>* dist) {
+            size_t batch, int in_mode, size_t n_in, const Fr* zeta2, int out_mode, const Fr* oscale3, const NttDistArgs<true>* dist,
+            NttDistChunks* chunks) {
     if (batch == 0) return DE_OK;
     if (dist && (batch != 1 || log_n < 11)) return fail(ctx, DE_ERR_ARG, "ntt (multi-GPU): local transform must be one vector of >= 2^11");
     if (batch > 65535) return fail(ctx, DE_ERR_ARG, "ntt: batch too large");
@@ -305,8 +324,25 @@ int ntt_run(de_ctx* ctx, const de_fr& omega, uint32_t log_n, const Fr* d_src, si
             prm.out_el = N / L;
             blocks = N / (T * L);
         }
-        if (last && dist) DE_TRY(launch_pass_dist(ctx, S, LT, prm, *dist, (unsigned int)blocks));
-        else DE_TRY(launch_pass(ctx, S, LT, prm, (unsigned int)blocks, (unsigned int)batch));
+        if (last && dist) {
+            // a contiguous range of CTAs covers the same contiguous range of column offsets c' = blockIdx.x * T + tt inside each
+            // of the L sub-rows (length N / L) of the pass' output
+            NttDistArgs<true> dx = *dist;
+            int K = chunks ? chunks->chunks : 1;
+            while (K > 1 && (blocks % K != 0 || blocks / K < 2ull * ctx->sm_count)) K >>= 1;
+            if (chunks) {
+                chunks->chunks = K;
+                chunks->period = N / L;
+            }
+            const unsigned int per = (unsigned int)(blocks / K);
+            for (int c = 0; c < K; c++) {
+                dx.block_off = (unsigned int)c * per;
+                DE_TRY(launch_pass_dist(ctx, S, LT, prm, dx, per));
+                if (chunks && chunks->after_chunk) DE_TRY(chunks->after_chunk(c));
+            }
+        } else {
+            DE_TRY(launch_pass(ctx, S, LT, prm, (unsigned int)blocks, (unsigned int)batch));
+        }
         Lprod *= L;
     }
     return DE_OK;
@@ -635,8 +671,11 @@ static int get_dist_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, uint32
     return DE_OK;
 }
 
+// chunk `ck` of `nck` (nck = 1: the whole exchange buffer) of the cross stage on `stream`; period = columns per sub-row of the
+// exchange pass (ignored when nck = 1)
 template <int LW>
-static int launch_cross(de_ctx* ctx, NttDistPlan* plan, const Fr* d_z, de_fr* const* d_out_peers, uint32_t rank) {
+static int launch_cross(de_ctx* ctx, NttDistPlan* plan, const Fr* d_z, de_fr* const* d_out_peers, uint32_t rank, cudaStream_t stream,
+                        int ck = 0, int nck = 1, unsigned long long period = 0) {
     NttCrossArgs<LW> a;
     memset(&a, 0, sizeof(a));
     const unsigned long long M = 1ull << (plan->log_n - LW);
@@ -649,18 +688,58 @@ static int launch_cross(de_ctx* ctx, NttDistPlan* plan, const Fr* d_z, de_fr* co
             plan->tw_rank = nullptr;
             return fail(ctx, DE_ERR_OOM, "ntt (multi-GPU): twiddle table allocation failed");
         }
-        k_dist_twiddles<<<(unsigned int)((cnt + 255) / 256), 256, 0, ctx->stream>>>(plan->tw_rank, a.C, (1u << LW) - 1, (unsigned long long)rank * a.C,
+        // built on the stream that consumes it (one-time per plan and rank)
+        k_dist_twiddles<<<(unsigned int)((cnt + 255) / 256), 256, 0, stream>>>(plan->tw_rank, a.C, (1u << LW) - 1, (unsigned long long)rank * a.C,
                                                                              plan->tw_hi, plan->tw_lo, plan->tw_lo_bits);
         DE_CHECK_LAUNCH(ctx);
         plan->tw_rank_of = rank;
     }
     a.tw = plan->tw_rank;
     a.out_off = (unsigned long long)rank * a.C;
+    if (nck <= 1 || period == 0 || period > a.C) {
+        a.period = a.chunk_len = a.C;
+        a.chunk_off = 0;
+    } else {
+        a.period = period;
+        a.chunk_len = period / (unsigned long long)nck;
+        a.chunk_off = (unsigned long long)ck * a.chunk_len;
+    }
     for (int i = 0; i < (1 << LW); i++) a.peer_out[i] = (Fr*)d_out_peers[i];
     for (int i = 0; i < ((1 << LW) / 2 < 1 ? 1 : (1 << LW) / 2); i++) a.w[i] = plan->wcross[i];
     const unsigned int threads = 128;
-    DE_TIMED(ctx, "k_ntt_cross", (double)M, (k_ntt_cross<LW><<<(unsigned int)((a.C + threads - 1) / threads), threads, 0, ctx->stream>>>(a)));
+    const unsigned long long cols = (a.C / a.period) * a.chunk_len;
+    if (stream == ctx->stream) {
+        DE_TIMED(ctx, "k_ntt_cross", (double)(cols << LW), (k_ntt_cross<LW><<<(unsigned int)((cols + threads - 1) / threads), threads, 0, stream>>>(a)));
+    } else {
+        k_ntt_cross<LW><<<(unsigned int)((cols + threads - 1) / threads), threads, 0, stream>>>(a);
+    }
     DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+static int launch_cross_any(de_ctx* ctx, NttDistPlan* plan, const Fr* d_z, de_fr* const* d_out_peers, uint32_t rank, cudaStream_t stream, int ck,
+                            int nck, unsigned long long period) {
+    switch (plan->log_w) {
+        case 0: return launch_cross<0>(ctx, plan, d_z, d_out_peers, rank, stream, ck, nck, period);
+        case 1: return launch_cross<1>(ctx, plan, d_z, d_out_peers, rank, stream, ck, nck, period);
+        case 2: return launch_cross<2>(ctx, plan, d_z, d_out_peers, rank, stream, ck, nck, period);
+        default: return launch_cross<3>(ctx, plan, d_z, d_out_peers, rank, stream, ck, nck, period);
+    }
+}
+// the context's second stream (cross stage, high priority so that its small CTAs are placed as soon as pass CTAs retire), the
+// events and the error word of the flag waits
+static int dist_resources(de_ctx* c) {
+    DE_CUDA(c, cudaSetDevice(c->device));
+    if (!c->dist_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        DE_CUDA(c, cudaStreamCreateWithPriority(&c->dist_stream, cudaStreamNonBlocking, hi));
+    }
+    for (auto& e : c->dist_ev)
+        if (!e) DE_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!c->dist_error) {
+        DE_CUDA(c, cudaMalloc((void**)&c->dist_error, sizeof(unsigned int)));
+        DE_CUDA(c, cudaMemsetAsync(c->dist_error, 0, sizeof(unsigned int), c->stream));
+    }
     return DE_OK;
 }
 
@@ -698,12 +777,81 @@ int de_ntt_dist_stage2(de_ctx* ctx, const de_fr* d_z, const de_fr* omega, uint32
     DE_CUDA(ctx, cudaSetDevice(ctx->device));
     NttDistPlan* plan = nullptr;
     DE_TRY(get_dist_plan(ctx, *omega, log_n, world, &plan));
-    switch (plan->log_w) {
-        case 0: return launch_cross<0>(ctx, plan, (const Fr*)d_z, d_out_peers, rank);
-        case 1: return launch_cross<1>(ctx, plan, (const Fr*)d_z, d_out_peers, rank);
-        case 2: return launch_cross<2>(ctx, plan, (const Fr*)d_z, d_out_peers, rank);
-        default: return launch_cross<3>(ctx, plan, (const Fr*)d_z, d_out_peers, rank);
+    return launch_cross_any(ctx, plan, (const Fr*)d_z, d_out_peers, rank, ctx->stream, 0, 1, 0);
+}
+
+// One call of the multi-GPU transform on THIS rank with the exchange pipelined in up to `chunks` column ranges and the stages
+// ordered across processes by flags in peer memory (d_flag_peers[r]: rank r's DE_DIST_FLAG_WORDS u32 words, zero-initialised
+// once; `epoch`: 1, 2, 3, ... the same on every rank for the same call):
+//   main stream   local passes, then per range k: peer-store pass over range k, signal (k, rank) to every rank
+//   cross stream  per range k: wait for (k, *) from every rank, cross stage of range k (peer stores into the output blocks);
+//                 then signal (done, rank)
+//   main stream   joins the cross stream and waits for (done, *): every rank's stores into this rank's block have landed and
+//                 every rank has finished reading its exchange buffer (the next call may overwrite it)
+// The cross stage of range k (NVLink-bound) thus runs under the pass of range k + 1 (multiply-bound).  A rank that never
+// arrives makes the waits give up after ~2 s: de_ntt_dist_error() then reports it.
+int de_ntt_dist_run(de_ctx* ctx, const de_fr* d_x, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank, de_fr* const* d_z_peers,
+                    de_fr* const* d_out_peers, uint32_t* const* d_flag_peers, uint32_t epoch, uint32_t chunks) {
+    if (!ctx) return DE_ERR_ARG;
+    DE_TRY(dist_args_ok(ctx, d_x, omega, (const void* const*)d_z_peers, world, rank));
+    DE_TRY(dist_args_ok(ctx, d_x, omega, (const void* const*)d_out_peers, world, rank));
+    DE_TRY(dist_args_ok(ctx, d_x, omega, (const void* const*)d_flag_peers, world, rank));
+    if (epoch == 0 || chunks == 0 || chunks > DE_DIST_MAX_CHUNKS) return fail(ctx, DE_ERR_ARG, "de_ntt_dist_run: epoch must be >= 1, 1 <= chunks <= 8");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    NttDistPlan* plan = nullptr;
+    DE_TRY(get_dist_plan(ctx, *omega, log_n, world, &plan));
+    DE_TRY(dist_resources(ctx));
+    const uint32_t m = log_n - plan->log_w;
+    const size_t M = (size_t)1 << m;
+    NttDistArgs<true> dx;
+    memset(&dx, 0, sizeof(dx));
+    for (uint32_t i = 0; i < world; i++) dx.peer[i] = (Fr*)d_z_peers[i];
+    dx.col_bits = m - plan->log_w;
+    dx.row_off = (unsigned long long)rank << dx.col_bits;
+    NttFlagPeers fp;
+    memset(&fp, 0, sizeof(fp));
+    for (uint32_t i = 0; i < world; i++) fp.flags[i] = (unsigned int*)d_flag_peers[i];
+    const unsigned int* my_flags = fp.flags[rank];
+    cudaStream_t sa = ctx->stream, sb = ctx->dist_stream;
+    // the cross stream starts behind whatever the main stream holds now (the caller's input, the twiddle tables of a first call)
+    DE_CUDA(ctx, cudaEventRecord(ctx->dist_ev[10], sa));
+    DE_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->dist_ev[10], 0));
+    NttDistChunks ch;
+    ch.chunks = (int)chunks;
+    ch.after_chunk = [&](int k) -> int {
+        k_flag_signal<<<1, 32, 0, sa>>>(fp, world, (unsigned int)k * 8 + rank, epoch);
+        DE_CHECK_LAUNCH(ctx);
+        return DE_OK;
+    };
+    DE_TRY(ntt_run(ctx, plan->omega_local, m, (const Fr*)d_x, M, nullptr, M, 1, 0, 0, nullptr, 0, nullptr, &dx, &ch));
+    // every rank derives the same chunk count from the same shape, so the flag steps match
+    const Fr* d_z = (const Fr*)d_z_peers[rank];
+    for (int k = 0; k < ch.chunks; k++) {
+        k_flag_wait<<<1, 32, 0, sb>>>(my_flags, world, (unsigned int)k, epoch, ctx->dist_error);
+        DE_CHECK_LAUNCH(ctx);
+        DE_TRY(launch_cross_any(ctx, plan, d_z, d_out_peers, rank, sb, k, ch.chunks, ch.period));
     }
+    k_flag_signal<<<1, 32, 0, sb>>>(fp, world, (unsigned int)DE_DIST_DONE_STEP * 8 + rank, epoch);
+    DE_CHECK_LAUNCH(ctx);
+    DE_CUDA(ctx, cudaEventRecord(ctx->dist_ev[8], sb));
+    DE_CUDA(ctx, cudaStreamWaitEvent(sa, ctx->dist_ev[8], 0));
+    k_flag_wait<<<1, 32, 0, sa>>>(my_flags, world, (unsigned int)DE_DIST_DONE_STEP, epoch, ctx->dist_error);
+    DE_CHECK_LAUNCH(ctx);
+    return DE_OK;
+}
+
+// 1 when a flag wait of de_ntt_dist_run gave up on this context since the last call of this function (synchronises the stream)
+int de_ntt_dist_error(de_ctx* ctx, int* timed_out) {
+    if (!ctx || !timed_out) return DE_ERR_ARG;
+    *timed_out = 0;
+    if (!ctx->dist_error) return DE_OK;
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned int v = 0;
+    DE_CUDA(ctx, cudaMemcpyAsync(&v, ctx->dist_error, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (v) DE_CUDA(ctx, cudaMemsetAsync(ctx->dist_error, 0, sizeof(v), ctx->stream));
+    *timed_out = (int)v;
+    return DE_OK;
 }
 
 int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x, de_fr* const* d_out, const de_fr* omega, uint32_t log_n) {
@@ -735,17 +883,20 @@ int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x,
         }
         z[r] = (de_fr*)c->ws[WS_NTT_DIST].ensure(sizeof(Fr) * M);
         if (!z[r]) return fail(c0, DE_ERR_OOM, "de_ntt_sharded_dev: exchange buffer allocation failed");
-        for (auto& e : c->dist_ev)
-            if (!e) DE_CUDA(c0, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        int rc = dist_resources(c);
+        if (rc != DE_OK) return fail(c0, rc, std::string(c->err));
     }
-    // stage 1 everywhere; stage 2 of a rank starts when every rank's stage-1 stores have landed; the call is complete on a
-    // rank's stream when every rank's stage-2 stores have landed (which also orders the next call's stage 1 behind them).
-    // Once the first kernel is queued an error must not return while peers may still be storing into buffers the caller is
-    // about to reuse or free: drain() waits for every participating stream first.
+    // Pipelined exchange (the single-process form of de_ntt_dist_run, ordered by CUDA events instead of flags): every rank's
+    // peer-store pass runs as K ranges of CTAs on its main stream; the cross stage of range k runs on the rank's second stream as
+    // soon as EVERY rank has finished range k, i.e. under the passes of the later ranges; the call is complete on a rank's main
+    // stream when every rank's cross stage has finished (which also orders the next call's stage 1 behind the readers of the
+    // exchange buffers).  Once the first kernel is queued an error must not return while peers may still be storing into buffers
+    // the caller is about to reuse or free: drain() waits for every participating stream first.
     auto drain = [&](int rc, const std::string& msg) -> int {
         for (int r = 0; r < n_gpus; r++) {
             cudaSetDevice(ctxs[r]->device);
             cudaStreamSynchronize(ctxs[r]->stream);
+            if (ctxs[r]->dist_stream) cudaStreamSynchronize(ctxs[r]->dist_stream);
         }
         cudaGetLastError();
         return fail(c0, rc, msg);
@@ -755,26 +906,49 @@ int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x,
         cudaError_t e__ = (expr);                                                                            \
         if (e__ != cudaSuccess) return drain(DE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
     } while (0)
+    int K = 0;
+    unsigned long long period = 0;
+    NttDistPlan* plans[8] = {};
     for (int r = 0; r < n_gpus; r++) {
         de_ctx* c = ctxs[r];
-        int rc = de_ntt_dist_stage1(c, d_x[r], omega, log_n, (uint32_t)n_gpus, (uint32_t)r, z);
+        DE_DIST_CUDA(cudaSetDevice(c->device));
+        int rc = get_dist_plan(c, *omega, log_n, (uint32_t)n_gpus, &plans[r]);
         if (rc != DE_OK) return drain(rc, std::string(c->err));
-        DE_DIST_CUDA(cudaEventRecord(c->dist_ev[0], c->stream));
+        DE_DIST_CUDA(cudaEventRecord(c->dist_ev[10], c->stream));
+        DE_DIST_CUDA(cudaStreamWaitEvent(c->dist_stream, c->dist_ev[10], 0));
+        const uint32_t m = log_n - lw;
+        NttDistArgs<true> dx;
+        memset(&dx, 0, sizeof(dx));
+        for (int i = 0; i < n_gpus; i++) dx.peer[i] = (Fr*)z[i];
+        dx.col_bits = m - lw;
+        dx.row_off = (unsigned long long)r << dx.col_bits;
+        NttDistChunks ch;
+        ch.chunks = 4;
+        ch.after_chunk = [&](int k) -> int {
+            cudaError_t e = cudaEventRecord(c->dist_ev[k], c->stream);
+            return e == cudaSuccess ? DE_OK : fail(c, DE_ERR_CUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e));
+        };
+        rc = ntt_run(c, plans[r]->omega_local, m, (const Fr*)d_x[r], M, nullptr, M, 1, 0, 0, nullptr, 0, nullptr, &dx, &ch);
+        if (rc != DE_OK) return drain(rc, std::string(c->err));
+        K = ch.chunks;  // the same on every rank: it depends on the shape only
+        period = ch.period;
+    }
+    for (int k = 0; k < K; k++)
+        for (int q = 0; q < n_gpus; q++) {
+            de_ctx* c = ctxs[q];
+            DE_DIST_CUDA(cudaSetDevice(c->device));
+            for (int r = 0; r < n_gpus; r++) DE_DIST_CUDA(cudaStreamWaitEvent(c->dist_stream, ctxs[r]->dist_ev[k], 0));
+            int rc = launch_cross_any(c, plans[q], (const Fr*)z[q], d_out, (uint32_t)q, c->dist_stream, k, K, period);
+            if (rc != DE_OK) return drain(rc, std::string(c->err));
+        }
+    for (int q = 0; q < n_gpus; q++) {
+        DE_DIST_CUDA(cudaSetDevice(ctxs[q]->device));
+        DE_DIST_CUDA(cudaEventRecord(ctxs[q]->dist_ev[8], ctxs[q]->dist_stream));
     }
     for (int q = 0; q < n_gpus; q++) {
         de_ctx* c = ctxs[q];
         DE_DIST_CUDA(cudaSetDevice(c->device));
-        for (int r = 0; r < n_gpus; r++)
-            if (r != q) DE_DIST_CUDA(cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[0], 0));
-        int rc = de_ntt_dist_stage2(c, z[q], omega, log_n, (uint32_t)n_gpus, (uint32_t)q, d_out);
-        if (rc != DE_OK) return drain(rc, std::string(c->err));
-        DE_DIST_CUDA(cudaEventRecord(c->dist_ev[1], c->stream));
-    }
-    for (int q = 0; q < n_gpus; q++) {
-        de_ctx* c = ctxs[q];
-        DE_DIST_CUDA(cudaSetDevice(c->device));
-        for (int r = 0; r < n_gpus; r++)
-            if (r != q) DE_DIST_CUDA(cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[1], 0));
+        for (int r = 0; r < n_gpus; r++) DE_DIST_CUDA(cudaStreamWaitEvent(c->stream, ctxs[r]->dist_ev[8], 0));
     }
 #undef DE_DIST_CUDA
     return DE_OK;
@@ -814,7 +988,7 @@ int de_ntt_sharded(de_ctx* const* ctxs, int n_gpus, de_fr* a, const de_fr* omega
         stage[r] = (Fr*)c->ws[WS_IO_A].ensure(sizeof(Fr) * M);
         x[r] = (Fr*)c->ws[WS_NTT_DIST_X].ensure(sizeof(Fr) * M);
         if (!stage[r] || !x[r]) return fail(c0, DE_ERR_OOM, "de_ntt_sharded: staging allocation failed");
-        if (!c->dist_ev[2]) DE_CUDA(c0, cudaEventCreateWithFlags(&c->dist_ev[2], cudaEventDisableTiming));
+        if (!c->dist_ev[9]) DE_CUDA(c0, cudaEventCreateWithFlags(&c->dist_ev[9], cudaEventDisableTiming));
     }
     std::vector<int> rc(n_gpus, DE_OK);
     auto each_gpu = [&](auto fn) {
@@ -839,13 +1013,13 @@ int de_ntt_sharded(de_ctx* const* ctxs, int n_gpus, de_fr* a, const de_fr* omega
         d.row_off = (unsigned long long)r * C;
         k_ntt_deal<<<(unsigned int)((M + 255) / 256), 256, 0, c->stream>>>(d);
         DE_CHECK_LAUNCH(c);
-        DE_CUDA(c, cudaEventRecord(c->dist_ev[2], c->stream));
+        DE_CUDA(c, cudaEventRecord(c->dist_ev[9], c->stream));
         return DE_OK;
     }));
     for (int q = 0; q < n_gpus; q++) {
         DE_CUDA(c0, cudaSetDevice(ctxs[q]->device));
         for (int r = 0; r < n_gpus; r++)
-            if (r != q) DE_CUDA(c0, cudaStreamWaitEvent(ctxs[q]->stream, ctxs[r]->dist_ev[2], 0));
+            if (r != q) DE_CUDA(c0, cudaStreamWaitEvent(ctxs[q]->stream, ctxs[r]->dist_ev[9], 0));
     }
     DE_TRY(de_ntt_sharded_dev(ctxs, n_gpus, (const de_fr* const*)x, (de_fr* const*)stage, omega, log_n));
     return each_gpu([&](int r) -> int {

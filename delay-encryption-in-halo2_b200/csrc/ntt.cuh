@@ -50,6 +50,7 @@ struct NttDistArgs<true> {
     Fr* peer[8];                   // exchange buffers of the ranks (peer-mapped device pointers), world <= 8
     unsigned int col_bits;         // log2 C, C = N / world^2 columns per destination rank
     unsigned long long row_off;    // rank * C: this rank's row inside every exchange buffer
+    unsigned int block_off;        // the pass is launched in chunks of CTAs (pipelined exchange): first CTA of this launch
 };
 
 __device__ __forceinline__ void sm_put(uint4* lo, uint4* hi, int slot, const Fr& v) {
@@ -176,7 +177,9 @@ __global__ void __launch_bounds__(NttShape<S, LT>::NTHREADS, NttShape<S, LT>::MI
     uint4* wlo = hi + Sh::MPAD;
     uint4* whi = wlo + Sh::WN;
     const int tid = threadIdx.x, nthreads = blockDim.x;
-    const unsigned int grp = blockIdx.x / p.G, tile = blockIdx.x % p.G;
+    unsigned int bx = blockIdx.x;
+    if constexpr (DIST) bx += dx.block_off;
+    const unsigned int grp = bx / p.G, tile = bx % p.G;
     const Fr* in = p.in + (unsigned long long)blockIdx.y * p.in_batch_stride;
     Fr* out = p.out + (unsigned long long)blockIdx.y * p.out_batch_stride;
     const unsigned long long in_base = grp * p.in_grp + tile * p.in_blk;
@@ -272,13 +275,19 @@ struct NttCrossArgs {
     Fr* peer_out[1 << LW];
     unsigned long long C;
     unsigned long long out_off;  // rank * C
+    // pipelined exchange: this launch covers the columns s * period + chunk_off + u, s < C / period, u < chunk_len - the columns
+    // a contiguous range of CTAs of every rank's exchange pass has produced (period = M / L of that pass).  Unchunked:
+    // period = chunk_len = C, chunk_off = 0.
+    unsigned long long period, chunk_off, chunk_len;
     Fr w[(1 << LW) / 2 < 1 ? 1 : (1 << LW) / 2];  // w_W^i, i < W/2
 };
 template <int LW>
 __global__ void __launch_bounds__(128) k_ntt_cross(const __grid_constant__ NttCrossArgs<LW> a) {
     constexpr int W = 1 << LW;
-    unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.C) return;
+    const unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long srow = id / a.chunk_len;  // sub-row of the exchange pass' output inside this rank's column range
+    const unsigned long long c = srow * a.period + a.chunk_off + (id - srow * a.chunk_len);
+    if (srow * a.period >= a.C) return;
     Fr x[W];
 #pragma unroll
     for (int i = 0; i < W; i++) x[i] = load256(&a.z[(unsigned long long)i * a.C + c]);
@@ -304,6 +313,43 @@ __global__ void __launch_bounds__(128) k_ntt_cross(const __grid_constant__ NttCr
 #pragma unroll
         for (int b = 0; b < LW; b++) j1 |= ((p >> b) & 1) << (LW - 1 - b);
         store256(&a.peer_out[j1][a.out_off + c], x[p]);
+    }
+}
+
+// ---- ordering of the exchange stages across PROCESSES (one process per GPU): flags in peer memory ----------------------------
+// Every rank owns an array of u32 flags that the others can store into (CUDA IPC mapping).  slot(k, r) = k * 8 + r holds the
+// epoch (a per-call counter, the same on all ranks) up to which rank r has completed step k: steps 0 .. K - 1 are the chunks
+// of the exchange pass, step DE_DIST_DONE_STEP the whole cross stage.  A signal is a system-scope release store after a system
+// fence (the data stores of the preceding kernels on the same stream have completed); a wait spins on acquire loads, gives
+// up after ~2 s and raises *error instead of hanging the GPU.
+#define DE_DIST_MAX_CHUNKS 8
+#define DE_DIST_DONE_STEP DE_DIST_MAX_CHUNKS
+#define DE_DIST_FLAG_WORDS ((DE_DIST_MAX_CHUNKS + 1) * 8)
+struct NttFlagPeers {
+    unsigned int* flags[8];
+};
+__global__ void k_flag_signal(const __grid_constant__ NttFlagPeers peers, unsigned int world, unsigned int slot, unsigned int epoch) {
+    if (threadIdx.x >= world) return;
+    __threadfence_system();
+    unsigned int* f = peers.flags[threadIdx.x] + slot;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+}
+__global__ void k_flag_wait(const unsigned int* flags, unsigned int world, unsigned int step, unsigned int epoch, unsigned int* error) {
+    if (threadIdx.x >= world) return;
+    const unsigned int* f = flags + step * 8 + threadIdx.x;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) {  // 2 s: a peer never arrived
+            atomicExch(error, 1u);
+            break;
+        }
+        __nanosleep(200);
     }
 }
 

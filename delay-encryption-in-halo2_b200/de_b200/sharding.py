@@ -197,13 +197,17 @@ class ShardedNtt:
 
 
 class DistNtt:
-    """The same transform with one process per GPU (torch.distributed, NCCL): every rank allocates its exchange and output buffers
-    with de_dev_alloc, the 64-byte CUDA IPC handles are all-gathered once, and each call is
-        stage 1 (peer stores into the owners' exchange buffers) -> barrier -> stage 2 (peer stores into the owners' output blocks)
-        -> barrier,
-    the barriers being 1-element all-reduces enqueued on the context's stream.  No bulk data goes through a library collective."""
+    """The same transform with one process per GPU (torch.distributed for the one-time set-up only): every rank allocates its
+    input, exchange and output buffers and a few flag words with de_dev_alloc, the 64-byte CUDA IPC handles are all-gathered
+    once, and each call is ONE de_ntt_dist_run per rank: the peer-store pass in `chunks` ranges, each followed by a flag store
+    to every rank; the cross stage of a range starts on the context's second stream as soon as every rank has signalled that
+    range (so it runs under the pass of the next range); a last flag round makes the call complete in stream order.  No library
+    collective is on the data path or between the stages.  pipelined=False keeps round 1's form (stage 1 -> 1-element NCCL
+    all-reduce -> stage 2 -> all-reduce) for comparison."""
 
-    def __init__(self, ctx, log_n: int, group=None):
+    FLAG_BYTES = 288  # DE_NTT_DIST_FLAG_BYTES
+
+    def __init__(self, ctx, log_n: int, group=None, pipelined: bool = True, chunks: int = 4):
         import ctypes as C
         import torch
         import torch.distributed as dist
@@ -213,14 +217,19 @@ class DistNtt:
         self.stream = torch.cuda.Stream(device=ctx.device)
         ctx.set_stream(self.stream.cuda_stream)
         self.token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{ctx.device}")
+        self.pipelined, self.chunks, self.epoch = pipelined, chunks, 0
         L = ctx.L
         self.own, self.mapped = [], []
         peers, err = [], None
-        for _ in range(3):  # input, exchange, output
+        for which in range(4):  # input, exchange, output, flags
             p = C.c_void_p()
             h = (C.c_uint8 * 64)()
             try:
-                ctx.check(L.de_dev_alloc(ctx.h, 32 * self.m, C.byref(p)))
+                ctx.check(L.de_dev_alloc(ctx.h, 32 * self.m if which < 3 else self.FLAG_BYTES, C.byref(p)))
+                if which == 3:
+                    zero = torch.zeros(self.FLAG_BYTES, dtype=torch.uint8, device=f"cuda:{ctx.device}")
+                    ctx.check(L.de_dev_copy(ctx.h, C.c_void_p(p.value), C.c_void_p(zero.data_ptr()), self.FLAG_BYTES))
+                    ctx.sync()
                 self.own.append(p.value)
                 ctx.check(L.de_ipc_export(ctx.h, C.c_void_p(p.value), h))
             except Exception as e:  # keep the collectives below matched on every rank, fail together afterwards
@@ -246,9 +255,11 @@ class DistNtt:
         if int(ok.item()) == 0:
             self._release(lambda: dist.barrier(group=group))
             raise RuntimeError(f"DistNtt: mapping the ranks' buffers failed on at least one rank ({err or 'another rank'})")
-        self.d_x, self.d_z, self.d_out = self.own
+        self.d_x, self.d_z, self.d_out, self.d_flags = self.own
         self.z_peers = (C.c_void_p * self.world)(*peers[1])
         self.out_peers = (C.c_void_p * self.world)(*peers[2])
+        self.flag_peers = (C.c_void_p * self.world)(*peers[3])
+        dist.barrier(group=group)  # every rank's flag words are zero before anybody signals
 
     def _barrier(self):
         import torch.distributed as dist
@@ -261,6 +272,11 @@ class DistNtt:
         import torch
         om = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
         ctx, L = self.ctx, self.ctx.L
+        if self.pipelined:
+            self.epoch += 1
+            ctx.check(L.de_ntt_dist_run(ctx.h, C.c_void_p(self.d_x), om.ctypes.data_as(C.c_void_p), self.log_n, self.world, self.rank,
+                                        self.z_peers, self.out_peers, self.flag_peers, self.epoch, self.chunks))
+            return
         with torch.cuda.stream(self.stream):
             ctx.check(L.de_ntt_dist_stage1(ctx.h, C.c_void_p(self.d_x), om.ctypes.data_as(C.c_void_p), self.log_n, self.world, self.rank,
                                            self.z_peers))
@@ -268,6 +284,13 @@ class DistNtt:
             ctx.check(L.de_ntt_dist_stage2(ctx.h, C.c_void_p(self.d_z), om.ctypes.data_as(C.c_void_p), self.log_n, self.world, self.rank,
                                            self.out_peers))
             self._barrier()
+
+    def timed_out(self) -> bool:
+        """True when a flag wait gave up (a rank never arrived) since the last call; synchronises the stream"""
+        import ctypes as C
+        v = C.c_int(0)
+        self.ctx.check(self.ctx.L.de_ntt_dist_error(self.ctx.h, C.byref(v)))
+        return bool(v.value)
 
     def _release(self, group_barrier=None):
         import ctypes as C
