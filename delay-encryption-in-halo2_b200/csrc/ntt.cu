@@ -3,6 +3,7 @@
 // Reference semantics: halo2_proofs::arithmetic::best_fft and poly::EvaluationDomain.
 #include <atomic>
 #include <functional>
+#include <stdlib.h>
 #include <string.h>
 
 #include <thread>
@@ -923,7 +924,11 @@ int de_ntt_sharded_dev(de_ctx* const* ctxs, int n_gpus, const de_fr* const* d_x,
         dx.col_bits = m - lw;
         dx.row_off = (unsigned long long)r << dx.col_bits;
         NttDistChunks ch;
-        ch.chunks = 4;
+        // ranges of the pipelined exchange: 1 (not pipelined) by default - measured on 8 B200s, 2 and 4 ranges are SLOWER (2^27:
+        // 4.42 ms with 1, 4.49 with 2, 4.67 with 4): both stages push their peer stores through the same NVLink egress, and the
+        // pass kernel's CTAs hold the whole register file, so the cross stage's CTAs only get in as the pass drains
+        ch.chunks = 1;
+        if (const char* e = getenv("DE_NTT_DIST_CHUNKS")) ch.chunks = atoi(e) >= 1 && atoi(e) <= DE_DIST_MAX_CHUNKS ? atoi(e) : 1;
         ch.after_chunk = [&](int k) -> int {
             cudaError_t e = cudaEventRecord(c->dist_ev[k], c->stream);
             return e == cudaSuccess ? DE_OK : fail(c, DE_ERR_CUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e));

@@ -201,13 +201,15 @@ class DistNtt:
     input, exchange and output buffers and a few flag words with de_dev_alloc, the 64-byte CUDA IPC handles are all-gathered
     once, and each call is ONE de_ntt_dist_run per rank: the peer-store pass in `chunks` ranges, each followed by a flag store
     to every rank; the cross stage of a range starts on the context's second stream as soon as every rank has signalled that
-    range (so it runs under the pass of the next range); a last flag round makes the call complete in stream order.  No library
-    collective is on the data path or between the stages.  pipelined=False keeps round 1's form (stage 1 -> 1-element NCCL
-    all-reduce -> stage 2 -> all-reduce) for comparison."""
+    range; a last flag round makes the call complete in stream order.  No library collective is on the data path or between the
+    stages.  chunks = 1 (default) orders the two stages with flags only; 2 / 4 pipeline the cross stage under the later ranges
+    of the pass, which measured slower on 8 B200s (2^27: 4.42 / 4.49 / 4.67 ms for 1 / 2 / 4 ranges: both stages share the
+    NVLink egress and the pass' CTAs fill the register file).  pipelined=False keeps round 1's form (stage 1 -> 1-element NCCL
+    all-reduce -> stage 2 -> all-reduce; 4.46 ms) for comparison."""
 
     FLAG_BYTES = 288  # DE_NTT_DIST_FLAG_BYTES
 
-    def __init__(self, ctx, log_n: int, group=None, pipelined: bool = True, chunks: int = 4):
+    def __init__(self, ctx, log_n: int, group=None, pipelined: bool = True, chunks: int = 1):
         import ctypes as C
         import torch
         import torch.distributed as dist

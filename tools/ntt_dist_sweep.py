@@ -147,14 +147,14 @@ def run_sharded(args):
     ref_ctx.close()
 
 
-def measure_dist(ctx, log_n, reps, emit=True, pipelined=True):
+def measure_dist(ctx, log_n, reps, emit=True, pipelined=True, chunks=1):
     """one process per GPU (torch.distributed already initialised, NCCL): transform one 2^log_n vector over all ranks with DistNtt,
     check it on rank 0 against the single-GPU transform, return the result line there (None elsewhere).  bench.py calls this too."""
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = f"cuda:{ctx.device}"
     omega = omega_for(log_n)
-    d = sharding.DistNtt(ctx, log_n, pipelined=pipelined)
+    d = sharding.DistNtt(ctx, log_n, pipelined=pipelined, chunks=chunks)
     m = d.m
     x = uniform_fr_dev(m, 0xDE06 + 97 * rank + log_n, dev)
     torch.cuda.synchronize()
@@ -187,7 +187,7 @@ def measure_dist(ctx, log_n, reps, emit=True, pipelined=True):
         ref_ctx = de_b200.Context(ctx.device)
         want, single_ms = single_gpu_reference(ref_ctx, xs, log_n, omega, reps, dev)
         ok = all(torch.equal(o, want[r * m:(r + 1) * m]) for r, o in enumerate(os_))
-        res = line("one process per GPU (CUDA IPC peer buffers; exchange pipelined in 4 ranges, stages ordered by peer-memory flags)" if pipelined
+        res = line(f"one process per GPU (CUDA IPC peer buffers; exchange in {chunks} range(s), stages ordered by peer-memory flags)" if pipelined
                    else "one process per GPU (CUDA IPC peer buffers, NCCL 1-element barriers)", world, log_n, best, ok, single_ms, emit=emit,
                    peer_bytes_per_gpu=2 * 32 * m * (world - 1) // world)
         ref_ctx.close()
@@ -206,7 +206,7 @@ def run_dist(args):
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     ctx = de_b200.Context(local)
     for log_n in args.log_n:
-        measure_dist(ctx, log_n, args.reps, pipelined=not args.barriers)
+        measure_dist(ctx, log_n, args.reps, pipelined=not args.barriers, chunks=args.chunks)
     ctx.close()
     dist.destroy_process_group()
 
@@ -216,6 +216,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=2, help="ranks of the single-process mode (ignored under torchrun)")
     ap.add_argument("--log-n", type=int, nargs="+", default=[20, 22, 24])
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--chunks", type=int, default=1, help="torchrun mode: column ranges of the pipelined exchange (1 = not pipelined, flags only)")
     ap.add_argument("--barriers", action="store_true", help="torchrun mode: round 1's unpipelined form with NCCL 1-element barriers")
     a = ap.parse_args()
     if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
