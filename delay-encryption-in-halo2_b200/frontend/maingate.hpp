@@ -268,8 +268,20 @@ struct Combination {
 
 class MainGate {
   public:
-    explicit MainGate(Assignment& a) : as(a) {}
+    explicit MainGate(Assignment& a) : as(a), one(F::one()), minus_one(-F::one()) {}
     Assignment& as;
+    const F one, minus_one;
+
+    // create_proof's pass (witness_only) needs the VALUES of a row and nothing else - no selectors, no copy constraints: the hot
+    // instructions write their up to five cells directly (nv = cells used, the rest of the row stays zero) and return cell `res`
+    Cell fast_row(const F* v, int nv, int res) {
+        as.need_rows(1);
+        const uint32_t row = (uint32_t)as.offset++;
+        for (int c = 0; c < nv; c++) as.advice[c][row] = v[c];
+        Cell out;
+        out.col = (uint32_t)res; out.row = row; out.value = v[res];
+        return out;
+    }
 
     // one gate row: the five terms go to a..e with their bases as sa..se.  Returns the five cells of the row.
     void apply(const Term (&t)[5], const F& constant, const Combination& opt, Cell (&out)[5]) {
@@ -301,13 +313,14 @@ class MainGate {
 
     // ---- assignment ----
     Cell assign_value(const F& v) {  // a witness cell, unconstrained
+        if (as.witness_only) return fast_row(&v, 1, 0);
         return apply1(Term::unassigned(v, F::zero()), Term::zero(), Term::zero(), Term::zero(), Term::zero(), F::zero(), Combination::add(), 0);
     }
     Cell assign_constant(const F& c) {  // -a + c = 0
-        return apply1(Term::unassigned(c, -F::one()), Term::zero(), Term::zero(), Term::zero(), Term::zero(), c, Combination::add(), 0);
+        return apply1(Term::unassigned(c, minus_one), Term::zero(), Term::zero(), Term::zero(), Term::zero(), c, Combination::add(), 0);
     }
     Cell assign_bit(const F& bit) {  // a b - c = 0 with a = b = c
-        Term t[5] = {Term::unassigned(bit, F::zero()), Term::unassigned(bit, F::zero()), Term::unassigned(bit, -F::one()), Term::zero(), Term::zero()};
+        Term t[5] = {Term::unassigned(bit, F::zero()), Term::unassigned(bit, F::zero()), Term::unassigned(bit, minus_one), Term::zero(), Term::zero()};
         Cell out[5];
         apply(t, F::zero(), Combination::mul(), out);
         as.copy(out[0], out[1]);
@@ -317,42 +330,66 @@ class MainGate {
     // ---- arithmetic: one row each ----
     Cell add(const Cell& a, const Cell& b) { return add_with_constant(a, b, F::zero()); }
     Cell add_with_constant(const Cell& a, const Cell& b, const F& k) {  // a + b + k - c = 0
-        return apply1(Term::assigned(a, F::one()), Term::assigned(b, F::one()), Term::unassigned(a.value + b.value + k, -F::one()), Term::zero(),
+        if (as.witness_only) {
+            const F v[3] = {a.value, b.value, a.value + b.value + k};
+            return fast_row(v, 3, 2);
+        }
+        return apply1(Term::assigned(a, one), Term::assigned(b, one), Term::unassigned(a.value + b.value + k, minus_one), Term::zero(),
                       Term::zero(), k, Combination::add(), 2);
     }
     Cell add_constant(const Cell& a, const F& k) {  // a + k - b = 0
-        return apply1(Term::assigned(a, F::one()), Term::unassigned(a.value + k, -F::one()), Term::zero(), Term::zero(), Term::zero(), k,
+        if (as.witness_only) {
+            const F v[2] = {a.value, a.value + k};
+            return fast_row(v, 2, 1);
+        }
+        return apply1(Term::assigned(a, one), Term::unassigned(a.value + k, minus_one), Term::zero(), Term::zero(), Term::zero(), k,
                       Combination::add(), 1);
     }
     Cell sub(const Cell& a, const Cell& b) {  // a - b - c = 0
-        return apply1(Term::assigned(a, F::one()), Term::assigned(b, -F::one()), Term::unassigned(a.value - b.value, -F::one()), Term::zero(),
+        if (as.witness_only) {
+            const F v[3] = {a.value, b.value, a.value - b.value};
+            return fast_row(v, 3, 2);
+        }
+        return apply1(Term::assigned(a, one), Term::assigned(b, minus_one), Term::unassigned(a.value - b.value, minus_one), Term::zero(),
                       Term::zero(), F::zero(), Combination::add(), 2);
     }
     Cell mul(const Cell& a, const Cell& b) {  // a b - c = 0
-        return apply1(Term::assigned(a, F::zero()), Term::assigned(b, F::zero()), Term::unassigned(a.value * b.value, -F::one()), Term::zero(),
+        if (as.witness_only) {
+            const F v[3] = {a.value, b.value, a.value * b.value};
+            return fast_row(v, 3, 2);
+        }
+        return apply1(Term::assigned(a, F::zero()), Term::assigned(b, F::zero()), Term::unassigned(a.value * b.value, minus_one), Term::zero(),
                       Term::zero(), F::zero(), Combination::mul(), 2);
     }
     Cell mul_add(const Cell& a, const Cell& b, const Cell& to_add) {  // a b + c - d = 0
-        return apply1(Term::assigned(a, F::zero()), Term::assigned(b, F::zero()), Term::assigned(to_add, F::one()),
-                      Term::unassigned(a.value * b.value + to_add.value, -F::one()), Term::zero(), F::zero(), Combination::mul(), 3);
+        if (as.witness_only) {
+            const F v[4] = {a.value, b.value, to_add.value, a.value * b.value + to_add.value};
+            return fast_row(v, 4, 3);
+        }
+        return apply1(Term::assigned(a, F::zero()), Term::assigned(b, F::zero()), Term::assigned(to_add, one),
+                      Term::unassigned(a.value * b.value + to_add.value, minus_one), Term::zero(), F::zero(), Combination::mul(), 3);
     }
     Cell mul_add_constant(const Cell& a, const Cell& b, const F& k) {  // a b + k - c = 0
-        return apply1(Term::assigned(a, F::zero()), Term::assigned(b, F::zero()), Term::unassigned(a.value * b.value + k, -F::one()), Term::zero(),
+        if (as.witness_only) {
+            const F v[3] = {a.value, b.value, a.value * b.value + k};
+            return fast_row(v, 3, 2);
+        }
+        return apply1(Term::assigned(a, F::zero()), Term::assigned(b, F::zero()), Term::unassigned(a.value * b.value + k, minus_one), Term::zero(),
                       Term::zero(), k, Combination::mul(), 2);
     }
     // ---- booleans ----
     Cell and_(const Cell& a, const Cell& b) { return mul(a, b); }
     Cell not_(const Cell& a) {  // 1 - a - b = 0
-        return apply1(Term::assigned(a, -F::one()), Term::unassigned(F::one() - a.value, -F::one()), Term::zero(), Term::zero(), Term::zero(), F::one(),
+        return apply1(Term::assigned(a, minus_one), Term::unassigned(one - a.value, minus_one), Term::zero(), Term::zero(), Term::zero(), one,
                       Combination::add(), 1);
     }
     // r = 1 if a == 0 else 0: r is a bit; a a' + r - 1 = 0; r a = 0
     Cell is_zero(const Cell& a) {
         const bool z = a.value.is_zero();
-        Cell r = assign_bit(z ? F::one() : F::zero());
+        Cell r = assign_bit(z ? one : F::zero());
         // a' = 1 / a (1 when a = 0) is needed by no later instruction: the cell takes the value now and its inverse in finalize()
-        const Cell inv_cell = apply1(Term::assigned(a, F::zero()), Term::unassigned(z ? F::one() : a.value, F::zero()), Term::assigned(r, F::one()),
-                                     Term::zero(), Term::zero(), -F::one(), Combination::mul(), 1);
+        const Cell inv_cell = apply1(Term::assigned(a, F::zero()), Term::unassigned(z ? one : a.value, F::zero()), Term::assigned(r, one),
+                                     Term::zero(), Term::zero(), minus_one, Combination::mul(), 1);
         if (!z) as.pending_inverse.push_back({inv_cell.col, inv_cell.row});
         apply1(Term::assigned(a, F::zero()), Term::assigned(r, F::zero()), Term::zero(), Term::zero(), Term::zero(), F::zero(), Combination::mul(), 0);
         return r;
@@ -361,21 +398,25 @@ class MainGate {
     // cond a + (1 - cond) b:  a cond - cond b + b - e = 0   (cells: a, cond, cond, b, result)
     Cell select(const Cell& a, const Cell& b, const Cell& cond) {
         const F res = cond.value * a.value + b.value - cond.value * b.value;
+        if (as.witness_only) {
+            const F v[5] = {a.value, cond.value, cond.value, b.value, res};
+            return fast_row(v, 5, 4);
+        }
         Combination opt;
-        opt.mul_ab = F::one();
-        opt.mul_cd = -F::one();
-        return apply1(Term::assigned(a, F::zero()), Term::assigned(cond, F::zero()), Term::assigned(cond, F::zero()), Term::assigned(b, F::one()),
-                      Term::unassigned(res, -F::one()), F::zero(), opt, 4);
+        opt.mul_ab = one;
+        opt.mul_cd = minus_one;
+        return apply1(Term::assigned(a, F::zero()), Term::assigned(cond, F::zero()), Term::assigned(cond, F::zero()), Term::assigned(b, one),
+                      Term::unassigned(res, minus_one), F::zero(), opt, 4);
     }
     // ---- assertions ----
     void assert_equal(const Cell& a, const Cell& b) { as.copy(a, b); }
     void assert_zero(const Cell& a) {
         if (!a.value.is_zero()) throw std::runtime_error("assert_zero on a non-zero cell (row " + std::to_string(a.row) + ")");
-        apply1(Term::assigned(a, F::one()), Term::zero(), Term::zero(), Term::zero(), Term::zero(), F::zero(), Combination::add(), 0);
+        apply1(Term::assigned(a, one), Term::zero(), Term::zero(), Term::zero(), Term::zero(), F::zero(), Combination::add(), 0);
     }
     void assert_one(const Cell& a) {
-        if (a.value != F::one()) throw std::runtime_error("assert_one on a cell that is not one (row " + std::to_string(a.row) + ")");
-        apply1(Term::assigned(a, F::one()), Term::zero(), Term::zero(), Term::zero(), Term::zero(), -F::one(), Combination::add(), 0);
+        if (a.value != one) throw std::runtime_error("assert_one on a cell that is not one (row " + std::to_string(a.row) + ")");
+        apply1(Term::assigned(a, one), Term::zero(), Term::zero(), Term::zero(), Term::zero(), minus_one, Combination::add(), 0);
     }
     // ---- compose / decompose: chunks of four terms, running sum in e ----
     // result = constant + sum of value_i * base_i.  Row j holds terms 4j .. 4j+3 in a..d and the remaining sum R_j in e with
@@ -400,7 +441,7 @@ class MainGate {
             sums[0] = sums[0] + constant;
             remaining = sums;
         }
-        const F minus_one = -F::one();
+        const F minus_one = minus_one;
         Cell result;
         for (size_t j = 0; j < chunks; j++) {
             Term row[5];
@@ -409,7 +450,7 @@ class MainGate {
             const bool last = j + 1 == chunks;
             on_row((uint32_t)as.offset, last);
             Cell out[5];
-            apply(row, j == 0 ? constant : F::zero(), last ? Combination::add() : Combination::add_to_next(F::one()), out);
+            apply(row, j == 0 ? constant : F::zero(), last ? Combination::add() : Combination::add_to_next(one), out);
             if (j == 0) result = out[4];
             if (term_cells)
                 for (size_t i = 0; i < 4 && 4 * j + i < terms.size(); i++) term_cells->push_back(out[i]);
@@ -426,7 +467,7 @@ class MainGate {
         std::vector<Cell> bits;
         std::vector<Term> terms;
         for (size_t i = 0; i < number_of_bits; i++) {
-            bits.push_back(assign_bit(v.extract(i, 1) ? F::one() : F::zero()));
+            bits.push_back(assign_bit(v.extract(i, 1) ? one : F::zero()));
             terms.push_back(Term::assigned(bits.back(), F::pow2(i)));
         }
         assert_equal(compose(terms, F::zero()), a);
