@@ -441,7 +441,6 @@ class MainGate {
             sums[0] = sums[0] + constant;
             remaining = sums;
         }
-        const F minus_one = minus_one;
         Cell result;
         for (size_t j = 0; j < chunks; j++) {
             Term row[5];
