@@ -150,7 +150,7 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CHECK_LAUNCH(ctx);
     k_msm_merge_small<<<ctx->sm_count * 4, 128, 0, st>>>(multi_small, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    k_msm_merge_large<<<ctx->sm_count * 2, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
+    k_msm_merge_large<<<ctx->sm_count * 4, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
     if (sh.c >= 11 && sh.c <= 16 && ctx->mode == DE_MODE_LATENCY) {
         // latency-oriented two-digit reduction (4c): row / column sums in one launch, bit sums, one warp per set for the fold

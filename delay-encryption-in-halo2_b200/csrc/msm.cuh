@@ -296,28 +296,45 @@ __global__ void __launch_bounds__(128) k_msm_merge_small(const unsigned int* mul
         store_xyzz(&buckets[b], acc);
     }
 }
-// heavy buckets (> 8 tasks): one warp per bucket, lanes stride over the partial sums, then a shuffle tree
+// heavy buckets (> 8 tasks): one 128-thread CTA per bucket - the threads stride over the partial sums (a witness column's 0 / 1
+// digits put thousands of partials into one bucket: 128 lanes keep that chain at count / 128 additions), a shuffle tree inside
+// every warp, then warp 0 adds the four warp sums.  Buckets with <= 32 partials use the first warp only.
 __global__ void __launch_bounds__(128) k_msm_merge_large(const unsigned int* multi_large, const unsigned int* scal, const unsigned int* task_off,
                                                          const XYZZ* partials, XYZZ* buckets) {
-    const unsigned int lane = threadIdx.x & 31;
-    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ XYZZ swarp[4];
+    const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned int total = scal[3];
-    for (unsigned int m = warp; m < total; m += nwarps) {
+    for (unsigned int m = blockIdx.x; m < total; m += gridDim.x) {
         const unsigned int b = multi_large[m];
         const unsigned int first = task_off[b], last = task_off[b + 1];
+        const unsigned int cnt = last - first;
+        const unsigned int stride = cnt > 32 ? 128u : 32u;  // CTA-uniform
         XYZZ acc = xyzz_identity();
-        for (unsigned int p = first + lane; p < last; p += 32) {
-            XYZZ v = load_xyzz(&partials[p]);
-            xyzz_add(acc, v);
+        if (tid < stride)
+            for (unsigned int p = first + tid; p < last; p += stride) {
+                XYZZ v = load_xyzz(&partials[p]);
+                xyzz_add(acc, v);
+            }
+        const unsigned int np = cnt < 32 ? cnt : 32;  // lanes >= np of warp 0 hold the identity when cnt < 32
+        if (stride == 128 || wid == 0) {
+            for (unsigned int d = 16; d >= 1; d >>= 1) {
+                if (stride == 32 && d >= np) continue;  // warp-uniform: nothing but identities above lane d
+                XYZZ o = shfl_down_xyzz(acc, (int)d);
+                if (lane + d < 32) xyzz_add(acc, o);
+            }
         }
-        const unsigned int np = (last - first) < 32 ? (last - first) : 32;  // lanes >= np hold the identity
-        for (unsigned int d = 16; d >= 1; d >>= 1) {
-            if (d >= np) continue;  // warp-uniform: nothing but identities above lane d
-            XYZZ o = shfl_down_xyzz(acc, (int)d);
-            if (lane + d < 32) xyzz_add(acc, o);
+        if (stride == 128) {
+            if (lane == 0) swarp[wid] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                for (unsigned int w = 1; w < 4; w++) {
+                    XYZZ o = swarp[w];
+                    xyzz_add(acc, o);
+                }
+            }
+            __syncthreads();  // swarp is reused by the next bucket of this CTA
         }
-        if (lane == 0) store_xyzz(&buckets[b], acc);
+        if (tid == 0) store_xyzz(&buckets[b], acc);
     }
 }
 
