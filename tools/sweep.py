@@ -85,7 +85,15 @@ def main():
     ap.add_argument("--msm-from", type=int, default=16, help="2^26 on one GPU wants DE_MSM_TABLE_MB=80000 (64 GiB of window tables)")
     ap.add_argument("--ntt-to", type=int, default=27)
     ap.add_argument("--ntt-from", type=int, default=16)
+    ap.add_argument("--cpu-to", type=int, default=0,
+                    help="also time the CPU restatement of the reference (best_multiexp / best_fft on all host cores, the checker library "
+                         "under oracle/) on the same inputs up to 2^CPU_TO and compare the results: BASELINE config 4's 'vs reference' column")
     args = ap.parse_args()
+    orc = None
+    if args.cpu_to:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc  # noqa: E402  (measurement tool: the CPU side of the comparison)
+        import time
     stream = torch.cuda.Stream()
     ctx = de_b200.Context(0)
     ctx.set_stream(stream.cuda_stream)
@@ -104,9 +112,23 @@ def main():
             ms = ev_time(stream, lambda: ctx.best_fft_dev(d, dom.omega, log_n), 5)
             gbs = 64.0 * n / (ms * 1e-3) / 1e9
             muls = n / 2 * log_n
-            print(json.dumps({"op": "ntt", "log_n": log_n, "ms": ms, "gb_s": gbs, "frac_hbm": gbs / HBM, "gmul_s": muls / (ms * 1e-3) / 1e9,
-                              "frac_int_pipe": muls / (ms * 1e-3) / MUL_PEAK, "ok": ok,
-                              "check": "lagrange_to_coeff(coeff_to_lagrange(a)) == a over the whole vector (device compare)"}), flush=True)
+            rec = {"op": "ntt", "log_n": log_n, "ms": ms, "gb_s": gbs, "frac_hbm": gbs / HBM, "gmul_s": muls / (ms * 1e-3) / 1e9,
+                   "frac_int_pipe": muls / (ms * 1e-3) / MUL_PEAK, "ok": ok,
+                   "check": "lagrange_to_coeff(coeff_to_lagrange(a)) == a over the whole vector (device compare)"}
+            if orc is not None and log_n <= args.cpu_to:
+                host = a.cpu().numpy().view(np.uint64)
+                t0 = time.perf_counter()
+                want = orc.best_fft(host, dom.omega, log_n)
+                rec["cpu_best_fft_ms"] = (time.perf_counter() - t0) * 1e3
+                rec["cpu_cores"] = orc.ncpu()
+                rec["cpu_gb_s"] = 64.0 * n / (rec["cpu_best_fft_ms"] * 1e-3) / 1e9
+                g = a.clone()
+                ctx.best_fft_dev(g, dom.omega, log_n)
+                ctx.sync()
+                rec["equals_cpu_best_fft"] = bool((g.cpu().numpy().view(np.uint64) == want).all())
+                rec["speedup_vs_cpu"] = rec["cpu_best_fft_ms"] / ms
+                del g
+            print(json.dumps(rec), flush=True)
             dom.close()
             del d, a
         # ---------------- MSM
@@ -143,9 +165,19 @@ def main():
                 ok = bool((aff[0] == aff[1]).all() and (aff[2] == aff[3]).all() and aff[2].any())
                 ms_c = ev_time(stream, lambda: params.commit_batch_dev(1, d_a, n, 1), 3)
                 ms_r = ev_time(stream, lambda: ctx.best_multiexp_dev(d_a, d_bases, n), 3)
-                print(json.dumps({"op": "msm", "log_n": log_n, "scalars": kind, "commit_ms": ms_c, "commit_gpts_s": n / (ms_c * 1e-3) / 1e9,
-                                  "raw_ms": ms_r, "raw_gpts_s": n / (ms_r * 1e-3) / 1e9, "ok": ok,
-                                  "check": "commit(a) + commit(b) == commit(a + b); raw best_multiexp == table-based commit"}), flush=True)
+                rec = {"op": "msm", "log_n": log_n, "scalars": kind, "commit_ms": ms_c, "commit_gpts_s": n / (ms_c * 1e-3) / 1e9,
+                       "raw_ms": ms_r, "raw_gpts_s": n / (ms_r * 1e-3) / 1e9, "ok": ok,
+                       "check": "commit(a) + commit(b) == commit(a + b); raw best_multiexp == table-based commit"}
+                if orc is not None and log_n <= args.cpu_to:
+                    bases_h = d_bases.cpu().numpy().view(np.uint64)
+                    t0 = time.perf_counter()
+                    want = orc.best_multiexp(ha, bases_h)
+                    rec["cpu_best_multiexp_ms"] = (time.perf_counter() - t0) * 1e3
+                    rec["cpu_cores"] = orc.ncpu()
+                    rec["cpu_gpts_s"] = n / (rec["cpu_best_multiexp_ms"] * 1e-3) / 1e9
+                    rec["equals_cpu_best_multiexp"] = bool((orc.g1_to_affine(want.reshape(1, 12)) == ctx.batch_normalize(ca.reshape(1, 12))).all())
+                    rec["speedup_vs_cpu"] = rec["cpu_best_multiexp_ms"] / ms_c
+                print(json.dumps(rec), flush=True)
                 del d_a, d_b, d_ab
             params.close()
             del d_bases
