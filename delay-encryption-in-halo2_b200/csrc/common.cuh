@@ -2,6 +2,8 @@
 // device workspaces, error capture.  No arithmetic lives here.
 #pragma once
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -168,6 +170,21 @@ inline void timing_end(de_ctx* ctx, TimedLaunch& tl) {
     if (ctx->timing) {
         cudaEventRecord(tl.e1, ctx->stream);
         ctx->timed.push_back(tl);
+    }
+}
+
+// Host wait for everything queued on `st`.  DE_MODE_LATENCY spins inside the driver (cudaStreamSynchronize: lowest wake-up
+// latency, one proof owns the machine).  DE_MODE_THROUGHPUT polls and YIELDS between polls: with 8 provers per GPU (x 8 GPUs on a
+// 32-core host) every prover thread waits several times per proof, and 64 spinning waiters would hold the cores the witness
+// passes of the end-to-end path need; sched_yield returns at once while cores are idle, so nothing is lost at one GPU.  (A
+// cudaEventBlockingSync wait was measured too: +2 % end to end on 8 GPUs but -2 % on one, from the interrupt wake-up latency.)
+inline cudaError_t stream_wait(de_ctx* ctx, cudaStream_t st) {
+    static const bool spin = getenv("DE_WAIT_SPIN") != nullptr;  // A/B switch for measurements
+    if (ctx->mode != DE_MODE_THROUGHPUT || spin) return cudaStreamSynchronize(st);
+    for (;;) {
+        cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaErrorNotReady) return e;
+        sched_yield();
     }
 }
 

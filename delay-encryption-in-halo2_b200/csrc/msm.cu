@@ -231,7 +231,7 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CUDA(ctx, cudaMemcpyAsync(out_mode == 1 ? (void*)jac_tmp.data() : host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));
     unsigned int total_entries = 0;
     if (ctx->timing) DE_CUDA(ctx, cudaMemcpyAsync(&total_entries, &scalars_u32[0], sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    DE_CUDA(ctx, cudaStreamSynchronize(st));
+    DE_CUDA(ctx, stream_wait(ctx, st));
     // transcript form: one batched inversion on the host for the round's handful of points
     if (out_mode == 1) host::g1_jacobian_to_canonical((const uint64_t*)jac_tmp.data(), count, (uint8_t*)host_out);
     if (ctx->timing) {

@@ -972,7 +972,7 @@ static int prove_core(de_prover* p, const de_fr* const* instances, const size_t*
     DE_TRY(eval_polynomials_dev(ctx, p->d_eval_polys, n, p->d_eval_pidx, p->d_points, p->n_evals, nullptr, p->d_evals));
     std::vector<uint8_t> evals(32 * p->n_evals);
     DE_CUDA(ctx, cudaMemcpyAsync(evals.data(), p->d_evals, 32 * p->n_evals, cudaMemcpyDeviceToHost, st));
-    DE_CUDA(ctx, cudaStreamSynchronize(st));
+    DE_CUDA(ctx, stream_wait(ctx, st));
     for (size_t i = 0; i < p->n_evals; i++) tr.write_scalar(evals.data() + 32 * i);
 
     mark("evaluations");
