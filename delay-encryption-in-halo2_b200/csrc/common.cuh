@@ -109,6 +109,7 @@ struct de_ctx {
     cudaEvent_t dist_ev[11] = {};
     cudaStream_t dist_stream = nullptr;
     unsigned int* dist_error = nullptr;
+    bool dist_peers_checked = false;  // peer access towards the devices of the other ranks' buffers enabled (same-process ranks)
 };
 
 namespace de {

@@ -672,6 +672,24 @@ static int get_dist_plan(de_ctx* ctx, const de_fr& omega, uint32_t log_n, uint32
     return DE_OK;
 }
 
+// inter-stage twiddles of `rank` (k_dist_twiddles), resident per plan; built on `stream` when missing (one-time: allocates)
+static int ensure_rank_twiddles(de_ctx* ctx, NttDistPlan* plan, uint32_t rank, cudaStream_t stream) {
+    const uint32_t LW = plan->log_w;
+    if (LW == 0 || (plan->tw_rank && plan->tw_rank_of == rank)) return DE_OK;
+    const unsigned long long C = (1ull << (plan->log_n - LW)) >> LW;
+    const unsigned long long cnt = C * ((1u << LW) - 1);
+    if (!plan->tw_rank && cudaMalloc((void**)&plan->tw_rank, sizeof(Fr) * cnt) != cudaSuccess) {
+        cudaGetLastError();
+        plan->tw_rank = nullptr;
+        return fail(ctx, DE_ERR_OOM, "ntt (multi-GPU): twiddle table allocation failed");
+    }
+    k_dist_twiddles<<<(unsigned int)((cnt + 255) / 256), 256, 0, stream>>>(plan->tw_rank, C, (1u << LW) - 1, (unsigned long long)rank * C, plan->tw_hi,
+                                                                           plan->tw_lo, plan->tw_lo_bits);
+    DE_CHECK_LAUNCH(ctx);
+    plan->tw_rank_of = rank;
+    return DE_OK;
+}
+
 // chunk `ck` of `nck` (nck = 1: the whole exchange buffer) of the cross stage on `stream`; period = columns per sub-row of the
 // exchange pass (ignored when nck = 1)
 template <int LW>
@@ -682,19 +700,7 @@ static int launch_cross(de_ctx* ctx, NttDistPlan* plan, const Fr* d_z, de_fr* co
     const unsigned long long M = 1ull << (plan->log_n - LW);
     a.z = d_z;
     a.C = M >> LW;
-    if (LW > 0 && (!plan->tw_rank || plan->tw_rank_of != rank)) {
-        const unsigned long long cnt = a.C * ((1u << LW) - 1);
-        if (!plan->tw_rank && cudaMalloc((void**)&plan->tw_rank, sizeof(Fr) * cnt) != cudaSuccess) {
-            cudaGetLastError();
-            plan->tw_rank = nullptr;
-            return fail(ctx, DE_ERR_OOM, "ntt (multi-GPU): twiddle table allocation failed");
-        }
-        // built on the stream that consumes it (one-time per plan and rank)
-        k_dist_twiddles<<<(unsigned int)((cnt + 255) / 256), 256, 0, stream>>>(plan->tw_rank, a.C, (1u << LW) - 1, (unsigned long long)rank * a.C,
-                                                                             plan->tw_hi, plan->tw_lo, plan->tw_lo_bits);
-        DE_CHECK_LAUNCH(ctx);
-        plan->tw_rank_of = rank;
-    }
+    DE_TRY(ensure_rank_twiddles(ctx, plan, rank, stream));
     a.tw = plan->tw_rank;
     a.out_off = (unsigned long long)rank * a.C;
     if (nck <= 1 || period == 0 || period > a.C) {
@@ -791,6 +797,26 @@ int de_ntt_dist_stage2(de_ctx* ctx, const de_fr* d_z, const de_fr* omega, uint32
 //                 every rank has finished reading its exchange buffer (the next call may overwrite it)
 // The cross stage of range k (NVLink-bound) thus runs under the pass of range k + 1 (multiply-bound).  A rank that never
 // arrives makes the waits give up after ~2 s: de_ntt_dist_error() then reports it.
+// Everything of de_ntt_dist_run that allocates or synchronises (plan tables, the local transform's plan and scratch, streams,
+// events, this rank's inter-stage twiddles), done ahead of time.  de_ntt_dist_run does it itself on first use; a caller that
+// drives SEVERAL ranks of one device from one thread must prepare all of them before the first run, because an allocation made
+// while another rank's wait kernel is spinning on that device may not return before the wait gives up.
+int de_ntt_dist_prepare(de_ctx* ctx, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank) {
+    if (!ctx) return DE_ERR_ARG;
+    if (!omega || world == 0 || world > 8 || rank >= world) return fail(ctx, DE_ERR_ARG, "de_ntt_dist_prepare: bad arguments");
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    NttDistPlan* plan = nullptr;
+    DE_TRY(get_dist_plan(ctx, *omega, log_n, world, &plan));
+    DE_TRY(dist_resources(ctx));
+    DE_TRY(ensure_rank_twiddles(ctx, plan, rank, ctx->stream));
+    const uint32_t m = log_n - plan->log_w;
+    NttPlan* local = nullptr;
+    DE_TRY(get_plan(ctx, plan->omega_local, m, &local));
+    if (local->npass > 1 && !ctx->ws[WS_NTT_SCRATCH].ensure(sizeof(Fr) << m)) return fail(ctx, DE_ERR_OOM, "de_ntt_dist_prepare: scratch allocation failed");
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+}
+
 int de_ntt_dist_run(de_ctx* ctx, const de_fr* d_x, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank, de_fr* const* d_z_peers,
                     de_fr* const* d_out_peers, uint32_t* const* d_flag_peers, uint32_t epoch, uint32_t chunks) {
     if (!ctx) return DE_ERR_ARG;
@@ -802,6 +828,23 @@ int de_ntt_dist_run(de_ctx* ctx, const de_fr* d_x, const de_fr* omega, uint32_t 
     NttDistPlan* plan = nullptr;
     DE_TRY(get_dist_plan(ctx, *omega, log_n, world, &plan));
     DE_TRY(dist_resources(ctx));
+    DE_TRY(ensure_rank_twiddles(ctx, plan, rank, ctx->stream));  // before anything that waits on a peer is queued
+    if (!ctx->dist_peers_checked) {
+        // ranks of the same process on other devices: their buffers are plain device pointers and need peer access from this
+        // device (buffers of other processes arrive IPC-mapped and already belong to this device's address space)
+        for (uint32_t i = 0; i < world; i++) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, d_z_peers[i]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != ctx->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    cudaGetLastError();
+                    return fail(ctx, DE_ERR_CUDA, std::string("de_ntt_dist_run: no peer access to the device of rank ") + std::to_string(i));
+                }
+            }
+            cudaGetLastError();
+        }
+        ctx->dist_peers_checked = true;
+    }
     const uint32_t m = log_n - plan->log_w;
     const size_t M = (size_t)1 << m;
     NttDistArgs<true> dx;

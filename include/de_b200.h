@@ -256,7 +256,9 @@ int de_ntt_dist_stage2(de_ctx* ctx, const de_fr* d_z, const de_fr* omega, uint32
  * barriers (one process per GPU): the peer-store pass runs as up to `chunks` (1 .. 8) ranges of CTAs, each followed by a flag
  * store to every rank; the cross stage of range k starts on a second, high-priority stream of the context as soon as every
  * rank has signalled range k, i.e. it runs (NVLink-bound) under the pass of range k + 1 (multiply-bound).
- * d_flag_peers[r] = rank r's flag words (de_dev_alloc of DE_NTT_DIST_FLAG_BYTES, zeroed once, mapped on every rank);
+ * ONE rank per device (a rank's stream parked on an event can hold the hardware queue another rank's kernels of the same device
+ * sit in; the spinning wait would then give up) - several ranks on one device belong to de_ntt_sharded_dev, which orders them with
+ * events.  d_flag_peers[r] = rank r's flag words (de_dev_alloc of DE_NTT_DIST_FLAG_BYTES, zeroed once, mapped on every rank);
  * epoch = 1, 2, 3, ... per call, identical on all ranks.  On return (stream order on the context's stream) this rank's
  * output block is complete and every rank has finished reading its exchange buffer.  A rank that never arrives makes the
  * waits give up after ~2 s instead of hanging the device; de_ntt_dist_error reports (and clears) that. */
@@ -264,6 +266,9 @@ int de_ntt_dist_stage2(de_ctx* ctx, const de_fr* d_z, const de_fr* omega, uint32
 int de_ntt_dist_run(de_ctx* ctx, const de_fr* d_x, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank,
                     de_fr* const* d_z_peers, de_fr* const* d_out_peers, uint32_t* const* d_flag_peers, uint32_t epoch, uint32_t chunks);
 int de_ntt_dist_error(de_ctx* ctx, int* timed_out);
+/* everything of de_ntt_dist_run that allocates or synchronises, ahead of time (optional with one rank per device; REQUIRED for
+ * all ranks before the first run when one thread drives several ranks of the same device) */
+int de_ntt_dist_prepare(de_ctx* ctx, const de_fr* omega, uint32_t log_n, uint32_t world, uint32_t rank);
 /* The same inside ONE process: ctxs[r] is rank r (normally one context per GPU; several contexts on one GPU also work), d_x[r] /
  * d_out[r] its input / output block (d_out[r] may equal d_x[r]); the exchange is pipelined in the same way, ordered by CUDA events
  * (cross stage of range k on every rank's second stream after all ranks' range k).  Asynchronous: the result is complete in stream order on every

@@ -115,6 +115,7 @@ extern "C" {
     pub fn de_int_peak(ctx: *mut de_ctx, gmul_per_s: *mut f64) -> c_int;
     pub fn de_ntt_dist_run(ctx: *mut de_ctx, d_x: *const de_fr, omega: *const de_fr, log_n: u32, world: u32, rank: u32, d_z_peers: *const *mut de_fr, d_out_peers: *const *mut de_fr, d_flag_peers: *const *mut u32, epoch: u32, chunks: u32) -> c_int;
     pub fn de_ntt_dist_error(ctx: *mut de_ctx, timed_out: *mut c_int) -> c_int;
+    pub fn de_ntt_dist_prepare(ctx: *mut de_ctx, omega: *const de_fr, log_n: u32, world: u32, rank: u32) -> c_int;
     // circuit front-end (host only)
     pub fn de_circuit_synthesize(desc: *const de_circuit_desc, out: *mut *mut de_assignment) -> c_int;
     pub fn de_circuit_witness(desc: *const de_circuit_desc, advice_out: *mut de_fr, info: *mut de_assignment_info_t) -> c_int;

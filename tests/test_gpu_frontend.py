@@ -73,3 +73,12 @@ def test_delay_enc_real_circuit_proof_and_witness_pass():
     proof2 = keys.prover.create_proof([buf[i] for i in range(5)], [np.zeros((0, 4), dtype=np.uint64)], draws)
     assert proof2 == proof
     keys.close(); ctx.close()
+
+
+def test_mod_pow_real_circuit_proof_k17():
+    """RSACircuit at the bench's K = 17 (/root/reference/benches/mod_pow.rs:258)"""
+    n, e, x = fe.sample_rsa_inputs(0xDE01)
+    syn = fe.mod_pow(n, e, x, k=17)
+    proof, want, ok, keys, ctx, draws = prove_both(syn, 0xE17, fast=True)
+    assert len(proof) == 2848 and proof == want and ok
+    keys.close(); ctx.close()

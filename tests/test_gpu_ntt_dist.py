@@ -145,3 +145,87 @@ def test_rejects_bad_arguments():
         assert rc == -1
     finally:
         s.close()
+
+
+def _flag_run(ctxs, xs, zs, outs, flags, omega, log_n, epoch, chunks, ranks):
+    world = len(ctxs)
+    om0 = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
+    for r, c in enumerate(ctxs):  # several ranks of one device driven by one thread: nothing may allocate once a wait is queued
+        c.check(c.L.de_ntt_dist_prepare(c.h, om0.ctypes.data_as(C.c_void_p), log_n, world, r))
+    zp = (C.c_void_p * world)(*[t.data_ptr() for t in zs])
+    op = (C.c_void_p * world)(*[t.data_ptr() for t in outs])
+    fp = (C.c_void_p * world)(*[t.data_ptr() for t in flags])
+    om = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
+    for r in ranks:
+        c = ctxs[r]
+        c.check(c.L.de_ntt_dist_run(c.h, C.c_void_p(xs[r].data_ptr()), om.ctypes.data_as(C.c_void_p), log_n, world, r, zp, op, fp, epoch, chunks))
+
+
+@pytest.mark.parametrize("world,log_n,chunks", [(2, 14, 1), (2, 21, 4), (4, 22, 2), (4, 23, 4)])
+def test_flag_ordered_run_matches_oracle(world, log_n, chunks):
+    """de_ntt_dist_run (the one-process-per-GPU form: stages ordered by flags in peer memory, exchange in `chunks` ranges) with the
+    ranks as contexts of this process, ONE PER DEVICE: equals the oracle's best_fft; two calls in a row (epochs 1, 2) reuse
+    buffers and flags.  (Several flag-ordered ranks on one device are not supported: a rank's stream parked on an event can hold
+    the hardware queue another rank's kernels sit in, and the spinning wait then never sees their signal - that configuration is
+    what the event-ordered de_ntt_sharded_dev is for.)"""
+    import torch
+    import de_b200
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs one GPU per rank")
+    devs = devices(world)
+    for a_ in devs:
+        for b_ in devs:
+            if a_ != b_ and not torch.cuda.can_device_access_peer(a_, b_):
+                pytest.skip("no peer access")
+    ctxs = [de_b200.Context(d) for d in devs]
+    try:
+        n, m = 1 << log_n, (1 << log_n) // world
+        w = omega_for(log_n)
+        mk = lambda d, rows: torch.zeros((rows, 4), dtype=torch.int64, device=f"cuda:{d}")
+        for d in devs:  # torch enables peer access between the devices on the first cross-device copy
+            mk(d, 1).to(f"cuda:{devs[0]}")
+        zs, outs = [mk(d, m) for d in devs], [mk(d, m) for d in devs]
+        flags = [torch.zeros(72, dtype=torch.int32, device=f"cuda:{d}") for d in devs]
+        for epoch in (1, 2):
+            a = orc.uniform_fr(0xF1A6 + epoch + log_n, n)
+            xs = [torch.from_numpy(np.ascontiguousarray(sharding.ntt_input_slice(a, r, world)).view(np.int64)).to(f"cuda:{d}") for r, d in enumerate(devs)]
+            torch.cuda.synchronize()
+            _flag_run(ctxs, xs, zs, outs, flags, w, log_n, epoch, chunks, range(world))
+            for c in ctxs:
+                c.sync()
+            got = np.concatenate([o.cpu().numpy().view(np.uint64) for o in outs], axis=0)
+            assert (got == orc.best_fft(a, w, log_n)).all(), epoch
+            for c in ctxs:
+                v = C.c_int(7)
+                c.check(c.L.de_ntt_dist_error(c.h, C.byref(v)))
+                assert v.value == 0
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_flag_wait_gives_up_instead_of_hanging():
+    """a rank that never arrives: the waits time out (~2 s each) and de_ntt_dist_error reports it; the device stays usable"""
+    import time
+    import torch
+    import de_b200
+    ctxs = [de_b200.Context(0), de_b200.Context(0)]
+    try:
+        log_n, m = 13, 1 << 12
+        w = omega_for(log_n)
+        mk = lambda: torch.zeros((m, 4), dtype=torch.int64, device="cuda:0")
+        xs, zs, outs = [mk(), mk()], [mk(), mk()], [mk(), mk()]
+        flags = [torch.zeros(72, dtype=torch.int32, device="cuda:0") for _ in range(2)]
+        t0 = time.time()
+        _flag_run(ctxs, xs, zs, outs, flags, w, log_n, 1, 1, [0])      # rank 1 never runs
+        v = C.c_int(0)
+        ctxs[0].check(ctxs[0].L.de_ntt_dist_error(ctxs[0].h, C.byref(v)))
+        assert v.value == 1 and time.time() - t0 < 30
+        ctxs[0].check(ctxs[0].L.de_ntt_dist_error(ctxs[0].h, C.byref(v)))
+        assert v.value == 0                                           # reading the flag clears it
+        # the device is still usable: an ordinary transform on the same context
+        a = orc.uniform_fr(0x71AE, 1 << log_n)
+        assert (ctxs[0].best_fft(a, w, log_n) == orc.best_fft(a, w, log_n)).all()
+    finally:
+        for c in ctxs:
+            c.close()
