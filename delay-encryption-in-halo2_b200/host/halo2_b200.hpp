@@ -5,6 +5,7 @@
 //   poly::kzg::commitment::ParamsKZG, plonk::ProvingKey (device staging), plonk::create_proof (Prover)
 // Element types are the C ABI's (include/de_b200.h): Montgomery limbs, byte-identical to halo2curves.
 #pragma once
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -141,6 +142,108 @@ inline std::vector<de_fr> kate_division(const Context& ctx, const std::vector<de
     std::vector<de_fr> q(a.size() - 1);
     ctx.check(de_kate_division(ctx.handle(), a.data(), a.size(), &b, q.data()), "kate_division");
     return q;
+}
+
+// ---- SerdeFormat::RawBytes key files (/root/reference/benches/delay_enc.rs:84-115: vk.write / VerifyingKey::read, pk.write /
+// ProvingKey::read).  Layout (halo2_proofs v2023_04_20; the Python twin is de_b200/serde.py):
+//   vk := k: u32 | n_fixed: u32 | fixed commitments (64 B raw affine each) | permutation commitments | selectors (n bits each)
+//   pk := vk | l0 | l_last | l_active_row | fixed_values | fixed_polys | fixed_cosets | permutations | polys | cosets
+//   polynomial := len: u32 | len x 32 B Montgomery limbs;  slice := count: u32 | polynomials;  u32 headers big-endian (a
+//   little-endian file is recognised by its k).  n_perm / n_selectors come from the constraint system, as in halo2.
+struct VerifyingKeyRaw {
+    uint32_t k = 0;
+    std::vector<de_g1_affine> fixed_commitments, permutation_commitments;
+    std::vector<std::vector<bool>> selectors;
+};
+struct ProvingKeyRaw {
+    VerifyingKeyRaw vk;
+    std::vector<de_fr> l0, l_last, l_active_row;
+    std::vector<std::vector<de_fr>> fixed_values, fixed_polys, fixed_cosets, permutations, polys, cosets;
+};
+namespace detail {
+struct RawReader {
+    const std::vector<uint8_t>& b;
+    size_t pos = 0;
+    bool big = true;
+    explicit RawReader(const std::vector<uint8_t>& bytes) : b(bytes) {
+        if (b.size() < 8) throw std::runtime_error("RawBytes key file is truncated");
+        const uint32_t be = (uint32_t(b[0]) << 24) | (uint32_t(b[1]) << 16) | (uint32_t(b[2]) << 8) | b[3];
+        const uint32_t le = (uint32_t(b[3]) << 24) | (uint32_t(b[2]) << 16) | (uint32_t(b[1]) << 8) | b[0];
+        if (be >= 1 && be <= 28) big = true;
+        else if (le >= 1 && le <= 28) big = false;
+        else throw std::runtime_error("not a RawBytes key file: k out of range in either byte order");
+    }
+    const uint8_t* take(size_t n) {
+        if (pos + n > b.size()) throw std::runtime_error("RawBytes key file is truncated");
+        const uint8_t* p = b.data() + pos;
+        pos += n;
+        return p;
+    }
+    uint32_t u32() {
+        const uint8_t* p = take(4);
+        return big ? (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]
+                   : (uint32_t(p[3]) << 24) | (uint32_t(p[2]) << 16) | (uint32_t(p[1]) << 8) | p[0];
+    }
+    std::vector<de_fr> polynomial() {
+        const uint32_t m = u32();
+        std::vector<de_fr> v(m);
+        std::memcpy(v.data(), take(size_t(m) * sizeof(de_fr)), size_t(m) * sizeof(de_fr));
+        return v;
+    }
+    std::vector<std::vector<de_fr>> slice() {
+        const uint32_t count = u32();
+        std::vector<std::vector<de_fr>> v;
+        for (uint32_t i = 0; i < count; i++) v.push_back(polynomial());
+        return v;
+    }
+    VerifyingKeyRaw vk(uint32_t n_perm, uint32_t n_selectors) {
+        VerifyingKeyRaw v;
+        v.k = u32();
+        const uint32_t nf = u32();
+        if (v.k < 1 || v.k > 28 || nf > 4096) throw std::runtime_error("not a RawBytes verifying key");
+        v.fixed_commitments.resize(nf);
+        std::memcpy(v.fixed_commitments.data(), take(size_t(nf) * 64), size_t(nf) * 64);
+        v.permutation_commitments.resize(n_perm);
+        std::memcpy(v.permutation_commitments.data(), take(size_t(n_perm) * 64), size_t(n_perm) * 64);
+        const size_t n = size_t(1) << v.k;
+        for (uint32_t s = 0; s < n_selectors; s++) {
+            const uint8_t* p = take((n + 7) / 8);
+            std::vector<bool> bits(n);
+            for (size_t i = 0; i < n; i++) bits[i] = (p[i / 8] >> (i % 8)) & 1;
+            v.selectors.push_back(bits);
+        }
+        return v;
+    }
+};
+}  // namespace detail
+// VerifyingKey::read(reader, SerdeFormat::RawBytes)
+inline VerifyingKeyRaw read_verifying_key_raw(const std::vector<uint8_t>& bytes, uint32_t n_perm, uint32_t n_selectors) {
+    detail::RawReader r(bytes);
+    VerifyingKeyRaw v = r.vk(n_perm, n_selectors);
+    if (r.pos != bytes.size()) throw std::runtime_error("trailing bytes after the verifying key");
+    return v;
+}
+// ProvingKey::read(reader, SerdeFormat::RawBytes): fixed_polys / polys are what de_pk_upload takes (the cosets are recomputed on
+// the device)
+inline ProvingKeyRaw read_proving_key_raw(const std::vector<uint8_t>& bytes, uint32_t n_perm, uint32_t n_selectors) {
+    detail::RawReader r(bytes);
+    ProvingKeyRaw pk;
+    pk.vk = r.vk(n_perm, n_selectors);
+    pk.l0 = r.polynomial();
+    pk.l_last = r.polynomial();
+    pk.l_active_row = r.polynomial();
+    pk.fixed_values = r.slice();
+    pk.fixed_polys = r.slice();
+    pk.fixed_cosets = r.slice();
+    pk.permutations = r.slice();
+    pk.polys = r.slice();
+    pk.cosets = r.slice();
+    if (r.pos != bytes.size()) throw std::runtime_error("trailing bytes after the proving key");
+    const size_t n = size_t(1) << pk.vk.k;
+    if (pk.polys.size() != n_perm || pk.fixed_polys.size() != pk.vk.fixed_commitments.size()) throw std::runtime_error("proving key does not match the constraint system");
+    for (auto& p : pk.fixed_polys) if (p.size() != n) throw std::runtime_error("proving key: wrong polynomial length");
+    for (auto& p : pk.polys) if (p.size() != n) throw std::runtime_error("proving key: wrong polynomial length");
+    return pk;
 }
 
 class ProvingKey {  // the evaluator's / prover's view of plonk::ProvingKey, staged in HBM (de_pk_upload)

@@ -93,9 +93,15 @@ int main(int argc, char** argv) {
             auto aq_col = rd<uint32_t>(p + "aq_col.bin"), fq_col = rd<uint32_t>(p + "fq_col.bin");
             auto aq_rot = rd<int32_t>(p + "aq_rot.bin"), fq_rot = rd<int32_t>(p + "fq_rot.bin");
             auto want = rd<uint8_t>(p + "want_proof.bin");
+            // the same polynomials through the RawBytes proving-key FILE (ProvingKey::read): the prover below is staged from it
+            auto pk_bytes = rd<uint8_t>(p + "pk.bin");
+            auto pkraw = halo2_b200::read_proving_key_raw(pk_bytes, n_perm, /* selectors of the MainGate-only shape */ 0);
+            if (pkraw.vk.k != pk_k || pkraw.fixed_polys.size() != n_fixed) { std::cerr << "pk.bin header mismatch\n"; fails++; }
+            for (uint32_t i = 0; i < n_fixed; i++)
+                if (std::memcmp(pkraw.fixed_polys[i].data(), fixed.data() + i * pn, pn * sizeof(de_fr)) != 0) { std::cerr << "pk.bin fixed poly mismatch\n"; fails++; break; }
             std::vector<const de_fr*> fptr, sptr, aptr;
-            for (uint32_t i = 0; i < n_fixed; i++) fptr.push_back(fixed.data() + i * pn);
-            for (uint32_t i = 0; i < n_perm; i++) sptr.push_back(sigma.data() + i * pn);
+            for (uint32_t i = 0; i < n_fixed; i++) fptr.push_back(pkraw.fixed_polys[i].data());
+            for (uint32_t i = 0; i < n_perm; i++) sptr.push_back(pkraw.polys[i].data());
             for (uint32_t i = 0; i < n_advice; i++) aptr.push_back(advice.data() + i * pn);
             de_pk_desc desc;
             std::memset(&desc, 0, sizeof(desc));

@@ -75,6 +75,14 @@ def test_cpp_mirror_matches_oracle(tmp_path):
               graph.n_intermediates, shape.degree()], dtype=np.uint32).tofile(pdir / "meta.bin")
     np.stack([pp.to_mont(p) for p in opk.fixed_polys]).tofile(pdir / "fixed_coeff.bin")
     np.stack([pp.to_mont(p) for p in opk.sigma_polys]).tofile(pdir / "sigma_coeff.bin")
+    # the same key as a SerdeFormat::RawBytes ProvingKey file (cosets / l-polynomials are not consumed by the reader's caller)
+    from de_b200 import serde
+    F_, P_, n_, ext_ = shape.n_fixed, len(shape.perm_columns), 1 << kk, 1 << orc.Domain(shape.degree(), kk).extended_k
+    zz = lambda *sh: np.zeros(sh, dtype=np.uint64)
+    mm = lambda cols: np.stack([pp.to_mont(c) for c in cols])
+    serde.write_pk(pdir / "pk.bin", serde.ProvingKeyRaw(serde.VerifyingKeyRaw(kk, zz(F_, 8), zz(P_, 8), []), zz(ext_, 4), zz(ext_, 4), zz(ext_, 4),
+                                                        mm(opk.fixed_values), mm(opk.fixed_polys), zz(F_, ext_, 4), mm(opk.sigma_values),
+                                                        mm(opk.sigma_polys), zz(P_, ext_, 4)))
     np.stack([pp.to_mont(c) for c in asg.advice]).tofile(pdir / "advice.bin")
     draws.tofile(pdir / "randoms.bin")
     np.array(plonk.mont_limbs(plonk.FR_DELTA), dtype=np.uint64).tofile(pdir / "delta.bin")
