@@ -79,21 +79,22 @@ def ev_time(stream, fn, reps):
     return best
 
 
-def main():
+def main(cpu=None):
+    """cpu: an object with best_multiexp / best_fft / g1_to_affine / ncpu (the CPU restatement of the reference's algorithms).  This
+    tool never imports the checker itself: tests/sweep_vs_cpu.py passes it in for the 'vs reference' column of BASELINE config 4."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--msm-to", type=int, default=24)
     ap.add_argument("--msm-from", type=int, default=16, help="2^26 on one GPU wants DE_MSM_TABLE_MB=80000 (64 GiB of window tables)")
     ap.add_argument("--ntt-to", type=int, default=27)
     ap.add_argument("--ntt-from", type=int, default=16)
     ap.add_argument("--cpu-to", type=int, default=0,
-                    help="also time the CPU restatement of the reference (best_multiexp / best_fft on all host cores, the checker library "
-                         "under oracle/) on the same inputs up to 2^CPU_TO and compare the results: BASELINE config 4's 'vs reference' column")
+                    help="with a CPU implementation passed to main() (tests/sweep_vs_cpu.py): time it on the same inputs up to 2^CPU_TO "
+                         "and compare the results - BASELINE config 4's 'vs reference' column")
     args = ap.parse_args()
-    orc = None
-    if args.cpu_to:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import orc  # noqa: E402  (measurement tool: the CPU side of the comparison)
-        import time
+    import time
+    orc = cpu if args.cpu_to else None
+    if args.cpu_to and cpu is None:
+        raise SystemExit("--cpu-to needs the CPU implementation: run tests/sweep_vs_cpu.py instead")
     stream = torch.cuda.Stream()
     ctx = de_b200.Context(0)
     ctx.set_stream(stream.cuda_stream)
