@@ -754,6 +754,14 @@ def main():
                                 "create_proof_s": dt_full, "proof_bytes_match_gpu": bool(cpu_proof == first_proof),
                                 "synthesis_ms": wp.info.synthesis_ms if wp is not None else None,
                                 "hot_path_only": {"s": dt, "sample": CPU_HOT_SAMPLE, "advice_commitments_match_gpu_proof": bool(same)}}
+        if "ntt" in line:
+            # the reference's coeff_to_extended (restated best_fft, all host cores) on one of the proof's columns
+            col = np.ascontiguousarray(advice_mont[0])
+            t0 = time.perf_counter()
+            ext_cpu = state["dom"].coeff_to_extended(col)
+            dt_ntt = time.perf_counter() - t0
+            line["ntt"]["cpu"] = {"what": f"coeff_to_extended of ONE column 2^{K} -> 2^{int(ext_cpu.shape[0]).bit_length() - 1} (restated best_fft)",
+                                  "ms": dt_ntt * 1e3, "gb_s": 64.0 * ext_cpu.shape[0] / dt_ntt / 1e9, "cores": orc.ncpu()}
         if msm_single:
             # the reference's best_multiexp (restated, all host cores) on the very inputs the GPU committed, results compared
             for rec in msm_single:
