@@ -61,6 +61,7 @@ DEFAULT_WORKLOAD = WORKLOAD = ("delay_enc k=16 create_proof of the reference's D
 DEFAULT_METRIC = METRIC = "delay_enc_create_proof_proofs_per_s"
 TRANSCRIPT_REPR = 0xDE1A7E9C0DE
 UNIT = "proofs/s"
+LATENCY_WITNESS_THREADS = max(1, min(12, (os.cpu_count() or 1) - 2))
 MUL_PEAK_FALLBACK_GMULS = 65.9  # only if de_int_peak fails: this pool's B200 by tools/int_peak (profiles/r01_int_peak.jsonl)
 MULS_PER_ADD = 10       # XYZZ mixed addition: 8M + 2S (field.cuh has no cheaper squaring)
 # DRAM bytes of a k_msm_accumulate launch per executed bucket addition, from ONE `ncu --set full` capture (dram__bytes_read.sum +
@@ -112,10 +113,10 @@ class Circuit:
             return np.stack([ctx.fr_to_mont(keygen.canonical_limbs(c)) for c in self.asg.advice])
         return self.syn.advice
 
-    def witness_pass(self):
+    def witness_pass(self, threads=1):
         """a fresh de_circuit_witness runner (None for the synthetic stand-in, which has no front-end)"""
         from de_b200 import frontend as fe
-        return fe.WitnessPass(**self.inputs) if self.syn is not None else None
+        return fe.WitnessPass(threads=threads, **self.inputs) if self.syn is not None else None
 
     def cpu_view(self):
         """(fixed columns as integer lists, copy constraints as tuples, advice columns in Montgomery form) for the CPU arm's own
@@ -382,6 +383,10 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
             # Circuit::synthesize of the next proof (a host thread; the C call releases the GIL) runs while the GPU proves the
             # current one - what a prover service with a queue of statements does
             self.wp = circ.witness_pass()
+            # the single-statement arm lets the pass use idle host cores (the RSA region's mul_mod row ranges are independent);
+            # the throughput arm keeps one thread per pass, its cores belong to the other provers in flight
+            self.wp_single = circ.witness_pass(threads=LATENCY_WITNESS_THREADS) if first is None else None
+            self.synth_single_ms = []
             self.stage = [torch.empty((shape.n_advice, n, 4), dtype=torch.int64).pin_memory() for _ in range(2)] if self.wp is not None else None
             self.synth_ms = []
 
@@ -393,7 +398,7 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
                 if host and self.wp is not None and serial:
                     # one statement at a time: synthesize, then prove (the latency a single caller of create_proof sees)
                     for _ in range(nsteps):
-                        self._synth(0)
+                        self.synth_single_ms.append(self.wp_single.run(self.stage[0]))
                         self.proof = self.keys.prover.create_proof([self.stage[0][c] for c in range(shape.n_advice)], [], randoms_h)
                     return
                 if host and self.wp is not None:
@@ -519,8 +524,11 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
         "clocks": clocks,
         "latency": {"create_proof_s": ms_lat / lat_steps / 1000.0, "proofs_in_flight": 1, "steps": lat_steps, "mode": "DE_MODE_LATENCY",
                     "e2e_create_proof_s": (ms_lat_e2e / lat_steps / 1000.0) if ms_lat_e2e else None,
+                    "e2e_witness_threads": LATENCY_WITNESS_THREADS if ms_lat_e2e else None,
+                    "e2e_synthesis_ms": (sum(workers[0].synth_single_ms[-lat_steps:]) / lat_steps) if ms_lat_e2e else None,
                     "note": "create_proof_s: witness resident in HBM; e2e_create_proof_s: Circuit::synthesize on the host, then H2D and the "
-                            "proof, strictly one after the other (what one caller of the reference's create_proof waits for)"},
+                            "proof, strictly one after the other (what one caller of the reference's create_proof waits for); that arm's "
+                            "witness pass runs the independent mul_mod row ranges of the RSA region on e2e_witness_threads host threads"},
     }
     line["config"]["witness"] = circ.kind
     line["config"]["used_rows"] = int(circ.used_rows)

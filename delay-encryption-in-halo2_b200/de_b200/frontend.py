@@ -31,7 +31,7 @@ class _Fr(C.Structure):
 class _Desc(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("k", C.c_uint32), ("bits_len", C.c_uint32), ("exp_bits", C.c_uint32),
                 ("n", C.c_void_p), ("n_len", C.c_size_t), ("e", C.c_void_p), ("e_len", C.c_size_t), ("x", C.c_void_p), ("x_len", C.c_size_t),
-                ("message", C.c_void_p), ("message_len", C.c_uint32), ("key", _Fr * 2), ("witness_only", C.c_uint32)]
+                ("message", C.c_void_p), ("message_len", C.c_uint32), ("key", _Fr * 2), ("witness_only", C.c_uint32), ("threads", C.c_uint32)]
 
 
 class _Info(C.Structure):
@@ -89,12 +89,14 @@ class _Handle:
 
 
 def synthesize(kind: int, k: int, n: int = 0, e: int = 0, x: int = 0, message=(), key=(0, 0), bits_len: int = BITS_LEN,
-               exp_bits: int = EXP_LIMB_BITS, witness_only: bool = False) -> SynthesizedCircuit:
-    """witness_only: the pass create_proof makes (advice columns only: `fixed` is empty, `copies` too)"""
+               exp_bits: int = EXP_LIMB_BITS, witness_only: bool = False, threads: int = 1) -> SynthesizedCircuit:
+    """witness_only: the pass create_proof makes (advice columns only: `fixed` is empty, `copies` too); threads: host threads
+    a witness-only pass may use for the RSA region (same rows for every value)"""
     L = _lib.load()
     d = _Desc()
     d.kind, d.k, d.bits_len, d.exp_bits = kind, k, bits_len, exp_bits
     d.witness_only = 1 if witness_only else 0
+    d.threads = threads
     nb = max(1, bits_len // 8)
     bufs = [np.frombuffer(int(v).to_bytes(nb, "little"), dtype=np.uint8).copy() for v in (n, e, x)]
     d.n, d.e, d.x = (b.ctypes.data for b in bufs)
@@ -135,10 +137,11 @@ class WitnessPass:
     releases the GIL."""
 
     def __init__(self, kind: int, k: int, n: int = 0, e: int = 0, x: int = 0, message=(), key=(0, 0), bits_len: int = BITS_LEN,
-                 exp_bits: int = EXP_LIMB_BITS):
+                 exp_bits: int = EXP_LIMB_BITS, threads: int = 1):
         self.L = _lib.load()
         d = _Desc()
         d.kind, d.k, d.bits_len, d.exp_bits = kind, k, bits_len, exp_bits
+        d.threads = threads
         nb = max(1, bits_len // 8)
         self._bufs = [np.frombuffer(int(v).to_bytes(nb, "little"), dtype=np.uint8).copy() for v in (n, e, x)]
         d.n, d.e, d.x = (b.ctypes.data for b in self._bufs)

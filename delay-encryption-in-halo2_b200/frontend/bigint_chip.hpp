@@ -4,6 +4,10 @@
 // (below 32 * 2^128 + 2^64 for 2048-bit operands).  Every function names the reference function it follows; the sequence of
 // MainGate / RangeChip instructions is the reference's, so the emitted rows carry the same witness values in the same order.
 #pragma once
+#include <atomic>
+#include <exception>
+#include <thread>
+
 #include "maingate.hpp"
 
 namespace de {
@@ -204,11 +208,144 @@ class BigIntChip {
             e_bits.insert(e_bits.end(), bits.begin(), bits.end());
         }
         AssignedInteger acc = assign_constant_fresh(BigUint(1));
+        if (gate.as.witness_only && gate.as.threads > 1 && !e_bits.empty() && a.size() == n.size())
+            return pow_mod_parallel(a, e_bits, acc, n);
         AssignedInteger squared = a;
         for (const Cell& e_bit : e_bits) {
             const AssignedInteger muled = mul_mod(acc, squared, n);
             for (size_t j = 0; j < acc.size(); j++) acc[j] = gate.select(muled[j], acc[j], e_bit);
             squared = square_mod(squared, n);
+        }
+        return acc;
+    }
+    // The loop of pow_mod for a witness-only pass on several threads.  The VALUES of the chain (acc_i, squared_i) are ten
+    // modular multiplications of plain integers; with them known, every mul_mod of the loop is an independent emitter of a row
+    // range whose length R depends on the limb counts only, so range i can be written by any thread into its reserved rows.
+    // The calling thread emits the select rows between the ranges.  The rows are the sequential pass's, cell for cell
+    // (tests/test_frontend.py compares the two).
+    AssignedInteger value_cells(const BigUint& v, size_t limbs) const {
+        AssignedInteger out(limbs);
+        const std::vector<BigUint> parts = decompose_big(v, (uint32_t)limbs, limb_width);
+        for (size_t i = 0; i < limbs; i++) out[i].value = F::from_big(parts[i]);
+        return out;
+    }
+    AssignedInteger pow_mod_parallel(const AssignedInteger& a, const std::vector<Cell>& e_bits, AssignedInteger acc, const AssignedInteger& n) {
+        Assignment& as = gate.as;
+        const size_t limbs = n.size();
+        const BigUint n_big = to_big_uint(n);
+        if (n_big.is_zero()) throw std::runtime_error("mul_mod: zero modulus");
+        struct Job {
+            AssignedInteger a, b;
+            size_t start = 0, end = 0;
+            std::vector<std::pair<uint32_t, uint32_t>> pending;
+            std::exception_ptr error;
+        };
+        std::vector<Job> jobs(2 * e_bits.size());
+        std::vector<BigUint> muled_values(e_bits.size());
+        {
+            BigUint acc_v = to_big_uint(acc), sq_v = to_big_uint(a), q;
+            for (size_t i = 0; i < e_bits.size(); i++) {
+                jobs[2 * i].a = value_cells(acc_v, limbs);
+                jobs[2 * i].b = jobs[2 * i + 1].a = jobs[2 * i + 1].b = i == 0 ? a : value_cells(sq_v, limbs);
+                BigUint::divmod(acc_v * sq_v, n_big, &q, &muled_values[i]);
+                if (!(e_bits[i].value == F::zero())) acc_v = muled_values[i];
+                BigUint sq_next;
+                BigUint::divmod(sq_v * sq_v, n_big, &q, &sq_next);
+                sq_v = sq_next;
+            }
+        }
+        auto run_job = [&](Job& j, size_t rows) {
+            try {
+                Assignment part;
+                part.view(as, j.start, rows);
+                MainGate g(part);
+                RangeChip r(part, g);
+                BigIntChip chip(g, r, limb_width, limb_width * num_limbs);
+                chip.mul_mod(j.a, j.b, n);
+                j.end = part.offset;
+                j.pending.swap(part.pending_inverse);
+            } catch (...) {
+                j.error = std::current_exception();
+            }
+        };
+        // R: rows of one mul_mod at these limb counts (a property of the layout, not of the values).  The first pass of a
+        // process at a given width emits the first range here, in place, and measures it; later passes know it.
+        trace_lap("pow_mod: values");
+        static std::atomic<size_t> known_rows[65];
+        const size_t first = as.offset;
+        size_t R = limbs <= 64 && limb_width == 64 ? known_rows[limbs].load() : 0;
+        const bool first_inline = R == 0;
+        if (first_inline) {
+            mul_mod(jobs[0].a, jobs[0].b, n);
+            R = as.offset - first;
+            if (limbs <= 64 && limb_width == 64) known_rows[limbs].store(R);
+            jobs[0].end = as.offset;
+        } else {
+            as.need_rows(R);
+            as.offset += R;
+        }
+        jobs[0].start = first;
+        // the ranges go to the workers while this thread writes the selects between them
+        std::atomic<size_t> next_job(first_inline ? 1 : 0);
+        std::vector<std::thread> workers;
+        const size_t n_workers = std::min<size_t>(as.threads - 1, jobs.size() - (first_inline ? 1 : 0));
+        auto drain = [&] {
+            for (;;) {
+                const size_t j = next_job.fetch_add(1);
+                if (j >= jobs.size()) return;
+                run_job(jobs[j], R);
+            }
+        };
+        // lay the ranges out first: mul_mod_i | selects_i | square_mod_i | mul_mod_(i+1) ...; the selects are one row per limb
+        // in every layout of this front-end, measured on the first iteration like R
+        std::exception_ptr main_error;
+        size_t select_rows = 0;
+        try {
+            for (size_t i = 0; i < e_bits.size(); i++) {
+                if (i == 1) jobs[2].start = as.offset;
+                else if (i > 1 && jobs[2 * i].start != as.offset) throw std::runtime_error("pow_mod: row ranges out of step");
+                if (i > 0) {
+                    as.need_rows(R);
+                    as.offset += R;
+                }
+                if (i == 1) {
+                    // all starts are known from here on: R and the select rows are both measured
+                    size_t at = as.offset;
+                    for (size_t t = 1; t < e_bits.size(); t++) {
+                        at += select_rows;            // selects of iteration t
+                        jobs[2 * t + 1].start = at;   // square_mod of iteration t
+                        at += R;
+                        if (t + 1 < e_bits.size()) jobs[2 * (t + 1)].start = at, at += R;
+                    }
+                    if (at > as.usable) throw std::runtime_error("not enough rows: the circuit needs more than 2^" + std::to_string(as.k) + " - 6 usable rows");
+                    for (size_t w = 0; w < n_workers; w++) workers.emplace_back(drain);
+                }
+                const size_t before = as.offset;
+                const AssignedInteger muled = value_cells(muled_values[i], limbs);
+                for (size_t j = 0; j < acc.size(); j++) acc[j] = gate.select(muled[j], acc[j], e_bits[i]);
+                if (i == 0) select_rows = as.offset - before;
+                else if (as.offset - before != select_rows) throw std::runtime_error("pow_mod: select rows differ between iterations");
+                as.need_rows(R);
+                if (i == 0) jobs[1].start = as.offset;
+                else if (jobs[2 * i + 1].start != as.offset) throw std::runtime_error("pow_mod: row ranges out of step");
+                as.offset += R;
+            }
+            if (e_bits.size() == 1)
+                for (size_t w = 0; w < n_workers; w++) workers.emplace_back(drain);
+        } catch (...) {
+            main_error = std::current_exception();
+            next_job.store(jobs.size());
+        }
+        trace_lap("pow_mod: selects");
+        if (!main_error) drain();
+        trace_lap("pow_mod: drained");
+        for (std::thread& t : workers) t.join();
+        trace_lap("pow_mod: joined");
+        if (main_error) std::rethrow_exception(main_error);
+        for (Job& j : jobs) {
+            if (j.error) std::rethrow_exception(j.error);
+            if (j.end != j.start + R) throw std::runtime_error("pow_mod: a mul_mod range did not fill its reserved rows");
+            as.pending_inverse.insert(as.pending_inverse.end(), j.pending.begin(), j.pending.end());
         }
         return acc;
     }

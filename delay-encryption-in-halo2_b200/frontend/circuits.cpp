@@ -47,7 +47,9 @@ AssignedInteger rsa_region(RSAChip& rsa, const RsaInputs& in) {
     const AssignedInteger n = bigint.assign_integer(decompose_big(in.n, num_limbs, RSAChip::LIMB_WIDTH));  // assign_public_key
     const AssignedInteger e = bigint.assign_integer(e_limbs);
     const AssignedInteger x = bigint.assign_integer(decompose_big(in.x, num_limbs, RSAChip::LIMB_WIDTH));
+    trace_lap("rsa: inputs assigned");
     const AssignedInteger powed = rsa.modpow_var(x, n, e);
+    trace_lap("rsa: modpow");
     const BigUint valid = big_pow_mod(in.x, in.e, in.n);
     const AssignedInteger valid_assigned = bigint.assign_constant_fresh(valid);
     bigint.assert_equal_fresh(powed, valid_assigned);
@@ -106,7 +108,9 @@ void synth_delay_enc(Assignment& as, const de_circuit_desc& d, const RsaInputs& 
     RangeChip range(as, gate);
     configure_range(range, d.bits_len);
     RSAChip rsa(gate, range, d.bits_len, d.exp_bits);
+    trace_lap("delay_enc: columns zeroed");
     const AssignedInteger rsa_output = rsa_region(rsa, in);
+    trace_lap("delay_enc: rsa region");
     range.load_table();
     if (rsa_output.size() != 32) throw std::runtime_error("delay_enc packs exactly 32 limbs (src/lib.rs:248-250): bits_len must be 2048");
     for (const Cell& c : rsa_output) as.outputs.push_back(c.value);
@@ -126,6 +130,7 @@ void synth_delay_enc(Assignment& as, const de_circuit_desc& d, const RsaInputs& 
     const Cell h_out[2] = {h[1], h[2]};
     as.outputs.push_back(h_out[0].value);
     as.outputs.push_back(h_out[1].value);
+    trace_lap("delay_enc: hash region");
     // region "poseidon region": the hash output is the encryption key
     enc_region(gate, spec, h_out[0].value, h_out[1].value, message, d.message_len, true, h_out, as);
 }
@@ -171,7 +176,9 @@ static int synthesize_into(const de_circuit_desc* d, de_fr* advice_out, de_assig
             in.x = BigUint::from_bytes_le(d->x, d->x_len);
         }
         a->as.witness_only = d->witness_only != 0;
+        a->as.threads = d->threads > 64 ? 64 : (d->threads ? d->threads : 1);
         const auto t0 = std::chrono::steady_clock::now();
+        trace_lap("pass begins", true);
         switch (d->kind) {
             case DE_CIRCUIT_MOD_POW: synth_mod_pow(a->as, *d, in); break;
             case DE_CIRCUIT_POSE_ENC: synth_pose_enc(a->as, *d, message); break;
@@ -179,7 +186,9 @@ static int synthesize_into(const de_circuit_desc* d, de_fr* advice_out, de_assig
             case DE_CIRCUIT_RSA_PKCS1: synth_rsa_pkcs1(a->as, *d, in); break;
             default: throw std::runtime_error("unknown circuit kind");
         }
+        trace_lap("circuit emitted");
         a->as.finalize();
+        trace_lap("inverses");
         a->synth_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         *out = a.release();
         return DE_OK;

@@ -13,10 +13,15 @@
 // Values are BN254 Fr elements in Montgomery form (host arithmetic of csrc/transcript.hpp).  Witness generation is
 // sequential big-integer work on a few 10^4 rows: it runs on the host, once per proof, before the GPU pipeline starts.
 #pragma once
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <chrono>
 
 #include <new>
 #include <stdexcept>
+#include <thread>
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -130,6 +135,15 @@ struct F {
     }
 };
 
+// DE_FE_TRACE=1: where a synthesis pass spends its time, on stderr (milliseconds since the pass began, per thread)
+inline void trace_lap(const char* what, bool restart = false) {
+    static const bool on = getenv("DE_FE_TRACE") != nullptr;
+    if (!on) return;
+    static thread_local std::chrono::steady_clock::time_point t0;
+    if (restart) t0 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[de frontend] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+}
+
 // ---- the assignment a synthesis pass produces ---------------------------------------------------------------------------
 enum FixedColumn { SA = 0, SB, SC, SD, SE, SE_NEXT, S_MUL_AB, S_MUL_CD, S_CONSTANT, T_TAG, T_VALUE, TAG_COMP, TAG_OVER, S_COMP, S_OVER };
 enum { N_ADVICE = 5, N_FIXED_MAIN = 9, N_FIXED_RANGE = 15, INSTANCE_POS = 5 /* position of the instance column in the permutation */ };
@@ -182,9 +196,26 @@ struct Assignment {
     // create_proof's second call of Circuit::synthesize only collects the advice values (WitnessCollection ignores fixed
     // assignments and copy constraints): witness_only skips both
     bool witness_only = false;
+    // witness-only passes may emit row ranges whose length does not depend on the values (every halo2 layout is value
+    // independent) from several threads: `threads` > 1 lets BigIntChip::pow_mod do so, each thread through a view()
+    uint32_t threads = 1;
     // cells that hold the inverse of a value (is_zero's auxiliary witness): filled by finalize() with ONE batched inversion
     std::vector<std::pair<uint32_t, uint32_t>> pending_inverse;  // (advice column, row); the cell currently holds the value itself
 
+    // 10 MB at k = 16: worth the helpers when the pass has them
+    void zero_columns(void* p, size_t bytes) const {
+        const size_t parts = threads > 1 && bytes >= ((size_t)4 << 20) ? std::min<size_t>(threads, 4) : 1;
+        if (parts == 1) {
+            memset(p, 0, bytes);
+            return;
+        }
+        const size_t each = (bytes / parts + 4095) & ~(size_t)4095;
+        std::vector<std::thread> helpers;
+        for (size_t i = 1; i < parts; i++)
+            if (i * each < bytes) helpers.emplace_back([=] { memset((char*)p + i * each, 0, std::min(each, bytes - i * each)); });
+        memset(p, 0, std::min(each, bytes));
+        for (std::thread& t : helpers) t.join();
+    }
     void init(uint32_t k_, bool with_range) {
         k = k_;
         n = (size_t)1 << k;
@@ -192,11 +223,21 @@ struct Assignment {
         n_fixed = with_range ? N_FIXED_RANGE : N_FIXED_MAIN;
         if (!witness_only) fixed.alloc(n_fixed, n);
         if (borrowed_advice) {
-            memset((void*)borrowed_advice, 0, sizeof(F) * N_ADVICE * n);
+            zero_columns(borrowed_advice, sizeof(F) * N_ADVICE * n);
             advice.borrow(borrowed_advice, N_ADVICE, n);
         } else {
             advice.alloc(N_ADVICE, n);
         }
+    }
+    // a witness-only emitter over the rows [start, start + rows) of parent's advice columns (the columns stay parent's)
+    void view(const Assignment& parent, size_t start, size_t rows) {
+        k = parent.k; n = parent.n; n_fixed = parent.n_fixed;
+        usable = start + rows;  // need_rows() stops a range that runs over its reservation
+        offset = start;
+        witness_only = true;
+        comp_tags = parent.comp_tags;
+        over_tags = parent.over_tags;
+        advice.borrow(parent.advice.base, N_ADVICE, parent.n);
     }
     void set_fixed(int column, uint32_t row, const F& v) {
         if (!witness_only) fixed[column][row] = v;

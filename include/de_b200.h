@@ -321,6 +321,8 @@ typedef struct {
     const de_fr* message; uint32_t message_len;   /* Montgomery field elements */
     de_fr key[2];                                  /* DE_CIRCUIT_POSE_ENC only */
     uint32_t witness_only;  /* 1: the pass create_proof makes - advice columns only, no fixed columns / copy constraints */
+    uint32_t threads;       /* witness-only passes: host threads that emit the independent row ranges of the RSA region (the
+                               mul_mod calls of pow_mod); 0 or 1 = the calling thread alone.  The rows do not depend on it. */
 } de_circuit_desc;
 typedef struct {
     uint32_t k, n_fixed, n_advice, n_outputs;

@@ -144,6 +144,33 @@ def test_delay_enc_circuit():
     assert abs((rows[6] - rows[3]) / 3 - 7981) / 7981 < 0.03
 
 
+def test_witness_pass_on_several_threads_writes_the_same_rows():
+    """de_circuit_desc.threads: the mul_mod row ranges of pow_mod are emitted by worker threads into reserved rows; every cell
+    must equal the one-thread pass (and the full synthesis) for any thread count, exponent and a dirty destination buffer"""
+    for seed, e_override in ((11, None), (12, 0), (13, 1), (14, 31)):
+        n, e, x = fe.sample_rsa_inputs(seed)
+        e = e if e_override is None else e_override
+        for kind, k in ((fe.DELAY_ENC, 16), (fe.MOD_POW, 17)):
+            if kind == fe.MOD_POW and e_override is not None:
+                continue
+            want = np.empty((5, 1 << k, 4), dtype=np.uint64)
+            fe.WitnessPass(kind, k, n=n, e=e, x=x, message=(0, 0)).run(want)
+            for threads in (2, 7):
+                got = np.full((5, 1 << k, 4), 0x5A5A5A5A5A5A5A5A, dtype=np.uint64)
+                wp = fe.WitnessPass(kind, k, n=n, e=e, x=x, message=(0, 0), threads=threads)
+                wp.run(got)
+                wp.run(got)  # second run: the row count of a range is known, all ranges go to the workers
+                assert np.array_equal(got, want), (seed, kind, threads)
+    # ... and the keygen-time synthesis (fixed columns and copy constraints as well) fills the advice columns identically
+    n, e, x = fe.sample_rsa_inputs(11)
+    got = np.empty((5, 1 << 16, 4), dtype=np.uint64)
+    fe.WitnessPass(fe.DELAY_ENC, 16, n=n, e=e, x=x, message=(0, 0), threads=5).run(got)
+    assert np.array_equal(got, fe.synthesize(fe.DELAY_ENC, 16, n, e, x, [0, 0]).advice)
+    # not enough rows: reported, not written past the reservation
+    with pytest.raises(Exception, match="not enough rows"):
+        fe.WitnessPass(fe.DELAY_ENC, 15, n=n, e=3, x=x, message=(0, 0), threads=4).run(np.empty((5, 1 << 15, 4), dtype=np.uint64))
+
+
 def test_rsa_pkcs1_known_answers():
     digest = [(RSA_DIGEST >> (64 * i)) & (2 ** 64 - 1) for i in range(4)]
     ok = fe.rsa_pkcs1(RSA_N1, 65537, RSA_SIG1, digest, k=17)
