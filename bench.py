@@ -528,7 +528,8 @@ def proof_bench(args, local_rank, world, steps, warmup, B, detail):
                     "e2e_synthesis_ms": (sum(workers[0].synth_single_ms[-lat_steps:]) / lat_steps) if ms_lat_e2e else None,
                     "note": "create_proof_s: witness resident in HBM; e2e_create_proof_s: Circuit::synthesize on the host, then H2D and the "
                             "proof, strictly one after the other (what one caller of the reference's create_proof waits for); that arm's "
-                            "witness pass runs the independent mul_mod row ranges of the RSA region on e2e_witness_threads host threads"},
+                            "witness pass emits the independent row ranges of the circuit (the mul_mod calls of pow_mod, x < n, the Poseidon "
+                            "regions) on e2e_witness_threads host threads"},
     }
     line["config"]["witness"] = circ.kind
     line["config"]["used_rows"] = int(circ.used_rows)

@@ -438,7 +438,32 @@ class RSAChip {
     }
     // rsa/chip.rs:102-117 modpow_public_key
     AssignedInteger modpow_var(const AssignedInteger& x, const AssignedInteger& n, const AssignedInteger& e) {
+        Assignment& as = gate.as;
+        const uint64_t key = ((uint64_t)x.size() << 32) | n.size();
+        const size_t check_rows = as.witness_only && as.threads > 1 ? known_rows("assert_in_field", key) : 0;
+        if (check_rows) {
+            // x < n on another thread, into its own rows, while this one (and its helpers) emits the exponentiation
+            as.need_rows(check_rows);
+            RangeTask check;
+            const uint32_t lw = bigint.limb_width, bits = bigint.limb_width * bigint.num_limbs;
+            check.run(as, as.offset, check_rows, [&x, &n, lw, bits](Assignment& part) {
+                MainGate g(part);
+                RangeChip r(part, g);
+                BigIntChip(g, r, lw, bits).assert_in_field(x, n);
+            });
+            as.offset += check_rows;
+            try {
+                const AssignedInteger powed = bigint.pow_mod(x, e, n, exp_limb_bits);
+                check.join(as, true);
+                return powed;
+            } catch (...) {
+                if (check.worker.joinable()) check.worker.join();
+                throw;
+            }
+        }
+        const size_t before = as.offset;
         bigint.assert_in_field(x, n);
+        if (as.witness_only) known_rows("assert_in_field", key, as.offset - before);
         return bigint.pow_mod(x, e, n, exp_limb_bits);
     }
     AssignedInteger modpow_fixed(const AssignedInteger& x, const AssignedInteger& n, const BigUint& e) {

@@ -102,19 +102,9 @@ void synth_pose_enc(Assignment& as, const de_circuit_desc& d, const Vec& message
     enc_region(gate, spec, fr_in(d.key[0]), fr_in(d.key[1]), message, d.message_len, false, nullptr, as);
 }
 
-void synth_delay_enc(Assignment& as, const de_circuit_desc& d, const RsaInputs& in, const Vec& message) {
-    as.init(d.k, true);
-    MainGate gate(as);
-    RangeChip range(as, gate);
-    configure_range(range, d.bits_len);
-    RSAChip rsa(gate, range, d.bits_len, d.exp_bits);
-    trace_lap("delay_enc: columns zeroed");
-    const AssignedInteger rsa_output = rsa_region(rsa, in);
-    trace_lap("delay_enc: rsa region");
-    range.load_table();
-    if (rsa_output.size() != 32) throw std::runtime_error("delay_enc packs exactly 32 limbs (src/lib.rs:248-250): bits_len must be 2048");
-    for (const Cell& c : rsa_output) as.outputs.push_back(c.value);
-    // region "hash mapping from 2048bit": three limbs per field element in base 2^64, the last element from limbs 30 and 31
+// regions "hash mapping from 2048bit" and "poseidon region" of DelayEncryptCircuit (src/lib.rs:240-300)
+void delay_enc_tail(MainGate& gate, Assignment& as, const AssignedInteger& rsa_output, const de_circuit_desc& d, const Vec& message) {
+    // three limbs per field element in base 2^64, the last element from limbs 30 and 31
     const Spec& spec = shared_spec(5, 8, 57);
     PoseidonChip hasher = PoseidonChip::new_hash(gate, spec);
     const Cell base1 = gate.assign_constant(F::from_big(BigUint::pow2(RSAChip::LIMB_WIDTH)));
@@ -131,8 +121,60 @@ void synth_delay_enc(Assignment& as, const de_circuit_desc& d, const RsaInputs& 
     as.outputs.push_back(h_out[0].value);
     as.outputs.push_back(h_out[1].value);
     trace_lap("delay_enc: hash region");
-    // region "poseidon region": the hash output is the encryption key
+    // the hash output is the encryption key
     enc_region(gate, spec, h_out[0].value, h_out[1].value, message, d.message_len, true, h_out, as);
+    trace_lap("delay_enc: poseidon region");
+}
+
+void synth_delay_enc(Assignment& as, const de_circuit_desc& d, const RsaInputs& in, const Vec& message) {
+    as.init(d.k, true);
+    MainGate gate(as);
+    RangeChip range(as, gate);
+    configure_range(range, d.bits_len);
+    RSAChip rsa(gate, range, d.bits_len, d.exp_bits);
+    trace_lap("delay_enc: columns zeroed");
+    const uint64_t key = ((uint64_t)d.bits_len << 32) | d.exp_bits;
+    const size_t rsa_rows = as.witness_only && as.threads > 1 ? known_rows("delay_enc rsa region", key) : 0;
+    if (rsa_rows) {
+        // a witness-only pass that knows where the RSA region ends: the two Poseidon regions need its VALUE only (x^e mod n, a
+        // plain integer computation), so they are emitted from row rsa_rows on by another thread while the RSA region is written
+        if (d.bits_len != 2048) throw std::runtime_error("delay_enc packs exactly 32 limbs (src/lib.rs:248-250): bits_len must be 2048");
+        if (in.n.is_zero()) throw std::runtime_error("mul_mod: zero modulus");
+        if (rsa_rows > as.usable) throw std::runtime_error("not enough rows: the circuit needs more than 2^" + std::to_string(as.k) + " - 6 usable rows");
+        AssignedInteger result_values(32);
+        {
+            const std::vector<BigUint> limbs = decompose_big(big_pow_mod(in.x, in.e, in.n), 32, RSAChip::LIMB_WIDTH);
+            for (size_t i = 0; i < 32; i++) result_values[i].value = F::from_big(limbs[i]);
+        }
+        RangeTask tail;
+        tail.run(as, rsa_rows, as.usable - rsa_rows, [&](Assignment& part) {
+            MainGate g(part);
+            delay_enc_tail(g, part, result_values, d, message);
+        });
+        AssignedInteger rsa_output;
+        try {
+            rsa_output = rsa_region(rsa, in);
+        } catch (...) {
+            if (tail.worker.joinable()) tail.worker.join();
+            throw;
+        }
+        trace_lap("delay_enc: rsa region");
+        tail.join(as, false);
+        if (as.offset != rsa_rows) throw std::runtime_error("delay_enc: the RSA region did not end where the Poseidon regions began");
+        for (size_t i = 0; i < 32; i++)
+            if (rsa_output[i].value != result_values[i].value) throw std::runtime_error("delay_enc: x^e mod n differs between the circuit and the integers");
+        as.offset = tail.part.offset;
+        for (const Cell& c : rsa_output) as.outputs.push_back(c.value);
+        as.outputs.insert(as.outputs.end(), tail.part.outputs.begin(), tail.part.outputs.end());
+        return;
+    }
+    const AssignedInteger rsa_output = rsa_region(rsa, in);
+    trace_lap("delay_enc: rsa region");
+    if (as.witness_only) known_rows("delay_enc rsa region", key, as.offset);
+    range.load_table();
+    if (rsa_output.size() != 32) throw std::runtime_error("delay_enc packs exactly 32 limbs (src/lib.rs:248-250): bits_len must be 2048");
+    for (const Cell& c : rsa_output) as.outputs.push_back(c.value);
+    delay_enc_tail(gate, as, rsa_output, d, message);
 }
 
 void synth_rsa_pkcs1(Assignment& as, const de_circuit_desc& d, const RsaInputs& in) {

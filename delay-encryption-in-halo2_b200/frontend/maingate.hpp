@@ -18,6 +18,9 @@
 
 #include <chrono>
 
+#include <exception>
+#include <map>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <thread>
@@ -135,11 +138,11 @@ struct F {
     }
 };
 
-// DE_FE_TRACE=1: where a synthesis pass spends its time, on stderr (milliseconds since the pass began, per thread)
+// DE_FE_TRACE=1: where a synthesis pass spends its time, on stderr (milliseconds since the latest pass of the process began)
 inline void trace_lap(const char* what, bool restart = false) {
     static const bool on = getenv("DE_FE_TRACE") != nullptr;
     if (!on) return;
-    static thread_local std::chrono::steady_clock::time_point t0;
+    static std::chrono::steady_clock::time_point t0;
     if (restart) t0 = std::chrono::steady_clock::now();
     fprintf(stderr, "[de frontend] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
@@ -269,6 +272,48 @@ struct Assignment {
         if (a.col == b.col && a.row == b.row) return;
         if (a.value != b.value) throw std::runtime_error("copy constraint between unequal cells (row " + std::to_string(a.row) + " / " + std::to_string(b.row) + ")");
         if (!witness_only) copies.push_back({a.col, a.row, b.col, b.row});
+    }
+};
+
+// ---- witness-only passes on several threads ----------------------------------------------------------------------------------
+// The rows a region takes do not depend on the witness (fixed columns and selectors are laid out at keygen), so a pass that has
+// seen a region once knows where everything after it starts.  known_rows() remembers such lengths per (region, shape key) for the
+// process; RangeTask emits a region into its reserved rows of the parent's columns on another thread.
+inline size_t known_rows(const char* region, uint64_t key, size_t set_to = 0) {
+    static std::mutex m;
+    static std::map<std::pair<std::string, uint64_t>, size_t> rows;
+    std::lock_guard<std::mutex> lock(m);
+    size_t& slot = rows[{region, key}];
+    if (set_to) slot = set_to;
+    return slot;
+}
+struct RangeTask {
+    Assignment part;
+    std::thread worker;
+    std::exception_ptr error;
+    size_t start = 0, reserved = 0;
+    template <class Body>
+    void run(const Assignment& parent, size_t start_row, size_t rows, Body body) {
+        start = start_row;
+        reserved = rows;
+        part.view(parent, start_row, rows);
+        worker = std::thread([this, body] {
+            try {
+                body(part);
+            } catch (...) {
+                error = std::current_exception();
+            }
+        });
+    }
+    // after join: rethrows the task's error; exact = the region must have filled its reservation to the row
+    void join(Assignment& parent, bool exact) {
+        if (worker.joinable()) worker.join();
+        if (error) std::rethrow_exception(error);
+        if (exact && part.offset != start + reserved) throw std::runtime_error("a region emitted on another thread did not fill its reserved rows");
+        parent.pending_inverse.insert(parent.pending_inverse.end(), part.pending_inverse.begin(), part.pending_inverse.end());
+    }
+    ~RangeTask() {
+        if (worker.joinable()) worker.join();
     }
 };
 
