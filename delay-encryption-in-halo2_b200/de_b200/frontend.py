@@ -31,7 +31,7 @@ class _Fr(C.Structure):
 class _Desc(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("k", C.c_uint32), ("bits_len", C.c_uint32), ("exp_bits", C.c_uint32),
                 ("n", C.c_void_p), ("n_len", C.c_size_t), ("e", C.c_void_p), ("e_len", C.c_size_t), ("x", C.c_void_p), ("x_len", C.c_size_t),
-                ("message", C.c_void_p), ("message_len", C.c_uint32), ("key", _Fr * 2), ("witness_only", C.c_uint32), ("threads", C.c_uint32)]
+                ("message", C.c_void_p), ("message_len", C.c_uint32), ("key", _Fr * 2), ("witness_only", C.c_uint32), ("threads", C.c_uint32), ("reuse_buffer", C.c_uint32)]
 
 
 class _Info(C.Structure):
@@ -155,9 +155,11 @@ class WitnessPass:
         self.desc, self.k = d, k
         self.info = _Info()
 
-    def run(self, out) -> float:
-        """fills `out` (5 * 2^k * 4 uint64); returns the synthesis time in ms"""
+    def run(self, out, reuse: bool = False) -> float:
+        """fills `out` (5 * 2^k * 4 uint64); returns the synthesis time in ms.  reuse: `out` holds the result of an earlier run of
+        this circuit (any inputs) and need not be zeroed again"""
         ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        self.desc.reuse_buffer = 1 if reuse else 0
         rc = self.L.de_circuit_witness(C.byref(self.desc), C.c_void_p(ptr), C.byref(self.info))
         if rc != 0:
             raise DeError(rc, self.L.de_frontend_last_error().decode())

@@ -38,6 +38,10 @@ struct RsaInputs {
 
 // the region "rsa modpow with 2048 bits" shared by RSACircuit and DelayEncryptCircuit (benches/mod_pow.rs:104-133,
 // src/lib.rs:179-206); returns the constant-assigned result x^e mod n
+// the one place where the reference's layout depends on a value: x^e mod n is assigned as a CONSTANT (src/lib.rs:200-203 through
+// chip.rs:1255-1285 assign_constant), limb by limb up to its top non-zero limb, so its limb count decides the region's row count
+uint32_t constant_limbs(const BigUint& v) { return (uint32_t)((v.bits() + RSAChip::LIMB_WIDTH - 1) / RSAChip::LIMB_WIDTH); }
+
 AssignedInteger rsa_region(RSAChip& rsa, const RsaInputs& in) {
     BigIntChip& bigint = rsa.bigint;
     const uint32_t num_limbs = rsa.bits_len / RSAChip::LIMB_WIDTH;
@@ -133,7 +137,9 @@ void synth_delay_enc(Assignment& as, const de_circuit_desc& d, const RsaInputs& 
     configure_range(range, d.bits_len);
     RSAChip rsa(gate, range, d.bits_len, d.exp_bits);
     trace_lap("delay_enc: columns zeroed");
-    const uint64_t key = ((uint64_t)d.bits_len << 32) | d.exp_bits;
+    // region lengths are remembered per layout: (bits_len, exp_bits, limbs of the constant result)
+    const BigUint result = in.n.is_zero() ? BigUint() : big_pow_mod(in.x, in.e, in.n);
+    const uint64_t key = ((uint64_t)d.bits_len << 32) | ((uint64_t)constant_limbs(result) << 16) | d.exp_bits;
     const size_t rsa_rows = as.witness_only && as.threads > 1 ? known_rows("delay_enc rsa region", key) : 0;
     if (rsa_rows) {
         // a witness-only pass that knows where the RSA region ends: the two Poseidon regions need its VALUE only (x^e mod n, a
@@ -143,7 +149,7 @@ void synth_delay_enc(Assignment& as, const de_circuit_desc& d, const RsaInputs& 
         if (rsa_rows > as.usable) throw std::runtime_error("not enough rows: the circuit needs more than 2^" + std::to_string(as.k) + " - 6 usable rows");
         AssignedInteger result_values(32);
         {
-            const std::vector<BigUint> limbs = decompose_big(big_pow_mod(in.x, in.e, in.n), 32, RSAChip::LIMB_WIDTH);
+            const std::vector<BigUint> limbs = decompose_big(result, 32, RSAChip::LIMB_WIDTH);
             for (size_t i = 0; i < 32; i++) result_values[i].value = F::from_big(limbs[i]);
         }
         RangeTask tail;
@@ -218,6 +224,7 @@ static int synthesize_into(const de_circuit_desc* d, de_fr* advice_out, de_assig
             in.x = BigUint::from_bytes_le(d->x, d->x_len);
         }
         a->as.witness_only = d->witness_only != 0;
+        a->as.reuse_borrowed = advice_out && d->witness_only && d->reuse_buffer;
         a->as.threads = d->threads > 64 ? 64 : (d->threads ? d->threads : 1);
         const auto t0 = std::chrono::steady_clock::now();
         trace_lap("pass begins", true);

@@ -192,6 +192,7 @@ struct Assignment {
         Columns& operator=(const Columns&) = delete;
     } fixed, advice;
     F* borrowed_advice = nullptr;  // set before init(): 5 * 2^k elements, need not be zeroed
+    bool reuse_borrowed = false;   // ... unless they hold an earlier pass of the same circuit: then nothing is zeroed at all
     std::vector<Copy> copies;
     std::vector<F> outputs;  // circuit-level results (ciphertext, RSA result limbs) for the callers' known-answer checks
     // range tables: bit length -> tag
@@ -226,7 +227,7 @@ struct Assignment {
         n_fixed = with_range ? N_FIXED_RANGE : N_FIXED_MAIN;
         if (!witness_only) fixed.alloc(n_fixed, n);
         if (borrowed_advice) {
-            zero_columns(borrowed_advice, sizeof(F) * N_ADVICE * n);
+            if (!reuse_borrowed) zero_columns(borrowed_advice, sizeof(F) * N_ADVICE * n);
             advice.borrow(borrowed_advice, N_ADVICE, n);
         } else {
             advice.alloc(N_ADVICE, n);

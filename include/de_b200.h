@@ -323,6 +323,11 @@ typedef struct {
     uint32_t witness_only;  /* 1: the pass create_proof makes - advice columns only, no fixed columns / copy constraints */
     uint32_t threads;       /* witness-only passes: host threads that emit the independent row ranges of the RSA region (the
                                mul_mod calls of pow_mod); 0 or 1 = the calling thread alone.  The rows do not depend on it. */
+    uint32_t reuse_buffer;  /* de_circuit_witness only: 1 = advice_out already holds the result of an earlier witness pass for the
+                               same proving key and is not zeroed first - a pass writes the same cells whatever the witness, so a
+                               prover that cycles its staging buffers saves the 10 MB memset.  (The reference's layout depends on
+                               one value: x^e mod n is assigned as a constant, limb by limb up to its top non-zero limb - a
+                               different limb count is a different circuit, with its own keys.) */
 } de_circuit_desc;
 typedef struct {
     uint32_t k, n_fixed, n_advice, n_outputs;

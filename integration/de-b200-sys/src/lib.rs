@@ -29,7 +29,7 @@ pub enum de_ctx {} pub enum de_params {} pub enum de_domain {} pub enum de_pk {}
 
 #[repr(C)] pub struct de_circuit_desc { pub kind: u32, pub k: u32, pub bits_len: u32, pub exp_bits: u32,
                                         pub n: *const u8, pub n_len: usize, pub e: *const u8, pub e_len: usize, pub x: *const u8, pub x_len: usize,
-                                        pub message: *const de_fr, pub message_len: u32, pub key: [de_fr; 2], pub witness_only: u32, pub threads: u32 }
+                                        pub message: *const de_fr, pub message_len: u32, pub key: [de_fr; 2], pub witness_only: u32, pub threads: u32, pub reuse_buffer: u32 }
 #[repr(C)] #[derive(Clone, Copy)] pub struct de_assignment_info_t { pub k: u32, pub n_fixed: u32, pub n_advice: u32, pub n_outputs: u32,
                                                                     pub used_rows: u64, pub n_copies: u64, pub synthesis_ms: f64 }
 pub enum de_assignment {}

@@ -166,6 +166,18 @@ def test_witness_pass_on_several_threads_writes_the_same_rows():
     got = np.empty((5, 1 << 16, 4), dtype=np.uint64)
     fe.WitnessPass(fe.DELAY_ENC, 16, n=n, e=e, x=x, message=(0, 0), threads=5).run(got)
     assert np.array_equal(got, fe.synthesize(fe.DELAY_ENC, 16, n, e, x, [0, 0]).advice)
+    # reuse_buffer: a destination that holds an earlier pass of the same circuit (other inputs) is not zeroed and still ends
+    # up identical - every pass writes the same cells
+    buf = np.full((5, 1 << 16, 4), 0xA5A5, dtype=np.uint64)
+    for seed, ex in ((21, 30), (22, 31), (23, 1), (11, None)):
+        n, e, x = fe.sample_rsa_inputs(seed)
+        e = e if ex is None else ex
+        for threads in (1, 6):
+            fe.WitnessPass(fe.DELAY_ENC, 16, n=n, e=e, x=x, message=(0, 0), threads=threads).run(buf, reuse=seed != 21 or threads != 1)
+    assert np.array_equal(buf, got)
+    # the one value the layout depends on: x^0 mod n = 1 is a one-limb constant, 31 rows fewer (its own keys, its own buffers)
+    short = [fe.synthesize(fe.DELAY_ENC, 16, n, ee, x, [0, 0], witness_only=True, threads=t).used_rows for ee in (0, e) for t in (1, 4, 4)]
+    assert short[0] == short[1] == short[2] == short[3] - 31 and short[3] == short[4] == short[5]
     # not enough rows: reported, not written past the reservation
     with pytest.raises(Exception, match="not enough rows"):
         fe.WitnessPass(fe.DELAY_ENC, 15, n=n, e=3, x=x, message=(0, 0), threads=4).run(np.empty((5, 1 << 15, 4), dtype=np.uint64))

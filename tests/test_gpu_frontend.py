@@ -72,6 +72,11 @@ def test_delay_enc_real_circuit_proof_and_witness_pass():
     assert (buf.numpy().view(np.uint64) == syn.advice).all()
     proof2 = keys.prover.create_proof([buf[i] for i in range(5)], [np.zeros((0, 4), dtype=np.uint64)], draws)
     assert proof2 == proof
+    # the same pass on several host threads, into the buffer it already filled (threads / reuse_buffer): the same proof
+    d.threads, d.reuse_buffer = 6, 1
+    for _ in range(2):
+        assert _lib.load().de_circuit_witness(C.byref(d), C.c_void_p(buf.data_ptr()), C.byref(info)) == 0
+        assert keys.prover.create_proof([buf[i] for i in range(5)], [np.zeros((0, 4), dtype=np.uint64)], draws) == proof
     keys.close(); ctx.close()
 
 
