@@ -271,14 +271,14 @@ class BigIntChip {
         // R: rows of one mul_mod at these limb counts (a property of the layout, not of the values).  The first pass of a
         // process at a given width emits the first range here, in place, and measures it; later passes know it.
         trace_lap("pow_mod: values");
-        static std::atomic<size_t> known_rows[65];
+        const uint64_t shape_key = ((uint64_t)limb_width << 32) | limbs;
         const size_t first = as.offset;
-        size_t R = limbs <= 64 && limb_width == 64 ? known_rows[limbs].load() : 0;
+        size_t R = known_rows("mul_mod", shape_key);
         const bool first_inline = R == 0;
         if (first_inline) {
             mul_mod(jobs[0].a, jobs[0].b, n);
             R = as.offset - first;
-            if (limbs <= 64 && limb_width == 64) known_rows[limbs].store(R);
+            known_rows("mul_mod", shape_key, R);
             jobs[0].end = as.offset;
         } else {
             as.need_rows(R);
