@@ -160,11 +160,11 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
         XYZZ* D1 = D0 + (size_t)nsets_total * V0;
         XYZZ* S = D1 + (size_t)nsets_total * V1;
         TimedLaunch tl = timing_begin(ctx, "k_msm_digit_sums", (double)n * count);
-        k_bucket_rowcol<<<dim3(V1 + V0 / 4, nsets_total), DE_RC_THREADS, 0, st>>>(buckets, sh.NB, w0, w1, D0, D1);
+        k_bucket_rowcol<<<dim3(V1 + V0 / DE_RC_COLS, nsets_total), DE_RC_THREADS, 0, st>>>(buckets, sh.NB, w0, w1, D0, D1);
         DE_CHECK_LAUNCH(ctx);
         k_bucket_bitsums<<<dim3(w0 + w1 + 1, nsets_total), DE_RC_THREADS, 0, st>>>(D0, D1, w0, w1, S);
         DE_CHECK_LAUNCH(ctx);
-        k_bucket_bits_final<<<nsets_total, 32, 0, st>>>(S, w0, w1, set_out);
+        k_bucket_bits_final<<<nsets_total, 64, 0, st>>>(S, w0, w1, set_out);
         DE_CHECK_LAUNCH(ctx);
         timing_end(ctx, tl);
     } else if (sh.c >= 11) {

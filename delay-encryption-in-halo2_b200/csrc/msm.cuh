@@ -15,7 +15,7 @@
 // With tables 2^(c*nsets*t) * P_i precomputed per ParamsKZG (k_msm_precompute) all windows of a scalar share one
 // bucket set (nsets = 1): one reduction, no doublings.
 #pragma once
-#include "ec.cuh"
+#include "ec_quad.cuh"
 
 namespace de {
 
@@ -281,6 +281,72 @@ __device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int delta) {
     return r;
 }
 
+// XYZZ points in shared memory as 8 planes of 16-byte words (plane p, slot i at planes[p * N + i]): consecutive threads touch
+// consecutive 16-byte words, where an array of 128-byte structures would put every thread of a quarter-warp on the same banks
+template <int N>
+struct SmemPoints {
+    uint4 w[8 * N];
+    __device__ __forceinline__ void put(unsigned int i, const XYZZ& v) {
+        const Fq* f = &v.x;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            w[(2 * q) * N + i] = make_uint4(f[q].l[0], f[q].l[1], f[q].l[2], f[q].l[3]);
+            w[(2 * q + 1) * N + i] = make_uint4(f[q].l[4], f[q].l[5], f[q].l[6], f[q].l[7]);
+        }
+    }
+    __device__ __forceinline__ XYZZ get(unsigned int i) const {
+        XYZZ v;
+        Fq* f = &v.x;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 a = w[(2 * q) * N + i], b = w[(2 * q + 1) * N + i];
+            f[q].l[0] = a.x; f[q].l[1] = a.y; f[q].l[2] = a.z; f[q].l[3] = a.w;
+            f[q].l[4] = b.x; f[q].l[5] = b.y; f[q].l[6] = b.z; f[q].l[7] = b.w;
+        }
+        return v;
+    }
+    // one coordinate (role 0 X, 1 Y, 2 ZZ, 3 ZZZ) of slot i: what a lane of a quad holds (ec_quad.cuh)
+    __device__ __forceinline__ Fq coord(unsigned int i, unsigned int role) const {
+        const uint4 a = w[(2 * role) * N + i], b = w[(2 * role + 1) * N + i];
+        Fq f;
+        f.l[0] = a.x; f.l[1] = a.y; f.l[2] = a.z; f.l[3] = a.w;
+        f.l[4] = b.x; f.l[5] = b.y; f.l[6] = b.z; f.l[7] = b.w;
+        return f;
+    }
+    __device__ __forceinline__ void put_coord(unsigned int i, unsigned int role, const Fq& f) {
+        w[(2 * role) * N + i] = make_uint4(f.l[0], f.l[1], f.l[2], f.l[3]);
+        w[(2 * role + 1) * N + i] = make_uint4(f.l[4], f.l[5], f.l[6], f.l[7]);
+    }
+};
+// one level of `adds` independent additions slot[lhs(j)] += slot[rhs(j)], j < adds, by quads (4 * adds <= threads; whole warps
+// only: a warp none of whose quads has an addition skips the level)
+template <int N, class Lhs, class Rhs>
+__device__ __forceinline__ void smem_quad_level(SmemPoints<N>& s, unsigned int tid, unsigned int adds, Lhs lhs, Rhs rhs) {
+    if ((tid & ~31u) >= 4 * adds) return;
+    const unsigned int j = tid >> 2, role = tid & 3;
+    const bool active = j < adds;
+    const Fq a = active ? s.coord(lhs(j), role) : Fq::zero();
+    const Fq b = active ? s.coord(rhs(j), role) : Fq::zero();
+    const Fq r = quad_add(a, b, role);
+    if (active) s.put_coord(lhs(j), role, r);
+}
+template <int N>
+__device__ __forceinline__ void smem_tree_sum(SmemPoints<N>& s, unsigned int tid, unsigned int len) {
+    // slot 0 <- sum of slots [0, len), len a power of two <= blockDim (a multiple of 32); ends with a barrier.  Levels with at
+    // most blockDim / 4 additions run four lanes per addition (6 multiplication latencies instead of 14)
+    for (unsigned int d = len >> 1; d >= 1; d >>= 1) {
+        __syncthreads();
+        if (4 * d <= blockDim.x) {
+            smem_quad_level(s, tid, d, [](unsigned int j) { return j; }, [d](unsigned int j) { return j + d; });
+        } else if (tid < d) {
+            XYZZ a = s.get(tid);
+            XYZZ b = s.get(tid + d);
+            xyzz_add(a, b);
+            s.put(tid, a);
+        }
+    }
+    __syncthreads();
+}
 // buckets split into 2..8 tasks: one thread adds the partial sums
 __global__ void __launch_bounds__(128) k_msm_merge_small(const unsigned int* multi_small, const unsigned int* scal, const unsigned int* task_off,
                                                          const XYZZ* partials, XYZZ* buckets) {
@@ -502,51 +568,14 @@ __global__ void __launch_bounds__(128) k_msm_digit_final2(const XYZZ* dsums0, un
 // chain of DEPENDENT point additions is short and no CTA occupies an SM for long (a dependent XYZZ addition costs ~6 us of
 // latency on one warp, whatever the occupancy):
 //   k_bucket_rowcol   one launch, 64-thread CTAs: a CTA per bucket row (<= 4 serial additions per thread + a 6-level tree in
-//                     shared memory) and a CTA per 4 columns (16 row groups, <= 8 serial additions + a 4-level tree)
+//                     shared memory) and a CTA per 4 columns (16 row groups, <= 8 serial additions + a 4-level tree);
+//                     tree levels of <= 16 additions run four lanes per addition (ec_quad.cuh)
 //   k_bucket_bitsums  sum_v v * D[v] = sum_j 2^j * S_j with S_j = sum of the D[v] whose index has bit j set: one 64-thread
 //                     CTA per (array, bit) forms S_j by a tree; one more forms T = sum of all buckets
 //   k_bucket_bits_final  one warp per bucket set: lane s doubles its term s times (bit j of D1 weighs 2^(w0 + j) and sits in
 //                     slot w0 + j), then a 4-level tree adds the <= 16 terms.  result = T + sum_s 2^s * S_s
 #define DE_RC_THREADS 64
-// XYZZ points in shared memory as 8 planes of 16-byte words (plane p, slot i at planes[p * N + i]): consecutive threads touch
-// consecutive 16-byte words, where an array of 128-byte structures would put every thread of a quarter-warp on the same banks
-template <int N>
-struct SmemPoints {
-    uint4 w[8 * N];
-    __device__ __forceinline__ void put(unsigned int i, const XYZZ& v) {
-        const Fq* f = &v.x;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            w[(2 * q) * N + i] = make_uint4(f[q].l[0], f[q].l[1], f[q].l[2], f[q].l[3]);
-            w[(2 * q + 1) * N + i] = make_uint4(f[q].l[4], f[q].l[5], f[q].l[6], f[q].l[7]);
-        }
-    }
-    __device__ __forceinline__ XYZZ get(unsigned int i) const {
-        XYZZ v;
-        Fq* f = &v.x;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint4 a = w[(2 * q) * N + i], b = w[(2 * q + 1) * N + i];
-            f[q].l[0] = a.x; f[q].l[1] = a.y; f[q].l[2] = a.z; f[q].l[3] = a.w;
-            f[q].l[4] = b.x; f[q].l[5] = b.y; f[q].l[6] = b.z; f[q].l[7] = b.w;
-        }
-        return v;
-    }
-};
-template <int N>
-__device__ __forceinline__ void smem_tree_sum(SmemPoints<N>& s, unsigned int tid, unsigned int len) {
-    // slot 0 <- sum of slots [0, len), len a power of two <= blockDim; ends with a barrier
-    for (unsigned int d = len >> 1; d >= 1; d >>= 1) {
-        __syncthreads();
-        if (tid < d) {
-            XYZZ a = s.get(tid);
-            XYZZ b = s.get(tid + d);
-            xyzz_add(a, b);
-            s.put(tid, a);
-        }
-    }
-    __syncthreads();
-}
+#define DE_RC_COLS 4  // 2 columns x 32 row groups (a shorter serial phase, twice the CTAs) measured 1 % slower per proof
 __global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_rowcol(const XYZZ* buckets, unsigned int NB, unsigned int w0, unsigned int w1, XYZZ* D0,
                                                                     XYZZ* D1) {
     __shared__ SmemPoints<DE_RC_THREADS> sm;
@@ -566,28 +595,35 @@ __global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_rowcol(const XYZZ* 
         smem_tree_sum(sm, tid, DE_RC_THREADS);
         if (tid == 0) store_xyzz(&D1[set * V1 + u], sm.get(0));
     } else {
-        // column sums of 4 adjacent columns: thread (g, cv) adds rows g, g + 16, ... of column v0 + cv, then a tree over g
-        const unsigned int v0 = (blockIdx.x - V1) * 4;
-        const unsigned int g = tid >> 2, cv = tid & 3;
+        // column sums of DE_RC_COLS adjacent columns: thread (g, cv) adds rows g, g + G, ... of column v0 + cv (G = 64 /
+        // DE_RC_COLS row groups), then a tree over g; its levels of at most 16 additions run four lanes per addition
+        constexpr unsigned int G = DE_RC_THREADS / DE_RC_COLS;
+        const unsigned int v0 = (blockIdx.x - V1) * DE_RC_COLS;
+        const unsigned int g = tid / DE_RC_COLS, cv = tid % DE_RC_COLS;
         XYZZ acc = xyzz_identity();
-        for (unsigned int u = g; u < V1; u += 16) {
+        for (unsigned int u = g; u < V1; u += G) {
             XYZZ x = load_xyzz(&B[(unsigned long long)u * V0 + v0 + cv]);
             xyzz_add(acc, x);
         }
-        // sm[cv * 16 + g]: each column's 16 partials are contiguous; tree over g inside every 16-element group
-        sm.put(cv * 16 + g, acc);
-        for (unsigned int d = 8; d >= 1; d >>= 1) {
+        // sm[cv * G + g]: each column's G partials are contiguous; tree over g inside every group
+        sm.put(cv * G + g, acc);
+        for (unsigned int d = G / 2; d >= 1; d >>= 1) {
             __syncthreads();
-            const unsigned int c = tid >> 4, gg = tid & 15;
+            if (4 * DE_RC_COLS * d <= DE_RC_THREADS) {
+                smem_quad_level(sm, tid, DE_RC_COLS * d, [d](unsigned int j) { return (j / d) * G + j % d; },
+                                [d](unsigned int j) { return (j / d) * G + j % d + d; });
+                continue;
+            }
+            const unsigned int c = tid / G, gg = tid % G;
             if (gg < d) {
-                XYZZ a = sm.get(c * 16 + gg);
-                XYZZ b = sm.get(c * 16 + gg + d);
+                XYZZ a = sm.get(c * G + gg);
+                XYZZ b = sm.get(c * G + gg + d);
                 xyzz_add(a, b);
-                sm.put(c * 16 + gg, a);
+                sm.put(c * G + gg, a);
             }
         }
         __syncthreads();
-        if (tid < 4) store_xyzz(&D0[set * V0 + v0 + tid], sm.get(tid * 16));
+        if (tid < DE_RC_COLS) store_xyzz(&D0[set * V0 + v0 + tid], sm.get(tid * G));
     }
 }
 // grid.x = slot: [0, w0) bit j of D0, [w0, w0 + w1) bit (slot - w0) of D1, w0 + w1: the plain total of D0.  grid.y = set.
@@ -618,20 +654,26 @@ __global__ void __launch_bounds__(DE_RC_THREADS, 8) k_bucket_bitsums(const XYZZ*
     smem_tree_sum(sm, tid, DE_RC_THREADS);
     if (tid == 0) store_xyzz(&S[set * nslots + slot], sm.get(0));
 }
-__global__ void __launch_bounds__(32) k_bucket_bits_final(const XYZZ* S, unsigned int w0, unsigned int w1, XYZZ* set_out) {
-    __shared__ SmemPoints<32> sm;
-    const unsigned int lane = threadIdx.x;
+__global__ void __launch_bounds__(64) k_bucket_bits_final(const XYZZ* S, unsigned int w0, unsigned int w1, XYZZ* set_out) {
+    // 16 terms x 4 lanes (ec_quad.cuh): term s is doubled s times - 4 multiplication latencies per doubling - then a 4-level tree
+    __shared__ SmemPoints<16> sm;
+    const unsigned int tid = threadIdx.x, role = tid & 3, term = tid >> 2;
     const unsigned long long set = blockIdx.x;
-    const unsigned int nslots = w0 + w1 + 1;  // <= 16 for c <= 16
-    XYZZ term = xyzz_identity();
-    if (lane < nslots) {
-        term = load_xyzz(&S[set * nslots + lane]);
-        const unsigned int doublings = lane == nslots - 1 ? 0 : lane;
-        for (unsigned int d = 0; d < doublings; d++) term = xyzz_dbl(term);
+    const unsigned int nslots = w0 + w1 + 1;  // <= 16 for c <= 16; the last slot is the plain total (no doublings)
+    Fq c = Fq::zero();
+    unsigned int doublings = 0;
+    if (term < nslots) {
+        c = quad_load(&S[set * nslots + term], role);
+        doublings = term == nslots - 1 ? 0 : term;
     }
-    sm.put(lane, term);
-    smem_tree_sum(sm, lane, 32);
-    if (lane == 0) store_xyzz(&set_out[set], sm.get(0));
+    const unsigned int warp_doublings = __reduce_max_sync(0xffffffffu, doublings);
+    for (unsigned int d = 0; d < warp_doublings; d++) {
+        const Fq twice = quad_dbl(c, role);
+        if (d < doublings) c = twice;
+    }
+    sm.put_coord(term, role, c);
+    smem_tree_sum(sm, tid, 16);
+    if (term == 0) quad_store(&set_out[set], role, sm.coord(0, role));
 }
 
 // ---- 5. combine bucket sets: out[b] = sum_u 2^(c*u) * R[b][u], written as Jacobian -------------------------------

@@ -183,6 +183,36 @@ def test_witness_pass_on_several_threads_writes_the_same_rows():
         fe.WitnessPass(fe.DELAY_ENC, 15, n=n, e=3, x=x, message=(0, 0), threads=4).run(np.empty((5, 1 << 15, 4), dtype=np.uint64))
 
 
+def test_witness_passes_run_concurrently():
+    """the bench keeps eight provers per GPU, each with its own witness pass on its own host thread (and, in the
+    single-statement arm, worker threads inside the pass): passes share nothing but the process-wide table of region lengths"""
+    import threading
+    stmts = [fe.sample_rsa_inputs(40 + i) for i in range(6)]
+    want = []
+    for n, e, x in stmts:
+        buf = np.empty((5, 1 << 16, 4), dtype=np.uint64)
+        fe.WitnessPass(fe.DELAY_ENC, 16, n=n, e=e, x=x, message=(0, 0)).run(buf)
+        want.append(buf)
+    got = [np.full((5, 1 << 16, 4), 7, dtype=np.uint64) for _ in stmts]
+    errors = []
+
+    def work(i):
+        try:
+            n, e, x = stmts[i]
+            wp = fe.WitnessPass(fe.DELAY_ENC, 16, n=n, e=e, x=x, message=(0, 0), threads=1 + i % 4)
+            for r in range(3):
+                wp.run(got[i], reuse=r > 0)
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(stmts))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
 def test_rsa_pkcs1_known_answers():
     digest = [(RSA_DIGEST >> (64 * i)) & (2 ** 64 - 1) for i in range(4)]
     ok = fe.rsa_pkcs1(RSA_N1, 65537, RSA_SIG1, digest, k=17)
