@@ -347,28 +347,40 @@ __device__ __forceinline__ void smem_tree_sum(SmemPoints<N>& s, unsigned int tid
     }
     __syncthreads();
 }
-// buckets split into 2..8 tasks: one thread adds the partial sums
+// buckets split into 2..8 tasks: a quad adds the partial sums (<= 7 dependent additions of 6 multiplication latencies each,
+// ec_quad.cuh; one thread per bucket took 14 per addition)
 __global__ void __launch_bounds__(128) k_msm_merge_small(const unsigned int* multi_small, const unsigned int* scal, const unsigned int* task_off,
                                                          const XYZZ* partials, XYZZ* buckets) {
     const unsigned int total = scal[2];
-    for (unsigned int m = blockIdx.x * blockDim.x + threadIdx.x; m < total; m += gridDim.x * blockDim.x) {
-        const unsigned int b = multi_small[m];
-        const unsigned int first = task_off[b], last = task_off[b + 1];
-        XYZZ acc = load_xyzz(&partials[first]);
-        for (unsigned int p = first + 1; p < last; p++) {
-            XYZZ v = load_xyzz(&partials[p]);
-            xyzz_add(acc, v);
+    const unsigned int role = threadIdx.x & 3u, quad = (threadIdx.x & 31u) >> 2;
+    const unsigned int quads = gridDim.x * blockDim.x / 4;
+    // every warp walks blocks of 8 buckets; the loop bound is warp-uniform (the shuffles inside need all 32 lanes)
+    for (unsigned int base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) / 4; base < total; base += quads) {
+        const unsigned int m = base + quad;
+        const bool active = m < total;
+        unsigned int b = 0, first = 0, n = 0;
+        if (active) {
+            b = multi_small[m];
+            first = task_off[b];
+            n = task_off[b + 1] - first;
         }
-        store_xyzz(&buckets[b], acc);
+        Fq acc = active ? quad_load(&partials[first], role) : Fq::zero();
+        const unsigned int longest = __reduce_max_sync(0xffffffffu, n);
+        for (unsigned int i = 1; i < longest; i++) {
+            const Fq v = i < n ? quad_load(&partials[first + i], role) : Fq::zero();  // identity: the sum is unchanged
+            acc = quad_add(acc, v, role);
+        }
+        if (active) quad_store(&buckets[b], role, acc);
     }
 }
 // heavy buckets (> 8 tasks): one 128-thread CTA per bucket - the threads stride over the partial sums (a witness column's 0 / 1
-// digits put thousands of partials into one bucket: 128 lanes keep that chain at count / 128 additions), a shuffle tree inside
-// every warp, then warp 0 adds the four warp sums.  Buckets with <= 32 partials use the first warp only.
+// digits put thousands of partials into one bucket: 128 lanes keep that chain at count / 128 additions), then a tree in shared
+// memory whose levels of <= 32 additions run four lanes per addition (smem_tree_sum, ec_quad.cuh).  Buckets with <= 32 partials
+// use the first warp for the strided part and a 32-wide tree.
 __global__ void __launch_bounds__(128) k_msm_merge_large(const unsigned int* multi_large, const unsigned int* scal, const unsigned int* task_off,
                                                          const XYZZ* partials, XYZZ* buckets) {
-    __shared__ XYZZ swarp[4];
-    const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ SmemPoints<128> sm;
+    const unsigned int tid = threadIdx.x;
     const unsigned int total = scal[3];
     for (unsigned int m = blockIdx.x; m < total; m += gridDim.x) {
         const unsigned int b = multi_large[m];
@@ -381,26 +393,10 @@ __global__ void __launch_bounds__(128) k_msm_merge_large(const unsigned int* mul
                 XYZZ v = load_xyzz(&partials[p]);
                 xyzz_add(acc, v);
             }
-        const unsigned int np = cnt < 32 ? cnt : 32;  // lanes >= np of warp 0 hold the identity when cnt < 32
-        if (stride == 128 || wid == 0) {
-            for (unsigned int d = 16; d >= 1; d >>= 1) {
-                if (stride == 32 && d >= np) continue;  // warp-uniform: nothing but identities above lane d
-                XYZZ o = shfl_down_xyzz(acc, (int)d);
-                if (lane + d < 32) xyzz_add(acc, o);
-            }
-        }
-        if (stride == 128) {
-            if (lane == 0) swarp[wid] = acc;
-            __syncthreads();
-            if (tid == 0) {
-                for (unsigned int w = 1; w < 4; w++) {
-                    XYZZ o = swarp[w];
-                    xyzz_add(acc, o);
-                }
-            }
-            __syncthreads();  // swarp is reused by the next bucket of this CTA
-        }
-        if (tid == 0) store_xyzz(&buckets[b], acc);
+        if (tid < stride) sm.put(tid, acc);
+        smem_tree_sum(sm, tid, stride);
+        if (tid == 0) store_xyzz(&buckets[b], sm.get(0));
+        __syncthreads();  // sm is reused by the next bucket of this CTA
     }
 }
 
