@@ -91,7 +91,8 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     const unsigned int ndigits = (sh.c - 1 + 4) / 5;
     const unsigned int nsets_total = (unsigned int)(count * sh.nsets);
 
-    DE_WS(ctx, keys, unsigned int, WS_MSM_KEYS, sizeof(unsigned int) * E);
+    DE_WS(ctx, keys, unsigned int, WS_MSM_KEYS, sizeof(unsigned int) * 2 * E);
+    unsigned int* ranks = keys + E;  // rank of every entry inside its bucket
     DE_WS(ctx, vals, unsigned int, WS_MSM_VALS, sizeof(unsigned int) * E);
     DE_WS(ctx, sorted, unsigned int, WS_MSM_SORTED, sizeof(unsigned int) * (E + 2) + sizeof(uint2) * max_tasks);
     uint2* task_list = (uint2*)(sorted + ((E + 1) & ~1ull));
@@ -128,11 +129,10 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * nbuckets, st));
 
     const unsigned long long nscal = (unsigned long long)n * count;
-    k_msm_digits<<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals, counts);
+    k_msm_digits<<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals, ranks, counts);
     DE_CHECK_LAUNCH(ctx);
     DE_TRY(scan_u32(ctx, counts, nbuckets + 1, offsets, block_sums, &scalars_u32[0]));
-    DE_CUDA(ctx, cudaMemcpyAsync(cursor, offsets, sizeof(unsigned int) * (nbuckets + 1), cudaMemcpyDeviceToDevice, st));
-    k_msm_scatter<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, vals, E, cursor, sorted);
+    k_msm_scatter<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, vals, ranks, E, offsets, sorted);
     DE_CHECK_LAUNCH(ctx);
     k_msm_choose_ch<<<1, 32, 0, st>>>(scalars_u32, (unsigned int)nbuckets, DE_MSM_MAX_CH, target_tasks);
     DE_CHECK_LAUNCH(ctx);

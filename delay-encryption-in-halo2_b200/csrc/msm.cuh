@@ -36,7 +36,7 @@ struct MsmShape {
 
 // ---- 1. digits -------------------------------------------------------------------------------------------------
 __global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmShape sh, unsigned int* keys, unsigned int* vals,
-                             unsigned int* counts) {
+                             unsigned int* ranks, unsigned int* counts) {
     unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= sh.n * sh.count) return;
     unsigned int b = (unsigned int)(gid / sh.n);
@@ -69,20 +69,21 @@ __global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmSh
             unsigned long long tb = table * sh.table_stride + sh.base_offset + i;
             if (b >= sh.alt_first) tb = (unsigned long long)((long long)tb + sh.alt_delta);
             vals[e] = (unsigned int)tb | (neg << 31);
-            atomicAdd(&counts[key], 1u);  // bucket histogram of the counting sort, fused here
+            // bucket histogram of the counting sort, fused here; the value the atomic returns is this entry's rank inside its
+            // bucket, which spares the scatter an atomic of its own
+            ranks[e] = atomicAdd(&counts[key], 1u);
         }
     }
 }
 
 // ---- 2. counting sort ------------------------------------------------------------------------------------------
-__global__ void k_msm_scatter(const unsigned int* keys, const unsigned int* vals, unsigned long long E, unsigned int* cursor,
-                              unsigned int* sorted) {
+__global__ void k_msm_scatter(const unsigned int* keys, const unsigned int* vals, const unsigned int* ranks, unsigned long long E,
+                              const unsigned int* offsets, unsigned int* sorted) {
     unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     unsigned int k = keys[e];
     if (k == DE_MSM_INVALID) return;
-    unsigned int pos = atomicAdd(&cursor[k], 1u);
-    sorted[pos] = vals[e];
+    sorted[offsets[k] + ranks[e]] = vals[e];
 }
 
 // exclusive scan of n u32 values in three kernels (4096 items per block; n <= 4096 * 4096).  out has n + 1 entries.
