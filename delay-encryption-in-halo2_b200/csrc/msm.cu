@@ -152,7 +152,8 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CHECK_LAUNCH(ctx);
     k_msm_merge_large<<<ctx->sm_count * 4, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    if (sh.c >= 11 && sh.c <= 16 && ctx->mode == DE_MODE_LATENCY) {
+    static const bool rowcol_always = getenv("DE_REDUCE_ROWCOL") != nullptr;  // A/B switch for measurements
+    if (sh.c >= 11 && sh.c <= 16 && (ctx->mode == DE_MODE_LATENCY || rowcol_always)) {
         // latency-oriented two-digit reduction (4c): row / column sums in one launch, bit sums, one warp per set for the fold
         const unsigned int cm1 = sh.c - 1, w0 = (cm1 + 1) / 2, w1 = cm1 - w0;
         const unsigned int V0 = 1u << w0, V1 = 1u << w1;
