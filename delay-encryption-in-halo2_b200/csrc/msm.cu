@@ -91,8 +91,10 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     const unsigned int ndigits = (sh.c - 1 + 4) / 5;
     const unsigned int nsets_total = (unsigned int)(count * sh.nsets);
 
-    DE_WS(ctx, keys, unsigned int, WS_MSM_KEYS, sizeof(unsigned int) * 2 * E);
-    unsigned int* ranks = keys + E;  // rank of every entry inside its bucket
+    static const char* force_ranks = getenv("DE_SCATTER_RANKS");  // A/B switch for measurements: "0" / "1"
+    const bool use_ranks = force_ranks ? force_ranks[0] == '1' : n <= (1ull << 20);  // measured crossover, see k_msm_scatter
+    DE_WS(ctx, keys, unsigned int, WS_MSM_KEYS, sizeof(unsigned int) * (use_ranks ? 2 : 1) * E);
+    unsigned int* ranks = use_ranks ? keys + E : nullptr;  // rank of every entry inside its bucket
     DE_WS(ctx, vals, unsigned int, WS_MSM_VALS, sizeof(unsigned int) * E);
     DE_WS(ctx, sorted, unsigned int, WS_MSM_SORTED, sizeof(unsigned int) * (E + 2) + sizeof(uint2) * max_tasks);
     uint2* task_list = (uint2*)(sorted + ((E + 1) & ~1ull));
@@ -132,7 +134,12 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     k_msm_digits<<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals, ranks, counts);
     DE_CHECK_LAUNCH(ctx);
     DE_TRY(scan_u32(ctx, counts, nbuckets + 1, offsets, block_sums, &scalars_u32[0]));
-    k_msm_scatter<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, vals, ranks, E, offsets, sorted);
+    if (use_ranks) {
+        k_msm_scatter<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, vals, ranks, E, offsets, sorted);
+    } else {
+        DE_CUDA(ctx, cudaMemcpyAsync(cursor, offsets, sizeof(unsigned int) * (nbuckets + 1), cudaMemcpyDeviceToDevice, st));
+        k_msm_scatter_cursor<<<(unsigned int)((E + 255) / 256), 256, 0, st>>>(keys, vals, E, cursor, sorted);
+    }
     DE_CHECK_LAUNCH(ctx);
     k_msm_choose_ch<<<1, 32, 0, st>>>(scalars_u32, (unsigned int)nbuckets, DE_MSM_MAX_CH, target_tasks);
     DE_CHECK_LAUNCH(ctx);
