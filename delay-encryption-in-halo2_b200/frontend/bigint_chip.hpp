@@ -267,6 +267,7 @@ class BigIntChip {
             } catch (...) {
                 j.error = std::current_exception();
             }
+            Assignment::fence();  // non-temporal stores of this range visible before the join
         };
         // R: rows of one mul_mod at these limb counts (a property of the layout, not of the values).  The first pass of a
         // process at a given width emits the first range here, in place, and measures it; later passes know it.
