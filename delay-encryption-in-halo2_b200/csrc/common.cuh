@@ -71,7 +71,7 @@ struct PinnedBuf {
 };
 
 enum { WS_IO_A = 0, WS_IO_B, WS_NTT_SCRATCH, WS_MSM_KEYS, WS_MSM_VALS, WS_MSM_SORTED, WS_MSM_COUNTS, WS_MSM_BUCKETS,
-       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_RED, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_NTT_DIST, WS_NTT_DIST_X, WS_COUNT };
+       WS_MSM_PARTIALS, WS_MSM_MISC, WS_MSM_RED, WS_MSM_OUT, WS_EVAL_A, WS_EVAL_B, WS_EVAL_C, WS_NTT_DIST, WS_NTT_DIST_X, WS_POLY_SCRATCH, WS_COUNT };
 
 }  // namespace de
 

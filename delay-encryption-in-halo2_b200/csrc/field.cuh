@@ -255,9 +255,79 @@ DE_D Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+// Dedicated squaring: 36 + 72 products instead of 64 + 72.  a^2 = sum_i a_i 2^(32i) * (a_i 2^(32i) + 2 * sum_{j>i} a_j 2^(32j)),
+// so CIOS row i multiplies a_i with the limbs c_i = a_i, c_(i+1) = a_(i+1) << 1, c_j = (2a)_j for j >= i + 2 only (a < p < 2^254,
+// so 2a still has 8 limbs) and the reduction rows stay as in mul().  Relative to the row's base the product a_i * c_j lands on
+// columns (j, j + 1) exactly as a * b_i does in mad_row, so the even / odd chains are the same with their leading products
+// replaced by carry ripples.  The running sum after row i is below 2^(32i + 288): it fits the 9-limb window like mul()'s.
+template <class P, int I>
+DE_D void sqr_row(uint32_t* even, uint32_t* odd, const uint32_t* c, uint32_t bi, const uint32_t* mod) {
+    if (I == 0) {
+        mul_n(odd, c + 1, bi);
+        mul_n(even, c, bi);
+    } else {
+        even[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (2 * k + 1 >= I) {
+                odd[2 * k] = ptx::madc_lo_cc(c[2 * k + 1], bi, odd[2 * k + 2]);
+                odd[2 * k + 1] = ptx::madc_hi_cc(c[2 * k + 1], bi, odd[2 * k + 3]);
+            } else {
+                odd[2 * k] = ptx::addc_cc(odd[2 * k + 2], 0);
+                odd[2 * k + 1] = ptx::addc_cc(odd[2 * k + 3], 0);
+            }
+        }
+        odd[6] = ptx::madc_lo_cc(c[7], bi, 0);
+        odd[7] = ptx::madc_hi(c[7], bi, 0);
+        constexpr int J0 = (I + 1) & ~1;  // first even column with a product in this row
+#pragma unroll
+        for (int j = J0; j < 8; j += 2) {
+            even[j] = j == J0 ? ptx::mad_lo_cc(c[j], bi, even[j]) : ptx::madc_lo_cc(c[j], bi, even[j]);
+            even[j + 1] = ptx::madc_hi_cc(c[j], bi, even[j + 1]);
+        }
+        if (J0 < 8) odd[7] = ptx::addc(odd[7], 0);
+    }
+    uint32_t mi = ptx::mul_lo(even[0], P::INV);
+    cmad_n(odd, mod + 1, mi);
+    cmad_n(even, mod, mi);
+    odd[7] = ptx::addc(odd[7], 0);
+}
+template <class P, int I>
+DE_D void sqr_row_operands(uint32_t* c, const uint32_t* a, const uint32_t* d) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) c[j] = j == I ? a[j] : j == I + 1 ? a[j] << 1 : d[j];
+}
+
 template <class P>
 DE_D Fp<P> sqr(const Fp<P>& a) {
+#if defined(DE_SQR_IS_MUL)
     return mul(a, a);
+#else
+    uint32_t even[8], odd[8], mod[8], d[8], c[8];
+    d[0] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) mod[i] = P::p(i);
+#pragma unroll
+    for (int j = 1; j < 8; j++) d[j] = (a.l[j] << 1) | (a.l[j - 1] >> 31);
+    sqr_row_operands<P, 0>(c, a.l, d); sqr_row<P, 0>(even, odd, c, a.l[0], mod);
+    sqr_row_operands<P, 1>(c, a.l, d); sqr_row<P, 1>(odd, even, c, a.l[1], mod);
+    sqr_row_operands<P, 2>(c, a.l, d); sqr_row<P, 2>(even, odd, c, a.l[2], mod);
+    sqr_row_operands<P, 3>(c, a.l, d); sqr_row<P, 3>(odd, even, c, a.l[3], mod);
+    sqr_row_operands<P, 4>(c, a.l, d); sqr_row<P, 4>(even, odd, c, a.l[4], mod);
+    sqr_row_operands<P, 5>(c, a.l, d); sqr_row<P, 5>(odd, even, c, a.l[5], mod);
+    sqr_row_operands<P, 6>(c, a.l, d); sqr_row<P, 6>(even, odd, c, a.l[6], mod);
+    sqr_row_operands<P, 7>(c, a.l, d); sqr_row<P, 7>(odd, even, c, a.l[7], mod);
+    uint32_t t[8];
+    t[0] = ptx::add_cc(odd[1], even[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) t[i] = ptx::addc_cc(odd[i + 1], even[i]);
+    t[7] = ptx::addc(even[7], 0);
+    final_sub<P>(t);
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = t[i];
+    return r;
+#endif
 }
 
 // Montgomery form -> canonical integer (Fr::to_repr): multiply by 1.

@@ -64,16 +64,11 @@ int scan_u32(de_ctx* ctx, const unsigned int* in, unsigned long long n, unsigned
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // d_scalars: `count` polynomials of n Montgomery scalars, `stride` elements apart.  d_tables: cfg.ntables base tables,
-// table_stride elements apart.  Writes `count` Jacobian points to host_out.
-// out_mode 0: Jacobian points (de_g1, Montgomery); 1: canonical affine x || y, 64 bytes per point (transcript form)
-static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, size_t count, const Affine* d_tables,
-                    size_t table_stride, size_t base_offset, const MsmCfg& cfg, void* host_out, int out_mode = 0,
-                    unsigned int alt_first = 0xffffffffu, long long alt_delta = 0) {
-    if (count == 0) return DE_OK;
-    if (n == 0) {
-        memset(host_out, 0, (out_mode ? sizeof(de_g1_affine) : sizeof(de_g1)) * count);
-        return DE_OK;
-    }
+// table_stride elements apart.  Queues the whole launch sequence on the context's stream and leaves `count` Jacobian points at
+// d_out (device); *d_entries (device, may be null) receives the number of bucket additions.
+static int msm_enqueue(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, size_t count, const Affine* d_tables,
+                       size_t table_stride, size_t base_offset, const MsmCfg& cfg, Jac* d_out, unsigned int alt_first, long long alt_delta,
+                       unsigned int* d_entries) {
     if ((unsigned long long)cfg.ntables * table_stride >= (1ull << 31) ||
         (alt_first != 0xffffffffu && 2ull * cfg.ntables * table_stride >= (1ull << 31)))
         return fail(ctx, DE_ERR_UNSUPPORTED, "msm: base table exceeds 2^31 points");
@@ -120,7 +115,6 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_WS(ctx, red, XYZZ, WS_MSM_MISC, sizeof(XYZZ) * ((size_t)ndigits * 32 * nsets_total + nsets_total));
     XYZZ* dsums = red;
     XYZZ* set_out = red + (size_t)ndigits * 32 * nsets_total;
-    DE_WS(ctx, d_out, Jac, WS_MSM_OUT, sizeof(Jac) * count);
     // scratch of the two-digit reduction: two ping-pong partial buffers, D0 / D1 and their digit sums
     DE_WS(ctx, red2, XYZZ, WS_MSM_RED, sizeof(XYZZ) * ((size_t)nsets_total * sh.NB + 4096 + (size_t)nsets_total * 4 * 2048));
 
@@ -131,7 +125,11 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CUDA(ctx, cudaMemsetAsync(buckets, 0, sizeof(XYZZ) * nbuckets, st));
 
     const unsigned long long nscal = (unsigned long long)n * count;
-    k_msm_digits<<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals, ranks, counts);
+    static const char* force_agg = getenv("DE_DIGITS_AGG");  // A/B switch for measurements: "0" / "1"
+    if (force_agg ? force_agg[0] == '1' : true)
+        k_msm_digits<true><<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals, ranks, counts);
+    else
+        k_msm_digits<false><<<(unsigned int)((nscal + 127) / 128), 128, 0, st>>>(d_scalars, stride, sh, keys, vals, ranks, counts);
     DE_CHECK_LAUNCH(ctx);
     DE_TRY(scan_u32(ctx, counts, nbuckets + 1, offsets, block_sums, &scalars_u32[0]));
     if (use_ranks) {
@@ -157,7 +155,13 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     DE_CHECK_LAUNCH(ctx);
     k_msm_merge_small<<<ctx->sm_count * 4, 128, 0, st>>>(multi_small, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
-    k_msm_merge_large<<<ctx->sm_count * 4, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
+    // A/B switch for measurements: "0" / "1".  A warp per 9 .. 32-partial bucket measured neutral (8.98 vs 9.02 ms per proof,
+    // 158.8 vs 158.7 proofs/s): off by default
+    static const char* merge_env = getenv("DE_MERGE_WARP");
+    if (merge_env ? merge_env[0] == '1' : false)
+        k_msm_merge_large<true><<<ctx->sm_count * 4, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
+    else
+        k_msm_merge_large<false><<<ctx->sm_count * 4, 128, 0, st>>>(multi_large, scalars_u32, task_off, partials, buckets);
     DE_CHECK_LAUNCH(ctx);
     static const bool rowcol_always = getenv("DE_REDUCE_ROWCOL") != nullptr;  // A/B switch for measurements
     if (sh.c >= 11 && sh.c <= 16 && (ctx->mode == DE_MODE_LATENCY || rowcol_always)) {
@@ -234,12 +238,45 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     }
     k_msm_combine<<<(unsigned int)count, 32, 0, st>>>(set_out, sh.nsets, sh.c, d_out);
     DE_CHECK_LAUNCH(ctx);
+    if (d_entries) DE_CUDA(ctx, cudaMemcpyAsync(d_entries, &scalars_u32[0], sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
+    return DE_OK;
+}
+
+// Writes `count` points to host_out.  out_mode 0: Jacobian points (de_g1, Montgomery); 1: canonical affine x || y, 64 bytes per
+// point (transcript form).  `dense` = the caller expects full-width scalars in every polynomial (the grand products of a proof).
+// DE_MSM_SPLIT=<m> (measurement switch, off by default): with one proof in flight a dense batch of more than m proof-sized
+// polynomials goes through the launch sequence in two halves.  Tried because the sort of 8 x 2^16 x 16 entries works on 134 MB of
+// keys, values, ranks and sorted values - more than the L2 holds; measured on the B200 it LOSES 0.33 ms per proof (9.02 vs 8.69 ms):
+// the second half's latency-bound reduction tail costs more than the smaller working set saves.
+static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, size_t count, const Affine* d_tables,
+                    size_t table_stride, size_t base_offset, const MsmCfg& cfg, void* host_out, int out_mode = 0,
+                    unsigned int alt_first = 0xffffffffu, long long alt_delta = 0, bool dense = false) {
+    if (count == 0) return DE_OK;
+    if (n == 0) {
+        memset(host_out, 0, (out_mode ? sizeof(de_g1_affine) : sizeof(de_g1)) * count);
+        return DE_OK;
+    }
+    static const char* split_env = getenv("DE_MSM_SPLIT");  // largest batch that is not split; 0 = never split
+    const size_t split_above = split_env ? (size_t)atoll(split_env) : 0;
+    const bool split = dense && split_above && count > split_above && ctx->mode == DE_MODE_LATENCY && n <= (1ull << 18);
+    DE_WS(ctx, d_out_all, Jac, WS_MSM_OUT, sizeof(Jac) * count + 2 * sizeof(unsigned int));
+    unsigned int* d_entries = (unsigned int*)(d_out_all + count);
+    cudaStream_t st = ctx->stream;
+    const size_t first = split ? (count + 1) / 2 : count;  // the larger half first: the grow-only workspaces are sized once
+    for (size_t c0 = 0, part = 0; c0 < count; c0 += first, part++) {
+        const size_t cnt = c0 + first <= count ? first : count - c0;
+        unsigned int af = alt_first == 0xffffffffu ? alt_first : alt_first > c0 ? (unsigned int)(alt_first - c0) : 0u;
+        DE_TRY(msm_enqueue(ctx, d_scalars + c0 * stride, stride, n, cnt, d_tables, table_stride, base_offset, cfg, d_out_all + c0, af, alt_delta,
+                           ctx->timing ? d_entries + part : nullptr));
+    }
+    Jac* d_out = d_out_all;
     std::vector<de_g1> jac_tmp;
     if (out_mode == 1) jac_tmp.resize(count);
     DE_CUDA(ctx, cudaMemcpyAsync(out_mode == 1 ? (void*)jac_tmp.data() : host_out, d_out, sizeof(Jac) * count, cudaMemcpyDeviceToHost, st));
-    unsigned int total_entries = 0;
-    if (ctx->timing) DE_CUDA(ctx, cudaMemcpyAsync(&total_entries, &scalars_u32[0], sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    unsigned int entries_h[2] = {0, 0};
+    if (ctx->timing) DE_CUDA(ctx, cudaMemcpyAsync(entries_h, d_entries, sizeof(unsigned int) * (split ? 2 : 1), cudaMemcpyDeviceToHost, st));
     DE_CUDA(ctx, stream_wait(ctx, st));
+    const unsigned int total_entries = entries_h[0] + entries_h[1];
     // transcript form: one batched inversion on the host for the round's handful of points
     if (out_mode == 1) host::g1_jacobian_to_canonical((const uint64_t*)jac_tmp.data(), count, (uint8_t*)host_out);
     if (ctx->timing) {
@@ -253,7 +290,7 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
             stat->name = "msm_bucket_adds";
         }
         stat->units += total_entries;
-        stat->launches++;
+        stat->launches += split ? 2 : 1;  // one k_msm_accumulate launch per half
     }
     return DE_OK;
 }
@@ -514,7 +551,7 @@ int commit_canonical_mixed_dev(de_params* p, const Fr* d_scalars, size_t stride,
     DE_CUDA(ctx, cudaSetDevice(ctx->device));
     // indices are offsets from the start of the shared allocation, so that both bases are reachable with non-negative indices
     return msm_core(ctx, d_scalars, stride, n, count_lagrange + count_coeff, p->block, p->n, (size_t)(p->tables[1] - p->block), p->cfg, out_xy, 1,
-                    (unsigned int)count_lagrange, (long long)(p->tables[0] - p->tables[1]));
+                    (unsigned int)count_lagrange, (long long)(p->tables[0] - p->tables[1]), true);
 }
 de_ctx* params_ctx(de_params* p) { return p->ctx; }
 size_t params_n(de_params* p) { return p->n; }

@@ -35,10 +35,16 @@ struct MsmShape {
 };
 
 // ---- 1. digits -------------------------------------------------------------------------------------------------
+// AGG: the histogram's atomics are aggregated per warp (lanes with equal keys elect a leader that adds their count once and
+// hands out consecutive ranks).  Neighbouring rows of a column often carry the SAME scalar - the constant tail of a grand product
+// behind the used rows, runs of 0 / 1 in a witness column - and then all 32 lanes of a warp hit one counter 16 times over.
+template <bool AGG>
 __global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmShape sh, unsigned int* keys, unsigned int* vals,
                              unsigned int* ranks, unsigned int* counts) {
     unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= sh.n * sh.count) return;
+    const bool live = gid < sh.n * sh.count;
+    if (!AGG && !live) return;
+    if (!live) gid = sh.n * sh.count - 1;  // AGG: the whole warp stays for the match; this lane repeats a scalar and writes nothing
     unsigned int b = (unsigned int)(gid / sh.n);
     unsigned long long i = gid % sh.n;
     Fr s = from_mont(load(&scalars[b * stride + i]));
@@ -61,7 +67,24 @@ __global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmSh
         }
         unsigned long long e = ((unsigned long long)b * sh.W + w) * sh.n + i;
         unsigned int set = w % sh.nsets, table = w / sh.nsets;
-        if (mag == 0) {
+        if (AGG) {
+            const unsigned int key = (live && mag) ? (b * sh.nsets + set) * sh.NB + (mag - 1) : DE_MSM_INVALID;
+            const unsigned int peers = __match_any_sync(0xffffffffu, key);
+            const unsigned int lane = threadIdx.x & 31u;
+            const unsigned int leader = __ffs(peers) - 1;
+            unsigned int first = 0;
+            if (lane == leader && key != DE_MSM_INVALID) first = atomicAdd(&counts[key], __popc(peers));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            if (live) {
+                keys[e] = key;
+                if (key != DE_MSM_INVALID) {
+                    unsigned long long tb = table * sh.table_stride + sh.base_offset + i;
+                    if (b >= sh.alt_first) tb = (unsigned long long)((long long)tb + sh.alt_delta);
+                    vals[e] = (unsigned int)tb | (neg << 31);
+                    if (ranks) ranks[e] = first + __popc(peers & ((1u << lane) - 1u));
+                }
+            }
+        } else if (mag == 0) {
             keys[e] = DE_MSM_INVALID;
         } else {
             const unsigned int key = (b * sh.nsets + set) * sh.NB + (mag - 1);
@@ -364,6 +387,22 @@ __device__ __forceinline__ void smem_tree_sum(SmemPoints<N>& s, unsigned int tid
     }
     __syncthreads();
 }
+// slot base <- sum of the 32 slots [base, base + 32) by ONE warp (no CTA barrier): 16 one-lane additions, then four quad levels
+template <int N>
+__device__ __forceinline__ void smem_warp_tree_sum(SmemPoints<N>& s, unsigned int base, unsigned int lane) {
+    __syncwarp();
+    if (lane < 16) {
+        XYZZ a = s.get(base + lane);
+        XYZZ b = s.get(base + lane + 16);
+        xyzz_add(a, b);
+        s.put(base + lane, a);
+    }
+    for (unsigned int d = 8; d >= 1; d >>= 1) {
+        __syncwarp();
+        smem_quad_level(s, lane, d, [base](unsigned int j) { return base + j; }, [base, d](unsigned int j) { return base + j + d; });
+    }
+    __syncwarp();
+}
 // buckets split into 2..8 tasks: a quad adds the partial sums (<= 7 dependent additions of 6 multiplication latencies each,
 // ec_quad.cuh; one thread per bucket took 14 per addition)
 __global__ void __launch_bounds__(128) k_msm_merge_small(const unsigned int* multi_small, const unsigned int* scal, const unsigned int* task_off,
@@ -390,10 +429,12 @@ __global__ void __launch_bounds__(128) k_msm_merge_small(const unsigned int* mul
         if (active) quad_store(&buckets[b], role, acc);
     }
 }
-// heavy buckets (> 8 tasks): one 128-thread CTA per bucket - the threads stride over the partial sums (a witness column's 0 / 1
-// digits put thousands of partials into one bucket: 128 lanes keep that chain at count / 128 additions), then a tree in shared
-// memory whose levels of <= 32 additions run four lanes per addition (smem_tree_sum, ec_quad.cuh).  Buckets with <= 32 partials
-// use the first warp for the strided part and a 32-wide tree.
+// heavy buckets (> 8 tasks).  More than 32 partial sums: one 128-thread CTA per bucket - the threads stride over the partial sums
+// (a witness column's 0 / 1 digits put thousands of partials into one bucket: 128 lanes keep that chain at count / 128
+// additions), then a tree in shared memory whose levels of <= 32 additions run four lanes per addition (smem_tree_sum,
+// ec_quad.cuh).  9 .. 32 partial sums - the hundreds of small-value buckets of a witness column at task length 8 - take ONE warp
+// each, four buckets per CTA at a time (WARP_MEDIUM; with a whole CTA per such bucket three of its four warps only held registers).
+template <bool WARP_MEDIUM>
 __global__ void __launch_bounds__(128) k_msm_merge_large(const unsigned int* multi_large, const unsigned int* scal, const unsigned int* task_off,
                                                          const XYZZ* partials, XYZZ* buckets) {
     __shared__ SmemPoints<128> sm;
@@ -403,6 +444,7 @@ __global__ void __launch_bounds__(128) k_msm_merge_large(const unsigned int* mul
         const unsigned int b = multi_large[m];
         const unsigned int first = task_off[b], last = task_off[b + 1];
         const unsigned int cnt = last - first;
+        if (WARP_MEDIUM && cnt <= 32) continue;             // CTA-uniform
         const unsigned int stride = cnt > 32 ? 128u : 32u;  // CTA-uniform
         XYZZ acc = xyzz_identity();
         if (tid < stride)
@@ -414,6 +456,20 @@ __global__ void __launch_bounds__(128) k_msm_merge_large(const unsigned int* mul
         smem_tree_sum(sm, tid, stride);
         if (tid == 0) store_xyzz(&buckets[b], sm.get(0));
         __syncthreads();  // sm is reused by the next bucket of this CTA
+    }
+    if (!WARP_MEDIUM) return;
+    const unsigned int lane = tid & 31u, wid = tid >> 5;
+    for (unsigned int m = blockIdx.x * 4 + wid; m < total; m += gridDim.x * 4) {  // warp-uniform
+        const unsigned int b = multi_large[m];
+        const unsigned int first = task_off[b];
+        const unsigned int cnt = task_off[b + 1] - first;
+        if (cnt > 32) continue;
+        XYZZ acc = xyzz_identity();
+        if (lane < cnt) acc = load_xyzz(&partials[first + lane]);
+        sm.put(32 * wid + lane, acc);
+        smem_warp_tree_sum(sm, 32 * wid, lane);
+        if (lane == 0) store_xyzz(&buckets[b], sm.get(32 * wid));
+        __syncwarp();  // this warp's slots are reused by its next bucket
     }
 }
 

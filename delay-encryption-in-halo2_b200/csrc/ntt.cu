@@ -446,6 +446,7 @@ __global__ void k_vec_op(int op, const F* a, const F* b, F* out, unsigned long l
     else if (op == DE_OP_SUB) r = sub(x, load(&b[i]));
     else if (op == DE_OP_FROM_MONT) r = from_mont(x);
     else if (op == DE_OP_INV) r = inv(x);
+    else if (op == DE_OP_SQR) r = sqr(x);
     else r = to_mont(x);
     store(&out[i], r);
 }
@@ -453,7 +454,7 @@ __global__ void k_vec_op(int op, const F* a, const F* b, F* out, unsigned long l
 template <class F>
 static int vec_op(de_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n) {
     if (!ctx) return DE_ERR_ARG;
-    if (op < DE_OP_MUL || op > DE_OP_INV) return fail(ctx, DE_ERR_ARG, "vec_op: unknown op");
+    if (op < DE_OP_MUL || op > DE_OP_SQR) return fail(ctx, DE_ERR_ARG, "vec_op: unknown op");
     if (n == 0) return DE_OK;
     bool binary = op <= DE_OP_SUB;
     if (!a || !out || (binary && !b)) return fail(ctx, DE_ERR_ARG, "vec_op: null pointer");

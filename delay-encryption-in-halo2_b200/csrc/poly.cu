@@ -24,37 +24,75 @@ __device__ __forceinline__ void block_sum(Fr* sm, int tid, int nthreads) {
     __syncthreads();
 }
 
-// one CTA per (polynomial, point) pair: thread t Horner-evaluates its contiguous chunk, scales by x^(t * chunk), tree sum.
+// grid (evaluation, segment): the SEGS x 512 threads of an evaluation Horner-evaluate contiguous chunks of `chunk` coefficients
+// (r_g for global thread g); with X = x^chunk the value is sum_g r_g X^g.  Inside a CTA that sum is a tree whose level d folds
+// slot t + d into slot t with ONE multiplication by X^d (the powers X^(2^k) come from a squaring chain of thread 0) - no
+// per-thread x^(g * chunk).  A segment leaves its sum in `partial`; the CTA that finishes last (counter `done`, zeroed by the
+// host before the launch) folds the SEGS partial sums by Horner in X^512.  58 evaluations of a proof thus occupy 232 SMs' worth
+// of CTAs instead of 58, each with a quarter of the serial chain (one proof in flight: 186 -> ~60 us).
 // polys[e] points at n coefficients; the result is written in Montgomery form and, when out_canonical != nullptr, also as
 // the canonical integer (Fr::to_repr), which is what the transcript hashes.
+#define DE_POLY_SEGS 4
+__device__ __forceinline__ Fr load_cg(const Fr* p) {  // bypasses L1: written by another CTA of the same launch
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p)), b = __ldcg(reinterpret_cast<const uint4*>(p) + 1);
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
 __global__ void __launch_bounds__(DE_POLY_THREADS) k_eval_polynomial(const Fr* const* polys, unsigned long long n, const unsigned int* point_index,
-                                                                     const Fr* points, Fr* out, Fr* out_canonical) {
+                                                                     const Fr* points, Fr* out, Fr* out_canonical, Fr* partial,
+                                                                     unsigned int* done) {
     __shared__ Fr sm[DE_POLY_THREADS];
+    __shared__ Fr pw[10];  // pw[k] = X^(2^k), X = x^chunk; pw[9] = X^512 steps from one segment to the next
+    __shared__ bool is_last;
     const int tid = threadIdx.x;
-    const Fr* p = polys[blockIdx.x];
-    const Fr x = load(&points[point_index ? point_index[blockIdx.x] : blockIdx.x]);
-    const unsigned long long chunk = (n + DE_POLY_THREADS - 1) / DE_POLY_THREADS;
-    const unsigned long long lo = (unsigned long long)tid * chunk;
+    const unsigned int e = blockIdx.x, seg = blockIdx.y, segs = gridDim.y;
+    const Fr* p = polys[e];
+    const Fr x = load(&points[point_index ? point_index[e] : e]);
+    const unsigned long long chunk = (n + (unsigned long long)segs * DE_POLY_THREADS - 1) / ((unsigned long long)segs * DE_POLY_THREADS);
+    const unsigned long long lo = ((unsigned long long)seg * DE_POLY_THREADS + tid) * chunk;
     unsigned long long hi = lo + chunk;
     if (hi > n) hi = n;
     Fr acc = Fr::zero();
     for (unsigned long long i = hi; i > lo; i--) acc = add(mul(acc, x), load(&p[i - 1]));
-    if (lo < n && lo > 0) {
-        // x^lo, LSB first: stops at the top set bit of the (small) offset
-        Fr pw = Fr::one(), base = x;
-        for (unsigned long long e = lo; e; e >>= 1) {
-            if (e & 1) pw = mul(pw, base);
+    store(&sm[tid], acc);
+    if (tid == 0) {
+        Fr X = Fr::one(), base = x;  // x^chunk, LSB first
+        for (unsigned long long b = chunk; b; b >>= 1) {
+            if (b & 1) X = mul(X, base);
             base = sqr(base);
         }
-        acc = mul(acc, pw);
+        store(&pw[0], X);
+        for (int k = 1; k < 10; k++) {
+            X = sqr(X);
+            store(&pw[k], X);
+        }
     }
-    store(&sm[tid], (lo < n) ? acc : Fr::zero());
-    block_sum(sm, tid, DE_POLY_THREADS);
+    __syncthreads();
+    for (int d = DE_POLY_THREADS >> 1, k = 8; d >= 1; d >>= 1, k--) {
+        if (tid < d) store(&sm[tid], add(load(&sm[tid]), mul(load(&sm[tid + d]), load(&pw[k]))));
+        __syncthreads();
+    }
     if (tid == 0) {
-        const Fr r = load(&sm[0]);
-        if (out) store(&out[blockIdx.x], r);
-        if (out_canonical) store(&out_canonical[blockIdx.x], from_mont(r));
+        is_last = true;
+        if (segs > 1) {
+            store(&partial[(unsigned long long)e * segs + seg], load(&sm[0]));
+            __threadfence();
+            is_last = atomicAdd(&done[e], 1u) == segs - 1;
+        }
     }
+    __syncthreads();
+    if (!is_last || tid != 0) return;
+    Fr r = load(&sm[0]);
+    if (segs > 1) {
+        __threadfence();
+        const Fr Y = load(&pw[9]);
+        r = load_cg(&partial[(unsigned long long)e * segs + segs - 1]);
+        for (int s = (int)segs - 2; s >= 0; s--) r = add(mul(r, Y), load_cg(&partial[(unsigned long long)e * segs + s]));
+    }
+    if (out) store(&out[e], r);
+    if (out_canonical) store(&out_canonical[e], from_mont(r));
 }
 
 // kate_division: with t_i = q[i-1] the quotient satisfies t_i = a[i] + b * t_(i+1), t_n = 0.
@@ -145,7 +183,19 @@ __global__ void k_kate_write(const Fr* const* as, unsigned long long n, const Fr
 int eval_polynomials_dev(de_ctx* ctx, const Fr* const* d_polys, size_t n, const unsigned int* d_point_index, const Fr* d_points, size_t count,
                          Fr* d_out, Fr* d_out_canonical) {
     if (count == 0) return DE_OK;
-    k_eval_polynomial<<<(unsigned int)count, DE_POLY_THREADS, 0, ctx->stream>>>(d_polys, n, d_point_index, d_points, d_out, d_out_canonical);
+    static const char* seg_env = getenv("DE_POLY_SEGS");  // A/B switch for measurements
+    const unsigned int segs = n >= 8192 ? (seg_env ? (unsigned int)atoi(seg_env) : DE_POLY_SEGS) : 1;
+    if (segs < 1 || segs > 64) return fail(ctx, DE_ERR_ARG, "eval_polynomial: DE_POLY_SEGS out of range");
+    Fr* partial = nullptr;
+    unsigned int* done = nullptr;
+    if (segs > 1) {
+        DE_WS(ctx, scratch, Fr, WS_POLY_SCRATCH, (sizeof(Fr) * segs + sizeof(unsigned int)) * count);
+        partial = scratch;
+        done = (unsigned int*)(scratch + (size_t)segs * count);
+        DE_CUDA(ctx, cudaMemsetAsync(done, 0, sizeof(unsigned int) * count, ctx->stream));
+    }
+    k_eval_polynomial<<<dim3((unsigned int)count, segs), DE_POLY_THREADS, 0, ctx->stream>>>(d_polys, n, d_point_index, d_points, d_out, d_out_canonical,
+                                                                                           partial, done);
     DE_CHECK_LAUNCH(ctx);
     return DE_OK;
 }

@@ -117,6 +117,8 @@ class Context:
     def fq_mul(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_MUL, a, b)
     def fq_add(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_ADD, a, b)
     def fq_sub(self, a, b): return self._vec(self.L.de_fq_vec_op, _lib.OP_SUB, a, b)
+    def fr_square(self, a): return self._vec(self.L.de_fr_vec_op, _lib.OP_SQR, a, None)
+    def fq_square(self, a): return self._vec(self.L.de_fq_vec_op, _lib.OP_SQR, a, None)
 
     # ---- a3 / a4 ----
     def best_multiexp(self, coeffs, bases):

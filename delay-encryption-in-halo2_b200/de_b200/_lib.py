@@ -6,10 +6,11 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libde_b200.so")
+# DE_B200_LIB: another build of the same library (A/B measurements of compile-time variants, tools/ab.sh)
+LIB_PATH = os.environ.get("DE_B200_LIB") or os.path.join(_PKG, "libde_b200.so")
 
 DE_OK, DE_ERR_ARG, DE_ERR_CUDA, DE_ERR_OOM, DE_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-OP_MUL, OP_ADD, OP_SUB, OP_FROM_MONT, OP_TO_MONT = 0, 1, 2, 3, 4
+OP_MUL, OP_ADD, OP_SUB, OP_FROM_MONT, OP_TO_MONT, OP_INV, OP_SQR = 0, 1, 2, 3, 4, 5, 6
 
 # every symbol include/de_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = [

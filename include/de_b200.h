@@ -76,7 +76,7 @@ int de_timing_get(de_ctx* ctx, const char* kernel, double* total_ms, double* tot
 
 /* ---- a1: halo2curves Fr / Fq element-wise arithmetic (parity surface for the field kernels) ---------------- */
 enum de_field_op { DE_OP_MUL = 0, DE_OP_ADD = 1, DE_OP_SUB = 2, DE_OP_FROM_MONT = 3, DE_OP_TO_MONT = 4,
-                   DE_OP_INV = 5 /* ff::Field::invert; 0 -> 0 */ };
+                   DE_OP_INV = 5 /* ff::Field::invert; 0 -> 0 */, DE_OP_SQR = 6 /* ff::Field::square: the dedicated squaring of field.cuh */ };
 int de_fr_vec_op(de_ctx* ctx, int op, const de_fr* a, const de_fr* b, de_fr* out, size_t n);
 int de_fq_vec_op(de_ctx* ctx, int op, const de_fq* a, const de_fq* b, de_fq* out, size_t n);
 

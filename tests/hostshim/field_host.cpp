@@ -18,6 +18,8 @@ void h_fr_sub(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run
 void h_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run<Fq>(a, b, o, n, [](Fq x, Fq y) { return mul(x, y); }); }
 void h_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run<Fq>(a, b, o, n, [](Fq x, Fq y) { return add(x, y); }); }
 void h_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run<Fq>(a, b, o, n, [](Fq x, Fq y) { return sub(x, y); }); }
+void h_fr_sqr(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run<Fr>(a, b, o, n, [](Fr x, Fr) { return sqr(x); }); }
+void h_fq_sqr(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run<Fq>(a, b, o, n, [](Fq x, Fq) { return sqr(x); }); }
 void h_fr_inv(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run<Fr>(a, b, o, n, [](Fr x, Fr) { return inv(x); }); }
 void h_fq_inv(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run<Fq>(a, b, o, n, [](Fq x, Fq) { return inv(x); }); }
 void h_fr_from_mont(const uint32_t* a, const uint32_t* b, uint32_t* o, size_t n) { run<Fr>(a, b, o, n, [](Fr x, Fr) { return from_mont(x); }); }

@@ -47,6 +47,20 @@ def test_device_field_schedule_on_host(shim, field, p):
         assert (call(shim, f"h_{field}_{op}", a, b) == f(a, b)).all(), op
 
 
+@pytest.mark.parametrize("field,p", [("fr", po.FR), ("fq", po.FQ)])
+def test_dedicated_squaring_on_host(shim, field, p):
+    """field.cuh sqr(): the 36-product CIOS rows (a_i times the doubled upper part) against the oracle's a * a, edge values
+    (0, 1, p - 1, p - 2, all-ones limbs, the largest inputs of the 9-limb window) included"""
+    n = 50000
+    a = orc.uniform_fr(21, n)
+    e = edge(p)
+    a[: len(e)] = e
+    more = orc.ints_to_limbs([p - 1 - (1 << k) for k in range(0, 250, 7)] + [(1 << k) - 1 for k in range(1, 254, 5)] + [((1 << 253) | (0x7FFFFFFF << s)) % p for s in range(0, 220, 32)])
+    a[len(e): len(e) + len(more)] = more
+    mul = getattr(orc, field + "_mul")
+    assert (call(shim, f"h_{field}_sqr", a, a) == mul(a, a)).all()
+
+
 def test_from_mont_on_host(shim):
     a = orc.uniform_fr(13, 1000)
     assert (call(shim, "h_fr_from_mont", a, a) == orc.fr_from_mont(a)).all()

@@ -26,6 +26,19 @@ def test_field_ops_bit_exact(ctx, field, p):
         assert (got == want).all(), op
 
 
+@pytest.mark.parametrize("field,p", [("fr", po.FR), ("fq", po.FQ)])
+def test_dedicated_squaring_bit_exact(ctx, field, p):
+    """DE_OP_SQR (ff::Field::square): field.cuh's 36-product squaring rows == the oracle's a * a"""
+    n = 1 << 16
+    a = orc.uniform_fr(25, n)
+    e = edge(p)
+    a[: len(e)] = e
+    more = orc.ints_to_limbs([p - 1 - (1 << k) for k in range(0, 250, 7)] + [(1 << k) - 1 for k in range(1, 254, 5)])
+    a[len(e): len(e) + len(more)] = more
+    got = getattr(ctx, f"{field}_square")(a)
+    assert (got == getattr(orc, f"{field}_mul")(a, a)).all()
+
+
 def test_mont_conversions(ctx):
     a = orc.uniform_fr(23, 5000)
     c = ctx.fr_from_mont(a)
