@@ -109,57 +109,51 @@ __global__ void k_kate_chunk_values(const Fr* const* as, unsigned long long n, c
     for (unsigned long long i = hi; i > lo; i--) acc = add(mul(acc, b), load(&a[i - 1]));
     store(&vals[blockIdx.y * nchunks + c], acc);
 }
-// pass 2 (one CTA per polynomial): carry[c] = t_(hi_c) = V_(c+1) + b^CHUNK * carry[c+1], carry[last] = 0: a suffix scan of
-// affine maps (Hillis-Steele), DE_KATE_SCAN chunks per sweep from the top of the polynomial down.
+// pass 2 (one CTA per polynomial): carry[c] = t_(hi_c) = V_(c+1) + B * carry[c+1] with B = b^CHUNK, carry[last] = 0: a suffix
+// scan of affine maps y -> a + B y that all share the multiplier B.  Two levels: thread t composes the maps of its G =
+// ceil(nchunks / DE_KATE_SCAN) consecutive chunks (Horner, G steps), one Hillis-Steele sweep over the threads follows in which
+// step d needs ONE multiplication, by (B^G)^d - a squaring chain every thread keeps for itself -, then the thread replays its G
+// chunks from the carry entering them.  G + 9 + G dependent steps (n = 2^16: 17) where sweeps of DE_KATE_SCAN single chunks with
+// both map components in shared memory took 9 * nchunks / DE_KATE_SCAN + ... (36): 105 -> ~50 us of a single proof's last round.
 __global__ void __launch_bounds__(DE_KATE_SCAN) k_kate_carries(const Fr* vals, unsigned long long nchunks, const Fr* b_pow_chunks, Fr* carries) {
     __shared__ Fr s_add[DE_KATE_SCAN];
-    __shared__ Fr s_mul[DE_KATE_SCAN];
-    __shared__ Fr s_carry;
     const int tid = threadIdx.x;
     vals += blockIdx.x * nchunks;
     carries += blockIdx.x * nchunks;
-    const Fr b_pow_chunk = load(&b_pow_chunks[blockIdx.x]);
-    if (tid == 0) store(&s_carry, Fr::zero());
+    const Fr B = load(&b_pow_chunks[blockIdx.x]);
+    const unsigned long long G = (nchunks + DE_KATE_SCAN - 1) / DE_KATE_SCAN;
+    // element e of the descending order is chunk c = nchunks - 1 - e; its addend is V_(c+1) (zero for the top chunk)
+    const unsigned long long e0 = (unsigned long long)tid * G;
+    Fr A = Fr::zero();
+    for (unsigned long long g = 0; g < G && e0 + g < nchunks; g++) {
+        const unsigned long long c = nchunks - 1 - (e0 + g);
+        const Fr a = c + 1 < nchunks ? load(&vals[c + 1]) : Fr::zero();
+        A = add(a, mul(B, A));
+    }
+    store(&s_add[tid], A);
+    Fr Md = Fr::one(), base = B;  // (B^G)^d, d = 1 to start with
+    for (unsigned long long g = G; g; g >>= 1) {
+        if (g & 1) Md = mul(Md, base);
+        base = sqr(base);
+    }
     __syncthreads();
-    for (long long top = (long long)nchunks; top > 0; top -= DE_KATE_SCAN) {
-        // element t of this sweep is chunk c = top - 1 - t (descending) with the map f_c(y) = V_(c+1) + m * y applied to the
-        // carry of chunk c + 1
-        const long long c = top - 1 - tid;
-        const bool live = c >= 0;
-        Fr addend = Fr::zero(), mult = Fr::one();
-        if (live) {
-            const bool has_above = c + 1 < (long long)nchunks;
-            addend = has_above ? load(&vals[c + 1]) : Fr::zero();
-            mult = has_above ? b_pow_chunk : Fr::zero();
-        }
-        store(&s_add[tid], addend);
-        store(&s_mul[tid], mult);
+    // inclusive scan: afterwards s_add[t] is the carry LEAVING thread t's chunks (the carry entering thread 0 is zero).  A thread
+    // with fewer than G chunks sits at the end of the order: its own entry is wrong then, and nobody reads it.
+    for (int d = 1; d < DE_KATE_SCAN; d <<= 1) {
+        Fr pa = Fr::zero();
+        const bool has = tid >= d;
+        if (has) pa = load(&s_add[tid - d]);
         __syncthreads();
-        // inclusive scan: afterwards (s_mul[t], s_add[t]) maps the carry ENTERING element 0 of the sweep to the carry of element t
-        for (int d = 1; d < DE_KATE_SCAN; d <<= 1) {
-            Fr pa = Fr::zero(), pm = Fr::one();
-            const bool has = tid >= d;
-            if (has) {
-                pa = load(&s_add[tid - d]);
-                pm = load(&s_mul[tid - d]);
-            }
-            __syncthreads();
-            if (has) {
-                // f_t o f_(t-d): y -> add_t + mul_t * (add_p + mul_p * y)
-                const Fr mt = load(&s_mul[tid]);
-                store(&s_add[tid], add(load(&s_add[tid]), mul(mt, pa)));
-                store(&s_mul[tid], mul(mt, pm));
-            }
-            __syncthreads();
-        }
-        const Fr carry_in = load(&s_carry);
-        const Fr mine = add(load(&s_add[tid]), mul(load(&s_mul[tid]), carry_in));
-        if (live) store(&carries[c], mine);
+        if (has) store(&s_add[tid], add(load(&s_add[tid]), mul(Md, pa)));
+        Md = sqr(Md);
         __syncthreads();
-        // the carry entering the next sweep is the carry of the lowest chunk of this one
-        const long long last_t = (top >= DE_KATE_SCAN) ? DE_KATE_SCAN - 1 : top - 1;
-        if (tid == last_t) store(&s_carry, mine);
-        __syncthreads();
+    }
+    Fr cur = tid ? load(&s_add[tid - 1]) : Fr::zero();
+    for (unsigned long long g = 0; g < G && e0 + g < nchunks; g++) {
+        const unsigned long long c = nchunks - 1 - (e0 + g);
+        const Fr a = c + 1 < nchunks ? load(&vals[c + 1]) : Fr::zero();
+        cur = add(a, mul(B, cur));
+        store(&carries[c], cur);
     }
 }
 // pass 3: per chunk, run the recurrence downwards from the incoming carry and write q (n - 1 coefficients; q[n-1] := 0 is

@@ -23,7 +23,7 @@ def mont(vals):
     return pp.to_mont(vals)
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 256, 257, 1000, (1 << 14) + 3])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 256, 257, 1000, 8191, 8192, (1 << 14) + 3, (1 << 16) + 1])
 def test_eval_polynomial_and_kate_division(ctx, n):
     rng = po.Xoshiro(0xE0 + n)
     a = [rng.uniform_fr() for _ in range(n)]
