@@ -87,6 +87,16 @@ struct KernelStat {
     double ms = 0, units = 0;
     uint64_t launches = 0;
 };
+// one captured launch sequence of a commitment round (msm.cu): replayed while every pointer, size and workspace address of the
+// call is the same as at capture time
+struct MsmGraph {
+    std::vector<uint64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    uint32_t seen = 0;       // calls with this key so far (the second one captures)
+    bool eager_only = false; // a capture of this key failed once: never again
+    uint64_t launches = 0;   // kernels inside the graph (de_launch_count keeps counting them on replay)
+    uint64_t last_used = 0;
+};
 }  // namespace de
 
 struct de_ctx {
@@ -101,6 +111,8 @@ struct de_ctx {
     std::string err;
     uint64_t launches = 0;
     de::DevBuf ws[de::WS_COUNT];
+    std::vector<de::MsmGraph> msm_graphs;
+    uint64_t msm_graph_clock = 0;
     de::PinnedBuf pinned;
     std::vector<de::NttPlan*> plans;
     std::vector<de::NttDistPlan*> dist_plans;           // multi-GPU transform tables (ntt.cu)

@@ -242,6 +242,77 @@ static int msm_enqueue(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n
     return DE_OK;
 }
 
+// The launch sequence of msm_enqueue as a CUDA graph.  A proof repeats the same commitment rounds on the same buffers, and at
+// the small circuits (pose_enc, k = 11: ~20 kernels of 3-6 us per round) the rounds are bound by launch and dependency latency,
+// not by work.  The first call with a given key runs eagerly (and sizes the grow-only workspaces), the second one is captured,
+// later ones replay.  The key holds every pointer, size and workspace address the sequence bakes in, so a reallocated workspace or
+// another prover's columns simply miss.  DE_MODE_LATENCY only: measured on the B200, one proof in flight gains (pose_enc 1.86 ->
+// 1.67 ms, mod_pow 15.45 -> 15.26, delay_enc 8.39 -> 8.35), while eight provers replaying graphs from eight host threads LOSE
+// (pose_enc 1678 -> 1575 proofs/s, delay_enc 158.1 -> 156.4): a graph launch is one unit of work to the driver and the streams
+// interleave more coarsely.  DE_MSM_GRAPH=0 switches it off, =2 forces it in throughput mode too; per-kernel timing
+// (de_timing_enable) bypasses it.
+static int msm_enqueue_graphed(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, size_t count, const Affine* d_tables,
+                               size_t table_stride, size_t base_offset, const MsmCfg& cfg, Jac* d_out, unsigned int alt_first, long long alt_delta) {
+    static const char* env = getenv("DE_MSM_GRAPH");
+    const bool enabled = !(env && env[0] == '0') && !ctx->timing && n <= (1ull << 17) &&
+                         (ctx->mode == DE_MODE_LATENCY || (env && env[0] == '2'));
+    if (!enabled) return msm_enqueue(ctx, d_scalars, stride, n, count, d_tables, table_stride, base_offset, cfg, d_out, alt_first, alt_delta, nullptr);
+    std::vector<uint64_t> key = {(uint64_t)d_scalars, stride, n, count, (uint64_t)d_tables, table_stride, base_offset,
+                                 ((uint64_t)cfg.c << 48) | ((uint64_t)cfg.W << 32) | ((uint64_t)cfg.nsets << 16) | cfg.ntables, (uint64_t)d_out,
+                                 alt_first, (uint64_t)alt_delta, (uint64_t)ctx->mode, (uint64_t)ctx->sm_count};
+    for (int s = WS_MSM_KEYS; s <= WS_MSM_OUT; s++) key.push_back((uint64_t)ctx->ws[s].p);
+    MsmGraph* slot = nullptr;
+    for (auto& g : ctx->msm_graphs)
+        if (g.key == key) slot = &g;
+    ctx->msm_graph_clock++;
+    if (!slot) {
+        if (ctx->msm_graphs.size() >= 32) {  // evict the least recently used entry
+            size_t lru = 0;
+            for (size_t i = 1; i < ctx->msm_graphs.size(); i++)
+                if (ctx->msm_graphs[i].last_used < ctx->msm_graphs[lru].last_used) lru = i;
+            if (ctx->msm_graphs[lru].exec) cudaGraphExecDestroy(ctx->msm_graphs[lru].exec);
+            ctx->msm_graphs.erase(ctx->msm_graphs.begin() + lru);
+        }
+        ctx->msm_graphs.emplace_back();
+        slot = &ctx->msm_graphs.back();
+        slot->key = key;
+    }
+    slot->last_used = ctx->msm_graph_clock;
+    slot->seen++;
+    if (slot->exec) {
+        DE_CUDA(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
+        ctx->launches += slot->launches;
+        return DE_OK;
+    }
+    if (slot->seen < 2 || slot->eager_only) {
+        const int rc = msm_enqueue(ctx, d_scalars, stride, n, count, d_tables, table_stride, base_offset, cfg, d_out, alt_first, alt_delta, nullptr);
+        // the eager run may have grown a workspace: the key to match next time carries the addresses as they are now
+        for (int s = WS_MSM_KEYS; s <= WS_MSM_OUT; s++) slot->key[13 + (s - WS_MSM_KEYS)] = (uint64_t)ctx->ws[s].p;
+        return rc;
+    }
+    const uint64_t launches_before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    DE_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = msm_enqueue(ctx, d_scalars, stride, n, count, d_tables, table_stride, base_offset, cfg, d_out, alt_first, alt_delta, nullptr);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    const uint64_t in_graph = ctx->launches - launches_before;
+    ctx->launches = launches_before;
+    cudaGraphExec_t exec = nullptr;
+    if (rc == DE_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        slot->exec = exec;
+        slot->launches = in_graph;
+        DE_CUDA(ctx, cudaGraphLaunch(exec, ctx->stream));
+        ctx->launches += in_graph;
+        return DE_OK;
+    }
+    // capture failed: nothing was executed; clear the error state and run eagerly, now and whenever this key comes back
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    slot->eager_only = true;
+    return msm_enqueue(ctx, d_scalars, stride, n, count, d_tables, table_stride, base_offset, cfg, d_out, alt_first, alt_delta, nullptr);
+}
+
 // Writes `count` points to host_out.  out_mode 0: Jacobian points (de_g1, Montgomery); 1: canonical affine x || y, 64 bytes per
 // point (transcript form).  `dense` = the caller expects full-width scalars in every polynomial (the grand products of a proof).
 // DE_MSM_SPLIT=<m> (measurement switch, off by default): with one proof in flight a dense batch of more than m proof-sized
@@ -266,8 +337,12 @@ static int msm_core(de_ctx* ctx, const Fr* d_scalars, size_t stride, size_t n, s
     for (size_t c0 = 0, part = 0; c0 < count; c0 += first, part++) {
         const size_t cnt = c0 + first <= count ? first : count - c0;
         unsigned int af = alt_first == 0xffffffffu ? alt_first : alt_first > c0 ? (unsigned int)(alt_first - c0) : 0u;
-        DE_TRY(msm_enqueue(ctx, d_scalars + c0 * stride, stride, n, cnt, d_tables, table_stride, base_offset, cfg, d_out_all + c0, af, alt_delta,
-                           ctx->timing ? d_entries + part : nullptr));
+        if (ctx->timing)
+            DE_TRY(msm_enqueue(ctx, d_scalars + c0 * stride, stride, n, cnt, d_tables, table_stride, base_offset, cfg, d_out_all + c0, af, alt_delta,
+                               d_entries + part));
+        else
+            DE_TRY(msm_enqueue_graphed(ctx, d_scalars + c0 * stride, stride, n, cnt, d_tables, table_stride, base_offset, cfg, d_out_all + c0, af,
+                                       alt_delta));
     }
     Jac* d_out = d_out_all;
     std::vector<de_g1> jac_tmp;

@@ -522,6 +522,8 @@ int de_ctx_destroy(de_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ntt_free_plans(ctx);
+    for (auto& g : ctx->msm_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& w : ctx->ws) w.release();
     ctx->pinned.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

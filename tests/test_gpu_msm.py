@@ -98,6 +98,29 @@ def test_commit_batch_and_ranges(ctx):
     assert same_point(ctx.g1_sum(parts), orc.best_multiexp(polys[0], gl))
 
 
+def test_commit_graph_replay(ctx):
+    """the commitment's launch sequence is captured as a CUDA graph on the second call with the same buffers (one proof in
+    flight) and replayed afterwards: new scalars written in place, a witness-like column (another task length chosen on the
+    device, heavy buckets) and a return to uniform ones must all give the oracle's points"""
+    import torch
+    k, count = 11, 3
+    n = 1 << k
+    gl = orc.gen_bases(n)
+    params = de_b200.ParamsKZG(k, None, gl, ctx)
+    d = torch.empty((count, n, 4), dtype=torch.int64, device="cuda")
+    launches = []
+    for it in range(6):
+        polys = [orc.witness_fr(300 + it, n, n // 2) if it == 3 else orc.uniform_fr(200 + 7 * it + j, n) for j in range(count)]
+        d.copy_(torch.from_numpy(np.stack(polys).view(np.int64)))
+        torch.cuda.synchronize()
+        before = ctx.launches
+        got = params.commit_batch_dev(1, d, n, count)
+        launches.append(ctx.launches - before)
+        for j in range(count):
+            assert same_point(got[j], orc.best_multiexp(polys[j], gl)), (it, j)
+    assert len(set(launches)) == 1, launches  # replays keep counting the kernels inside the graph
+
+
 def test_commit_delay_enc_size(ctx):
     # the bench configuration: k = 16 commit_lagrange, uniform and witness-like columns
     k = 16
