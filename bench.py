@@ -63,7 +63,7 @@ TRANSCRIPT_REPR = 0xDE1A7E9C0DE
 UNIT = "proofs/s"
 LATENCY_WITNESS_THREADS = max(1, min(12, (os.cpu_count() or 1) - 2))
 MUL_PEAK_FALLBACK_GMULS = 65.9  # only if de_int_peak fails: this pool's B200 by tools/int_peak (profiles/r01_int_peak.jsonl)
-MULS_PER_ADD = 10       # XYZZ mixed addition: 8M + 2S (field.cuh has no cheaper squaring)
+MULS_PER_ADD = 10       # XYZZ mixed addition: 8M + 2S (the convention of round 1; add_rooflines weighs the 2 squarings by their measured cost)
 # DRAM bytes of a k_msm_accumulate launch per executed bucket addition, from ONE `ncu --set full` capture (dram__bytes_read.sum +
 # dram__bytes_write.sum of the launch / its bucket additions); the file names the capture it came from.  Absent -> traffic: null.
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "msm_accumulate_traffic.json")
@@ -558,11 +558,18 @@ def add_rooflines(line, art, rank):
     peaks, peak_kind = _peaks()
     mul_peak, mul_peak_src = measure_int_peak(ctx)
     line["int_peak_gmul_s"] = mul_peak
+    try:
+        sqr_peak = ctx.int_peak_sqr()
+    except Exception:  # noqa: BLE001
+        sqr_peak = mul_peak
+    line["int_peak_gsqr_s"] = sqr_peak
+    # one mixed bucket addition in multiplication-equivalents: 8 products + 2 squarings at their measured relative cost
+    muls_per_add = 8.0 + 2.0 * mul_peak / sqr_peak
     if acc_n:
         pts_per_launch = acc_pts / acc_n
         adds_per_launch = bucket_adds / acc_n
         avg_ms = acc_ms / acc_n
-        gmuls = MULS_PER_ADD * bucket_adds / (acc_ms * 1e-3) / 1e9
+        gmuls = muls_per_add * bucket_adds / (acc_ms * 1e-3) / 1e9
         hbm_gbs = 96.0 * pts_per_launch / (avg_ms * 1e-3) / 1e9
         traffic, traffic_src = None, "no ncu capture on file"
         try:
@@ -575,9 +582,11 @@ def add_rooflines(line, art, rank):
         line["roofline"] = {
             "kernel": "k_msm_accumulate", "bound": "int_pipe", "achieved": gmuls, "peak": mul_peak, "unit": "Gmul/s (Fr/Fq Montgomery multiplications)",
             "frac": gmuls / mul_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": mul_peak_src,
-            "work": {"bucket_adds_per_launch": adds_per_launch, "muls_per_bucket_add": MULS_PER_ADD, "points_per_launch": pts_per_launch,
+            "work": {"bucket_adds_per_launch": adds_per_launch, "muls_per_bucket_add": muls_per_add, "points_per_launch": pts_per_launch,
+                     "muls_per_bucket_add_note": "8 products + 2 squarings x (int_peak_gmul_s / int_peak_gsqr_s): the dedicated squaring "
+                                                 "is cheaper than a product, and counting it as one would overstate the fraction",
                      "bucket_adds_per_proof": bucket_adds / lat_steps,
-                     "note": "achieved = 10 x bucket additions actually executed (counted on the device: non-zero signed 16-bit digits) / "
+                     "note": "achieved = muls_per_bucket_add x bucket additions actually executed (counted on the device: non-zero signed 16-bit digits) / "
                              "kernel time; SURVEY.md 8d's fixed 160 mul/point convention would also count the zero digits of the "
                              "witness columns, which are legitimately skipped"},
             "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"], "peak_source": peak_kind,

@@ -69,19 +69,29 @@ __global__ void k_msm_digits(const Fr* scalars, unsigned long long stride, MsmSh
         unsigned int set = w % sh.nsets, table = w / sh.nsets;
         if (AGG) {
             const unsigned int key = (live && mag) ? (b * sh.nsets + set) * sh.NB + (mag - 1) : DE_MSM_INVALID;
-            const unsigned int peers = __match_any_sync(0xffffffffu, key);
             const unsigned int lane = threadIdx.x & 31u;
-            const unsigned int leader = __ffs(peers) - 1;
-            unsigned int first = 0;
-            if (lane == leader && key != DE_MSM_INVALID) first = atomicAdd(&counts[key], __popc(peers));
-            first = __shfl_sync(0xffffffffu, first, leader);
+            // the match is worth its latency only where keys repeat, and repeated keys come in RUNS (equal scalars in neighbouring
+            // rows): one shuffle and a vote decide per warp and window; uniform columns take the plain atomics
+            const unsigned int next_key = __shfl_down_sync(0xffffffffu, key, 1);
+            const bool runs = __any_sync(0xffffffffu, lane < 31 && key == next_key && key != DE_MSM_INVALID);
+            unsigned int rank = 0;
+            if (runs) {
+                const unsigned int peers = __match_any_sync(0xffffffffu, key);
+                const unsigned int leader = __ffs(peers) - 1;
+                unsigned int first = 0;
+                if (lane == leader && key != DE_MSM_INVALID) first = atomicAdd(&counts[key], __popc(peers));
+                first = __shfl_sync(0xffffffffu, first, leader);
+                rank = first + __popc(peers & ((1u << lane) - 1u));
+            } else if (key != DE_MSM_INVALID) {
+                rank = atomicAdd(&counts[key], 1u);
+            }
             if (live) {
                 keys[e] = key;
                 if (key != DE_MSM_INVALID) {
                     unsigned long long tb = table * sh.table_stride + sh.base_offset + i;
                     if (b >= sh.alt_first) tb = (unsigned long long)((long long)tb + sh.alt_delta);
                     vals[e] = (unsigned int)tb | (neg << 31);
-                    if (ranks) ranks[e] = first + __popc(peers & ((1u << lane) - 1u));
+                    if (ranks) ranks[e] = rank;
                 }
             }
         } else if (mag == 0) {

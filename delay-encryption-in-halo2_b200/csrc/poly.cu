@@ -235,7 +235,7 @@ int kate_division_dev(de_ctx* ctx, const Fr* const* d_as, size_t n, const de_fr*
 // ---- roofline denominator measured in the run (bench.py `roofline.peak`): dependent chains of Fr Montgomery products, the
 // instruction mix every hot kernel of this library is made of (136 IMAD.WIDE.U32(.X) per product).  ILP independent chains
 // per thread; the result is stored so that nothing is eliminated.
-template <int ILP>
+template <int ILP, bool SQUARE = false>
 __global__ void __launch_bounds__(128) k_int_peak(Fr* out, const Fr* in, int iters) {
     Fr x[ILP];
     const Fr y = load(&in[threadIdx.x & 31]);
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(128) k_int_peak(Fr* out, const Fr* in, int ite
     for (int i = 0; i < ILP; i++) x[i] = load(&in[(threadIdx.x + i) & 63]);
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int i = 0; i < ILP; i++) x[i] = mul(x[i], y);
+        for (int i = 0; i < ILP; i++) x[i] = SQUARE ? sqr(x[i]) : mul(x[i], y);
     }
     Fr s = x[0];
 #pragma unroll
@@ -257,7 +257,10 @@ using namespace de;
 
 extern "C" {
 
-int de_int_peak(de_ctx* ctx, double* gmul_per_s) {
+static int int_peak(de_ctx* ctx, bool square, double* gmul_per_s);
+int de_int_peak(de_ctx* ctx, double* gmul_per_s) { return int_peak(ctx, false, gmul_per_s); }
+int de_int_peak_sqr(de_ctx* ctx, double* gsqr_per_s) { return int_peak(ctx, true, gsqr_per_s); }
+static int int_peak(de_ctx* ctx, bool square, double* gmul_per_s) {
     if (!ctx) return DE_ERR_ARG;
     if (!gmul_per_s) return fail(ctx, DE_ERR_ARG, "de_int_peak: null pointer");
     DE_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -276,7 +279,8 @@ int de_int_peak(de_ctx* ctx, double* gmul_per_s) {
     float best = 1e30f;
     for (int rep = 0; rep < 6; rep++) {  // the first two launches warm the clocks up
         cudaEventRecord(e0, ctx->stream);
-        k_int_peak<ILP><<<blocks, tpb, 0, ctx->stream>>>(buf, in, iters);
+        if (square) k_int_peak<ILP, true><<<blocks, tpb, 0, ctx->stream>>>(buf, in, iters);
+        else k_int_peak<ILP, false><<<blocks, tpb, 0, ctx->stream>>>(buf, in, iters);
         ctx->launches++;
         cudaEventRecord(e1, ctx->stream);
         cudaError_t e = cudaEventSynchronize(e1);

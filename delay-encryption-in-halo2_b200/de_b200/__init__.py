@@ -88,6 +88,12 @@ class Context:
         self.check(self.L.de_int_peak(self.h, C.byref(v)))
         return v.value
 
+    def int_peak_sqr(self) -> float:
+        """de_int_peak_sqr: Fr squarings per second (in G/s), the dedicated squaring of field.cuh"""
+        v = C.c_double()
+        self.check(self.L.de_int_peak_sqr(self.h, C.byref(v)))
+        return v.value
+
     def close(self):
         if getattr(self, "h", None):
             self.L.de_ctx_destroy(self.h)

@@ -24,7 +24,7 @@ SYMBOLS = [
     "de_commit_batch_canonical_dev", "de_eval_polynomial", "de_kate_division", "de_prover_create", "de_prover_free",
     "de_prover_random_count", "de_prover_proof_size", "de_create_proof", "de_create_proof_dev", "de_g1_mul_base_dev", "de_ctx_set_mode", "de_commit_sharded",
     "de_ntt_dist_stage1", "de_ntt_dist_stage2", "de_ntt_sharded_dev", "de_ntt_sharded", "de_dev_alloc", "de_dev_free", "de_dev_copy", "de_ipc_export", "de_ipc_import",
-    "de_ipc_release", "de_int_peak", "de_ntt_dist_run", "de_ntt_dist_error", "de_ntt_dist_prepare",
+    "de_ipc_release", "de_int_peak", "de_int_peak_sqr", "de_ntt_dist_run", "de_ntt_dist_error", "de_ntt_dist_prepare",
     "de_circuit_synthesize", "de_circuit_witness", "de_assignment_free", "de_assignment_info", "de_assignment_fixed", "de_assignment_advice",
     "de_assignment_copies", "de_assignment_outputs", "de_assignment_sigma", "de_frontend_last_error", "de_poseidon_permute",
     "de_poseidon_cipher",
@@ -119,6 +119,7 @@ def load():
     L.de_ipc_import.argtypes = [P, P, C.POINTER(P)]
     L.de_ipc_release.argtypes = [P, P]
     L.de_int_peak.argtypes = [P, C.POINTER(C.c_double)]
+    L.de_int_peak_sqr.argtypes = [P, C.POINTER(C.c_double)]
     L.de_ntt_dist_run.argtypes = [P, P, P, U32, U32, U32, C.POINTER(P), C.POINTER(P), C.POINTER(P), U32, U32]
     L.de_ntt_dist_error.argtypes = [P, C.POINTER(I)]
     L.de_ntt_dist_prepare.argtypes = [P, P, U32, U32, U32]

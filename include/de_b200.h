@@ -67,6 +67,9 @@ uint64_t de_launch_count(de_ctx* ctx);
  * independent chains per thread) - the 136 IMAD.WIDE.U32 carry-chain multiplier every hot kernel here is made of.  Best of four
  * timed launches after two warm-up launches, ~10 ms in total; synchronises the context's stream. */
 int de_int_peak(de_ctx* ctx, double* gmul_per_s);
+/* The same measurement for the dedicated squaring (field.cuh sqr: 36 + 72 products): Fr squarings per second.  bench.py weighs
+ * the 2 squarings of a mixed bucket addition by mul_peak / sqr_peak when it states executed work in multiplications. */
+int de_int_peak_sqr(de_ctx* ctx, double* gsqr_per_s);
 
 /* per-kernel device timing: CUDA events recorded around the named kernels on the context's stream.
  * Known names: "k_msm_accumulate", "k_msm_digit_sums", "k_ntt_pass", "k_eval_h".  units = points / elements / rows. */

@@ -113,6 +113,7 @@ extern "C" {
     pub fn de_g1_mul_base_dev(ctx: *mut de_ctx, base: *const de_g1_affine, d_scalars: *const de_fr, n: usize, d_out: *mut de_g1_affine) -> c_int;
     pub fn de_g1_batch_normalize(ctx: *mut de_ctx, points: *const de_g1, count: usize, out: *mut de_g1_affine) -> c_int;
     pub fn de_int_peak(ctx: *mut de_ctx, gmul_per_s: *mut f64) -> c_int;
+    pub fn de_int_peak_sqr(ctx: *mut de_ctx, gsqr_per_s: *mut f64) -> c_int;
     pub fn de_ntt_dist_run(ctx: *mut de_ctx, d_x: *const de_fr, omega: *const de_fr, log_n: u32, world: u32, rank: u32, d_z_peers: *const *mut de_fr, d_out_peers: *const *mut de_fr, d_flag_peers: *const *mut u32, epoch: u32, chunks: u32) -> c_int;
     pub fn de_ntt_dist_error(ctx: *mut de_ctx, timed_out: *mut c_int) -> c_int;
     pub fn de_ntt_dist_prepare(ctx: *mut de_ctx, omega: *const de_fr, log_n: u32, world: u32, rank: u32) -> c_int;

@@ -163,3 +163,5 @@ def test_int_peak_is_plausible(ctx):
     """de_int_peak (the roofline denominator bench.py measures in the run): B200 sustains ~66 G Fr multiplications / s"""
     v = ctx.int_peak()
     assert 20.0 < v < 200.0, v
+    s = ctx.int_peak_sqr()  # the dedicated squaring: fewer wide products, never slower than a product
+    assert v * 0.98 < s < 2.0 * v, (v, s)
