@@ -7,7 +7,7 @@ for s in "$@"; do
   tag=$(echo "$s" | tr ',=/' '___')
   envs=""
   if [ "$s" != "base" ]; then envs=$(echo "$s" | tr ',' ' '); fi
-  env $envs timeout 400 python bench.py --no-cpu-baseline --no-msm --no-other-configs --steps ${AB_STEPS:-12} > $O/ab_${tag}.json 2> $O/ab_${tag}.err
+  env $envs timeout 400 python bench.py --no-cpu-baseline --no-msm --no-other-configs --steps ${AB_STEPS:-12} ${AB_ARGS} > $O/ab_${tag}.json 2> $O/ab_${tag}.err
   python - "$s" $O/ab_${tag}.json <<'P'
 import json, sys
 try:
