@@ -52,15 +52,17 @@ int de_ctx_destroy(de_ctx* ctx);
 int de_ctx_set_stream(de_ctx* ctx, void* cuda_stream);
 int de_ctx_sync(de_ctx* ctx);
 /* Scheduling hint.  DE_MODE_LATENCY (default): one proof / one MSM at a time owns the GPU, so latency-bound tails are given
- * short dependency chains even at the price of idle lanes (tree-shaped bucket reduction).  DE_MODE_THROUGHPUT: several
- * contexts run concurrently on the same GPU (batches of proofs), so kernels keep every lane busy and leave the overlap to the
- * other streams (serial segmented sums).  Results are identical; measured at k = 16: 10.0 ms vs 11.5 ms per proof alone,
- * 139 vs 145 proofs/s with 8 proofs in flight. */
+ * short dependency chains even at the price of idle lanes (tree-shaped bucket reduction), and a commitment's launch sequence
+ * is replayed as a CUDA graph from the third call with the same buffers on.  DE_MODE_THROUGHPUT: several contexts run
+ * concurrently on the same GPU (batches of proofs), so kernels keep every lane busy and leave the overlap to the other
+ * streams (serial segmented sums, eager launches).  Results are identical; measured at k = 16 (round 2): 8.1 ms per proof
+ * alone in latency mode, 162 proofs/s with 8 proofs in flight in throughput mode. */
 enum de_mode { DE_MODE_LATENCY = 0, DE_MODE_THROUGHPUT = 1 };
 int de_ctx_set_mode(de_ctx* ctx, int mode);
 const char* de_last_error(de_ctx* ctx); /* ctx may be NULL: returns the last error of a failed de_ctx_create */
 const char* de_version(void);
-/* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
+/* number of kernels this library launched on the context since creation (bench.py's gpu_launches); kernels inside a replayed
+ * graph are counted at every replay */
 uint64_t de_launch_count(de_ctx* ctx);
 /* Roofline denominator, measured on the device the context is bound to ("the build must measure it on
  * the box"): Fr Montgomery multiplications per second of dependent-product chains at full occupancy (16 warps per SM, two
