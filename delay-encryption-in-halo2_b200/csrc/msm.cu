@@ -220,7 +220,12 @@ static int msm_enqueue_graphed(de_ctx* ctx, const Fr* d_scalars, size_t stride, 
     }
     const uint64_t launches_before = ctx->launches;
     cudaGraph_t graph = nullptr;
-    DE_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        // e.g. the caller is capturing this stream itself: leave its capture alone and launch eagerly from now on
+        cudaGetLastError();
+        slot->eager_only = true;
+        return msm_enqueue(ctx, d_scalars, stride, n, count, d_tables, table_stride, base_offset, cfg, d_out, alt_first, alt_delta, nullptr);
+    }
     const int rc = msm_enqueue(ctx, d_scalars, stride, n, count, d_tables, table_stride, base_offset, cfg, d_out, alt_first, alt_delta, nullptr);
     const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
     const uint64_t in_graph = ctx->launches - launches_before;
