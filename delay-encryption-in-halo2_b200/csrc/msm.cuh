@@ -312,10 +312,14 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(const unsigned int* s
     unsigned int len = cnt - local * CH;
     if (len > CH) len = CH;
     XYZZ acc = xyzz_identity();
+    // the sorted index runs two entries ahead of the addition and the 64-byte point one: the point gather never waits for the
+    // index load it depends on (and the loop then fits 128 registers without its 8 bytes of stack)
     Affine next = msm_fetch(bases, sorted[start]);
+    unsigned int idx_next = len > 1 ? sorted[start + 1] : 0;
     for (unsigned int k = 0; k < len; k++) {
         Affine cur = next;
-        if (k + 1 < len) next = msm_fetch(bases, sorted[start + k + 1]);
+        if (k + 1 < len) next = msm_fetch(bases, idx_next);
+        if (k + 2 < len) idx_next = sorted[start + k + 2];
         xyzz_madd(acc, cur);
     }
     if (cnt <= CH) store_xyzz(&buckets[b], acc);
