@@ -9,8 +9,8 @@
 //   3. k_msm_accumulate one thread per task (a run of <= CH entries of one bucket): gathers 64-byte affine bases with
 //                       16-byte loads and adds them into an XYZZ accumulator (8M + 2S per point); heavy buckets are
 //                       split into several tasks whose partial sums are merged warp-cooperatively (k_msm_merge)
-//   4. k_msm_reduce_*   sum_b (b+1) * B_b per bucket set by chunked running sums
-//   5. k_msm_combine    sum over bucket sets of 2^(c*u) * R_u
+//   4. bucket reduction sum_b (b+1) * B_b per bucket set            } msm_reduce.cuh / msm_reduce.cu (their own translation unit;
+//   5. k_msm_combine    sum over bucket sets of 2^(c*u) * R_u       } shared-memory point trees: msm_smem.cuh)
 //
 // With tables 2^(c*nsets*t) * P_i precomputed per ParamsKZG (k_msm_precompute) all windows of a scalar share one
 // bucket set (nsets = 1): one reduction, no doublings.
