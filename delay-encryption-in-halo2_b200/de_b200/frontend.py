@@ -19,7 +19,7 @@ import numpy as np
 from . import _lib, plonk
 from ._lib import DeError
 
-MOD_POW, POSE_ENC, DELAY_ENC, RSA_PKCS1 = 0, 1, 2, 3
+MOD_POW, POSE_ENC, DELAY_ENC, RSA_PKCS1, BIGINT_SQUARE, BIGINT_OPS = 0, 1, 2, 3, 4, 5
 BITS_LEN, EXP_LIMB_BITS = 2048, 5       # src/lib.rs:122-124
 MESSAGE_CAPACITY = 2                    # src/encryption/poseidon_enc.rs:10
 
@@ -98,9 +98,9 @@ def synthesize(kind: int, k: int, n: int = 0, e: int = 0, x: int = 0, message=()
     d.witness_only = 1 if witness_only else 0
     d.threads = threads
     nb = max(1, bits_len // 8)
-    bufs = [np.frombuffer(int(v).to_bytes(nb, "little"), dtype=np.uint8).copy() for v in (n, e, x)]
+    bufs = [np.frombuffer(int(v).to_bytes(max(nb, (int(v).bit_length() + 7) // 8), "little"), dtype=np.uint8).copy() for v in (n, e, x)]
     d.n, d.e, d.x = (b.ctypes.data for b in bufs)
-    d.n_len = d.e_len = d.x_len = nb
+    d.n_len, d.e_len, d.x_len = (len(b) for b in bufs)
     msg = _mont(message)
     d.message, d.message_len = (msg.ctypes.data if len(message) else None), len(message)
     kk = _mont(key)
@@ -180,6 +180,30 @@ def pose_enc(key, message=(0,) * MESSAGE_CAPACITY, k: int = 11) -> SynthesizedCi
 
 def rsa_pkcs1(n: int, e: int, signature: int, digest_limbs, k: int = 17) -> SynthesizedCircuit:
     return synthesize(RSA_PKCS1, k, n, e, signature, digest_limbs)
+
+
+def bigint_square(a: int, expected: int, bits_len: int = BITS_LEN, k: int = 14) -> SynthesizedCircuit:
+    """the big-integer chip's square test circuit (/root/reference/src/big_integer/chip.rs:2918-3030): outputs[0] is the
+    is_equal_muled bit of a * a against `expected`, outputs[1:] the 2 * num_limbs - 1 uncarried ("Muled") limbs of a * a"""
+    return synthesize(BIGINT_SQUARE, k, a, 0, expected, bits_len=bits_len)
+
+
+BIGINT_OPS_RECORDS = ("add", "sub", "sub_overflow", "mul_mod", "pow_mod", "pow_mod_fixed_exp", "is_equal_fresh", "is_less_than",
+                      "is_less_than_or_equal", "in_field")
+
+
+def bigint_ops(a: int, b: int, n: int, bits_len: int = 256, exp_bits: int = EXP_LIMB_BITS, k: int = 14):
+    """the big-integer chip's operator tests in one circuit (/root/reference/src/big_integer/chip.rs:1479-2806); returns
+    (SynthesizedCircuit, {operator: integer value of its result}) - limbs recomposed with 64-bit weights"""
+    syn = synthesize(BIGINT_OPS, k, n, b, a, bits_len=bits_len, exp_bits=exp_bits)
+    out, at = {}, 0
+    for name in BIGINT_OPS_RECORDS:
+        cnt = syn.outputs[at]
+        limbs = syn.outputs[at + 1: at + 1 + cnt]
+        out[name] = sum(v << (64 * i) for i, v in enumerate(limbs))
+        at += 1 + cnt
+    assert at == len(syn.outputs)
+    return syn, out
 
 
 def poseidon_permute(state, t: int = 5, r_f: int = 8, r_p: int = 57) -> List[int]:

@@ -4,6 +4,8 @@
 //   DE_CIRCUIT_POSE_ENC   src/encryption/chip.rs:114-198  PoseidonEncCircuit: duplex encryption of MESSAGE_CAPACITY words
 //   DE_CIRCUIT_DELAY_ENC  src/lib.rs:103-318              DelayEncryptCircuit: mod-pow -> Poseidon hash -> key -> encryption
 //   DE_CIRCUIT_RSA_PKCS1  src/rsa/chip.rs:119-212         signature check with e = 65537 (the reference's known-answer triples)
+//   DE_CIRCUIT_BIGINT_SQUARE src/big_integer/chip.rs:2918-3030  the chip's own square test (its 31 limb products are a known answer)
+//   DE_CIRCUIT_BIGINT_OPS    src/big_integer/chip.rs:1479-2806  the chip's operator tests (add, sub, mul_mod, pow_mod, comparisons)
 // A synthesis pass fills the fixed columns (selectors, constants, range tables), the advice columns (the witness) and the
 // copy constraints of de_b200/plonk.py: main_gate_shape().  keygen consumes fixed + copies (de_assignment_sigma builds the
 // permutation columns), create_proof consumes the advice columns.  Host code only: no GPU is needed or used.
@@ -201,6 +203,64 @@ void synth_rsa_pkcs1(Assignment& as, const de_circuit_desc& d, const RsaInputs& 
     as.outputs.push_back(rsa.verify_pkcs1v15_signature(n, in.e, hashed, sig).value);
 }
 
+// the reference's big-integer chip test circuits (src/big_integer/chip.rs:2918-3030 "test_square_circuit" and its siblings): a is
+// a constant Fresh integer, the chip squares it (mul: one mul_add row per limb product), the expected product is a constant with
+// n1 + n1 - 1 limbs and is_equal_muled compares the two through the carry chain.  n = a, x = the expected product.
+// Outputs: the accept bit (the reference asserts it; returning it lets a test see a rejection), then the Muled limbs of a * a.
+void synth_bigint_square(Assignment& as, const de_circuit_desc& d, const RsaInputs& in) {
+    as.init(d.k, true);
+    MainGate gate(as);
+    RangeChip range(as, gate);
+    configure_range(range, d.bits_len);
+    range.load_table();
+    BigIntChip bigint(gate, range, RSAChip::LIMB_WIDTH, d.bits_len);
+    if (in.n.bits() > d.bits_len) throw std::runtime_error("bigint_square: a wider than bits_len");
+    const AssignedInteger a = bigint.assign_constant_fresh(in.n);
+    const uint32_t n1 = (uint32_t)a.size();
+    const AssignedInteger aa = bigint.mul(a, a);                                  // chip.rs:434-440 square = mul(a, a)
+    const AssignedInteger want = bigint.assign_constant(in.x, 2 * n1 - 1);        // chip.rs:122-131 assign_constant_muled
+    as.outputs.push_back(bigint.is_equal_muled(aa, want, n1, n1).value);
+    for (const Cell& c : aa) as.outputs.push_back(c.value);
+}
+
+// the remaining operator tests of the reference's big-integer chip in ONE circuit (src/big_integer/chip.rs:1479-2806: TestAdd,
+// TestSub / TestOverflowSub, TestMulModEqual, TestPowMod, TestPowModFixedExp, TestFreshEqual, TestLessThan,
+// TestLessThanOrEqual, TestInField): x = a, e = b, n = the modulus; a, b < n for the modular operators; the exponent of the two
+// pow_mod forms is the low exp_bits bits of b.  Outputs: one record per operator, (limb count, limbs ...), in the order
+// add, sub, sub's overflow bit, mul_mod, pow_mod, pow_mod_fixed_exp, is_equal_fresh, is_less_than, is_less_than_or_equal,
+// is_less_than(a, n).
+void synth_bigint_ops(Assignment& as, const de_circuit_desc& d, const RsaInputs& in) {
+    as.init(d.k, true);
+    MainGate gate(as);
+    RangeChip range(as, gate);
+    configure_range(range, d.bits_len);
+    range.load_table();
+    BigIntChip bigint(gate, range, RSAChip::LIMB_WIDTH, d.bits_len);
+    const uint32_t L = bigint.num_limbs;
+    if (in.n.bits() > d.bits_len || in.x.bits() > d.bits_len || in.e.bits() > d.bits_len) throw std::runtime_error("bigint_ops: an operand is wider than bits_len");
+    if (d.exp_bits == 0 || d.exp_bits > 64) throw std::runtime_error("bigint_ops: exp_bits out of range");
+    const AssignedInteger a = bigint.assign_integer(decompose_big(in.x, L, RSAChip::LIMB_WIDTH));
+    const AssignedInteger b = bigint.assign_integer(decompose_big(in.e, L, RSAChip::LIMB_WIDTH));
+    const AssignedInteger n = bigint.assign_integer(decompose_big(in.n, L, RSAChip::LIMB_WIDTH));
+    auto record = [&](const AssignedInteger& v) {
+        as.outputs.push_back(F::from_u64(v.size()));
+        for (const Cell& c : v) as.outputs.push_back(c.value);
+    };
+    record(bigint.add(a, b));
+    const std::pair<AssignedInteger, Cell> subbed = bigint.sub(a, b);
+    record(subbed.first);
+    record({subbed.second});
+    record(bigint.mul_mod(a, b, n));
+    const BigUint e_small = in.e.low_bits(d.exp_bits);
+    const AssignedInteger e_limb = bigint.assign_integer({e_small});
+    record(bigint.pow_mod(a, e_limb, n, d.exp_bits));
+    record(bigint.pow_mod_fixed_exp(a, e_small, n));
+    record({bigint.is_equal_fresh(a, b)});
+    record({bigint.is_less_than(a, b)});
+    record({bigint.is_less_than_or_equal(a, b)});
+    record({bigint.is_less_than(a, n)});
+}
+
 }  // namespace
 
 extern "C" {
@@ -233,6 +293,8 @@ static int synthesize_into(const de_circuit_desc* d, de_fr* advice_out, de_assig
             case DE_CIRCUIT_POSE_ENC: synth_pose_enc(a->as, *d, message); break;
             case DE_CIRCUIT_DELAY_ENC: synth_delay_enc(a->as, *d, in, message); break;
             case DE_CIRCUIT_RSA_PKCS1: synth_rsa_pkcs1(a->as, *d, in); break;
+            case DE_CIRCUIT_BIGINT_SQUARE: synth_bigint_square(a->as, *d, in); break;
+            case DE_CIRCUIT_BIGINT_OPS: synth_bigint_ops(a->as, *d, in); break;
             default: throw std::runtime_error("unknown circuit kind");
         }
         trace_lap("circuit emitted");

@@ -312,9 +312,17 @@ int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_
  *   DE_CIRCUIT_DELAY_ENC  src/lib.rs:103-318               DelayEncryptCircuit (n, e, x, message)
  *   DE_CIRCUIT_RSA_PKCS1  src/rsa/chip.rs:119-212          verify_pkcs1v15_signature (n, e fixed, x = signature, message =
  *                                                          SHA-256 digest as four 64-bit limbs); output = the accept bit
+ *   DE_CIRCUIT_BIGINT_SQUARE src/big_integer/chip.rs:2918-3030  the big-integer chip's square test (n = a, x = expected a * a as one
+ *                                                          integer); outputs = the is_equal_muled bit, then the 2 n1 - 1 Muled limbs
+ *   DE_CIRCUIT_BIGINT_OPS    src/big_integer/chip.rs:1479-2806  the chip's operator tests in one circuit (x = a, e = b, n = modulus,
+ *                                                          a, b < n): outputs = (limb count, limbs...) records of add, sub, sub's
+ *                                                          overflow bit, mul_mod, pow_mod and pow_mod_fixed_exp with the low
+ *                                                          exp_bits bits of b, is_equal_fresh, is_less_than, is_less_than_or_equal,
+ *                                                          is_less_than(a, n)
  * One pass yields the fixed columns, the advice columns and the copy constraints; keygen uses fixed + copies, create_proof
  * the advice columns.  No context and no GPU: these run wherever the library loads.  Errors: de_frontend_last_error(). */
-enum de_circuit_kind { DE_CIRCUIT_MOD_POW = 0, DE_CIRCUIT_POSE_ENC = 1, DE_CIRCUIT_DELAY_ENC = 2, DE_CIRCUIT_RSA_PKCS1 = 3 };
+enum de_circuit_kind { DE_CIRCUIT_MOD_POW = 0, DE_CIRCUIT_POSE_ENC = 1, DE_CIRCUIT_DELAY_ENC = 2, DE_CIRCUIT_RSA_PKCS1 = 3,
+                       DE_CIRCUIT_BIGINT_SQUARE = 4, DE_CIRCUIT_BIGINT_OPS = 5 };
 typedef struct {
     uint32_t kind;       /* de_circuit_kind */
     uint32_t k;          /* 2^k rows */

@@ -230,3 +230,83 @@ def test_errors():
         fe.mod_pow(n, 1 << 6, x, k=17)            # e wider than EXP_LIMB_BITS
     with pytest.raises(fe.DeError):
         fe.mod_pow(n, e, n + 5, k=17)             # x >= n: assert_in_field
+
+
+# /root/reference/src/big_integer/chip.rs:2940-3020 (test_square_circuit): a 1000-bit integer in 64-bit limbs and the 31
+# uncarried ("Muled") limb products of its square, as the reference's own test writes them
+BIG_SQUARE_A_LIMBS = [4819187580044832333, 9183764011217009606, 11426964127496009747, 17898263845095661790, 12102522037140783322,
+                      4029304176671511763, 11339410859987005436, 12120243430436644729, 2888435820322958146, 7612614626488966390,
+                      3872170484348249672, 9589147526444685354, 16391157694429928307, 12256166884204507566, 4257963982333550934,
+                      916988490704]
+BIG_SQUARE_MULED = [int(v) for v in """
+    23224568931658367244754058218082222889 88516562921839445888640380379840781596 194478888615417946406783868151393774738
+    382395265476432217957523230769986571504 575971019676008360859069855433378813941 670174995752918677131397897218932582682
+    780239872348808029089572423614905198300 850410093737715640261630122959874522628 800314959349304909735238452892956199392
+    906862855407309870283714027678210238070 967727310654811444144097720329196927129 825671020037461535758117365587238596380
+    991281789723902700168027417052185830252 1259367815833216292413970809061165585320 1351495628781923848799708082622582598675
+    1451028634949220760698564802414695011932 1290756126635958771067082204577975256756 936482288980049848345464202850902738826
+    886330568585033438612679243731110283692 823948310509772835433730556487356331346 649341353489205691855914543942648985328
+    497838205323760437611385487609464464168 430091148520710550273018448938020664564 474098876922017329965321439330710234148
+    536697574159375092388958994084813127393 483446024935732188792400155524449880972 289799562463011227421662267162524920264
+    104372664369829937912234314161010649544 18130279752377737976455635841349605284 7809007931264072381739139035072
+    840867892083599894415616""".split()]
+
+
+def test_bigint_square_known_answer():
+    """the big-integer chip's own square test: the chip's limb convolution reproduces the reference's 31 limb products, the
+    carry-chain comparison with the constant product accepts, the circuit is satisfied; a product off by one is rejected"""
+    a = sum(v << (64 * i) for i, v in enumerate(BIG_SQUARE_A_LIMBS))
+    want = sum(v << (64 * i) for i, v in enumerate(BIG_SQUARE_MULED))
+    assert len(BIG_SQUARE_MULED) == 31 and want == a * a
+    syn = fe.bigint_square(a, want, bits_len=2048, k=14)       # LIMB_WIDTH 64, BITS_LEN 2048 as in the reference's test macro
+    assert syn.outputs[0] == 1
+    muled = syn.outputs[1:]
+    assert len(muled) == 2 * 32 - 1
+    assert muled[:31] == BIG_SQUARE_MULED and not any(muled[31:])
+    mock_check(syn)
+    # a wrong product: the circuit stays satisfiable (is_equal_muled returns a bit), the bit is zero
+    bad = fe.bigint_square(a, want + 1, bits_len=2048, k=14)
+    assert bad.outputs[0] == 0 and bad.outputs[1:32] == BIG_SQUARE_MULED
+    mock_check(bad)
+    # a 1024-bit chip has 31 Muled limbs, the 2000-bit product needs 32 carried ones: the reference's assign_constant
+    # asserts num_limbs <= max_num_limbs (chip.rs:1270), the front-end reports the same condition as an error
+    from de_b200._lib import DeError
+    with pytest.raises(DeError, match="too many limbs"):
+        fe.bigint_square(a, want, bits_len=1024, k=13)
+
+
+def _bigint_ops_expected(a, b, n, exp_bits):
+    e = b & ((1 << exp_bits) - 1)
+    return {"add": a + b, "sub": abs(a - b), "sub_overflow": int(a <= b), "mul_mod": a * b % n, "pow_mod": pow(a, e, n),
+            "pow_mod_fixed_exp": pow(a, e, n), "is_equal_fresh": int(a == b), "is_less_than": int(a < b),
+            "is_less_than_or_equal": int(a <= b), "in_field": int(a < n)}
+
+
+@pytest.mark.parametrize("bits_len", [128, 256, 512])
+def test_bigint_chip_operators(bits_len):
+    """the operator tests of the reference's big-integer chip (src/big_integer/chip.rs:1479-2806: add, sub with and without
+    overflow, mul_mod, pow_mod with a variable and a fixed exponent, equality and order comparisons, in-field) against Python
+    integers, each circuit checked by the MockProver restatement as the reference's tests do"""
+    import random
+    rng = random.Random(0xB16 + bits_len)
+    n = rng.getrandbits(bits_len) | (1 << (bits_len - 1)) | 1
+    cases = []
+    for _ in range(2):
+        a, b = rng.randrange(n), rng.randrange(n)
+        cases += [(a, b), (b, a)]
+    a = rng.randrange(n)
+    cases += [(a, a), (0, a), (a, 0), (n - 1, n - 1), (1, (1 << 64) - 1), ((1 << 64) - 1, 1 << 64)]
+    for i, (a, b) in enumerate(cases):
+        syn, got = fe.bigint_ops(a, b, n, bits_len=bits_len, k=14 if bits_len < 512 else 15)
+        assert got == _bigint_ops_expected(a, b, n, fe.EXP_LIMB_BITS), (bits_len, i)
+        if i < 3 or a == b:
+            mock_check(syn)
+
+
+def test_bigint_chip_operator_errors():
+    """mul_mod needs the quotient to fit the limbs of b (the reference's decompose panics); operands wider than the chip are refused"""
+    from de_b200._lib import DeError
+    with pytest.raises(DeError):
+        fe.bigint_ops(1 << 130, 1, (1 << 127) | 1, bits_len=128)
+    with pytest.raises(DeError, match="does not fit"):
+        fe.bigint_ops((1 << 128) - 1, (1 << 128) - 1, 3, bits_len=128)
