@@ -51,6 +51,17 @@ def test_poseidon_permutation_known_answers():
     assert fe.poseidon_permute([5, 6, 7, 8, 9], 5, 8, 57) == po.poseidon_permute_ref([5, 6, 7, 8, 9], 5, 8, 57)
 
 
+@pytest.mark.parametrize("t", range(3, 11))
+def test_poseidon_optimised_against_plain_rounds(t):
+    """/root/reference/src/poseidon/permutation.rs:84-129 cross_test: the optimised parameter set (sparse MDS factorisation,
+    pre-merged constants) against the plain round function, R_F = 8, R_P = 57, every width the reference runs (3 ... 10)"""
+    import random
+    rng = random.Random(0xC705 + t)
+    for _ in range(2):
+        state = [rng.randrange(po.FR) for _ in range(t)]
+        assert fe.poseidon_permute(state, t, 8, 57) == po.poseidon_permute_ref(state, t, 8, 57)
+
+
 def test_encrypt_decrypt_round_trip():
     for key in ((0, 0), (0x1234, po.FR - 5)):
         c = fe.poseidon_encrypt(key, [0, 0])   # the message of the reference's test and benches
