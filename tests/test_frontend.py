@@ -130,6 +130,17 @@ def test_mod_pow_circuit():
     mock_check(syn)
 
 
+def test_mod_pow_circuit_1024_bits():
+    """/root/reference/src/rsa/chip.rs:462-513 TestRSAModPow1024Circuit: the same chip at BITS_LEN = 1024 (16 limbs)"""
+    for seed in (7, 8):
+        n, e, x = fe.sample_rsa_inputs(seed, bits_len=1024)
+        syn = fe.synthesize(fe.MOD_POW, 15, n, e, x, bits_len=1024)
+        assert len(syn.outputs) <= 16 and sum(l << (64 * i) for i, l in enumerate(syn.outputs)) == pow(x, e, n)
+        mock_check(syn)
+        wit = fe.synthesize(fe.MOD_POW, 15, n, e, x, bits_len=1024, witness_only=True, threads=3)
+        assert (wit.advice == syn.advice).all()
+
+
 def test_delay_enc_circuit():
     n, e, x = fe.sample_rsa_inputs(0xDE03)
     syn = fe.delay_enc(n, e, x, [0, 0], k=16)
