@@ -19,7 +19,7 @@ import numpy as np
 from . import _lib, plonk
 from ._lib import DeError
 
-MOD_POW, POSE_ENC, DELAY_ENC, RSA_PKCS1, BIGINT_SQUARE, BIGINT_OPS = 0, 1, 2, 3, 4, 5
+MOD_POW, POSE_ENC, DELAY_ENC, RSA_PKCS1, BIGINT_SQUARE, BIGINT_OPS, POSEIDON_HASH = 0, 1, 2, 3, 4, 5, 6
 BITS_LEN, EXP_LIMB_BITS = 2048, 5       # src/lib.rs:122-124
 MESSAGE_CAPACITY = 2                    # src/encryption/poseidon_enc.rs:10
 
@@ -186,6 +186,12 @@ def bigint_square(a: int, expected: int, bits_len: int = BITS_LEN, k: int = 14) 
     """the big-integer chip's square test circuit (/root/reference/src/big_integer/chip.rs:2918-3030): outputs[0] is the
     is_equal_muled bit of a * a against `expected`, outputs[1:] the 2 * num_limbs - 1 uncarried ("Muled") limbs of a * a"""
     return synthesize(BIGINT_SQUARE, k, a, 0, expected, bits_len=bits_len)
+
+
+def poseidon_hash(inputs, k: int = 12) -> SynthesizedCircuit:
+    """PoseidonHashCircuit of the reference's hasher test (/root/reference/src/hash/chip.rs:113-236): outputs = the five state
+    words after HasherChip::hash (words 1..4 are constrained equal to the native sponge's update + squeeze(1))"""
+    return synthesize(POSEIDON_HASH, k, message=list(inputs))
 
 
 BIGINT_OPS_RECORDS = ("add", "sub", "sub_overflow", "mul_mod", "pow_mod", "pow_mod_fixed_exp", "is_equal_fresh", "is_less_than",

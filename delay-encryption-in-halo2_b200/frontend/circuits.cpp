@@ -6,6 +6,7 @@
 //   DE_CIRCUIT_RSA_PKCS1  src/rsa/chip.rs:119-212         signature check with e = 65537 (the reference's known-answer triples)
 //   DE_CIRCUIT_BIGINT_SQUARE src/big_integer/chip.rs:2918-3030  the chip's own square test (its 31 limb products are a known answer)
 //   DE_CIRCUIT_BIGINT_OPS    src/big_integer/chip.rs:1479-2806  the chip's operator tests (add, sub, mul_mod, pow_mod, comparisons)
+//   DE_CIRCUIT_POSEIDON_HASH src/hash/chip.rs:113-236           PoseidonHashCircuit: HasherChip against the native sponge
 // A synthesis pass fills the fixed columns (selectors, constants, range tables), the advice columns (the witness) and the
 // copy constraints of de_b200/plonk.py: main_gate_shape().  keygen consumes fixed + copies (de_assignment_sigma builds the
 // permutation columns), create_proof consumes the advice columns.  Host code only: no GPU is needed or used.
@@ -106,6 +107,28 @@ void synth_pose_enc(Assignment& as, const de_circuit_desc& d, const Vec& message
     MainGate gate(as);
     const Spec& spec = shared_spec(5, 8, 57);
     enc_region(gate, spec, fr_in(d.key[0]), fr_in(d.key[1]), message, d.message_len, false, nullptr, as);
+}
+
+// src/hash/chip.rs:113-193 PoseidonHashCircuit (the circuit of test_example_hash): the native sponge's digest words as witnesses,
+// HasherChip over the inputs one update() each, hash(), the RATE words after the capacity word constrained equal to the expected
+void synth_poseidon_hash(Assignment& as, const de_circuit_desc& d, const Vec& inputs) {
+    as.init(d.k, false);
+    MainGate gate(as);
+    const Spec& spec = shared_spec(5, 8, 57);
+    const uint32_t rate = spec.t - 1;
+    Poseidon ref_hasher(spec, Poseidon::hash_state(spec.t));
+    ref_hasher.update(inputs);
+    const Vec expected = ref_hasher.squeeze(1);
+    std::vector<Cell> expected_cells;
+    for (uint32_t i = 0; i < rate; i++) expected_cells.push_back(gate.assign_value(expected[spec.t - rate + i]));
+    PoseidonChip hasher = PoseidonChip::new_hash(gate, spec);
+    for (const F& v : inputs) hasher.absorbing.push_back(gate.assign_value(v));
+    const std::vector<Cell> out = hasher.hash();
+    for (uint32_t i = 0; i < rate; i++) {
+        if (out[spec.t - rate + i].value != expected_cells[i].value) throw std::runtime_error("poseidon_hash: HasherChip and the native sponge disagree");
+        gate.assert_equal(out[spec.t - rate + i], expected_cells[i]);
+    }
+    for (const Cell& c : out) as.outputs.push_back(c.value);
 }
 
 // regions "hash mapping from 2048bit" and "poseidon region" of DelayEncryptCircuit (src/lib.rs:240-300)
@@ -277,7 +300,7 @@ static int synthesize_into(const de_circuit_desc* d, de_fr* advice_out, de_assig
         RsaInputs in;
         Vec message;
         for (uint32_t i = 0; i < d->message_len; i++) message.push_back(fr_in(d->message[i]));
-        if (d->kind != DE_CIRCUIT_POSE_ENC) {
+        if (d->kind != DE_CIRCUIT_POSE_ENC && d->kind != DE_CIRCUIT_POSEIDON_HASH) {
             if (!d->n || !d->e || !d->x || d->bits_len == 0 || d->bits_len % 64) throw std::runtime_error("RSA inputs missing or bits_len not a multiple of 64");
             in.n = BigUint::from_bytes_le(d->n, d->n_len);
             in.e = BigUint::from_bytes_le(d->e, d->e_len);
@@ -295,6 +318,7 @@ static int synthesize_into(const de_circuit_desc* d, de_fr* advice_out, de_assig
             case DE_CIRCUIT_RSA_PKCS1: synth_rsa_pkcs1(a->as, *d, in); break;
             case DE_CIRCUIT_BIGINT_SQUARE: synth_bigint_square(a->as, *d, in); break;
             case DE_CIRCUIT_BIGINT_OPS: synth_bigint_ops(a->as, *d, in); break;
+            case DE_CIRCUIT_POSEIDON_HASH: synth_poseidon_hash(a->as, *d, message); break;
             default: throw std::runtime_error("unknown circuit kind");
         }
         trace_lap("circuit emitted");

@@ -319,10 +319,12 @@ int de_g1_batch_normalize(de_ctx* ctx, const de_g1* points, size_t count, de_g1_
  *                                                          overflow bit, mul_mod, pow_mod and pow_mod_fixed_exp with the low
  *                                                          exp_bits bits of b, is_equal_fresh, is_less_than, is_less_than_or_equal,
  *                                                          is_less_than(a, n)
+ *   DE_CIRCUIT_POSEIDON_HASH src/hash/chip.rs:113-236           PoseidonHashCircuit (message = the inputs, any count): HasherChip's
+ *                                                          digest constrained equal to the native sponge's; outputs = the 5 state words
  * One pass yields the fixed columns, the advice columns and the copy constraints; keygen uses fixed + copies, create_proof
  * the advice columns.  No context and no GPU: these run wherever the library loads.  Errors: de_frontend_last_error(). */
 enum de_circuit_kind { DE_CIRCUIT_MOD_POW = 0, DE_CIRCUIT_POSE_ENC = 1, DE_CIRCUIT_DELAY_ENC = 2, DE_CIRCUIT_RSA_PKCS1 = 3,
-                       DE_CIRCUIT_BIGINT_SQUARE = 4, DE_CIRCUIT_BIGINT_OPS = 5 };
+                       DE_CIRCUIT_BIGINT_SQUARE = 4, DE_CIRCUIT_BIGINT_OPS = 5, DE_CIRCUIT_POSEIDON_HASH = 6 };
 typedef struct {
     uint32_t kind;       /* de_circuit_kind */
     uint32_t k;          /* 2^k rows */

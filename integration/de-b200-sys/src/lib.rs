@@ -39,6 +39,7 @@ pub const DE_CIRCUIT_DELAY_ENC: u32 = 2;
 pub const DE_CIRCUIT_RSA_PKCS1: u32 = 3;
 pub const DE_CIRCUIT_BIGINT_SQUARE: u32 = 4; // the big-integer chip's square test (src/big_integer/chip.rs:2918-3030)
 pub const DE_CIRCUIT_BIGINT_OPS: u32 = 5;    // its operator tests in one circuit (chip.rs:1479-2806)
+pub const DE_CIRCUIT_POSEIDON_HASH: u32 = 6; // PoseidonHashCircuit (src/hash/chip.rs:113-236)
 
 pub const DE_OK: c_int = 0;
 pub const DE_ERR_ARG: c_int = -1;

@@ -62,6 +62,36 @@ def test_poseidon_optimised_against_plain_rounds(t):
         assert fe.poseidon_permute(state, t, 8, 57) == po.poseidon_permute_ref(state, t, 8, 57)
 
 
+def _sponge_hash(inputs):
+    """poseidon.rs: Poseidon::new_hash(8, 57), update(inputs), squeeze(1), on the plain round function of the checker"""
+    state = [1 << 64, 0, 0, 0, 0]
+    full, rest = len(inputs) // 4 * 4, len(inputs) % 4
+    for off in range(0, full, 4):
+        for i in range(4):
+            state[1 + i] = (state[1 + i] + inputs[off + i]) % po.FR
+        state = po.poseidon_permute_ref(state, 5, 8, 57)
+    for i, v in enumerate(list(inputs[full:]) + [1]):
+        state[1 + i] = (state[1 + i] + v) % po.FR
+    return po.poseidon_permute_ref(state, 5, 8, 57)
+
+
+def test_poseidon_hash_circuit():
+    """/root/reference/src/hash/chip.rs:203-236 test_example_hash (four zero inputs, T = 5, RATE = 4) and the same circuit for
+    every input count around the rate: HasherChip equals the native sponge (constrained inside the circuit) and the checker's
+    plain-round restatement; the circuit is satisfied"""
+    import random
+    rng = random.Random(0x4A54)
+    syn = fe.poseidon_hash([0, 0, 0, 0])
+    assert syn.outputs == _sponge_hash([0, 0, 0, 0])
+    mock_check(syn)
+    for count in (0, 1, 3, 4, 5, 8, 11):
+        inputs = [rng.randrange(po.FR) for _ in range(count)]
+        syn = fe.poseidon_hash(inputs)
+        assert syn.outputs == _sponge_hash(inputs), count
+        mock_check(syn)
+    # the hash region of DelayEncryptCircuit is this circuit over the 11 packed limbs (test_delay_enc_circuit checks the key)
+
+
 def test_encrypt_decrypt_round_trip():
     for key in ((0, 0), (0x1234, po.FR - 5)):
         c = fe.poseidon_encrypt(key, [0, 0])   # the message of the reference's test and benches
