@@ -2,7 +2,8 @@
 // The reference's host language is Rust, which this environment cannot compile; this mirror keeps the reference's names,
 // argument meaning and failure behaviour (the Rust functions panic on violated asserts; these throw std::runtime_error).
 //   halo2_proofs::arithmetic::{best_multiexp, best_fft, eval_polynomial, kate_division}, poly::EvaluationDomain,
-//   poly::kzg::commitment::ParamsKZG, plonk::ProvingKey (device staging), plonk::create_proof (Prover)
+//   poly::kzg::commitment::ParamsKZG, plonk::ProvingKey (device staging), plonk::create_proof (Prover);
+//   the reference's own circuits as witness generators: DelayEncryptCircuit, RSACircuit, PoseidonEncCircuit (Circuit::synthesize)
 // Element types are the C ABI's (include/de_b200.h): Montgomery limbs, byte-identical to halo2curves.
 #pragma once
 #include <cstring>
@@ -310,5 +311,137 @@ inline void best_fft_sharded(const std::vector<const Context*>& ctxs, std::vecto
     for (auto* c : ctxs) h.push_back(c->handle());
     ctxs[0]->check(de_ntt_sharded(h.data(), (int)h.size(), a.data(), &omega, log_n), "best_fft_sharded");
 }
+
+// ---- the reference's circuits (Circuit::synthesize as a host witness generator; no Context, no GPU) ------------------------
+// What halo2's two synthesis passes hand to keygen (fixed columns, copy constraints -> sigma) and to create_proof (advice).
+class Assignment {
+public:
+    explicit Assignment(de_assignment* h) : h_(h) {
+        if (de_assignment_info(h_, &info_) != DE_OK) throw std::runtime_error("de_assignment_info failed");
+    }
+    ~Assignment() { de_assignment_free(h_); }
+    Assignment(const Assignment&) = delete;
+    Assignment(Assignment&& o) noexcept : h_(o.h_), info_(o.info_) { o.h_ = nullptr; }
+    uint32_t k() const { return info_.k; }
+    size_t rows() const { return size_t(1) << info_.k; }
+    uint32_t n_fixed() const { return info_.n_fixed; }
+    uint32_t n_advice() const { return info_.n_advice; }
+    uint64_t used_rows() const { return info_.used_rows; }
+    double synthesis_ms() const { return info_.synthesis_ms; }
+    std::vector<de_fr> fixed(uint32_t column) const { return column_of(de_assignment_fixed, column, "fixed"); }
+    std::vector<de_fr> advice(uint32_t column) const { return column_of(de_assignment_advice, column, "advice"); }
+    // (left column, left row, right column, right row) per copy constraint; columns are positions in the permutation
+    std::vector<uint32_t> copies() const {
+        std::vector<uint32_t> c(4 * info_.n_copies);
+        if (info_.n_copies && de_assignment_copies(h_, c.data()) != DE_OK) throw std::runtime_error("de_assignment_copies failed");
+        return c;
+    }
+    // the circuit's results (x^e mod n limbs, key words, ciphertext ...; de_b200.h: de_assignment_outputs)
+    std::vector<de_fr> outputs() const {
+        std::vector<de_fr> o(info_.n_outputs ? info_.n_outputs : 1);
+        if (de_assignment_outputs(h_, o.data()) != DE_OK) throw std::runtime_error("de_assignment_outputs failed");
+        o.resize(info_.n_outputs);
+        return o;
+    }
+    // permutation::keygen::Assembly::build_pk: n_columns sigma columns in lagrange form
+    std::vector<de_fr> sigma(const de_fr& omega, const de_fr& delta, uint32_t n_columns) const {
+        std::vector<de_fr> s(size_t(n_columns) * rows());
+        if (de_assignment_sigma(h_, &omega, &delta, n_columns, s.data()) != DE_OK) throw std::runtime_error(de_frontend_last_error());
+        return s;
+    }
+
+private:
+    template <typename Fn>
+    std::vector<de_fr> column_of(Fn fn, uint32_t column, const char* what) const {
+        std::vector<de_fr> v(rows());
+        if (fn(h_, column, v.data()) != DE_OK) throw std::runtime_error(std::string("no such ") + what + " column");
+        return v;
+    }
+    de_assignment* h_;
+    de_assignment_info_t info_;
+};
+
+// Common part of the three bench circuits: synthesize() is keygen's pass, witness() the pass create_proof makes - advice columns
+// only, written column after column into the caller's buffer (5 * 2^k elements, e.g. the pinned buffer the prover uploads from).
+class Circuit {
+public:
+    Assignment synthesize(uint32_t k) const {
+        de_circuit_desc d = desc(k);
+        de_assignment* a = nullptr;
+        if (de_circuit_synthesize(&d, &a) != DE_OK) throw std::runtime_error(de_frontend_last_error());
+        return Assignment(a);
+    }
+    de_assignment_info_t witness(uint32_t k, de_fr* advice_out, uint32_t threads = 1, bool reuse_buffer = false) const {
+        de_circuit_desc d = desc(k);
+        d.threads = threads;
+        d.reuse_buffer = reuse_buffer ? 1 : 0;
+        de_assignment_info_t info;
+        if (de_circuit_witness(&d, advice_out, &info) != DE_OK) throw std::runtime_error(de_frontend_last_error());
+        return info;
+    }
+    virtual ~Circuit() {}
+
+protected:
+    virtual de_circuit_desc desc(uint32_t k) const = 0;
+    static de_circuit_desc blank(uint32_t kind, uint32_t k) {
+        de_circuit_desc d;
+        std::memset(&d, 0, sizeof d);
+        d.kind = kind;
+        d.k = k;
+        d.bits_len = 2048;  // BITS_LEN, src/lib.rs:38
+        d.exp_bits = 5;     // EXP_LIMB_BITS, src/lib.rs:39
+        return d;
+    }
+};
+
+// benches/mod_pow.rs:36-140 RSACircuit: x^e mod n; integers as little-endian bytes
+class RSACircuit : public Circuit {
+public:
+    RSACircuit(std::vector<uint8_t> n, std::vector<uint8_t> e, std::vector<uint8_t> x) : n_(std::move(n)), e_(std::move(e)), x_(std::move(x)) {}
+
+protected:
+    de_circuit_desc desc(uint32_t k) const override { return with_rsa(blank(DE_CIRCUIT_MOD_POW, k)); }
+    de_circuit_desc with_rsa(de_circuit_desc d) const {
+        d.n = n_.data(); d.n_len = n_.size();
+        d.e = e_.data(); d.e_len = e_.size();
+        d.x = x_.data(); d.x_len = x_.size();
+        return d;
+    }
+    std::vector<uint8_t> n_, e_, x_;
+};
+
+// src/lib.rs:103-318 DelayEncryptCircuit: x^e mod n -> Poseidon hash -> key -> Poseidon encryption of `message`
+class DelayEncryptCircuit : public RSACircuit {
+public:
+    DelayEncryptCircuit(std::vector<uint8_t> n, std::vector<uint8_t> e, std::vector<uint8_t> x, std::vector<de_fr> message)
+        : RSACircuit(std::move(n), std::move(e), std::move(x)), message_(std::move(message)) {}
+
+protected:
+    de_circuit_desc desc(uint32_t k) const override {
+        de_circuit_desc d = with_rsa(blank(DE_CIRCUIT_DELAY_ENC, k));
+        d.message = message_.data();
+        d.message_len = (uint32_t)message_.size();
+        return d;
+    }
+    std::vector<de_fr> message_;
+};
+
+// src/encryption/chip.rs:114-198 PoseidonEncCircuit: duplex encryption of `message` under key (k0, k1)
+class PoseidonEncCircuit : public Circuit {
+public:
+    PoseidonEncCircuit(const de_fr& k0, const de_fr& k1, std::vector<de_fr> message) : message_(std::move(message)) { key_[0] = k0; key_[1] = k1; }
+
+protected:
+    de_circuit_desc desc(uint32_t k) const override {
+        de_circuit_desc d = blank(DE_CIRCUIT_POSE_ENC, k);
+        d.message = message_.data();
+        d.message_len = (uint32_t)message_.size();
+        d.key[0] = key_[0];
+        d.key[1] = key_[1];
+        return d;
+    }
+    de_fr key_[2];
+    std::vector<de_fr> message_;
+};
 
 }  // namespace halo2_b200

@@ -103,3 +103,43 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     open(pdir / "want_proof.bin", "wb").write(want)
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+CIRCUITS_EXE = os.path.join(ROOT, "tests", "hostcpp", "host_circuits_test")
+
+
+def test_cpp_mirror_circuits_match_python_frontend(tmp_path):
+    """DelayEncryptCircuit / RSACircuit / PoseidonEncCircuit of host/halo2_b200.hpp (the reference's circuit types: src/lib.rs:103,
+    benches/mod_pow.rs:36, src/encryption/chip.rs:114) against the Python mirror of the same front-end: results, advice, copy
+    constraints, used rows; threaded witness pass equals the keygen pass; too few rows throws.  No GPU involved."""
+    from de_b200 import frontend as fe
+    src = os.path.join(ROOT, "tests", "hostcpp", "host_circuits_test.cpp")
+    hdr = os.path.join(PKG, "host", "halo2_b200.hpp")
+    lib = os.path.join(PKG, "libde_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__ as g
+        g.build()
+    if not os.path.exists(CIRCUITS_EXE) or os.path.getmtime(CIRCUITS_EXE) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(lib)):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(PKG, "host"), src, "-o", CIRCUITS_EXE, "-L", PKG, "-lde_b200",
+                               f"-Wl,-rpath,{PKG}"])
+    n, e, x = fe.sample_rsa_inputs(0xC99)
+    for name, v in (("n", n), ("e", e), ("x", x)):
+        (tmp_path / f"{name}.bin").write_bytes(int(v).to_bytes(256, "little"))
+    key = (0x5EED1, 0x5EED2)
+    orc.fr_mont_from_ints(list(key)).tofile(tmp_path / "key.bin")
+    r = subprocess.run([CIRCUITS_EXE, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
+
+    def ints(name):
+        return orc.fr_ints_from_mont(np.fromfile(tmp_path / name, dtype=np.uint64).reshape(-1, 4))
+
+    d = fe.delay_enc(n, e, x, [0, 0], k=16)
+    assert ints("delay_outputs.bin") == d.outputs
+    assert sum(l << (64 * i) for i, l in enumerate(d.outputs[:32])) == pow(x, e, n)
+    assert (np.fromfile(tmp_path / "delay_advice0.bin", dtype=np.uint64).reshape(-1, 4) == d.advice[0]).all()
+    assert (np.fromfile(tmp_path / "delay_copies.bin", dtype=np.uint32).reshape(-1, 4) == d.copies).all()
+    assert int((tmp_path / "delay_rows.txt").read_text()) == d.used_rows
+    assert ints("rsa_outputs.bin") == fe.mod_pow(n, e, x, k=17).outputs
+    p = fe.pose_enc(key, [0, 0], k=11)
+    assert ints("pose_outputs.bin") == p.outputs == fe.poseidon_encrypt(key, [0, 0])
+    assert (np.fromfile(tmp_path / "pose_fixed3.bin", dtype=np.uint64).reshape(-1, 4) == p.fixed[3]).all()
