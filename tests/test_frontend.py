@@ -362,3 +362,29 @@ def test_bigint_chip_operator_errors():
         fe.bigint_ops(1 << 130, 1, (1 << 127) | 1, bits_len=128)
     with pytest.raises(DeError, match="does not fit"):
         fe.bigint_ops((1 << 128) - 1, (1 << 128) - 1, 3, bits_len=128)
+
+
+def test_bigint_chip_operators_edge_limb_fuzz():
+    """the same circuit on operands whose limbs are drawn from {0, 1, 2, 2^32 +- 1, 2^63 +- 1, 2^64 - 1, 2^64 - 2} and random words,
+    moduli that are not normalised (top limb small or zero bits below): the carries of add / sub, the quotient estimate of the
+    front-end's long division (biguint.hpp, Knuth D) and the carry chain of is_equal_muled at their corner values"""
+    import random
+    rng = random.Random(12345)
+    alpha = [0, 1, 2, 1 << 63, (1 << 64) - 1, (1 << 63) - 1, (1 << 63) + 1, 1 << 32, (1 << 32) - 1, (1 << 64) - 2]
+
+    def pick(nl):
+        return sum((rng.choice(alpha) if rng.random() < 0.7 else rng.getrandbits(64)) << (64 * i) for i in range(nl))
+
+    done = 0
+    for it in range(160):
+        nl = rng.choice([2, 3, 4])
+        n = pick(nl)
+        if n < 2:
+            continue
+        a, b = pick(nl) % n, pick(nl) % n
+        syn, got = fe.bigint_ops(a, b, n, bits_len=64 * nl, k=14)
+        assert got == _bigint_ops_expected(a, b, n, fe.EXP_LIMB_BITS), (hex(a), hex(b), hex(n))
+        if it % 40 == 0:
+            mock_check(syn)
+        done += 1
+    assert done > 140
