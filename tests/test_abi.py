@@ -74,3 +74,18 @@ def test_rust_sys_crate_declares_every_header_symbol():
     src = open(os.path.join(ROOT, "integration", "de-b200-sys", "src", "lib.rs")).read()
     declared = set(re.findall(r"pub fn (de_[a-z0-9_]+)\(", src))
     assert declared == set(_lib.SYMBOLS)
+
+
+def test_circuit_kinds_agree_across_header_python_and_rust():
+    """enum de_circuit_kind of include/de_b200.h, the constants of de_b200/frontend.py and of the Rust -sys crate"""
+    import re
+    from de_b200 import frontend as fe
+    hdr = open(os.path.join(ROOT, "include", "de_b200.h")).read()
+    body = re.search(r"enum de_circuit_kind \{(.*?)\};", hdr, re.S).group(1)
+    kinds = {m.group(1): int(m.group(2)) for m in re.finditer(r"DE_CIRCUIT_([A-Z0-9_]+) = (\d+)", body)}
+    assert sorted(kinds.values()) == list(range(len(kinds))) and len(kinds) == 7
+    for name, value in kinds.items():
+        assert getattr(fe, name) == value, name
+    rs = open(os.path.join(ROOT, "integration", "de-b200-sys", "src", "lib.rs")).read()
+    rust = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const DE_CIRCUIT_([A-Z0-9_]+): u32 = (\d+);", rs)}
+    assert rust == kinds
