@@ -388,3 +388,18 @@ def test_bigint_chip_operators_edge_limb_fuzz():
             mock_check(syn)
         done += 1
     assert done > 140
+
+
+def test_frontend_golden_digests():
+    """tests/golden/frontend_v1.json (generator: tests/golden/make_golden_frontend.py): the rows the front-end emits for seeded inputs
+    do not move - a proving key made by one build fits the witness of another"""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_frontend", os.path.join(here, "golden", "make_golden_frontend.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    want = json.load(open(os.path.join(here, "golden", "frontend_v1.json")))
+    got = {name: gen.describe(syn) for name, syn in gen.cases()}
+    assert got == want
